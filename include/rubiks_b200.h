@@ -1,0 +1,132 @@
+/*
+ * rubiks_b200.h -- C ABI of librubiks_b200.so: RubiksNet's learnable-shift hot path for B200 (sm_100a).
+ *
+ * This is the drop-in boundary.  Each entry point replaces one function of the reference's native
+ * module `rubiksnet_cuda` (pybind11, /root/reference/cuda_src/rubiks.cpp:384-396); the citation next
+ * to each prototype names the reference interface it stands in for.  Plain pointers and sizes only:
+ * no torch / ATen types cross this boundary (INTEGRATION.md shows the reference-side binding).
+ *
+ * Conventions
+ *  - All tensor pointers are DEVICE pointers to contiguous memory of the given dtype.
+ *      3D: x [N,T,C,H,W], shift [3,C] rows (T,H,W), out / out_grad [N,To,C,Ho,Wo]
+ *      2D: x [N,C,H,W],   shift [2,C] rows (H,W),   out / out_grad [N,C,Ho,Wo]
+ *      output extent per axis = (in + 2*pad - 1) / stride + 1     (rubiks.cpp:14-30,161-178)
+ *  - `dtype` is the activation type, `shift_dtype` the type of shift AND shift_grad (RB_F32 when
+ *    activations are bf16/f16 and the parameter stays fp32; the reference requires them equal:
+ *    rubiksnet/shiftlib/rubiks3d/primitive.py:65).
+ *  - `stream` is a cudaStream_t (NULL = legacy default stream).  Every launch goes to that stream;
+ *    nothing synchronises.  The caller selects the device (cudaSetDevice) before calling.
+ *  - Every output element is written: callers need not pre-zero buffers (the reference's Python side
+ *    does, rubiksnet/utils.py:25-26; elements it would have left at 0 are written as 0 here).
+ *  - shift_grad is OVERWRITTEN, as in the reference (addmv_ with beta = 0, rubiks.cpp:344-345).
+ *  - Return value: RB_OK (0) on success -- the reference's entry points always return 0 and the
+ *    Python side asserts that (primitive.py:79,139).  Invalid arguments and CUDA launch errors
+ *    return a non-zero rb_status_t; rb_last_error() gives the message (the reference throws a C++
+ *    exception -> RuntimeError, which is what the Python mirror raises on non-zero).
+ */
+#ifndef RUBIKS_B200_H_
+#define RUBIKS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RB_ABI_VERSION 1
+
+typedef enum { RB_F32 = 0, RB_F64 = 1, RB_F16 = 2, RB_BF16 = 3 } rb_dtype_t;
+
+typedef enum {
+    RB_OK = 0,
+    RB_ERR_INVALID_ARGUMENT = 1, /* bad dtype / non-positive extent or stride / null pointer */
+    RB_ERR_UNSUPPORTED = 2,      /* combination not implemented (message says which) */
+    RB_ERR_CUDA = 3,             /* cudaGetLastError() after a launch was not cudaSuccess */
+    RB_ERR_WORKSPACE = 4         /* workspace pointer null or smaller than *_workspace_bytes() */
+} rb_status_t;
+
+/* which implementation the dispatcher may use; RB_IMPL_AUTO picks the tiled sm_100a kernels
+ * whenever the geometry allows and the generic gather kernels otherwise */
+typedef enum { RB_IMPL_AUTO = 0, RB_IMPL_GENERIC = 1, RB_IMPL_TILED = 2 } rb_impl_t;
+
+int rb_abi_version(void);
+/* message of the last non-zero status returned on this thread ("" if none) */
+const char *rb_last_error(void);
+/* number of kernels this library has launched since load / the last reset (all threads) */
+uint64_t rb_launch_count(void);
+void rb_launch_count_reset(void);
+/* force an implementation for subsequent calls from any thread (tests / benchmarks) */
+void rb_set_impl(int impl);
+/* implementation the last forward / backward call on this thread actually used (rb_impl_t) */
+int rb_last_impl(void);
+
+/* compute_output_shape, rubiks.cpp:161-178 (and compute_output_len :14-30) */
+int rb_out_len(int in_len, int stride, int pad);
+
+/* ---------------------------------------------------------------- 3D learnable shift ---------- */
+
+/* replaces rubiks_shift_3d_forward<T> (rubiks.cpp:181-253) -> RubiksShift3DForward<T>
+ * (rubiks3d_kernels.cu:1002-1038) -> rubiks_shift_3d_forward_cuda (:15-205).
+ * strides / pads are (T,H,W). */
+int rb_shift3d_forward(const void *x, const void *shift, void *out, int dtype, int shift_dtype,
+                       int N, int T, int C, int H, int W, int sT, int sH, int sW, int pT, int pH,
+                       int pW, int quantize, void *stream);
+
+/* scratch bytes rb_shift3d_backward needs (replaces the torch::zeros({3C,Ho,Wo}) + torch::ones
+ * temporaries of rubiks.cpp:294-299) */
+size_t rb_shift3d_backward_workspace_bytes(int dtype, int N, int T, int C, int H, int W, int sT,
+                                           int sH, int sW, int pT, int pH, int pW);
+
+/* replaces rubiks_shift_3d_backward<T> (rubiks.cpp:256-379): shift-grad kernel
+ * (rubiks3d_kernels.cu:218-452) + addmv_ reduction (rubiks.cpp:344-345) + optional
+ * normalisation (:932-960) + input-grad kernel (:455-929).
+ * x_grad and/or shift_grad may be NULL to skip that output.  normalize_t_factor < 0 selects the
+ * temporal-only normalisation.  `quantize` affects x_grad only (as in the reference). */
+int rb_shift3d_backward(const void *x, const void *shift, const void *out_grad, void *x_grad,
+                        void *shift_grad, int dtype, int shift_dtype, int N, int T, int C, int H,
+                        int W, int sT, int sH, int sW, int pT, int pH, int pW, int normalize_grad,
+                        double normalize_t_factor, int quantize, void *workspace,
+                        size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------- 2D learnable shift ---------- */
+
+/* replaces rubiks2d_forward (rubiks.cpp:44-67) -> rubiks2d_forward_kernel
+ * (rubiks2d_kernels.cu:94-145).  strides / pads are (H,W). */
+int rb_shift2d_forward(const void *x, const void *shift, void *out, int dtype, int shift_dtype,
+                       int N, int C, int H, int W, int sH, int sW, int pH, int pW, int quantize,
+                       void *stream);
+
+size_t rb_shift2d_backward_workspace_bytes(int dtype, int N, int C, int H, int W, int sH, int sW,
+                                           int pH, int pW);
+
+/* replaces rubiks2d_backward (rubiks.cpp:94-155): rubiks2d_backward_shift_kernel
+ * (rubiks2d_kernels.cu:147-266) + addmv_ + rubiks2d_normalize_shift_grad_kernel (:381-397) +
+ * rubiks2d_backward_input_kernel (:269-379).  enable_shift_grad = 0 leaves shift_grad untouched
+ * (rubiks.cpp:126). */
+int rb_shift2d_backward(const void *x, const void *shift, const void *out_grad, void *x_grad,
+                        void *shift_grad, int dtype, int shift_dtype, int N, int C, int H, int W,
+                        int sH, int sW, int pH, int pW, int normalize_grad, int enable_shift_grad,
+                        int quantize, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------- AttentionShift -------------- */
+
+/* The 3-tap temporal mix of rubiksnet/attention_shift.py:32-39 (the depth-wise F.conv1d with
+ * C*H*W groups): out[n,t,c,:] = taps[c,0] x[n,t-1,c,:] + taps[c,1] x[n,t,c,:] + taps[c,2] x[n,t+1,c,:]
+ * with zeros beyond the clip.  x / out are [N*T, C, HW] contiguous, taps is fp32 [C,3] (the softmax
+ * of :29-30 is a [C,3] computation done by the host mirror). */
+int rb_attention_shift_forward(const void *x, const float *taps, void *out, int dtype, int N, int T,
+                               int C, int HW, void *stream);
+
+size_t rb_attention_shift_backward_workspace_bytes(int N, int T, int C, int HW);
+
+/* adjoint of the above: x_grad [N*T,C,HW] and taps_grad fp32 [C,3] (overwritten); either may be
+ * NULL. */
+int rb_attention_shift_backward(const void *x, const float *taps, const void *out_grad, void *x_grad,
+                                float *taps_grad, int dtype, int N, int T, int C, int HW,
+                                void *workspace, size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RUBIKS_B200_H_ */

@@ -1,0 +1,122 @@
+"""ctypes binding of librubiks_b200.so (the C ABI declared in include/rubiks_b200.h).
+
+PyTorch is used here for device memory, streams and the device guard only: every entry point
+receives raw device pointers (``tensor.data_ptr()``) and the current CUDA stream handle.
+There is NO fallback: if the library is missing or a call fails, this raises.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "librubiks_b200.so")
+
+RB_F32, RB_F64, RB_F16, RB_BF16 = 0, 1, 2, 3
+RB_IMPL_AUTO, RB_IMPL_GENERIC, RB_IMPL_TILED = 0, 1, 2
+_DTYPES = {torch.float32: RB_F32, torch.float64: RB_F64, torch.float16: RB_F16, torch.bfloat16: RB_BF16}
+
+_lib = None
+
+
+class RubiksCudaError(RuntimeError):
+    """Raised for a non-zero rb_status_t (the reference raises RuntimeError from C++ exceptions)."""
+
+
+def _declare(lib):
+    vp, i, sz, dbl = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_double
+    lib.rb_abi_version.restype = i
+    lib.rb_last_error.restype = ctypes.c_char_p
+    lib.rb_launch_count.restype = ctypes.c_uint64
+    lib.rb_launch_count_reset.restype = None
+    lib.rb_set_impl.argtypes = [i]
+    lib.rb_set_impl.restype = None
+    lib.rb_last_impl.restype = i
+    lib.rb_out_len.argtypes = [i, i, i]
+    lib.rb_out_len.restype = i
+    lib.rb_shift3d_forward.argtypes = [vp, vp, vp, i, i] + [i] * 5 + [i] * 6 + [i, vp]
+    lib.rb_shift3d_forward.restype = i
+    lib.rb_shift3d_backward_workspace_bytes.argtypes = [i] + [i] * 5 + [i] * 6
+    lib.rb_shift3d_backward_workspace_bytes.restype = sz
+    lib.rb_shift3d_backward.argtypes = [vp] * 5 + [i, i] + [i] * 5 + [i] * 6 + [i, dbl, i, vp, sz, vp]
+    lib.rb_shift3d_backward.restype = i
+    lib.rb_shift2d_forward.argtypes = [vp, vp, vp, i, i] + [i] * 4 + [i] * 4 + [i, vp]
+    lib.rb_shift2d_forward.restype = i
+    lib.rb_shift2d_backward_workspace_bytes.argtypes = [i] + [i] * 4 + [i] * 4
+    lib.rb_shift2d_backward_workspace_bytes.restype = sz
+    lib.rb_shift2d_backward.argtypes = [vp] * 5 + [i, i] + [i] * 4 + [i] * 4 + [i, i, i, vp, sz, vp]
+    lib.rb_shift2d_backward.restype = i
+    lib.rb_attention_shift_forward.argtypes = [vp, vp, vp, i, i, i, i, i, vp]
+    lib.rb_attention_shift_forward.restype = i
+    lib.rb_attention_shift_backward_workspace_bytes.argtypes = [i, i, i, i]
+    lib.rb_attention_shift_backward_workspace_bytes.restype = sz
+    lib.rb_attention_shift_backward.argtypes = [vp] * 5 + [i, i, i, i, i, vp, sz, vp]
+    lib.rb_attention_shift_backward.restype = i
+
+
+def lib():
+    """The loaded library.  Raises ImportError when it has not been built (no silent fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "librubiks_b200.so is not built: run `python -m rubiksnet_b200.build` "
+                "(or __graft_entry__.build()); there is no CPU / PyTorch fallback for the shift kernels")
+        handle = ctypes.CDLL(LIB_PATH)
+        _declare(handle)
+        if handle.rb_abi_version() != 1:
+            raise ImportError("librubiks_b200.so ABI version mismatch; rebuild it")
+        _lib = handle
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RubiksCudaError("librubiks_b200 status %d: %s" % (rc, lib().rb_last_error().decode()))
+
+
+def dtype_code(t):
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise ValueError("rubiks shift supports float32/float64/float16/bfloat16, got %s" % t.dtype)
+
+
+def ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_handle(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+# one growing scratch buffer per (device, stream): stream-ordered reuse is safe because every kernel
+# that touches it is enqueued on that same stream
+_workspaces = {}
+
+
+def workspace(nbytes, device):
+    if nbytes == 0:
+        return None
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+def launch_count():
+    return int(lib().rb_launch_count())
+
+
+def reset_launch_count():
+    lib().rb_launch_count_reset()
+
+
+def set_impl(impl):
+    lib().rb_set_impl(int(impl))
+
+
+def last_impl():
+    return int(lib().rb_last_impl())

@@ -1,0 +1,228 @@
+// extern "C" entry points of librubiks_b200.so (include/rubiks_b200.h): argument checks, output
+// geometry, workspace carving and implementation dispatch -- the role of the host drivers in
+// /root/reference/cuda_src/rubiks.cpp:44-67,94-155,181-253,256-379, without ATen.
+#include "common.cuh"
+
+namespace rb {
+
+thread_local char g_err[512] = {0};
+thread_local int g_last_impl = RB_IMPL_AUTO;
+std::atomic<uint64_t> g_launches{0};
+std::atomic<int> g_forced_impl{RB_IMPL_AUTO};
+
+int sm_count() {
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        if (cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) cached = 148;
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+// shift3d_generic.cu
+int generic_bwd_chunks(const Geom3 &g);
+int shift3d_forward_generic(const void *, const void *, void *, int, int, const Geom3 &, int, cudaStream_t);
+int shift3d_bwd_input_generic(const void *, const void *, void *, int, int, const Geom3 &, int, cudaStream_t);
+int shift3d_bwd_shift_generic(const void *, const void *, const void *, void *, int, int, const Geom3 &, int,
+                              double, double *, cudaStream_t);
+// shift3d_tiled.cu
+bool shift3d_tiled_supported(int dt, const Geom3 &g, int quantize);
+int shift3d_forward_tiled(const void *, const void *, void *, int, int, const Geom3 &, cudaStream_t);
+size_t shift3d_backward_tiled_workspace(int dt, const Geom3 &g);
+int shift3d_backward_tiled(const void *, const void *, const void *, void *, void *, int, int, const Geom3 &,
+                           int, double, void *, cudaStream_t);
+// shift2d_generic.cu
+int shift2d_bwd_chunks(const Geom2 &g);
+int shift2d_forward_generic(const void *, const void *, void *, int, int, const Geom2 &, int, cudaStream_t);
+int shift2d_bwd_input_generic(const void *, const void *, void *, int, int, const Geom2 &, int, cudaStream_t);
+int shift2d_bwd_shift_generic(const void *, const void *, const void *, void *, int, int, const Geom2 &, int,
+                              double *, cudaStream_t);
+
+static int make_geom3(Geom3 &g, int N, int T, int C, int H, int W, int sT, int sH, int sW, int pT, int pH,
+                      int pW) {
+    if (N < 0 || T < 0 || C < 0 || H < 0 || W < 0)
+        return fail(RB_ERR_INVALID_ARGUMENT, "negative extent [%d,%d,%d,%d,%d]", N, T, C, H, W);
+    // the reference only prints to stderr for stride <= 0 (rubiks.cpp:162-164) and then divides by it
+    if (sT <= 0 || sH <= 0 || sW <= 0)
+        return fail(RB_ERR_INVALID_ARGUMENT, "stride must be > 0, got (%d,%d,%d)", sT, sH, sW);
+    if (pT < 0 || pH < 0 || pW < 0)
+        return fail(RB_ERR_INVALID_ARGUMENT, "padding must be >= 0, got (%d,%d,%d)", pT, pH, pW);
+    g.N = N; g.T = T; g.C = C; g.H = H; g.W = W;
+    g.sT = sT; g.sH = sH; g.sW = sW; g.pT = pT; g.pH = pH; g.pW = pW;
+    g.To = T > 0 ? rb_out_len(T, sT, pT) : 0;
+    g.Ho = H > 0 ? rb_out_len(H, sH, pH) : 0;
+    g.Wo = W > 0 ? rb_out_len(W, sW, pW) : 0;
+    if ((int64_t)N * T * C * H * W > 0x7fffffffLL || (int64_t)N * g.To * C * g.Ho * g.Wo > 0x7fffffffLL)
+        return fail(RB_ERR_UNSUPPORTED, "tensors with more than 2^31-1 elements are not supported");
+    return RB_OK;
+}
+
+static int check_dtypes(int dt, int sdt) {
+    if (dtype_size(dt) == 0) return fail(RB_ERR_INVALID_ARGUMENT, "unknown dtype %d", dt);
+    if (dtype_size(sdt) == 0) return fail(RB_ERR_INVALID_ARGUMENT, "unknown shift dtype %d", sdt);
+    if (dt == RB_F64 && sdt != RB_F64)
+        return fail(RB_ERR_INVALID_ARGUMENT, "float64 activations need a float64 shift");
+    return RB_OK;
+}
+
+static bool use_tiled(int dt, const Geom3 &g, int quantize, int *err) {
+    const int forced = g_forced_impl.load(std::memory_order_relaxed);
+    const bool ok = shift3d_tiled_supported(dt, g, quantize);
+    *err = RB_OK;
+    if (forced == RB_IMPL_GENERIC) return false;
+    if (forced == RB_IMPL_TILED && !ok)
+        *err = fail(RB_ERR_UNSUPPORTED, "RB_IMPL_TILED forced but geometry is not covered by the tiled kernels");
+    return ok;
+}
+
+}  // namespace rb
+
+using namespace rb;
+
+extern "C" {
+
+int rb_abi_version(void) { return RB_ABI_VERSION; }
+const char *rb_last_error(void) { return g_err; }
+uint64_t rb_launch_count(void) { return g_launches.load(); }
+void rb_launch_count_reset(void) { g_launches.store(0); }
+void rb_set_impl(int impl) { g_forced_impl.store(impl); }
+int rb_last_impl(void) { return g_last_impl; }
+
+int rb_out_len(int in_len, int stride, int pad) { return (in_len + 2 * pad - 1) / stride + 1; }
+
+int rb_shift3d_forward(const void *x, const void *shift, void *out, int dtype, int shift_dtype, int N,
+                       int T, int C, int H, int W, int sT, int sH, int sW, int pT, int pH, int pW,
+                       int quantize, void *stream) {
+    Geom3 g;
+    int rc = make_geom3(g, N, T, C, H, W, sT, sH, sW, pT, pH, pW);
+    if (rc) return rc;
+    if ((rc = check_dtypes(dtype, shift_dtype))) return rc;
+    if ((int64_t)N * g.To * C * g.Ho * g.Wo == 0) return RB_OK;
+    if (!x || !shift || !out) return fail(RB_ERR_INVALID_ARGUMENT, "null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool tiled = use_tiled(dtype, g, quantize, &rc);
+    if (rc) return rc;
+    g_last_impl = tiled ? RB_IMPL_TILED : RB_IMPL_GENERIC;
+    if (tiled) return shift3d_forward_tiled(x, shift, out, dtype, shift_dtype, g, s);
+    return shift3d_forward_generic(x, shift, out, dtype, shift_dtype, g, quantize, s);
+}
+
+size_t rb_shift3d_backward_workspace_bytes(int dtype, int N, int T, int C, int H, int W, int sT, int sH,
+                                           int sW, int pT, int pH, int pW) {
+    Geom3 g;
+    if (make_geom3(g, N, T, C, H, W, sT, sH, sW, pT, pH, pW)) return 0;
+    if ((int64_t)N * g.To * C * g.Ho * g.Wo == 0) return 0;
+    size_t generic = (size_t)C * generic_bwd_chunks(g) * 3 * sizeof(double);
+    size_t tiled = shift3d_tiled_supported(dtype, g, 0) ? shift3d_backward_tiled_workspace(dtype, g) : 0;
+    size_t need = generic > tiled ? generic : tiled;
+    return (need + 255) & ~(size_t)255;
+}
+
+int rb_shift3d_backward(const void *x, const void *shift, const void *out_grad, void *x_grad,
+                        void *shift_grad, int dtype, int shift_dtype, int N, int T, int C, int H, int W,
+                        int sT, int sH, int sW, int pT, int pH, int pW, int normalize_grad,
+                        double normalize_t_factor, int quantize, void *workspace, size_t workspace_bytes,
+                        void *stream) {
+    Geom3 g;
+    int rc = make_geom3(g, N, T, C, H, W, sT, sH, sW, pT, pH, pW);
+    if (rc) return rc;
+    if ((rc = check_dtypes(dtype, shift_dtype))) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!x_grad && !shift_grad) return RB_OK;
+    if ((int64_t)N * g.To * C * g.Ho * g.Wo == 0) {
+        // empty upstream gradient: x_grad is all zeros, shift_grad = addmv_ of nothing = 0
+        if (x_grad && (int64_t)N * T * C * H * W > 0)
+            cudaMemsetAsync(x_grad, 0, (size_t)N * T * C * H * W * dtype_size(dtype), s);
+        if (shift_grad && C > 0) cudaMemsetAsync(shift_grad, 0, (size_t)3 * C * dtype_size(shift_dtype), s);
+        return RB_OK;
+    }
+    if (!x || !shift || !out_grad) return fail(RB_ERR_INVALID_ARGUMENT, "null pointer");
+    const size_t need = rb_shift3d_backward_workspace_bytes(dtype, N, T, C, H, W, sT, sH, sW, pT, pH, pW);
+    if (shift_grad && (!workspace || workspace_bytes < need))
+        return fail(RB_ERR_WORKSPACE, "shift3d backward needs %zu workspace bytes, got %zu", need,
+                    workspace_bytes);
+    const bool tiled = use_tiled(dtype, g, quantize, &rc);
+    if (rc) return rc;
+    g_last_impl = tiled ? RB_IMPL_TILED : RB_IMPL_GENERIC;
+    if (tiled)
+        return shift3d_backward_tiled(x, shift, out_grad, x_grad, shift_grad, dtype, shift_dtype, g,
+                                      normalize_grad, normalize_t_factor, workspace, s);
+    // host order of rubiks.cpp:324-376: shift gradient (+reduce, normalise), then input gradient
+    if (shift_grad) {
+        rc = shift3d_bwd_shift_generic(x, shift, out_grad, shift_grad, dtype, shift_dtype, g, normalize_grad,
+                                       normalize_t_factor, (double *)workspace, s);
+        if (rc) return rc;
+    }
+    if (x_grad) rc = shift3d_bwd_input_generic(shift, out_grad, x_grad, dtype, shift_dtype, g, quantize, s);
+    return rc;
+}
+
+static int make_geom2(Geom2 &g, int N, int C, int H, int W, int sH, int sW, int pH, int pW) {
+    if (N < 0 || C < 0 || H < 0 || W < 0) return fail(RB_ERR_INVALID_ARGUMENT, "negative extent");
+    if (sH <= 0 || sW <= 0) return fail(RB_ERR_INVALID_ARGUMENT, "stride must be > 0, got (%d,%d)", sH, sW);
+    if (pH < 0 || pW < 0) return fail(RB_ERR_INVALID_ARGUMENT, "padding must be >= 0, got (%d,%d)", pH, pW);
+    g.N = N; g.C = C; g.H = H; g.W = W; g.sH = sH; g.sW = sW; g.pH = pH; g.pW = pW;
+    g.Ho = H > 0 ? rb_out_len(H, sH, pH) : 0;
+    g.Wo = W > 0 ? rb_out_len(W, sW, pW) : 0;
+    if ((int64_t)N * C * H * W > 0x7fffffffLL || (int64_t)N * C * g.Ho * g.Wo > 0x7fffffffLL)
+        return fail(RB_ERR_UNSUPPORTED, "tensors with more than 2^31-1 elements are not supported");
+    return RB_OK;
+}
+
+int rb_shift2d_forward(const void *x, const void *shift, void *out, int dtype, int shift_dtype, int N,
+                       int C, int H, int W, int sH, int sW, int pH, int pW, int quantize, void *stream) {
+    Geom2 g;
+    int rc = make_geom2(g, N, C, H, W, sH, sW, pH, pW);
+    if (rc) return rc;
+    if ((rc = check_dtypes(dtype, shift_dtype))) return rc;
+    if ((int64_t)N * C * g.Ho * g.Wo == 0) return RB_OK;
+    if (!x || !shift || !out) return fail(RB_ERR_INVALID_ARGUMENT, "null pointer");
+    g_last_impl = RB_IMPL_GENERIC;
+    return shift2d_forward_generic(x, shift, out, dtype, shift_dtype, g, quantize, (cudaStream_t)stream);
+}
+
+size_t rb_shift2d_backward_workspace_bytes(int dtype, int N, int C, int H, int W, int sH, int sW, int pH,
+                                           int pW) {
+    (void)dtype;
+    Geom2 g;
+    if (make_geom2(g, N, C, H, W, sH, sW, pH, pW)) return 0;
+    if ((int64_t)N * C * g.Ho * g.Wo == 0) return 0;
+    size_t need = (size_t)C * shift2d_bwd_chunks(g) * 2 * sizeof(double);
+    return (need + 255) & ~(size_t)255;
+}
+
+int rb_shift2d_backward(const void *x, const void *shift, const void *out_grad, void *x_grad,
+                        void *shift_grad, int dtype, int shift_dtype, int N, int C, int H, int W, int sH,
+                        int sW, int pH, int pW, int normalize_grad, int enable_shift_grad, int quantize,
+                        void *workspace, size_t workspace_bytes, void *stream) {
+    Geom2 g;
+    int rc = make_geom2(g, N, C, H, W, sH, sW, pH, pW);
+    if (rc) return rc;
+    if ((rc = check_dtypes(dtype, shift_dtype))) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!enable_shift_grad) shift_grad = nullptr;  // rubiks.cpp:126
+    if (!x_grad && !shift_grad) return RB_OK;
+    if ((int64_t)N * C * g.Ho * g.Wo == 0) {
+        if (x_grad && (int64_t)N * C * H * W > 0)
+            cudaMemsetAsync(x_grad, 0, (size_t)N * C * H * W * dtype_size(dtype), s);
+        if (shift_grad && C > 0) cudaMemsetAsync(shift_grad, 0, (size_t)2 * C * dtype_size(shift_dtype), s);
+        return RB_OK;
+    }
+    if (!x || !shift || !out_grad) return fail(RB_ERR_INVALID_ARGUMENT, "null pointer");
+    const size_t need = rb_shift2d_backward_workspace_bytes(dtype, N, C, H, W, sH, sW, pH, pW);
+    if (shift_grad && (!workspace || workspace_bytes < need))
+        return fail(RB_ERR_WORKSPACE, "shift2d backward needs %zu workspace bytes, got %zu", need,
+                    workspace_bytes);
+    g_last_impl = RB_IMPL_GENERIC;
+    if (shift_grad) {
+        rc = shift2d_bwd_shift_generic(x, shift, out_grad, shift_grad, dtype, shift_dtype, g, normalize_grad,
+                                       (double *)workspace, s);
+        if (rc) return rc;
+    }
+    if (x_grad) rc = shift2d_bwd_input_generic(shift, out_grad, x_grad, dtype, shift_dtype, g, quantize, s);
+    return rc;
+}
+
+}  // extern "C"
