@@ -1,0 +1,454 @@
+#!/usr/bin/env python
+"""Headline benchmark: clips/s of one training step (forward + backward + SGD update) of RubiksNet-Large,
+8 frames x 224^2, bf16 activations, synthetic clips, random-init weights -- BASELINE.json config C3 (C5 when
+--gpus > 1: batch data parallel, one process per GPU, NCCL gradient all-reduce).
+
+    python bench.py --gpus 1 --steps K --warmup W                 # this repo (rubiksnet_b200)
+    python bench.py --impl reference --gpus N --steps K --warmup W  # the unmodified reference (baseline/_ref)
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Prints ONE JSON line (rank 0).  Keys beyond the base contract:
+  value        clips/s, whole job, inputs already resident in HBM (device-timed, max over ranks)
+  e2e          same step driven from pinned HOST clips: H2D copy of every batch and a D2H read of the
+               loss inside the timed region
+  roofline     achieved algorithmic HBM GB/s of the dominant hand-written kernel (the fused 3D-shift
+               backward), measured live with CUDA events around its launches on the launching stream
+  cpu_baseline the CPU port (oracle/ C restatement of the shift + PyTorch CPU ops for the rest of the
+               network) timed on this box's host cores on a bounded sample
+  gpu_launches number of librubiks_b200 kernels launched inside the timed region
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+NUM_CLASSES = 174  # Something-Something-v2, as in the reference's checkpoints
+FRAMES = 8
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="clips per GPU (weak scaling)")
+    ap.add_argument("--tier", default="large")
+    ap.add_argument("--variant", default="rubiks3d")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ref-device", default="auto", choices=["auto", "cuda", "cpu"])
+    ap.add_argument("--cpu-sample-clips", type=int, default=1)
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------- helpers
+
+def dist_setup(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    elif torch.cuda.is_available():
+        torch.cuda.set_device(local)
+    return world, rank, local
+
+
+def max_over_ranks(ms, world):
+    if world == 1:
+        return ms
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.path = gpu_index, None, "/tmp/rubiks_bench_clocks_%d.csv" % os.getpid()
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            p = [s.strip() for s in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def synthetic_batch(batch, seed):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    clips = torch.randn(batch, FRAMES, 3, 224, 224, generator=g)
+    labels = torch.randint(0, NUM_CLASSES, (batch,), generator=g)
+    return clips, labels
+
+
+# ------------------------------------------------------------------------------------ training steps
+
+class Trainer:
+    """fwd + bwd + (all-reduce) + SGD on one GPU.  `kind` = "ours" (rubiksnet_b200) or "reference"."""
+
+    def __init__(self, kind, args, world):
+        import torch
+        self.torch, self.kind, self.world, self.args = torch, kind, world, args
+        torch.manual_seed(0)
+        torch.backends.cudnn.benchmark = True  # as the reference does (scripts/test_models.py:46)
+        if kind == "ours":
+            import rubiksnet_b200 as rb
+            from rubiksnet_b200.dp import FlatGradAllReduce
+            self.net = rb.RubiksNet(tier=args.tier, num_classes=NUM_CLASSES, num_frames=FRAMES,
+                                    variant=args.variant).cuda().train()
+            self.reducer = FlatGradAllReduce(self.net)
+            self.fwd_net = self.net
+            self.autocast = args.dtype == "bf16"
+        else:
+            sys.path.insert(0, os.path.join(REPO, "baseline", "_ref"))
+            import contextlib
+            import io
+            with contextlib.redirect_stdout(io.StringIO()):  # the reference prints banners
+                from rubiksnet.models import RubiksNet  # noqa: E402  (the reference package)
+                self.net = RubiksNet(tier=args.tier, num_classes=NUM_CLASSES, num_frames=FRAMES,
+                                     variant=args.variant).cuda().train()
+            self.reducer = None
+            self.fwd_net = self.net
+            if world > 1:
+                self.fwd_net = torch.nn.parallel.DistributedDataParallel(self.net, device_ids=[torch.cuda.current_device()])
+            self.autocast = False  # the reference's 3D shift is float/double only (primitive.py:66-75)
+        shift_params = [p for n, p in self.net.named_parameters() if n.endswith("shift")]
+        other = [p for n, p in self.net.named_parameters() if not n.endswith("shift")]
+        # shift parameters get lr * 0.01 as in scripts/example_finetune.py:49-64
+        self.opt = torch.optim.SGD([{"params": shift_params, "lr": 1e-4}, {"params": other}], lr=1e-2,
+                                   momentum=0.9, weight_decay=1e-4, foreach=True)
+        self.loss_fn = torch.nn.CrossEntropyLoss()
+
+    def step(self, clips, labels):
+        torch = self.torch
+        if self.reducer is not None:
+            self.reducer.zero_grad()
+        else:
+            self.opt.zero_grad(set_to_none=False)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.autocast):
+            logits = self.fwd_net(clips)
+        loss = self.loss_fn(logits.float(), labels)
+        loss.backward()
+        if self.reducer is not None:
+            self.reducer.all_reduce()
+        self.opt.step()
+        return loss
+
+
+def time_resident(tr, args, world, clips, labels):
+    import torch
+    for _ in range(args.warmup):
+        tr.step(clips, labels)
+    barrier(world)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        tr.step(clips, labels)
+    b.record()
+    barrier(world)
+    torch.cuda.synchronize()
+    return max_over_ranks(a.elapsed_time(b), world)
+
+
+def time_e2e(tr, args, world, host_batches):
+    """Pinned host clips -> H2D on a copy stream (double-buffered) -> step -> loss.item() every step."""
+    import torch
+    copy_stream = torch.cuda.Stream()
+    main = torch.cuda.current_stream()
+
+    def upload(i):
+        hc, hl = host_batches[i % len(host_batches)]
+        with torch.cuda.stream(copy_stream):
+            dc = hc.cuda(non_blocking=True)
+            dl = hl.cuda(non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return dc, dl, ev
+
+    def run(n_steps):
+        nxt = upload(0)
+        total = 0.0
+        for i in range(n_steps):
+            dc, dl, ev = nxt
+            main.wait_event(ev)
+            dc.record_stream(main)
+            dl.record_stream(main)
+            if i + 1 < n_steps:
+                nxt = upload(i + 1)  # overlaps with this step's compute
+            total += tr.step(dc, dl).item()  # D2H read of the step's result
+        return total
+
+    run(max(1, min(args.warmup, 2)))
+    barrier(world)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    run(args.steps)
+    b.record()
+    barrier(world)
+    torch.cuda.synchronize()
+    hc, hl = host_batches[0]
+    return max_over_ranks(a.elapsed_time(b), world), hc.numel() * hc.element_size() + hl.numel() * hl.element_size()
+
+
+def kernel_roofline(tr, clips, labels):
+    """Times every librubiks_b200 shift launch of ONE extra step with CUDA events on the launching stream and
+    reports the dominant kernel (by total time) against the measured HBM copy peak."""
+    import torch
+    from rubiksnet_b200 import rubiksnet_cuda as native
+    records = []
+    orig_f, orig_b = native.rubiks_shift_3d_forward, native.rubiks_shift_3d_backward
+
+    def wrap(fn, kind):
+        def inner(*a, **k):
+            x = a[0]
+            if kind == "fwd":
+                nbytes = (x.numel() + a[5].numel()) * x.element_size()          # in + out
+            else:
+                nbytes = (2 * x.numel() + a[2].numel()) * x.element_size()      # x + out_grad + x_grad
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            records.append((kind, nbytes, e0, e1))
+            return r
+        return inner
+
+    import rubiksnet_b200.shiftlib.rubiks3d.primitive as prim
+    prim._native.rubiks_shift_3d_forward = wrap(orig_f, "fwd")
+    prim._native.rubiks_shift_3d_backward = wrap(orig_b, "bwd")
+    try:
+        tr.step(clips, labels)
+        torch.cuda.synchronize()
+    finally:
+        prim._native.rubiks_shift_3d_forward, prim._native.rubiks_shift_3d_backward = orig_f, orig_b
+    agg = {}
+    for kind, nbytes, e0, e1 in records:
+        d = agg.setdefault(kind, [0, 0.0, 0])
+        d[0] += nbytes
+        d[1] += e0.elapsed_time(e1)
+        d[2] += 1
+    if not agg:
+        return None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    peak, peak_src = (peaks["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs") if "hbm_gbs" in peaks else (6650.0, "fallback B200_PROFILING.md")
+    kind = max(agg, key=lambda k: agg[k][1])
+    nbytes, ms, n = agg[kind]
+    achieved = nbytes / ms / 1e6
+    name = {"fwd": "k_shift3d_tiled<fwd>", "bwd": "k_shift3d_tiled<bwd> (+k_shift3d_finalize)"}[kind]
+    out = {"bound": "hbm", "kernel": name, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+           "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+           "launches_per_step": n, "algorithmic_bytes_per_step": nbytes, "kernel_ms_per_step": round(ms, 3)}
+    other = "fwd" if kind == "bwd" else "bwd"
+    if other in agg:
+        ob, oms, on = agg[other]
+        out["other_kernel"] = {"kernel": "k_shift3d_tiled<%s>" % other, "achieved": round(ob / oms / 1e6, 1),
+                               "frac": round(ob / oms / 1e6 / peak, 4), "kernel_ms_per_step": round(oms, 3)}
+    return out
+
+
+# ------------------------------------------------------------------------------------ CPU port arm
+
+def cpu_port_clips_per_s(args, clips_in_sample):
+    """RubiksNet on the host cores: PyTorch CPU ops for conv/BN/ReLU and the C oracle (OpenMP, all cores) for
+    the shift, which the reference cannot run on CPU at all (primitive.py:61).  One fwd+bwd of a bounded
+    sample."""
+    import torch
+    import oracle
+    import rubiksnet_b200 as rb
+    import rubiksnet_b200.shiftlib.rubiks3d.layer as layer3d
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    oracle.set_num_threads(cores)
+
+    class OracleShift3D(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, shift, stride, padding, normalize_grad, t_factor, quantize):
+            ctx.cfg = (stride, padding, normalize_grad, t_factor, quantize)
+            ctx.save_for_backward(x, shift)
+            return torch.from_numpy(oracle.shift3d_forward(x, shift, stride, padding, quantize))
+
+        @staticmethod
+        def backward(ctx, g):
+            x, shift = ctx.saved_tensors
+            stride, padding, ng, tf, q = ctx.cfg
+            gin, gs = oracle.shift3d_backward(x, shift, g.contiguous(), stride, padding, ng, tf, q)
+            return torch.from_numpy(gin), torch.from_numpy(gs), None, None, None, None, None
+
+    def cpu_shift(x, shift, stride=1, padding=0, normalize_grad=True, normalize_t_factor=1.0, quantize=False):
+        return OracleShift3D.apply(x.contiguous(), shift, stride, padding, normalize_grad, normalize_t_factor, quantize)
+
+    torch.manual_seed(0)
+    net = rb.RubiksNet(tier=args.tier, num_classes=NUM_CLASSES, num_frames=FRAMES, variant="rubiks3d").train()
+    for m in net.modules():
+        if isinstance(m, layer3d.RubiksShiftBase):
+            m.shift_function = cpu_shift
+    clips, labels = synthetic_batch(clips_in_sample, 1)
+    t0 = time.perf_counter()
+    loss = torch.nn.functional.cross_entropy(net(clips), labels)
+    loss.backward()
+    dt = time.perf_counter() - t0
+    return clips_in_sample / dt, cores, dt
+
+
+# --------------------------------------------------------------------------------------------- main
+
+def main():
+    args = parse()
+    import torch
+    have_cuda = torch.cuda.is_available()
+    metric = "clips/sec (fwd+bwd) RubiksNet-%s 8x224^2" % args.tier.capitalize()
+    config = {"workload": "BASELINE C3: RubiksNet-%s %s, 8 frames x 224^2, fwd+bwd+SGD, synthetic clips, random init"
+                          % (args.tier.capitalize(), args.variant),
+              "clips_per_gpu": args.batch, "frames": FRAMES, "num_classes": NUM_CLASSES,
+              "parallelism": "dp%d (batch sharded, NCCL grad all-reduce)" % args.gpus,
+              "l2": "working set per step (>10 GB of activations) far exceeds the 126 MB L2; no flush needed"}
+
+    if args.impl == "reference":
+        ref_ok = os.path.isdir(os.path.join(REPO, "baseline", "_ref", "rubiksnet"))
+        use_cuda = have_cuda and ref_ok and args.ref_device != "cpu"
+        if not use_cuda:
+            # fallback: CPU port (oracle) -- rank 0 only
+            if int(os.environ.get("RANK", "0")) != 0:
+                return
+            v, cores, dt = cpu_port_clips_per_s(args, args.cpu_sample_clips)
+            line = {"impl": "reference", "metric": metric, "value": v, "unit": "clips/s", "n_gpus": args.gpus,
+                    "steps": 1, "warmup": 0, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+                    "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                    "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": "port",
+                                     "sample": "%d clip(s) fwd+bwd, oracle C shift + PyTorch CPU ops" % args.cpu_sample_clips},
+                    "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            print(json.dumps(line))
+            return
+
+    world, rank, local = dist_setup(args)
+    assert have_cuda, "bench.py needs a CUDA device (there is no CPU fallback for the product path)"
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node %d" % args.gpus
+    tr = Trainer("ours" if args.impl == "ours" else "reference", args, world)
+    clips, labels = synthetic_batch(args.batch, 100 + rank)
+    dclips, dlabels = clips.cuda(), labels.cuda()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = 0
+    if args.impl == "ours":
+        from rubiksnet_b200 import _lib
+    # ---- resident-input timing
+    for _ in range(1):
+        tr.step(dclips, dlabels)  # cudnn autotune / allocator warm-up outside everything
+    if sampler:
+        sampler.start()
+    if args.impl == "ours":
+        # launches are counted over the timed steps only: reset after warm-up inside time_resident is not
+        # possible without a hook, so count (warmup + steps) and scale
+        _lib.reset_launch_count()
+    ms = time_resident(tr, args, world, dclips, dlabels)
+    if args.impl == "ours":
+        launches0 = _lib.launch_count() * args.steps // (args.steps + args.warmup)
+    clocks = sampler.stop() if sampler else None
+    total_clips = args.batch * world * args.steps
+    value = total_clips / (ms / 1e3)
+
+    e2e = None
+    if not args.no_e2e:
+        host = []
+        for i in range(2):
+            c, l = synthetic_batch(args.batch, 200 + 10 * rank + i)
+            host.append((c.pin_memory(), l.pin_memory()))
+        ems, h2d = time_e2e(tr, args, world, host)
+        e2e = {"value": total_clips / (ems / 1e3), "unit": "clips/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": 4, "ms_per_step": ems / args.steps}
+
+    line = {"metric": metric, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16" if tr.autocast else "f32", "data": "synthetic", "config": config,
+            "clocks": clocks, "e2e": e2e}
+    if args.impl == "reference":
+        line["impl"] = "reference"
+        line["config"]["reference"] = ("unmodified reference package + its CUDA extension (baseline/_ref, built for sm_100), "
+                                       "fp32: its 3D shift has no 16-bit path; DDP for n_gpus>1")
+        line["gpu_launches"] = None
+    else:
+        line["impl"] = "rubiksnet_b200"
+        line["gpu_launches"] = launches0
+        if rank == 0:
+            line["roofline"] = kernel_roofline(tr, dclips, dlabels)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            v, cores, dt = cpu_port_clips_per_s(args, args.cpu_sample_clips)
+            line["cpu_baseline"] = {"value": v, "unit": "clips/s", "cores": cores, "kind": "port",
+                                    "sample": "%d clip(s), one fwd+bwd of the same network in fp32: oracle C shift (OpenMP) + "
+                                              "PyTorch CPU conv/BN; %.1f s" % (args.cpu_sample_clips, dt)}
+        except Exception as e:  # noqa: BLE001
+            line["cpu_baseline"] = {"value": None, "error": repr(e)}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -10,6 +10,6 @@ from . import _lib, rubiksnet_cuda, shiftlib  # noqa: F401
 from .attention_shift import AttentionShift  # noqa: F401
 from .backbone import RubiksNetBackbone, RubiksShiftBlock  # noqa: F401
 from .models import RubiksNet  # noqa: F401
-from .shiftlib import *  # noqa: F401,F403
+from .shiftlib import RubiksShift2D, RubiksShift3D, RubiksShiftBase  # noqa: F401
 
 __version__ = "0.1.0"
