@@ -126,6 +126,31 @@ int rb_attention_shift_backward(const void *x, const float *taps, const void *ou
                                 float *taps_grad, int dtype, int N, int T, int C, int HW,
                                 void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---------------------------------------------------------------- BatchNorm (+ReLU) ------------ */
+
+/* The bn1->relu / bn2->relu / bn_last->relu stages of RubiksShiftBlock / RubiksNetBackbone
+ * (rubiksnet/backbone.py:50-53,123-135,196), which the reference delegates to nn.BatchNorm2d + nn.ReLU.
+ * x / y / dy / dx are [NI, C, HW] contiguous (NCHW), parameters and statistics are fp32.
+ *   mean_invstd [C,2] and scale_bias [C,2] are OUTPUTS of the forward pass that the backward pass
+ *   (and the fused shift) consume: y = act(x * scale + bias), scale = gamma * invstd,
+ *   bias = beta - mean * scale.
+ * training != 0: batch statistics (biased variance), running stats updated with `momentum`
+ * (unbiased variance), exactly torch.nn.BatchNorm2d.  training == 0: running statistics.
+ * relu != 0 applies max(.,0) in forward and masks dy with (y > 0) in backward. */
+size_t rb_bn_workspace_bytes(int NI, int C);
+
+int rb_bn_act_forward(const void *x, const float *gamma, const float *beta, float *running_mean,
+                      float *running_var, void *y, float *mean_invstd, float *scale_bias, int dtype,
+                      int NI, int C, int HW, int training, float momentum, float eps, int relu,
+                      void *workspace, size_t workspace_bytes, void *stream);
+
+/* dx = dL/dx (+ residual if non-NULL: same shape as x, e.g. the identity-shortcut gradient),
+ * dgamma / dbeta fp32 [C] (overwritten; may be NULL).  dx may be NULL (parameter gradients only). */
+int rb_bn_act_backward(const void *x, const void *dy, const void *residual, const float *gamma,
+                       const float *mean_invstd, const float *scale_bias, void *dx, float *dgamma,
+                       float *dbeta, int dtype, int NI, int C, int HW, int training, int relu,
+                       void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,6 +52,13 @@ def _declare(lib):
     lib.rb_attention_shift_backward_workspace_bytes.restype = sz
     lib.rb_attention_shift_backward.argtypes = [vp] * 5 + [i, i, i, i, i, vp, sz, vp]
     lib.rb_attention_shift_backward.restype = i
+    fl = ctypes.c_float
+    lib.rb_bn_workspace_bytes.argtypes = [i, i]
+    lib.rb_bn_workspace_bytes.restype = sz
+    lib.rb_bn_act_forward.argtypes = [vp] * 8 + [i, i, i, i, i, fl, fl, i, vp, sz, vp]
+    lib.rb_bn_act_forward.restype = i
+    lib.rb_bn_act_backward.argtypes = [vp] * 9 + [i, i, i, i, i, i, vp, sz, vp]
+    lib.rb_bn_act_backward.restype = i
 
 
 def lib():

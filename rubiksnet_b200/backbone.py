@@ -9,6 +9,7 @@ import math
 import torch
 import torch.nn as nn
 
+from . import fused
 from .shiftlib import RubiksShift2D, RubiksShiftBase
 
 __all__ = ["RubiksNetBackbone", "RubiksShiftBlock", "SELayer"]
@@ -23,6 +24,11 @@ def _bn(planes):
     nn.init.constant_(bn.weight, 1.0)
     nn.init.constant_(bn.bias, 0.0)
     return bn
+
+
+# CUDA tensors take the fused path (librubiks_b200 BN+ReLU kernels, batched-GEMM 1x1 convs); set to False to
+# run the plain nn.Module graph (used by tests to check that both give the same numbers)
+FUSED_BLOCK = True
 
 
 class SELayer(nn.Module):
@@ -64,6 +70,8 @@ class RubiksShiftBlock(nn.Module):
             self.shortcut = nn.Identity()
 
     def forward(self, x):
+        if x.is_cuda and FUSED_BLOCK:
+            return self._forward_fused(x)
         out = self.relu(self.bn1(x))
         shortcut = x if isinstance(self.shortcut, nn.Identity) else self.shortcut(out)
         out = self.relu(self.bn2(self.conv2(out)))
@@ -73,6 +81,24 @@ class RubiksShiftBlock(nn.Module):
         out = self.conv3(out)
         out += shortcut
         return out
+
+    def _forward_fused(self, x):
+        """Same arithmetic with librubiks_b200's BN+ReLU passes and NCHW batched-GEMM 1x1 convolutions; the
+        residual add is the epilogue of the conv3 GEMM."""
+        out = fused.bn_act(x, self.bn1, relu=True)
+        if isinstance(self.shortcut, nn.Identity):
+            shortcut = x
+        else:
+            shortcut = fused.conv1x1(out, self.shortcut.weight, stride=self.shortcut.stride[0])
+        if isinstance(self.conv2, nn.Sequential):  # rubiks3d-aq: AttentionShift in front of conv2
+            out = fused.conv1x1(self.conv2[0](out), self.conv2[1].weight)
+        else:
+            out = fused.conv1x1(out, self.conv2.weight)
+        out = fused.bn_act(out, self.bn2, relu=True)
+        out = self.as3(out)
+        if self.se is not None:
+            out = self.se(out)
+        return fused.conv1x1(out, self.conv3.weight, residual=shortcut)
 
 
 class RubiksNetBackbone(nn.Module):
@@ -111,7 +137,10 @@ class RubiksNetBackbone(nn.Module):
         x = self.conv1(x)
         for i in range(5):
             x = getattr(self, "layer%d" % i)(x)
-        x = self.avgpool(self.relu(self.bn_last(x)))
+        if x.is_cuda and FUSED_BLOCK:
+            x = self.avgpool(fused.bn_act(x, self.bn_last, relu=True))
+        else:
+            x = self.avgpool(self.relu(self.bn_last(x)))
         return self.fc(x.view(x.size(0), -1))
 
     def get_optim_policy(self, shift_lr_mult=0.01):

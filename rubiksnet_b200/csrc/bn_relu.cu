@@ -1,0 +1,382 @@
+// Fused BatchNorm2d (+ReLU) for the RubiksShiftBlock (rubiksnet/backbone.py:50-53,123-135: bn1->relu,
+// bn2->relu, bn_last->relu) on NCHW activations [NI, C, HW] in bf16 / fp16 / fp32 with fp32 parameters.
+//
+// The reference leaves these to ATen/cuDNN; in bf16 that path costs 90 of 135 ms of a RubiksNet-Large
+// training step on B200 (profiles/r01a_*): three generic ATen kernels per BN.  These are pure streaming
+// ops, so each one here is a single vectorised (128-bit) pass bound by HBM:
+//   forward  (training): stats pass (1 read)            -> apply pass  y = relu(x*scale+bias)   (1R + 1W)
+//   backward           : reduce pass (reads dy, x)      -> apply pass  dx = c1*dyr + c2*x + c3 [+ residual]
+// The ReLU mask is recomputed from x (no mask tensor), the per-channel sums are reduced
+// registers -> warp shuffles -> smem -> double partials -> finalize kernel (deterministic, no atomics).
+#include "common.cuh"
+
+namespace rb {
+
+static constexpr int kBT = 256;
+
+struct FastDiv {  // exact unsigned division by a runtime constant for n < 2^31 (Granlund-Montgomery)
+    uint32_t d, mul, shr;
+};
+static FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f;
+    f.d = d;
+    if (d == 1) { f.mul = 0; f.shr = 0; return f; }
+    uint32_t l = 0;
+    while ((1u << l) < d) ++l;  // ceil(log2 d)
+    uint64_t m = ((uint64_t(1) << (31 + l)) + d - 1) / d;  // fits in 32 bits for n < 2^31
+    f.mul = (uint32_t)m;
+    f.shr = l - 1;
+    return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv &f) {
+    return f.d == 1 ? n : (__umulhi(n, f.mul) >> f.shr);
+}
+
+template <typename T> struct Vec {};
+template <> struct Vec<float> { static constexpr int N = 4; };
+template <> struct Vec<__half> { static constexpr int N = 8; };
+template <> struct Vec<__nv_bfloat16> { static constexpr int N = 8; };
+template <> struct Vec<double> { static constexpr int N = 2; };
+
+template <typename T, int N> struct alignas(sizeof(T) * N) Pack { T v[N]; };
+
+template <typename T> __device__ __forceinline__ float tof(T v) { return (float)v; }
+template <> __device__ __forceinline__ float tof<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float tof<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+// ---- per-channel reductions ---------------------------------------------------------------------
+// grid (SPLIT, C).  MODE 0: sum x, sum x^2.  MODE 1: sum dyr, sum dyr * xhat  (dyr = relu-masked dy).
+template <typename T, int MODE>
+__global__ void __launch_bounds__(kBT)
+k_bn_reduce(const T *__restrict__ x, const T *__restrict__ dy, const float *__restrict__ mean_invstd,
+            const float *__restrict__ scale_bias, double *__restrict__ partial, int NI, int C, int HW, int relu) {
+    constexpr int V = Vec<T>::N;
+    const int sp = blockIdx.x, c = blockIdx.y, splits = gridDim.x;
+    float s0 = 0.f, s1 = 0.f;
+    float mean = 0.f, invstd = 1.f, sc = 1.f, bi = 0.f;
+    if (MODE == 1) {
+        mean = mean_invstd[2 * c];
+        invstd = mean_invstd[2 * c + 1];
+        sc = scale_bias[2 * c];
+        bi = scale_bias[2 * c + 1];
+    }
+    const bool vec_ok = (HW % V == 0);
+    for (int n = sp; n < NI; n += splits) {
+        const int64_t base = ((int64_t)n * C + c) * HW;
+        if (vec_ok) {
+            const Pack<T, V> *xp = reinterpret_cast<const Pack<T, V> *>(x + base);
+            const Pack<T, V> *gp = reinterpret_cast<const Pack<T, V> *>(dy + base);
+            for (int i = threadIdx.x; i < HW / V; i += kBT) {
+                const Pack<T, V> xv = xp[i];
+                if (MODE == 0) {
+#pragma unroll
+                    for (int k = 0; k < V; ++k) {
+                        const float f = tof(xv.v[k]);
+                        s0 += f;
+                        s1 += f * f;
+                    }
+                } else {
+                    const Pack<T, V> gv = gp[i];
+#pragma unroll
+                    for (int k = 0; k < V; ++k) {
+                        const float f = tof(xv.v[k]);
+                        float g = tof(gv.v[k]);
+                        if (relu && !(f * sc + bi > 0.f)) g = 0.f;
+                        s0 += g;
+                        s1 += g * ((f - mean) * invstd);
+                    }
+                }
+            }
+        } else {
+            for (int i = threadIdx.x; i < HW; i += kBT) {
+                const float f = tof(x[base + i]);
+                if (MODE == 0) {
+                    s0 += f;
+                    s1 += f * f;
+                } else {
+                    float g = tof(dy[base + i]);
+                    if (relu && !(f * sc + bi > 0.f)) g = 0.f;
+                    s0 += g;
+                    s1 += g * ((f - mean) * invstd);
+                }
+            }
+        }
+    }
+    __shared__ double red[2][kBT / 32];
+    s0 = warp_sum(s0);
+    s1 = warp_sum(s1);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        red[0][warp] = (double)s0;
+        red[1][warp] = (double)s1;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        double s = 0;
+#pragma unroll
+        for (int w = 0; w < kBT / 32; ++w) s += red[threadIdx.x][w];
+        partial[((int64_t)c * splits + sp) * 2 + threadIdx.x] = s;
+    }
+}
+
+// one warp per channel: batch statistics -> save (mean, invstd), (scale, bias); running stats update
+__global__ void k_bn_stats_finalize(const double *__restrict__ partial, int splits, int C, double count,
+                                    const float *__restrict__ gamma, const float *__restrict__ beta,
+                                    float *running_mean, float *running_var, float momentum, float eps,
+                                    float *__restrict__ mean_invstd, float *__restrict__ scale_bias) {
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= C) return;
+    const int lane = threadIdx.x & 31;
+    double s = 0, ss = 0;
+    for (int i = lane; i < splits; i += 32) {
+        s += partial[((int64_t)c * splits + i) * 2];
+        ss += partial[((int64_t)c * splits + i) * 2 + 1];
+    }
+    s = warp_sum(s);
+    ss = warp_sum(ss);
+    if (lane != 0) return;
+    const double mean = s / count;
+    double var = ss / count - mean * mean;
+    if (var < 0) var = 0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    mean_invstd[2 * c] = (float)mean;
+    mean_invstd[2 * c + 1] = invstd;
+    const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+    scale_bias[2 * c] = g * invstd;
+    scale_bias[2 * c + 1] = b - (float)mean * g * invstd;
+    if (running_mean) {  // torch.nn.BatchNorm2d: unbiased variance in the running estimate
+        const double unbiased = count > 1 ? var * count / (count - 1) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+}
+
+// eval mode: (scale, bias) and (mean, invstd) from the running statistics
+__global__ void k_bn_eval_coeffs(const float *__restrict__ gamma, const float *__restrict__ beta,
+                                 const float *__restrict__ running_mean, const float *__restrict__ running_var,
+                                 float eps, int C, float *__restrict__ mean_invstd, float *__restrict__ scale_bias) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float invstd = rsqrtf(running_var[c] + eps);
+    const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+    mean_invstd[2 * c] = running_mean[c];
+    mean_invstd[2 * c + 1] = invstd;
+    scale_bias[2 * c] = g * invstd;
+    scale_bias[2 * c + 1] = b - running_mean[c] * g * invstd;
+}
+
+// backward finalize: dgamma, dbeta and the per-channel coefficients of dx = c1*dyr + c2*x + c3
+__global__ void k_bn_bwd_finalize(const double *__restrict__ partial, int splits, int C, double count,
+                                  const float *__restrict__ gamma, const float *__restrict__ mean_invstd,
+                                  int training, float *__restrict__ dgamma, float *__restrict__ dbeta,
+                                  float *__restrict__ coef) {
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= C) return;
+    const int lane = threadIdx.x & 31;
+    double s = 0, sx = 0;
+    for (int i = lane; i < splits; i += 32) {
+        s += partial[((int64_t)c * splits + i) * 2];
+        sx += partial[((int64_t)c * splits + i) * 2 + 1];
+    }
+    s = warp_sum(s);
+    sx = warp_sum(sx);
+    if (lane != 0) return;
+    if (dgamma) dgamma[c] = (float)sx;
+    if (dbeta) dbeta[c] = (float)s;
+    const float g = gamma ? gamma[c] : 1.f;
+    const float mean = mean_invstd[2 * c], invstd = mean_invstd[2 * c + 1];
+    const float k = g * invstd;
+    float c1 = k, c2 = 0.f, c3 = 0.f;
+    if (training) {
+        const float m1 = (float)(s / count), m2 = (float)(sx / count);
+        c2 = -k * m2 * invstd;
+        c3 = k * m2 * invstd * mean - k * m1;
+    }
+    coef[4 * c] = c1;
+    coef[4 * c + 1] = c2;
+    coef[4 * c + 2] = c3;
+}
+
+// ---- streaming apply passes ----------------------------------------------------------------------
+// MODE 0: y  = act(x*scale + bias)
+// MODE 1: dx = c1*dyr + c2*x + c3 (+ residual), dyr = relu-masked dy
+template <typename T, int MODE>
+__global__ void __launch_bounds__(kBT)
+k_bn_apply(const T *__restrict__ x, const T *__restrict__ dy, const T *__restrict__ residual,
+           const float *__restrict__ scale_bias, const float *__restrict__ coef, T *__restrict__ out,
+           int64_t total, int C, FastDiv hw, int relu) {
+    constexpr int V = Vec<T>::N;
+    const int64_t nvec = total / V;
+    const Pack<T, V> *xp = reinterpret_cast<const Pack<T, V> *>(x);
+    const Pack<T, V> *gp = reinterpret_cast<const Pack<T, V> *>(dy);
+    const Pack<T, V> *rp = reinterpret_cast<const Pack<T, V> *>(residual);
+    Pack<T, V> *op = reinterpret_cast<Pack<T, V> *>(out);
+    const int HW = (int)hw.d;
+    for (int64_t v = (int64_t)blockIdx.x * kBT + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * kBT) {
+        const uint32_t e0 = (uint32_t)(v * V);
+        const uint32_t plane = fdiv(e0, hw);
+        const int within = (int)(e0 - plane * (uint32_t)HW);
+        int c = (int)(plane % (uint32_t)C);
+        int nextb = HW - within;  // index within this vector of the first element of the next plane
+        const Pack<T, V> xv = xp[v];
+        Pack<T, V> gv, rv, ov;
+        if (MODE == 1) {
+            gv = gp[v];
+            if (residual) rv = rp[v];
+        }
+        float sc = __ldg(scale_bias + 2 * c), bi = __ldg(scale_bias + 2 * c + 1);
+        float c1 = 0.f, c2 = 0.f, c3 = 0.f;
+        if (MODE == 1) {
+            c1 = __ldg(coef + 4 * c);
+            c2 = __ldg(coef + 4 * c + 1);
+            c3 = __ldg(coef + 4 * c + 2);
+        }
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            if (k == nextb) {  // vector straddles a plane boundary (HW % V != 0)
+                nextb += HW;
+                c = (c + 1 == C) ? 0 : c + 1;
+                sc = __ldg(scale_bias + 2 * c);
+                bi = __ldg(scale_bias + 2 * c + 1);
+                if (MODE == 1) {
+                    c1 = __ldg(coef + 4 * c);
+                    c2 = __ldg(coef + 4 * c + 1);
+                    c3 = __ldg(coef + 4 * c + 2);
+                }
+            }
+            const float f = tof(xv.v[k]);
+            const float y = f * sc + bi;
+            if (MODE == 0) {
+                ov.v[k] = cvt<T, float>(relu ? fmaxf(y, 0.f) : y);
+            } else {
+                float g = tof(gv.v[k]);
+                if (relu && !(y > 0.f)) g = 0.f;
+                float d = c1 * g + c2 * f + c3;
+                if (residual) d += tof(rv.v[k]);
+                ov.v[k] = cvt<T, float>(d);
+            }
+        }
+        op[v] = ov;
+    }
+    // tail (total % V elements), handled by the first threads of block 0
+    if (blockIdx.x == 0 && threadIdx.x < (int)(total - nvec * V)) {
+        const int64_t e = nvec * V + threadIdx.x;
+        const int c = (int)((e / HW) % C);
+        const float f = tof(x[e]);
+        const float y = f * scale_bias[2 * c] + scale_bias[2 * c + 1];
+        if (MODE == 0) {
+            out[e] = cvt<T, float>(relu ? fmaxf(y, 0.f) : y);
+        } else {
+            float g = tof(dy[e]);
+            if (relu && !(y > 0.f)) g = 0.f;
+            float d = coef[4 * c] * g + coef[4 * c + 1] * f + coef[4 * c + 2];
+            if (residual) d += tof(residual[e]);
+            out[e] = cvt<T, float>(d);
+        }
+    }
+}
+
+static int bn_splits(int NI, int C) {
+    int want = cdiv(4 * 148, C);
+    if (want < 1) want = 1;
+    return want < NI ? want : NI;
+}
+static size_t bn_ws_bytes(int NI, int C) {
+    return ((size_t)C * bn_splits(NI, C) * 2 * sizeof(double) + (size_t)C * 4 * sizeof(float) + 255) & ~(size_t)255;
+}
+
+}  // namespace rb
+
+using namespace rb;
+
+extern "C" size_t rb_bn_workspace_bytes(int NI, int C) {
+    if (NI <= 0 || C <= 0) return 0;
+    return bn_ws_bytes(NI, C);
+}
+
+// NB: `Tn`-style naming is not needed here, but RB_DISPATCH_DTYPE binds `T`, so no parameter is called T.
+extern "C" int rb_bn_act_forward(const void *x, const float *gamma, const float *beta, float *running_mean,
+                                 float *running_var, void *y, float *mean_invstd, float *scale_bias, int dtype,
+                                 int NI, int C, int HW, int training, float momentum, float eps, int relu,
+                                 void *workspace, size_t workspace_bytes, void *stream) {
+    if (NI < 0 || C < 0 || HW < 0) return fail(RB_ERR_INVALID_ARGUMENT, "negative extent");
+    if (dtype_size(dtype) == 0 || dtype == RB_F64) return fail(RB_ERR_INVALID_ARGUMENT, "bn: dtype %d not supported", dtype);
+    const int64_t total = (int64_t)NI * C * HW;
+    if (total == 0) return RB_OK;
+    if (total > 0x7fffffffLL) return fail(RB_ERR_UNSUPPORTED, "bn: tensor too large");
+    if (!x || !y || !mean_invstd || !scale_bias) return fail(RB_ERR_INVALID_ARGUMENT, "null pointer");
+    if (!training && (!running_mean || !running_var)) return fail(RB_ERR_INVALID_ARGUMENT, "eval mode needs running stats");
+    if (C > 65535) return fail(RB_ERR_UNSUPPORTED, "bn: C > 65535");
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc;
+    if (training) {
+        if (!workspace || workspace_bytes < bn_ws_bytes(NI, C))
+            return fail(RB_ERR_WORKSPACE, "bn forward needs %zu workspace bytes", bn_ws_bytes(NI, C));
+        const int splits = bn_splits(NI, C);
+        dim3 grid(splits, C);
+        RB_DISPATCH_DTYPE(dtype, (k_bn_reduce<T, 0><<<grid, kBT, 0, s>>>((const T *)x, (const T *)x, nullptr, nullptr,
+                                                                        (double *)workspace, NI, C, HW, 0)));
+        if ((rc = launched("k_bn_reduce<stats>"))) return rc;
+        k_bn_stats_finalize<<<cdiv(C, 4), 128, 0, s>>>((const double *)workspace, splits, C, (double)NI * HW, gamma, beta,
+                                                       running_mean, running_var, momentum, eps, mean_invstd, scale_bias);
+        if ((rc = launched("k_bn_stats_finalize"))) return rc;
+    } else {
+        k_bn_eval_coeffs<<<cdiv(C, 128), 128, 0, s>>>(gamma, beta, running_mean, running_var, eps, C, mean_invstd,
+                                                      scale_bias);
+        if ((rc = launched("k_bn_eval_coeffs"))) return rc;
+    }
+    const FastDiv hw = make_fastdiv((uint32_t)HW);
+    RB_DISPATCH_DTYPE(dtype, {
+        const int64_t nvec = total / Vec<T>::N;
+        int blocks = (int)((nvec + kBT - 1) / kBT);
+        const int cap = sm_count() * 16;
+        if (blocks > cap) blocks = cap;
+        if (blocks < 1) blocks = 1;
+        k_bn_apply<T, 0><<<blocks, kBT, 0, s>>>((const T *)x, nullptr, nullptr, scale_bias, nullptr, (T *)y, total, C, hw,
+                                               relu);
+    });
+    return launched("k_bn_apply<fwd>");
+}
+
+extern "C" int rb_bn_act_backward(const void *x, const void *dy, const void *residual, const float *gamma,
+                                  const float *mean_invstd, const float *scale_bias, void *dx, float *dgamma,
+                                  float *dbeta, int dtype, int NI, int C, int HW, int training, int relu,
+                                  void *workspace, size_t workspace_bytes, void *stream) {
+    if (NI < 0 || C < 0 || HW < 0) return fail(RB_ERR_INVALID_ARGUMENT, "negative extent");
+    if (dtype_size(dtype) == 0 || dtype == RB_F64) return fail(RB_ERR_INVALID_ARGUMENT, "bn: dtype %d not supported", dtype);
+    const int64_t total = (int64_t)NI * C * HW;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (total == 0) {
+        if (dgamma && C > 0) cudaMemsetAsync(dgamma, 0, C * sizeof(float), s);
+        if (dbeta && C > 0) cudaMemsetAsync(dbeta, 0, C * sizeof(float), s);
+        return RB_OK;
+    }
+    if (total > 0x7fffffffLL) return fail(RB_ERR_UNSUPPORTED, "bn: tensor too large");
+    if (!x || !dy || !mean_invstd || !scale_bias) return fail(RB_ERR_INVALID_ARGUMENT, "null pointer");
+    if (C > 65535) return fail(RB_ERR_UNSUPPORTED, "bn: C > 65535");
+    if (!workspace || workspace_bytes < bn_ws_bytes(NI, C))
+        return fail(RB_ERR_WORKSPACE, "bn backward needs %zu workspace bytes", bn_ws_bytes(NI, C));
+    const int splits = bn_splits(NI, C);
+    double *partial = (double *)workspace;
+    float *coef = (float *)((char *)workspace + (size_t)C * splits * 2 * sizeof(double));
+    dim3 grid(splits, C);
+    int rc;
+    RB_DISPATCH_DTYPE(dtype, (k_bn_reduce<T, 1><<<grid, kBT, 0, s>>>((const T *)x, (const T *)dy, mean_invstd, scale_bias,
+                                                                    partial, NI, C, HW, relu)));
+    if ((rc = launched("k_bn_reduce<bwd>"))) return rc;
+    k_bn_bwd_finalize<<<cdiv(C, 4), 128, 0, s>>>(partial, splits, C, (double)NI * HW, gamma, mean_invstd, training, dgamma,
+                                                 dbeta, coef);
+    if ((rc = launched("k_bn_bwd_finalize"))) return rc;
+    if (!dx) return RB_OK;
+    const FastDiv hw = make_fastdiv((uint32_t)HW);
+    RB_DISPATCH_DTYPE(dtype, {
+        const int64_t nvec = total / Vec<T>::N;
+        int blocks = (int)((nvec + kBT - 1) / kBT);
+        const int cap = sm_count() * 16;
+        if (blocks > cap) blocks = cap;
+        if (blocks < 1) blocks = 1;
+        k_bn_apply<T, 1><<<blocks, kBT, 0, s>>>((const T *)x, (const T *)dy, (const T *)residual, scale_bias, coef,
+                                               (T *)dx, total, C, hw, relu);
+    });
+    return launched("k_bn_apply<bwd>");
+}

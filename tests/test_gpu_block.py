@@ -1,0 +1,163 @@
+"""GPU tests of the RubiksShiftBlock path: fused BN+ReLU kernels and batched-GEMM 1x1 convs against
+torch.nn modules, the fused block against the plain module graph, and the whole network against the
+reference package + extension (baseline/_ref) on a pretrained checkpoint."""
+import contextlib
+import io
+import os
+import sys
+
+import pytest
+import torch
+import torch.nn as nn
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from helpers import REPO  # noqa: E402
+
+import rubiksnet_b200 as rb  # noqa: E402
+from rubiksnet_b200 import backbone, fused  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return (a.double() - b.double()).abs().max().item() / max(1.0, b.double().abs().max().item())
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 1e-2), (torch.float16, 1e-2)])
+@pytest.mark.parametrize("shape", [(16, 72, 28, 28), (8, 288, 14, 14), (8, 54, 7, 7), (3, 5, 3, 3), (4, 9, 56, 57)])
+@pytest.mark.parametrize("relu", [True, False])
+def test_bn_act_training(shape, dtype, tol, relu):
+    torch.manual_seed(0)
+    c = shape[1]
+    x = (torch.randn(shape, device="cuda") * 1.5 + 0.3).to(dtype)
+    bn_ref = nn.BatchNorm2d(c).cuda()
+    with torch.no_grad():
+        bn_ref.weight.uniform_(0.5, 1.5)
+        bn_ref.bias.uniform_(-0.5, 0.5)
+    bn_new = nn.BatchNorm2d(c).cuda()
+    bn_new.load_state_dict(bn_ref.state_dict())
+    xr = x.float().requires_grad_()
+    yr = bn_ref(xr)
+    yr = torch.relu(yr) if relu else yr
+    g = torch.randn_like(yr)
+    yr.backward(g)
+    xn = x.clone().requires_grad_()
+    yn = fused.bn_act(xn, bn_new, relu=relu)
+    yn.backward(g.to(dtype))
+    assert yn.dtype == dtype
+    assert _rel(yn, yr) <= tol
+    assert _rel(xn.grad, xr.grad) <= tol
+    assert _rel(bn_new.weight.grad, bn_ref.weight.grad) <= max(tol, 2e-3 if dtype != torch.float32 else tol)
+    assert _rel(bn_new.bias.grad, bn_ref.bias.grad) <= max(tol, 2e-3 if dtype != torch.float32 else tol)
+    assert _rel(bn_new.running_mean, bn_ref.running_mean) <= 1e-4
+    assert _rel(bn_new.running_var, bn_ref.running_var) <= 1e-4
+    assert int(bn_new.num_batches_tracked) == 1
+
+
+def test_bn_act_eval_mode():
+    torch.manual_seed(1)
+    bn = nn.BatchNorm2d(12).cuda()
+    with torch.no_grad():
+        bn.running_mean.uniform_(-1, 1)
+        bn.running_var.uniform_(0.5, 2)
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.uniform_(-0.5, 0.5)
+    bn.eval()
+    x = torch.randn(4, 12, 9, 9, device="cuda", requires_grad=True)
+    xr = x.detach().clone().requires_grad_()
+    y = fused.bn_act(x, bn, relu=True)
+    yr = torch.relu(bn(xr))
+    g = torch.randn_like(y)
+    y.backward(g)
+    yr.backward(g)
+    assert _rel(y, yr) <= 1e-5 and _rel(x.grad, xr.grad) <= 1e-5
+    assert int(bn.num_batches_tracked) == 0
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-3), (torch.bfloat16, 2e-2)])  # fp32 matmul may use TF32
+def test_conv1x1_matches_conv2d(dtype, tol):
+    torch.manual_seed(2)
+    x = torch.randn(8, 72, 14, 14, device="cuda").to(dtype).requires_grad_()
+    w = (torch.randn(144, 72, 1, 1, device="cuda") * 0.1).requires_grad_()
+    res = torch.randn(8, 144, 7, 7, device="cuda").to(dtype).requires_grad_()
+    out = fused.conv1x1(x, w, residual=res, stride=2)
+    ref = torch.nn.functional.conv2d(x.float(), w, stride=2) + res.float()
+    g = torch.randn_like(ref)
+    gx, gw, gr = torch.autograd.grad(out, (x, w, res), g.to(dtype))
+    rx, rw, rr = torch.autograd.grad(ref, (x, w, res), g)
+    assert _rel(out, ref) <= tol and _rel(gx, rx) <= tol and _rel(gw, rw) <= tol and _rel(gr, rr) <= tol
+    assert gw.dtype == torch.float32
+
+
+@pytest.mark.parametrize("variant", ["rubiks3d", "rubiks3d-aq"])
+def test_fused_block_equals_module_graph(variant):
+    torch.manual_seed(3)
+    net = rb.RubiksNet(tier="tiny", num_classes=7, num_frames=8, variant=variant).cuda().train()
+    clips = torch.randn(1, 8, 3, 224, 224, device="cuda")
+    results = []
+    for flag in (True, False):
+        backbone.FUSED_BLOCK = flag
+        try:
+            sd = {k: v.clone() for k, v in net.state_dict().items()}
+            net.zero_grad(set_to_none=True)
+            logits = net(clips)
+            logits.square().sum().backward()
+            grads = {n: p.grad.clone() for n, p in net.named_parameters()}
+            results.append((logits.detach().clone(), grads, net.backbone.bn_last.running_var.clone()))
+            net.load_state_dict(sd)  # undo the running-stat update
+        finally:
+            backbone.FUSED_BLOCK = True
+    (l1, g1, rv1), (l0, g0, rv0) = results
+    assert _rel(l1, l0) <= 5e-3
+    assert _rel(rv1, rv0) <= 1e-3
+    for name in ("backbone.conv1.weight", "backbone.layer2.1.conv2.weight" if variant == "rubiks3d" else "backbone.layer2.1.conv2.1.weight",
+                 "backbone.layer3.0.bn2.weight", "new_fc.weight"):
+        assert _rel(g1[name], g0[name]) <= 2e-2, name
+
+
+def _reference_package():
+    ref = os.path.join(REPO, "baseline", "_ref")
+    ckpt = os.path.join(ref, "pretrained", "ssv2_tiny.pth.tar")
+    if not (os.path.isdir(os.path.join(ref, "rubiksnet")) and os.path.exists(ckpt)):
+        return None, None
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            from rubiksnet.models import RubiksNet as RefNet
+        return RefNet, ckpt
+    except Exception:
+        return None, None
+
+
+def test_whole_model_matches_reference_on_pretrained_checkpoint():
+    """Logits (eval) and a training step's gradients of RubiksNet-Tiny (ssv2 checkpoint): this package vs the
+    reference package running its own CUDA extension."""
+    RefNet, ckpt = _reference_package()
+    if RefNet is None:
+        pytest.skip("baseline/_ref (reference package + checkpoint) not available on this box")
+    torch.manual_seed(4)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref = RefNet.load_pretrained(ckpt).cuda()
+    new = rb.RubiksNet.load_pretrained(ckpt).cuda()
+    clips = torch.randn(2, 8, 3, 224, 224, device="cuda")
+    old_tf32 = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref.eval()
+        new.eval()
+        with torch.no_grad():
+            lr, ln = ref(clips), new(clips)
+        assert _rel(ln, lr) <= 1e-3, "eval logits differ from the reference"
+        assert torch.equal(ln.argmax(1), lr.argmax(1))
+        ref.train()
+        new.train()
+        labels = torch.tensor([3, 100], device="cuda")
+        torch.nn.functional.cross_entropy(ref(clips), labels).backward()
+        torch.nn.functional.cross_entropy(new(clips), labels).backward()
+        gr = dict(ref.named_parameters())
+        for name, p in new.named_parameters():
+            if name.endswith("shift") or name in ("new_fc.weight", "backbone.conv1.weight", "backbone.layer3.2.conv3.weight"):
+                assert _rel(p.grad, gr[name].grad) <= 5e-3, name
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old_tf32
