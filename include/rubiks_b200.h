@@ -46,9 +46,10 @@ typedef enum {
     RB_ERR_WORKSPACE = 4         /* workspace pointer null or smaller than *_workspace_bytes() */
 } rb_status_t;
 
-/* which implementation the dispatcher may use; RB_IMPL_AUTO picks the tiled sm_100a kernels
- * whenever the geometry allows and the generic gather kernels otherwise */
-typedef enum { RB_IMPL_AUTO = 0, RB_IMPL_GENERIC = 1, RB_IMPL_TILED = 2 } rb_impl_t;
+/* which 3D-shift implementation the dispatcher may use.  RB_IMPL_AUTO picks, in this order, the strip
+ * kernels (spatial stride 1), the tiled kernels (spatial stride 1 or 2) -- both TMA-staged sm_100a kernels
+ * for temporal stride 1 / no padding / no quantize -- and the generic gather kernels otherwise */
+typedef enum { RB_IMPL_AUTO = 0, RB_IMPL_GENERIC = 1, RB_IMPL_TILED = 2, RB_IMPL_STRIP = 3 } rb_impl_t;
 
 int rb_abi_version(void);
 /* message of the last non-zero status returned on this thread ("" if none) */

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "librubiks_b200.so")
 
 RB_F32, RB_F64, RB_F16, RB_BF16 = 0, 1, 2, 3
-RB_IMPL_AUTO, RB_IMPL_GENERIC, RB_IMPL_TILED = 0, 1, 2
+RB_IMPL_AUTO, RB_IMPL_GENERIC, RB_IMPL_TILED, RB_IMPL_STRIP = 0, 1, 2, 3
 _DTYPES = {torch.float32: RB_F32, torch.float64: RB_F64, torch.float16: RB_F16, torch.bfloat16: RB_BF16}
 
 _lib = None

@@ -33,6 +33,12 @@ int shift3d_forward_tiled(const void *, const void *, void *, int, int, const Ge
 size_t shift3d_backward_tiled_workspace(int dt, const Geom3 &g);
 int shift3d_backward_tiled(const void *, const void *, const void *, void *, void *, int, int, const Geom3 &,
                            int, double, void *, cudaStream_t);
+// shift3d_strip.cu
+bool shift3d_strip_supported(int dt, const Geom3 &g, int quantize);
+int shift3d_forward_strip(const void *, const void *, void *, int, int, const Geom3 &, cudaStream_t);
+size_t shift3d_backward_strip_workspace(int dt, const Geom3 &g);
+int shift3d_backward_strip(const void *, const void *, const void *, void *, void *, int, int, const Geom3 &, int,
+                           double, void *, cudaStream_t);
 // shift2d_generic.cu
 int shift2d_bwd_chunks(const Geom2 &g);
 int shift2d_forward_generic(const void *, const void *, void *, int, int, const Geom2 &, int, cudaStream_t);
@@ -67,14 +73,22 @@ static int check_dtypes(int dt, int sdt) {
     return RB_OK;
 }
 
-static bool use_tiled(int dt, const Geom3 &g, int quantize, int *err) {
+// AUTO: strip kernels (stride 1) > tiled kernels (stride 1 / 2) > generic gather kernels
+static int pick_impl(int dt, const Geom3 &g, int quantize, int *err) {
     const int forced = g_forced_impl.load(std::memory_order_relaxed);
-    const bool ok = shift3d_tiled_supported(dt, g, quantize);
+    const bool strip_ok = shift3d_strip_supported(dt, g, quantize);
+    const bool tiled_ok = shift3d_tiled_supported(dt, g, quantize);
     *err = RB_OK;
-    if (forced == RB_IMPL_GENERIC) return false;
-    if (forced == RB_IMPL_TILED && !ok)
-        *err = fail(RB_ERR_UNSUPPORTED, "RB_IMPL_TILED forced but geometry is not covered by the tiled kernels");
-    return ok;
+    if (forced == RB_IMPL_GENERIC) return RB_IMPL_GENERIC;
+    if (forced == RB_IMPL_TILED) {
+        if (!tiled_ok) *err = fail(RB_ERR_UNSUPPORTED, "RB_IMPL_TILED forced but geometry is not covered by the tiled kernels");
+        return RB_IMPL_TILED;
+    }
+    if (forced == RB_IMPL_STRIP) {
+        if (!strip_ok) *err = fail(RB_ERR_UNSUPPORTED, "RB_IMPL_STRIP forced but geometry is not covered by the strip kernels");
+        return RB_IMPL_STRIP;
+    }
+    return strip_ok ? RB_IMPL_STRIP : (tiled_ok ? RB_IMPL_TILED : RB_IMPL_GENERIC);
 }
 
 }  // namespace rb
@@ -102,10 +116,11 @@ int rb_shift3d_forward(const void *x, const void *shift, void *out, int dtype, i
     if ((int64_t)N * g.To * C * g.Ho * g.Wo == 0) return RB_OK;
     if (!x || !shift || !out) return fail(RB_ERR_INVALID_ARGUMENT, "null pointer");
     cudaStream_t s = (cudaStream_t)stream;
-    const bool tiled = use_tiled(dtype, g, quantize, &rc);
+    const int impl = pick_impl(dtype, g, quantize, &rc);
     if (rc) return rc;
-    g_last_impl = tiled ? RB_IMPL_TILED : RB_IMPL_GENERIC;
-    if (tiled) return shift3d_forward_tiled(x, shift, out, dtype, shift_dtype, g, s);
+    g_last_impl = impl;
+    if (impl == RB_IMPL_STRIP) return shift3d_forward_strip(x, shift, out, dtype, shift_dtype, g, s);
+    if (impl == RB_IMPL_TILED) return shift3d_forward_tiled(x, shift, out, dtype, shift_dtype, g, s);
     return shift3d_forward_generic(x, shift, out, dtype, shift_dtype, g, quantize, s);
 }
 
@@ -116,7 +131,9 @@ size_t rb_shift3d_backward_workspace_bytes(int dtype, int N, int T, int C, int H
     if ((int64_t)N * g.To * C * g.Ho * g.Wo == 0) return 0;
     size_t generic = (size_t)C * generic_bwd_chunks(g) * 3 * sizeof(double);
     size_t tiled = shift3d_tiled_supported(dtype, g, 0) ? shift3d_backward_tiled_workspace(dtype, g) : 0;
+    size_t strip = shift3d_strip_supported(dtype, g, 0) ? shift3d_backward_strip_workspace(dtype, g) : 0;
     size_t need = generic > tiled ? generic : tiled;
+    if (strip > need) need = strip;
     return (need + 255) & ~(size_t)255;
 }
 
@@ -143,10 +160,13 @@ int rb_shift3d_backward(const void *x, const void *shift, const void *out_grad, 
     if (shift_grad && (!workspace || workspace_bytes < need))
         return fail(RB_ERR_WORKSPACE, "shift3d backward needs %zu workspace bytes, got %zu", need,
                     workspace_bytes);
-    const bool tiled = use_tiled(dtype, g, quantize, &rc);
+    const int impl = pick_impl(dtype, g, quantize, &rc);
     if (rc) return rc;
-    g_last_impl = tiled ? RB_IMPL_TILED : RB_IMPL_GENERIC;
-    if (tiled)
+    g_last_impl = impl;
+    if (impl == RB_IMPL_STRIP)
+        return shift3d_backward_strip(x, shift, out_grad, x_grad, shift_grad, dtype, shift_dtype, g,
+                                      normalize_grad, normalize_t_factor, workspace, s);
+    if (impl == RB_IMPL_TILED)
         return shift3d_backward_tiled(x, shift, out_grad, x_grad, shift_grad, dtype, shift_dtype, g,
                                       normalize_grad, normalize_t_factor, workspace, s);
     // host order of rubiks.cpp:324-376: shift gradient (+reduce, normalise), then input gradient
