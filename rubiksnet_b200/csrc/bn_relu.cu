@@ -46,11 +46,14 @@ template <> __device__ __forceinline__ float tof<__nv_bfloat16>(__nv_bfloat16 v)
 
 // ---- per-channel reductions ---------------------------------------------------------------------
 // grid (SPLIT, C).  MODE 0: sum x, sum x^2.  MODE 1: sum dyr, sum dyr * xhat  (dyr = relu-masked dy).
-template <typename T, int MODE>
+// Block (sp, c) owns images sp, sp+SPLIT, ... of channel c and walks the flattened (image, vector) space so
+// that all threads stay busy even when a plane holds fewer vectors than the block has threads (14x14, 7x7).
+// V = widest vector (elements) dividing HW, so every plane start is V-aligned.
+template <typename T, int MODE, int V>
 __global__ void __launch_bounds__(kBT)
 k_bn_reduce(const T *__restrict__ x, const T *__restrict__ dy, const float *__restrict__ mean_invstd,
-            const float *__restrict__ scale_bias, double *__restrict__ partial, int NI, int C, int HW, int relu) {
-    constexpr int V = Vec<T>::N;
+            const float *__restrict__ scale_bias, double *__restrict__ partial, int NI, int C, int HW, FastDiv vpp,
+            int relu) {
     const int sp = blockIdx.x, c = blockIdx.y, splits = gridDim.x;
     float s0 = 0.f, s1 = 0.f;
     float mean = 0.f, invstd = 1.f, sc = 1.f, bi = 0.f;
@@ -60,45 +63,31 @@ k_bn_reduce(const T *__restrict__ x, const T *__restrict__ dy, const float *__re
         sc = scale_bias[2 * c];
         bi = scale_bias[2 * c + 1];
     }
-    const bool vec_ok = (HW % V == 0);
-    for (int n = sp; n < NI; n += splits) {
-        const int64_t base = ((int64_t)n * C + c) * HW;
-        if (vec_ok) {
-            const Pack<T, V> *xp = reinterpret_cast<const Pack<T, V> *>(x + base);
-            const Pack<T, V> *gp = reinterpret_cast<const Pack<T, V> *>(dy + base);
-            for (int i = threadIdx.x; i < HW / V; i += kBT) {
-                const Pack<T, V> xv = xp[i];
-                if (MODE == 0) {
+    const int n_count = (NI - sp + splits - 1) / splits;
+    const uint32_t total = (uint32_t)n_count * vpp.d;
+    const int64_t img_stride = (int64_t)splits * C * HW;
+    const int64_t base0 = ((int64_t)sp * C + c) * HW;
+    for (uint32_t idx = threadIdx.x; idx < total; idx += kBT) {
+        const uint32_t nl = fdiv(idx, vpp);
+        const uint32_t i = idx - nl * vpp.d;
+        const int64_t off = base0 + (int64_t)nl * img_stride + (int64_t)i * V;
+        const Pack<T, V> xv = *reinterpret_cast<const Pack<T, V> *>(x + off);
+        if (MODE == 0) {
 #pragma unroll
-                    for (int k = 0; k < V; ++k) {
-                        const float f = tof(xv.v[k]);
-                        s0 += f;
-                        s1 += f * f;
-                    }
-                } else {
-                    const Pack<T, V> gv = gp[i];
-#pragma unroll
-                    for (int k = 0; k < V; ++k) {
-                        const float f = tof(xv.v[k]);
-                        float g = tof(gv.v[k]);
-                        if (relu && !(f * sc + bi > 0.f)) g = 0.f;
-                        s0 += g;
-                        s1 += g * ((f - mean) * invstd);
-                    }
-                }
+            for (int k = 0; k < V; ++k) {
+                const float f = tof(xv.v[k]);
+                s0 += f;
+                s1 += f * f;
             }
         } else {
-            for (int i = threadIdx.x; i < HW; i += kBT) {
-                const float f = tof(x[base + i]);
-                if (MODE == 0) {
-                    s0 += f;
-                    s1 += f * f;
-                } else {
-                    float g = tof(dy[base + i]);
-                    if (relu && !(f * sc + bi > 0.f)) g = 0.f;
-                    s0 += g;
-                    s1 += g * ((f - mean) * invstd);
-                }
+            const Pack<T, V> gv = *reinterpret_cast<const Pack<T, V> *>(dy + off);
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                const float f = tof(xv.v[k]);
+                float g = tof(gv.v[k]);
+                if (relu && !(f * sc + bi > 0.f)) g = 0.f;
+                s0 += g;
+                s1 += g * ((f - mean) * invstd);
             }
         }
     }
@@ -117,6 +106,26 @@ k_bn_reduce(const T *__restrict__ x, const T *__restrict__ dy, const float *__re
         for (int w = 0; w < kBT / 32; ++w) s += red[threadIdx.x][w];
         partial[((int64_t)c * splits + sp) * 2 + threadIdx.x] = s;
     }
+}
+
+template <typename T, int MODE>
+static void launch_bn_reduce(const T *x, const T *dy, const float *mean_invstd, const float *scale_bias, double *partial,
+                             int NI, int C, int HW, int relu, int splits, cudaStream_t s) {
+    dim3 grid(splits, C);
+    constexpr int VMAX = Vec<T>::N;
+    int V = VMAX;
+    while (V > 1 && HW % V != 0) V >>= 1;
+    const FastDiv vpp = make_fastdiv((uint32_t)(HW / V));
+#define RB_BN_REDUCE(VV)                                                                                          \
+    k_bn_reduce<T, MODE, (VV <= VMAX ? VV : 1)><<<grid, kBT, 0, s>>>(x, dy, mean_invstd, scale_bias, partial, NI, C, HW, \
+                                                                    vpp, relu)
+    switch (V) {
+        case 8: RB_BN_REDUCE(8); break;
+        case 4: RB_BN_REDUCE(4); break;
+        case 2: RB_BN_REDUCE(2); break;
+        default: RB_BN_REDUCE(1); break;
+    }
+#undef RB_BN_REDUCE
 }
 
 // one warp per channel: batch statistics -> save (mean, invstd), (scale, bias); running stats update
@@ -313,9 +322,8 @@ extern "C" int rb_bn_act_forward(const void *x, const float *gamma, const float 
         if (!workspace || workspace_bytes < bn_ws_bytes(NI, C))
             return fail(RB_ERR_WORKSPACE, "bn forward needs %zu workspace bytes", bn_ws_bytes(NI, C));
         const int splits = bn_splits(NI, C);
-        dim3 grid(splits, C);
-        RB_DISPATCH_DTYPE(dtype, (k_bn_reduce<T, 0><<<grid, kBT, 0, s>>>((const T *)x, (const T *)x, nullptr, nullptr,
-                                                                        (double *)workspace, NI, C, HW, 0)));
+        RB_DISPATCH_DTYPE(dtype, (launch_bn_reduce<T, 0>((const T *)x, (const T *)x, nullptr, nullptr, (double *)workspace,
+                                                         NI, C, HW, 0, splits, s)));
         if ((rc = launched("k_bn_reduce<stats>"))) return rc;
         k_bn_stats_finalize<<<cdiv(C, 4), 128, 0, s>>>((const double *)workspace, splits, C, (double)NI * HW, gamma, beta,
                                                        running_mean, running_var, momentum, eps, mean_invstd, scale_bias);
@@ -359,10 +367,9 @@ extern "C" int rb_bn_act_backward(const void *x, const void *dy, const void *res
     const int splits = bn_splits(NI, C);
     double *partial = (double *)workspace;
     float *coef = (float *)((char *)workspace + (size_t)C * splits * 2 * sizeof(double));
-    dim3 grid(splits, C);
     int rc;
-    RB_DISPATCH_DTYPE(dtype, (k_bn_reduce<T, 1><<<grid, kBT, 0, s>>>((const T *)x, (const T *)dy, mean_invstd, scale_bias,
-                                                                    partial, NI, C, HW, relu)));
+    RB_DISPATCH_DTYPE(dtype, (launch_bn_reduce<T, 1>((const T *)x, (const T *)dy, mean_invstd, scale_bias, partial, NI, C,
+                                                     HW, relu, splits, s)));
     if ((rc = launched("k_bn_reduce<bwd>"))) return rc;
     k_bn_bwd_finalize<<<cdiv(C, 4), 128, 0, s>>>(partial, splits, C, (double)NI * HW, gamma, mean_invstd, training, dgamma,
                                                  dbeta, coef);
