@@ -152,6 +152,46 @@ int rb_bn_act_backward(const void *x, const void *dy, const void *residual, cons
                        float *dbeta, int dtype, int NI, int C, int HW, int training, int relu,
                        void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---------------------------------------------------------------- pointwise (1x1) convolutions -- */
+
+/* Conv1x1 of RubiksShiftBlock (rubiksnet/backbone.py:45-47: nn.Conv2d(k=1, bias=False); conv2 / conv3 /
+ * shortcut at :123-135) as ONE tcgen05 tensor-core GEMM launch on NCHW bf16 activations:
+ *     out[i, n, p] = sum_k weight[n, k] * A[i, k, p]  (+ residual[i, n, p])
+ * x [NI, K, HW], weight [N, K] (= Conv2d weight [N,K,1,1]), residual / out [NI, N, HW]; dtype must be
+ * RB_BF16 (fp32 accumulation in tensor memory).  residual may be NULL; it may alias out.
+ * in_scale / in_bias (fp32 [K], both NULL or both set) fold  A = relu(x * in_scale[k] + in_bias[k])  --
+ * the bn1 -> relu in front of conv2 (backbone.py:123,127) -- into the operand producer; NULL: A = x.
+ * The same entry point computes the input gradient of a 1x1 conv (pass the transposed weight). */
+int rb_pw_conv_forward(const void *x, const void *weight, const void *residual, void *out, int dtype,
+                       int NI, int K, int N, int HW, const float *in_scale, const float *in_bias,
+                       void *stream);
+
+/* as3 -> conv3 -> `out += shortcut` of RubiksShiftBlock.forward (backbone.py:129-135, with as3 the
+ * _Rubiks3DWrap of rubiksnet/models.py:128-145) in ONE launch: the 3D learnable shift
+ * (rubiks_shift_3d_forward_cuda, rubiks3d_kernels.cu:15-205; stride (1,1,1), padding 0, no quantize) is the
+ * A-operand producer of the tensor-core GEMM, so the shifted tensor never exists in HBM.
+ * x [N, T, C, H, W] bf16, shift [3, C] (shift_dtype), weight [Cout, C] bf16, residual / out
+ * [N*T, Cout, H, W] bf16.  Equals rb_shift3d_forward followed by rb_pw_conv_forward bit for bit. */
+int rb_shift3d_pw_conv_forward(const void *x, const void *shift, const void *weight, const void *residual,
+                               void *out, int dtype, int shift_dtype, int N, int T, int C, int H, int W,
+                               int Cout, void *stream);
+
+/* Weight gradient of the same 1x1 convolution (what autograd computes for nn.Conv2d(k=1) in the reference's
+ * backward pass): weight_grad[n, k] = sum_{i,p} out_grad[i, n, p] * A[i, k, p], fp32 [N, K], OVERWRITTEN.
+ * A is recomputed from x by the operand producer exactly as in the forward (in_scale / in_bias as above).
+ * One tensor-core launch that reduces disjoint pixel ranges into fp32 partial slices in `workspace`, plus a
+ * fixed-order reduction over the slices (deterministic). */
+size_t rb_pw_conv_wgrad_workspace_bytes(int NI, int K, int N, int HW);
+int rb_pw_conv_wgrad(const void *out_grad, const void *x, float *weight_grad, int dtype, int NI, int K, int N,
+                     int HW, const float *in_scale, const float *in_bias, void *workspace,
+                     size_t workspace_bytes, void *stream);
+
+/* conv3 weight gradient with the 3D shift recomputed in the operand producer (the shifted tensor was never
+ * stored by rb_shift3d_pw_conv_forward): weight_grad[co, c] = sum out_grad[i, co, p] * shift3d(x)[i, c, p]. */
+int rb_shift3d_pw_conv_wgrad(const void *out_grad, const void *x, const void *shift, float *weight_grad,
+                             int dtype, int shift_dtype, int N, int T, int C, int H, int W, int Cout,
+                             void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

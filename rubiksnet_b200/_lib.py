@@ -59,6 +59,16 @@ def _declare(lib):
     lib.rb_bn_act_forward.restype = i
     lib.rb_bn_act_backward.argtypes = [vp] * 9 + [i, i, i, i, i, i, vp, sz, vp]
     lib.rb_bn_act_backward.restype = i
+    lib.rb_pw_conv_forward.argtypes = [vp, vp, vp, vp, i, i, i, i, i, vp, vp, vp]
+    lib.rb_pw_conv_forward.restype = i
+    lib.rb_shift3d_pw_conv_forward.argtypes = [vp] * 5 + [i] * 8 + [vp]
+    lib.rb_shift3d_pw_conv_forward.restype = i
+    lib.rb_pw_conv_wgrad_workspace_bytes.argtypes = [i, i, i, i]
+    lib.rb_pw_conv_wgrad_workspace_bytes.restype = sz
+    lib.rb_pw_conv_wgrad.argtypes = [vp, vp, vp, i, i, i, i, i, vp, vp, vp, sz, vp]
+    lib.rb_pw_conv_wgrad.restype = i
+    lib.rb_shift3d_pw_conv_wgrad.argtypes = [vp] * 4 + [i] * 8 + [vp, sz, vp]
+    lib.rb_shift3d_pw_conv_wgrad.restype = i
 
 
 def lib():
