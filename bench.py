@@ -11,8 +11,8 @@ Prints ONE JSON line (rank 0).  Keys beyond the base contract:
   value        clips/s, whole job, inputs already resident in HBM (device-timed, max over ranks)
   e2e          same step driven from pinned HOST clips: H2D copy of every batch and a D2H read of the
                loss inside the timed region
-  roofline     achieved algorithmic HBM GB/s of the dominant hand-written kernel (the fused 3D-shift
-               backward), measured live with CUDA events around its launches on the launching stream
+  roofline     achieved algorithmic HBM GB/s of the dominant hand-written kernel, measured live with CUDA
+               events around every librubiks_b200 launch on the launching stream (all kernels listed)
   cpu_baseline the CPU port (oracle/ C restatement of the shift + PyTorch CPU ops for the rest of the
                network) timed on this box's host cores on a bounded sample
   gpu_launches number of librubiks_b200 kernels launched inside the timed region
@@ -251,42 +251,17 @@ def time_e2e(tr, args, world, host_batches):
 
 
 def kernel_roofline(tr, clips, labels):
-    """Times every librubiks_b200 shift launch of ONE extra step with CUDA events on the launching stream and
-    reports the dominant kernel (by total time) against the measured HBM copy peak."""
+    """Brackets every librubiks_b200 call of ONE extra step with CUDA events on the launching stream
+    (rubiksnet_b200._lib.timing) and reports the dominant hand-written kernel (by total time) against the measured
+    HBM copy peak: achieved = algorithmic bytes (each operand tensor once) / event time."""
     import torch
-    from rubiksnet_b200 import rubiksnet_cuda as native
-    records = []
-    orig_f, orig_b = native.rubiks_shift_3d_forward, native.rubiks_shift_3d_backward
-
-    def wrap(fn, kind):
-        def inner(*a, **k):
-            x = a[0]
-            if kind == "fwd":
-                nbytes = (x.numel() + a[5].numel()) * x.element_size()          # in + out
-            else:
-                nbytes = (2 * x.numel() + a[2].numel()) * x.element_size()      # x + out_grad + x_grad
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            r = fn(*a, **k)
-            e1.record()
-            records.append((kind, nbytes, e0, e1))
-            return r
-        return inner
-
-    import rubiksnet_b200.shiftlib.rubiks3d.primitive as prim
-    prim._native.rubiks_shift_3d_forward = wrap(orig_f, "fwd")
-    prim._native.rubiks_shift_3d_backward = wrap(orig_b, "bwd")
+    from rubiksnet_b200 import _lib
+    _lib.timing.start()
     try:
         tr.step(clips, labels)
         torch.cuda.synchronize()
     finally:
-        prim._native.rubiks_shift_3d_forward, prim._native.rubiks_shift_3d_backward = orig_f, orig_b
-    agg = {}
-    for kind, nbytes, e0, e1 in records:
-        d = agg.setdefault(kind, [0, 0.0, 0])
-        d[0] += nbytes
-        d[1] += e0.elapsed_time(e1)
-        d[2] += 1
+        agg = _lib.timing.stop()
     if not agg:
         return None
     peaks = {}
@@ -295,18 +270,23 @@ def kernel_roofline(tr, clips, labels):
     except Exception:  # noqa: BLE001
         pass
     peak, peak_src = (peaks["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs") if "hbm_gbs" in peaks else (6650.0, "fallback B200_PROFILING.md")
-    kind = max(agg, key=lambda k: agg[k][1])
-    nbytes, ms, n = agg[kind]
-    achieved = nbytes / ms / 1e6
-    name = {"fwd": "k_shift3d_tiled<fwd>", "bwd": "k_shift3d_tiled<bwd> (+k_shift3d_finalize)"}[kind]
-    out = {"bound": "hbm", "kernel": name, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-           "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
-           "launches_per_step": n, "algorithmic_bytes_per_step": nbytes, "kernel_ms_per_step": round(ms, 3)}
-    other = "fwd" if kind == "bwd" else "bwd"
-    if other in agg:
-        ob, oms, on = agg[other]
-        out["other_kernel"] = {"kernel": "k_shift3d_tiled<%s>" % other, "achieved": round(ob / oms / 1e6, 1),
-                               "frac": round(ob / oms / 1e6 / peak, 4), "kernel_ms_per_step": round(oms, 3)}
+    tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    top = max(agg, key=lambda k: agg[k]["ms"])
+
+    def entry(name):
+        d = agg[name]
+        gbs = d["bytes"] / d["ms"] / 1e6
+        e = {"kernel": name, "achieved": round(gbs, 1), "frac": round(gbs / peak, 4), "launches_per_step": d["launches"],
+             "algorithmic_bytes_per_step": d["bytes"], "kernel_ms_per_step": round(d["ms"], 3)}
+        if d["flops"]:
+            e["tensor_tflops"] = round(d["flops"] / d["ms"] / 1e9, 1)
+            e["tensor_frac"] = round(d["flops"] / d["ms"] / 1e9 / tf_peak, 4)
+        return e
+
+    out = {"bound": "hbm", "peak": peak, "unit": "GB/s", "traffic": None, "peak_source": peak_src}
+    out.update(entry(top))
+    out["all_kernels"] = [entry(k) for k in sorted(agg, key=lambda k: -agg[k]["ms"]) if k != top]
+    out["timed_ms_per_step"] = round(sum(d["ms"] for d in agg.values()), 3)
     return out
 
 

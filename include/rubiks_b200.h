@@ -137,7 +137,9 @@ int rb_attention_shift_backward(const void *x, const float *taps, const void *ou
  *   bias = beta - mean * scale.
  * training != 0: batch statistics (biased variance), running stats updated with `momentum`
  * (unbiased variance), exactly torch.nn.BatchNorm2d.  training == 0: running statistics.
- * relu != 0 applies max(.,0) in forward and masks dy with (y > 0) in backward. */
+ * relu != 0 applies max(.,0) in forward and masks dy with (y > 0) in backward.
+ * rb_bn_act_forward with y == NULL computes only the statistics / coefficients (the apply pass is then
+ * folded into a consumer, e.g. rb_pw_conv_forward's in_scale_bias). */
 size_t rb_bn_workspace_bytes(int NI, int C);
 
 int rb_bn_act_forward(const void *x, const float *gamma, const float *beta, float *running_mean,
@@ -157,34 +159,38 @@ int rb_bn_act_backward(const void *x, const void *dy, const void *residual, cons
 /* Conv1x1 of RubiksShiftBlock (rubiksnet/backbone.py:45-47: nn.Conv2d(k=1, bias=False); conv2 / conv3 /
  * shortcut at :123-135) as ONE tcgen05 tensor-core GEMM launch on NCHW bf16 activations:
  *     out[i, n, p] = sum_k weight[n, k] * A[i, k, p]  (+ residual[i, n, p])
- * x [NI, K, HW], weight [N, K] (= Conv2d weight [N,K,1,1]), residual / out [NI, N, HW]; dtype must be
- * RB_BF16 (fp32 accumulation in tensor memory).  residual may be NULL; it may alias out.
- * in_scale / in_bias (fp32 [K], both NULL or both set) fold  A = relu(x * in_scale[k] + in_bias[k])  --
- * the bn1 -> relu in front of conv2 (backbone.py:123,127) -- into the operand producer; NULL: A = x.
- * The same entry point computes the input gradient of a 1x1 conv (pass the transposed weight). */
-int rb_pw_conv_forward(const void *x, const void *weight, const void *residual, void *out, int dtype,
-                       int NI, int K, int N, int HW, const float *in_scale, const float *in_bias,
-                       void *stream);
+ * x [NI, K, HW], residual / out [NI, N, HW]; dtype must be RB_BF16 (fp32 accumulation in tensor memory).
+ * weight is the Conv2d parameter [N, K, 1, 1] in weight_dtype RB_F32 (the fp32 master copy, rounded to bf16
+ * by the kernel) or RB_BF16.  weight_transposed != 0: the buffer holds [K, N] instead -- passing a conv's own
+ * weight with N and K swapped computes that conv's INPUT GRADIENT (out_grad -> x_grad) with the same kernel.
+ * residual may be NULL; it may alias out.
+ * in_scale_bias (fp32 [K, 2] = the scale_bias output of rb_bn_act_forward, or NULL) folds
+ * A = relu(x * scale[k] + bias[k]) -- the bn1 -> relu in front of conv2 (backbone.py:123,127) -- into the
+ * operand producer; NULL: A = x. */
+int rb_pw_conv_forward(const void *x, const void *weight, int weight_dtype, int weight_transposed,
+                       const void *residual, void *out, int dtype, int NI, int K, int N, int HW,
+                       const float *in_scale_bias, void *stream);
 
 /* as3 -> conv3 -> `out += shortcut` of RubiksShiftBlock.forward (backbone.py:129-135, with as3 the
  * _Rubiks3DWrap of rubiksnet/models.py:128-145) in ONE launch: the 3D learnable shift
  * (rubiks_shift_3d_forward_cuda, rubiks3d_kernels.cu:15-205; stride (1,1,1), padding 0, no quantize) is the
  * A-operand producer of the tensor-core GEMM, so the shifted tensor never exists in HBM.
- * x [N, T, C, H, W] bf16, shift [3, C] (shift_dtype), weight [Cout, C] bf16, residual / out
- * [N*T, Cout, H, W] bf16.  Equals rb_shift3d_forward followed by rb_pw_conv_forward bit for bit. */
-int rb_shift3d_pw_conv_forward(const void *x, const void *shift, const void *weight, const void *residual,
-                               void *out, int dtype, int shift_dtype, int N, int T, int C, int H, int W,
-                               int Cout, void *stream);
+ * x [N, T, C, H, W] bf16, shift [3, C] (shift_dtype), weight [Cout, C] (weight_dtype), residual / out
+ * [N*T, Cout, H, W] bf16.  Same arithmetic as rb_shift3d_forward followed by rb_pw_conv_forward: fp32 trilinear
+ * interpolation in the reference's association order, rounded to bf16 once, then the GEMM. */
+int rb_shift3d_pw_conv_forward(const void *x, const void *shift, const void *weight, int weight_dtype,
+                               const void *residual, void *out, int dtype, int shift_dtype, int N, int T,
+                               int C, int H, int W, int Cout, void *stream);
 
 /* Weight gradient of the same 1x1 convolution (what autograd computes for nn.Conv2d(k=1) in the reference's
  * backward pass): weight_grad[n, k] = sum_{i,p} out_grad[i, n, p] * A[i, k, p], fp32 [N, K], OVERWRITTEN.
- * A is recomputed from x by the operand producer exactly as in the forward (in_scale / in_bias as above).
+ * A is recomputed from x by the operand producer exactly as in the forward (in_scale_bias as above).
  * One tensor-core launch that reduces disjoint pixel ranges into fp32 partial slices in `workspace`, plus a
  * fixed-order reduction over the slices (deterministic). */
 size_t rb_pw_conv_wgrad_workspace_bytes(int NI, int K, int N, int HW);
 int rb_pw_conv_wgrad(const void *out_grad, const void *x, float *weight_grad, int dtype, int NI, int K, int N,
-                     int HW, const float *in_scale, const float *in_bias, void *workspace,
-                     size_t workspace_bytes, void *stream);
+                     int HW, const float *in_scale_bias, void *workspace, size_t workspace_bytes,
+                     void *stream);
 
 /* conv3 weight gradient with the 3D shift recomputed in the operand producer (the shifted tensor was never
  * stored by rb_shift3d_pw_conv_forward): weight_grad[co, c] = sum out_grad[i, co, p] * shift3d(x)[i, c, p]. */

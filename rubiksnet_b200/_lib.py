@@ -59,13 +59,13 @@ def _declare(lib):
     lib.rb_bn_act_forward.restype = i
     lib.rb_bn_act_backward.argtypes = [vp] * 9 + [i, i, i, i, i, i, vp, sz, vp]
     lib.rb_bn_act_backward.restype = i
-    lib.rb_pw_conv_forward.argtypes = [vp, vp, vp, vp, i, i, i, i, i, vp, vp, vp]
+    lib.rb_pw_conv_forward.argtypes = [vp, vp, i, i, vp, vp, i, i, i, i, i, vp, vp]
     lib.rb_pw_conv_forward.restype = i
-    lib.rb_shift3d_pw_conv_forward.argtypes = [vp] * 5 + [i] * 8 + [vp]
+    lib.rb_shift3d_pw_conv_forward.argtypes = [vp, vp, vp, i, vp, vp] + [i] * 8 + [vp]
     lib.rb_shift3d_pw_conv_forward.restype = i
     lib.rb_pw_conv_wgrad_workspace_bytes.argtypes = [i, i, i, i]
     lib.rb_pw_conv_wgrad_workspace_bytes.restype = sz
-    lib.rb_pw_conv_wgrad.argtypes = [vp, vp, vp, i, i, i, i, i, vp, vp, vp, sz, vp]
+    lib.rb_pw_conv_wgrad.argtypes = [vp, vp, vp, i, i, i, i, i, vp, vp, sz, vp]
     lib.rb_pw_conv_wgrad.restype = i
     lib.rb_shift3d_pw_conv_wgrad.argtypes = [vp] * 4 + [i] * 8 + [vp, sz, vp]
     lib.rb_shift3d_pw_conv_wgrad.restype = i
@@ -121,6 +121,55 @@ def workspace(nbytes, device):
         buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
         _workspaces[key] = buf
     return buf
+
+
+class _Timing:
+    """Per-kernel CUDA-event timing, switched on by bench.py for one extra step."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = []  # (name, algorithmic bytes, flops, start event, end event)
+
+    def start(self):
+        self.enabled, self.records = True, []
+
+    def stop(self):
+        self.enabled = False
+        torch.cuda.synchronize()
+        agg = {}
+        for name, nbytes, flops, e0, e1 in self.records:
+            d = agg.setdefault(name, {"bytes": 0, "flops": 0, "ms": 0.0, "launches": 0})
+            d["bytes"] += nbytes
+            d["flops"] += flops
+            d["ms"] += e0.elapsed_time(e1)
+            d["launches"] += 1
+        self.records = []
+        return agg
+
+
+timing = _Timing()
+
+
+class timed:
+    def __init__(self, name, nbytes, flops=0):
+        self.name, self.nbytes, self.flops = name, nbytes, flops
+
+    def __enter__(self):
+        if timing.enabled:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if timing.enabled:
+            self.e1.record()
+            timing.records.append((self.name, self.nbytes, self.flops, self.e0, self.e1))
+        return False
+
+
+
+def nbytes(*tensors):
+    return sum(t.numel() * t.element_size() for t in tensors if t is not None)
 
 
 def launch_count():

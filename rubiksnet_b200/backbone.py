@@ -29,6 +29,8 @@ def _bn(planes):
 # CUDA tensors take the fused path (librubiks_b200 BN+ReLU kernels, batched-GEMM 1x1 convs); set to False to
 # run the plain nn.Module graph (used by tests to check that both give the same numbers)
 FUSED_BLOCK = True
+# identity-shortcut rubiks3d blocks with bf16 activations: one autograd Function, shift fused into conv3 (fused.py)
+FUSED_WHOLE_BLOCK = True
 
 
 class SELayer(nn.Module):
@@ -83,8 +85,10 @@ class RubiksShiftBlock(nn.Module):
         return out
 
     def _forward_fused(self, x):
-        """Same arithmetic with librubiks_b200's BN+ReLU passes and NCHW batched-GEMM 1x1 convolutions; the
-        residual add is the epilogue of the conv3 GEMM."""
+        """Same arithmetic with librubiks_b200's BN+ReLU passes and GEMM 1x1 convolutions; the residual add is the
+        epilogue of the conv3 GEMM.  Identity-shortcut 3D blocks in bf16 run as one fused autograd Function."""
+        if FUSED_WHOLE_BLOCK and fused.rubiks_block_supported(self, x):
+            return fused.rubiks_block(self, x)
         out = fused.bn_act(x, self.bn1, relu=True)
         if isinstance(self.shortcut, nn.Identity):
             shortcut = x

@@ -47,14 +47,11 @@ int shift2d_bwd_shift_generic(const void *, const void *, const void *, void *, 
                               double *, cudaStream_t);
 
 // pw_conv.cu
-int pw_conv_forward(const void *x, const void *w, const void *residual, void *out, int NI, int K, int N, int HW,
-                    const float *a_scale, const float *a_bias, const void *shift, int shift_dt, int T, int H, int W,
-                    cudaStream_t s);
-
+int pw_conv_forward(const void *x, const void *w, int w_dt, int w_trans, const void *residual, void *out, int NI, int K,
+                    int N, int HW, const float *a_sb, const void *shift, int shift_dt, int T, int H, int W, cudaStream_t s);
 size_t pw_conv_wgrad_workspace(int NI, int M, int N, int HW);
-int pw_conv_wgrad(const void *g, const void *x, float *dw, int NI, int M, int N, int HW, const float *x_scale,
-                  const float *x_bias, const void *shift, int shift_dt, int T, int H, int W, void *workspace,
-                  cudaStream_t s);
+int pw_conv_wgrad(const void *g, const void *x, float *dw, int NI, int M, int N, int HW, const float *x_sb,
+                  const void *shift, int shift_dt, int T, int H, int W, void *workspace, cudaStream_t s);
 
 static int make_geom3(Geom3 &g, int N, int T, int C, int H, int W, int sT, int sH, int sW, int pT, int pH,
                       int pW) {
@@ -255,34 +252,41 @@ int rb_shift2d_backward(const void *x, const void *shift, const void *out_grad, 
     return rc;
 }
 
-int rb_pw_conv_forward(const void *x, const void *weight, const void *residual, void *out, int dtype, int NI,
-                       int K, int N, int HW, const float *in_scale, const float *in_bias, void *stream) {
+static int check_weight_dtype(int wdt) {
+    if (wdt != RB_F32 && wdt != RB_BF16) return fail(RB_ERR_INVALID_ARGUMENT, "weight dtype must be RB_F32 or RB_BF16, got %d", wdt);
+    return RB_OK;
+}
+
+int rb_pw_conv_forward(const void *x, const void *weight, int weight_dtype, int weight_transposed, const void *residual,
+                       void *out, int dtype, int NI, int K, int N, int HW, const float *in_scale_bias, void *stream) {
     if (dtype != RB_BF16) return fail(RB_ERR_UNSUPPORTED, "rb_pw_conv_forward: bf16 activations only (got dtype %d)", dtype);
+    int rc = check_weight_dtype(weight_dtype);
+    if (rc) return rc;
     if (NI < 0 || K <= 0 || N <= 0 || HW < 0) return fail(RB_ERR_INVALID_ARGUMENT, "bad extent [%d,%d,%d,%d]", NI, K, N, HW);
-    if ((in_scale == nullptr) != (in_bias == nullptr))
-        return fail(RB_ERR_INVALID_ARGUMENT, "in_scale and in_bias must both be given or both be NULL");
     if ((int64_t)NI * K * HW > 0x7fffffffLL || (int64_t)NI * N * HW > 0x7fffffffLL)
         return fail(RB_ERR_UNSUPPORTED, "tensors with more than 2^31-1 elements are not supported");
     if ((int64_t)NI * HW == 0) return RB_OK;
     if (!x || !weight || !out) return fail(RB_ERR_INVALID_ARGUMENT, "null pointer");
-    return pw_conv_forward(x, weight, residual, out, NI, K, N, HW, in_scale, in_bias, nullptr, 0, 0, 0, 0,
-                           (cudaStream_t)stream);
+    return pw_conv_forward(x, weight, weight_dtype, weight_transposed != 0, residual, out, NI, K, N, HW, in_scale_bias,
+                           nullptr, 0, 0, 0, 0, (cudaStream_t)stream);
 }
 
-int rb_shift3d_pw_conv_forward(const void *x, const void *shift, const void *weight, const void *residual, void *out,
-                               int dtype, int shift_dtype, int N, int T, int C, int H, int W, int Cout, void *stream) {
+int rb_shift3d_pw_conv_forward(const void *x, const void *shift, const void *weight, int weight_dtype, const void *residual,
+                               void *out, int dtype, int shift_dtype, int N, int T, int C, int H, int W, int Cout,
+                               void *stream) {
     if (dtype != RB_BF16)
         return fail(RB_ERR_UNSUPPORTED, "rb_shift3d_pw_conv_forward: bf16 activations only (got dtype %d)", dtype);
     int rc = check_dtypes(dtype, shift_dtype);
     if (rc) return rc;
+    if ((rc = check_weight_dtype(weight_dtype))) return rc;
     if (N < 0 || T < 0 || C <= 0 || H < 0 || W < 0 || Cout <= 0)
         return fail(RB_ERR_INVALID_ARGUMENT, "bad extent [%d,%d,%d,%d,%d] -> %d", N, T, C, H, W, Cout);
     if ((int64_t)N * T * C * H * W > 0x7fffffffLL || (int64_t)N * T * Cout * H * W > 0x7fffffffLL)
         return fail(RB_ERR_UNSUPPORTED, "tensors with more than 2^31-1 elements are not supported");
     if ((int64_t)N * T * H * W == 0) return RB_OK;
     if (!x || !shift || !weight || !out) return fail(RB_ERR_INVALID_ARGUMENT, "null pointer");
-    return pw_conv_forward(x, weight, residual, out, N * T, C, Cout, H * W, nullptr, nullptr, shift, shift_dtype, T, H,
-                           W, (cudaStream_t)stream);
+    return pw_conv_forward(x, weight, weight_dtype, 0, residual, out, N * T, C, Cout, H * W, nullptr, shift, shift_dtype, T,
+                           H, W, (cudaStream_t)stream);
 }
 
 size_t rb_pw_conv_wgrad_workspace_bytes(int NI, int K, int N, int HW) {
@@ -291,12 +295,10 @@ size_t rb_pw_conv_wgrad_workspace_bytes(int NI, int K, int N, int HW) {
 }
 
 static int wgrad_common(const void *out_grad, const void *x, float *weight_grad, int dtype, int NI, int K, int N, int HW,
-                        const float *in_scale, const float *in_bias, const void *shift, int shift_dtype, int T, int H,
-                        int W, void *workspace, size_t workspace_bytes, void *stream) {
+                        const float *in_scale_bias, const void *shift, int shift_dtype, int T, int H, int W,
+                        void *workspace, size_t workspace_bytes, void *stream) {
     if (dtype != RB_BF16) return fail(RB_ERR_UNSUPPORTED, "pw_conv wgrad: bf16 activations only (got dtype %d)", dtype);
     if (NI < 0 || K <= 0 || N <= 0 || HW < 0) return fail(RB_ERR_INVALID_ARGUMENT, "bad extent [%d,%d,%d,%d]", NI, K, N, HW);
-    if ((in_scale == nullptr) != (in_bias == nullptr))
-        return fail(RB_ERR_INVALID_ARGUMENT, "in_scale and in_bias must both be given or both be NULL");
     if ((int64_t)NI * K * HW > 0x7fffffffLL || (int64_t)NI * N * HW > 0x7fffffffLL)
         return fail(RB_ERR_UNSUPPORTED, "tensors with more than 2^31-1 elements are not supported");
     if (!weight_grad) return fail(RB_ERR_INVALID_ARGUMENT, "null pointer");
@@ -310,12 +312,12 @@ static int wgrad_common(const void *out_grad, const void *x, float *weight_grad,
     if (!workspace || workspace_bytes < need)
         return fail(RB_ERR_WORKSPACE, "pw_conv wgrad needs %zu workspace bytes, got %zu", need, workspace_bytes);
     // GEMM rows m = output channels (N of the conv), columns = input channels (K of the conv)
-    return pw_conv_wgrad(out_grad, x, weight_grad, NI, N, K, HW, in_scale, in_bias, shift, shift_dtype, T, H, W, workspace, s);
+    return pw_conv_wgrad(out_grad, x, weight_grad, NI, N, K, HW, in_scale_bias, shift, shift_dtype, T, H, W, workspace, s);
 }
 
 int rb_pw_conv_wgrad(const void *out_grad, const void *x, float *weight_grad, int dtype, int NI, int K, int N, int HW,
-                     const float *in_scale, const float *in_bias, void *workspace, size_t workspace_bytes, void *stream) {
-    return wgrad_common(out_grad, x, weight_grad, dtype, NI, K, N, HW, in_scale, in_bias, nullptr, 0, 0, 0, 0, workspace,
+                     const float *in_scale_bias, void *workspace, size_t workspace_bytes, void *stream) {
+    return wgrad_common(out_grad, x, weight_grad, dtype, NI, K, N, HW, in_scale_bias, nullptr, 0, 0, 0, 0, workspace,
                         workspace_bytes, stream);
 }
 
@@ -326,8 +328,8 @@ int rb_shift3d_pw_conv_wgrad(const void *out_grad, const void *x, const void *sh
     if (rc) return rc;
     if (!shift) return fail(RB_ERR_INVALID_ARGUMENT, "null pointer");
     if (N < 0 || T < 0 || H < 0 || W < 0) return fail(RB_ERR_INVALID_ARGUMENT, "negative extent");
-    return wgrad_common(out_grad, x, weight_grad, dtype, N * T, C, Cout, H * W, nullptr, nullptr, shift, shift_dtype, T, H,
-                        W, workspace, workspace_bytes, stream);
+    return wgrad_common(out_grad, x, weight_grad, dtype, N * T, C, Cout, H * W, nullptr, shift, shift_dtype, T, H, W,
+                        workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

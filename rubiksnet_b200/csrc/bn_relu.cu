@@ -313,7 +313,7 @@ extern "C" int rb_bn_act_forward(const void *x, const float *gamma, const float 
     const int64_t total = (int64_t)NI * C * HW;
     if (total == 0) return RB_OK;
     if (total > 0x7fffffffLL) return fail(RB_ERR_UNSUPPORTED, "bn: tensor too large");
-    if (!x || !y || !mean_invstd || !scale_bias) return fail(RB_ERR_INVALID_ARGUMENT, "null pointer");
+    if (!x || !mean_invstd || !scale_bias) return fail(RB_ERR_INVALID_ARGUMENT, "null pointer");
     if (!training && (!running_mean || !running_var)) return fail(RB_ERR_INVALID_ARGUMENT, "eval mode needs running stats");
     if (C > 65535) return fail(RB_ERR_UNSUPPORTED, "bn: C > 65535");
     cudaStream_t s = (cudaStream_t)stream;
@@ -333,6 +333,7 @@ extern "C" int rb_bn_act_forward(const void *x, const float *gamma, const float 
                                                       scale_bias);
         if ((rc = launched("k_bn_eval_coeffs"))) return rc;
     }
+    if (!y) return RB_OK;  // statistics only: the apply pass is folded into the consumer
     const FastDiv hw = make_fastdiv((uint32_t)HW);
     RB_DISPATCH_DTYPE(dtype, {
         const int64_t nvec = total / Vec<T>::N;

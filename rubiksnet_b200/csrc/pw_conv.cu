@@ -48,10 +48,11 @@ struct ShiftSrc {
 
 struct PwArgs {
     const __nv_bfloat16 *x;    // [NI, K, HW]
-    const __nv_bfloat16 *w;    // [N, K]
+    const void *w;             // [N, K] (w_trans: [K, N]), bf16 or fp32 (w_dt)
+    int w_dt, w_trans;
     const __nv_bfloat16 *res;  // [NI, N, HW] or null
     __nv_bfloat16 *out;        // [NI, N, HW]
-    const float *a_scale, *a_bias;  // PROD_BNRELU: per input channel
+    const float *a_sb;              // PROD_BNRELU: per input channel (scale, bias) pairs [K, 2]
     const void *shift;              // PROD_SHIFT3D: [3, K]
     int shift_dt;
     int T, H, W;                    // PROD_SHIFT3D: frames per clip, map size (HW = H*W)
@@ -195,30 +196,40 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_conv(const PwArgs a) {
         }
         mbar_fence_init();
     }
-    if (warp == 0) tmem_alloc(&hdr->tmem_base, (uint32_t)a.tmem_cols);
+    if (warp == 0) {
+        __syncwarp();
+        tmem_alloc(&hdr->tmem_base, (uint32_t)a.tmem_cols);
+    }
     {
         // B[n, k] -> (k/8)*b_lbo + (n/8)*b_sbo + (n%8)*16 + (k%8)*2 ; rows n0+n >= N and columns k >= K are zero
         const int kgroups = a.Kpad >> 3;
-        const bool kvec = (a.K & 7) == 0;
+        const bool fast = a.w_dt == RB_BF16 && !a.w_trans && (a.K & 7) == 0;
+        const __nv_bfloat16 *wb = reinterpret_cast<const __nv_bfloat16 *>(a.w);
+        const float *wf = reinterpret_cast<const float *>(a.w);
         for (int u = tid; u < a.Ncta * kgroups; u += kThreads) {
             const int kg = u / a.Ncta, n = u - kg * a.Ncta;
             uint4 v = make_uint4(0u, 0u, 0u, 0u);
             if (n0 + n < a.N) {
-                const __nv_bfloat16 *src = a.w + (int64_t)(n0 + n) * a.K + kg * 8;
-                if (kvec) {
-                    if (kg * 8 < a.K) v = ldg16(src);
+                if (fast) {
+                    if (kg * 8 < a.K) v = ldg16(wb + (int64_t)(n0 + n) * a.K + kg * 8);
                 } else {
-                    uint32_t r[4];
-                    load_unit<1>(src, a.K - kg * 8, r);
-                    v = make_uint4(r[0], r[1], r[2], r[3]);
+                    float f[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int k = kg * 8 + e;
+                        const int64_t idx = a.w_trans ? (int64_t)k * a.N + (n0 + n) : (int64_t)(n0 + n) * a.K + k;
+                        f[e] = k < a.K ? (a.w_dt == RB_BF16 ? __bfloat162float(wb[idx]) : __ldg(wf + idx)) : 0.f;
+                    }
+                    v = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                                   pack_bf16x2(f[6], f[7]));
                 }
             }
             *reinterpret_cast<uint4 *>(smem_b + (size_t)kg * a.b_lbo + (size_t)(n >> 3) * a.b_sbo + (n & 7) * 16) = v;
         }
         if (PROD == PROD_BNRELU)
             for (int k = tid; k < a.Kpad; k += kThreads) {
-                smem_sb[k] = k < a.K ? a.a_scale[k] : 0.f;
-                smem_sb[a.Kpad + k] = k < a.K ? a.a_bias[k] : 0.f;
+                smem_sb[k] = k < a.K ? a.a_sb[2 * k] : 0.f;
+                smem_sb[a.Kpad + k] = k < a.K ? a.a_sb[2 * k + 1] : 0.f;
             }
         fence_proxy_async_smem();
     }
@@ -279,6 +290,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_conv(const PwArgs a) {
             const int64_t obase = ((int64_t)img * a.N + n0) * a.HW + p;
             for (int c0 = 0; c0 < a.Ncta && n0 + c0 < a.N; c0 += 16) {
                 uint32_t v[16];
+                __syncwarp();
                 tmem_ld16(taddr + c0, v);
                 float rr[16];
 #pragma unroll
@@ -351,7 +363,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_conv(const PwArgs a) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+    if (warp == 0) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+    }
 }
 
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -436,7 +451,7 @@ struct WgArgs {
     const __nv_bfloat16 *g;  // [NI, M, HW]
     const __nv_bfloat16 *x;  // [NI, N, HW]
     float *partial;          // [splits, M, N]
-    const float *x_scale, *x_bias;
+    const float *x_sb;       // PROD_BNRELU: (scale, bias) pairs [N, 2]
     const void *shift;
     int shift_dt, T, H, W;
     int NI, M, N, HW;
@@ -472,11 +487,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_wgrad(const WgArgs a) {
         mbar_init(&hdr->tmem_full, 1);
         mbar_fence_init();
     }
-    if (warp == 0) tmem_alloc(&hdr->tmem_base, (uint32_t)a.tmem_cols);
+    if (warp == 0) {
+        __syncwarp();
+        tmem_alloc(&hdr->tmem_base, (uint32_t)a.tmem_cols);
+    }
     if (PROD == PROD_BNRELU)
         for (int k = tid; k < a.N; k += kThreads) {
-            smem_sb[k] = a.x_scale[k];
-            smem_sb[a.N + k] = a.x_bias[k];
+            smem_sb[k] = a.x_sb[2 * k];
+            smem_sb[a.N + k] = a.x_sb[2 * k + 1];
         }
     tc_fence_before();
     __syncthreads();
@@ -523,6 +541,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_wgrad(const WgArgs a) {
             const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + mt * a.Nc;
             for (int c0 = 0; c0 < nrows; c0 += 16) {
                 uint32_t v[16];
+                __syncwarp();
                 tmem_ld16(taddr + c0, v);
                 tmem_ld_wait();
                 if (valid) {
@@ -606,7 +625,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_wgrad(const WgArgs a) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+    if (warp == 0) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+    }
 }
 
 __global__ void k_wg_reduce(const float *__restrict__ partial, float *__restrict__ out, int splits, int64_t count) {
@@ -683,14 +705,13 @@ template <int PROD> int wg_launch_vec(const WgArgs &a, dim3 grid, size_t smem_by
 
 }  // namespace
 
-int pw_conv_forward(const void *x, const void *w, const void *residual, void *out, int NI, int K, int N, int HW,
-                    const float *a_scale, const float *a_bias, const void *shift, int shift_dt, int T, int H, int W,
-                    cudaStream_t s) {
+int pw_conv_forward(const void *x, const void *w, int w_dt, int w_trans, const void *residual, void *out, int NI, int K,
+                    int N, int HW, const float *a_sb, const void *shift, int shift_dt, int T, int H, int W, cudaStream_t s) {
     PwArgs a{};
-    a.x = (const __nv_bfloat16 *)x; a.w = (const __nv_bfloat16 *)w; a.res = (const __nv_bfloat16 *)residual;
-    a.out = (__nv_bfloat16 *)out; a.a_scale = a_scale; a.a_bias = a_bias; a.shift = shift; a.shift_dt = shift_dt;
+    a.x = (const __nv_bfloat16 *)x; a.w = w; a.w_dt = w_dt; a.w_trans = w_trans; a.res = (const __nv_bfloat16 *)residual;
+    a.out = (__nv_bfloat16 *)out; a.a_sb = a_sb; a.shift = shift; a.shift_dt = shift_dt;
     a.T = T; a.H = H; a.W = W; a.NI = NI; a.K = K; a.N = N; a.HW = HW;
-    const int prod = shift ? PROD_SHIFT3D : (a_scale ? PROD_BNRELU : PROD_PLAIN);
+    const int prod = shift ? PROD_SHIFT3D : (a_sb ? PROD_BNRELU : PROD_PLAIN);
     dim3 grid;
     size_t smem_bytes = 0;
     if (!plan(a, prod, &grid, &smem_bytes))
@@ -719,14 +740,13 @@ size_t pw_conv_wgrad_workspace(int NI, int M, int N, int HW) {
     return (size_t)grid.x * M * N * sizeof(float);
 }
 
-int pw_conv_wgrad(const void *g, const void *x, float *dw, int NI, int M, int N, int HW, const float *x_scale,
-                  const float *x_bias, const void *shift, int shift_dt, int T, int H, int W, void *workspace,
-                  cudaStream_t s) {
+int pw_conv_wgrad(const void *g, const void *x, float *dw, int NI, int M, int N, int HW, const float *x_sb,
+                  const void *shift, int shift_dt, int T, int H, int W, void *workspace, cudaStream_t s) {
     WgArgs a{};
     a.g = (const __nv_bfloat16 *)g; a.x = (const __nv_bfloat16 *)x; a.partial = (float *)workspace;
-    a.x_scale = x_scale; a.x_bias = x_bias; a.shift = shift; a.shift_dt = shift_dt; a.T = T; a.H = H; a.W = W;
+    a.x_sb = x_sb; a.shift = shift; a.shift_dt = shift_dt; a.T = T; a.H = H; a.W = W;
     a.NI = NI; a.M = M; a.N = N; a.HW = HW;
-    const int prod = shift ? PROD_SHIFT3D : (x_scale ? PROD_BNRELU : PROD_PLAIN);
+    const int prod = shift ? PROD_SHIFT3D : (x_sb ? PROD_BNRELU : PROD_PLAIN);
     dim3 grid;
     size_t smem_bytes = 0;
     if (!wg_plan(a, PROD_BNRELU, &grid, &smem_bytes))

@@ -1,18 +1,24 @@
 """Fused building blocks of RubiksShiftBlock (rubiksnet/backbone.py:74-135) on CUDA:
 
   bn_act(x, bn, relu)            BatchNorm2d (+ReLU) in two streaming passes of librubiks_b200 (bn_relu.cu)
-  conv1x1(x, weight, residual)   the block's 1x1 convolutions as NCHW batched GEMMs  out[n] = W @ x[n] (+ residual[n])
-                                 on cuBLAS (plain library GEMM; the residual add `out += shortcut` rides in the GEMM
-                                 epilogue), avoiding cuDNN's NCHW<->NHWC transposes around every 1x1 conv
+  conv1x1(x, weight, residual)   the block's 1x1 convolutions.  bf16 activations: librubiks_b200's tcgen05 GEMM
+                                 kernels (pw_conv.cu) for forward, input gradient and weight gradient, the residual
+                                 add `out += shortcut` in the epilogue.  fp32 activations: NCHW batched GEMMs on cuBLAS.
+  rubiks_block(block, x)         a whole identity-shortcut RubiksShiftBlock (rubiks3d variant, bf16) as ONE autograd
+                                 Function with a hand-scheduled kernel sequence:
+                                   fwd  bn1 stats | conv2 with bn1+relu folded into its operand producer |
+                                        bn2 stats+apply | 3D shift + conv3 + residual in one tensor-core launch
+                                   bwd  conv3 dgrad | conv3 wgrad (shift recomputed in the producer) | shift backward |
+                                        bn2 backward | conv2 dgrad | conv2 wgrad | bn1 backward (+ shortcut gradient)
 
-Both are autograd Functions over [N*T, C, H, W] activations; parameters stay fp32 (activations may be bf16).
+All are autograd Functions over [N*T, C, H, W] activations; parameters stay fp32 (activations may be bf16).
 """
 import torch
 
-from . import _lib
+from . import _lib, ops
 from .rubiksnet_cuda import _on_device
 
-__all__ = ["bn_act", "conv1x1"]
+__all__ = ["bn_act", "conv1x1", "rubiks_block", "rubiks_block_supported"]
 
 
 class _BNAct(torch.autograd.Function):
@@ -73,6 +79,32 @@ def bn_act(x, bn, relu=True):
                         bn.running_var if bn.track_running_stats else None, training, momentum, bn.eps, relu)
 
 
+class _Conv1x1TC(torch.autograd.Function):
+    """bf16 activations: tcgen05 kernels of librubiks_b200 (fp32 master weight read directly by the kernels)."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, x, weight, residual):
+        x = x.contiguous()
+        if residual is not None:
+            residual = residual.contiguous()
+        ctx.save_for_backward(x, weight)
+        ctx.has_res = residual is not None
+        return ops.pw_conv(x, weight, residual=residual)
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        g = g.contiguous()
+        gx = ops.pw_conv(g, weight, transposed=True, name="pw_conv<dgrad>") if ctx.needs_input_grad[0] else None
+        gw = None
+        if ctx.needs_input_grad[1]:
+            gw = ops.pw_conv_wgrad(g, x).view(weight.shape).to(weight.dtype)
+        gres = g if ctx.has_res and ctx.needs_input_grad[2] else None
+        return gx, gw, gres
+
+
 class _Conv1x1(torch.autograd.Function):
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda")
@@ -114,4 +146,87 @@ def conv1x1(x, weight, residual=None, stride=1):
     epilogue; stride > 1 sub-samples x first (backbone.py:104-105 shortcut)."""
     if stride != 1:
         x = x[:, :, ::stride, ::stride]
+    if x.dtype == torch.bfloat16 and weight.dtype in (torch.float32, torch.bfloat16):
+        return _Conv1x1TC.apply(x, weight, residual)
     return _Conv1x1.apply(x, weight, residual)
+
+
+# ------------------------------------------------------------------------------------- whole block
+
+def _bn_cfg(bn):
+    training = bn.training or bn.running_mean is None
+    momentum = 0.1 if bn.momentum is None else bn.momentum
+    track = bn.track_running_stats and bn.running_mean is not None
+    return training, momentum, bn.eps, (bn.running_mean if track else None), (bn.running_var if track else None)
+
+
+class _RubiksBlockFn(torch.autograd.Function):
+    """Identity-shortcut RubiksShiftBlock with a 3D shift (backbone.py:109-135 + models.py:128-145), bf16."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, x, g1, b1, w2, g2, b2, shift, w3, bn1, bn2, frames, normalize_grad, normalize_t_factor):
+        x = x.contiguous()
+        tr1, mom1, eps1, rm1, rv1 = _bn_cfg(bn1)
+        tr2, mom2, eps2, rm2, rv2 = _bn_cfg(bn2)
+        _, mi1, sb1 = ops.bn_forward(x, g1, b1, rm1, rv1, tr1, mom1, eps1, relu=True, apply=False)
+        y2 = ops.pw_conv(x, w2, in_scale_bias=sb1, name="pw_conv<bn+relu>")
+        a2, mi2, sb2 = ops.bn_forward(y2, g2, b2, rm2, rv2, tr2, mom2, eps2, relu=True, apply=True)
+        out = ops.shift3d_pw_conv(a2, shift, w3, x, frames)
+        ctx.save_for_backward(x, y2, a2, mi1, sb1, mi2, sb2, g1, g2, w2, w3, shift)
+        ctx.cfg = (tr1, tr2, frames, normalize_grad, normalize_t_factor)
+        return out
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, g):
+        x, y2, a2, mi1, sb1, mi2, sb2, g1, g2, w2, w3, shift = ctx.saved_tensors
+        tr1, tr2, frames, normalize_grad, normalize_t_factor = ctx.cfg
+        g = g.contiguous()
+        need = ctx.needs_input_grad
+        gs = ops.pw_conv(g, w3, transposed=True, name="pw_conv<dgrad>")
+        gw3 = ops.shift3d_pw_conv_wgrad(g, a2, shift, frames).view(w3.shape) if need[7] else None
+        ga2, gshift = ops.shift3d_backward(a2, shift, gs, frames, normalize_grad, normalize_t_factor, need_shift=need[6])
+        del gs
+        gy2, dg2, db2 = ops.bn_backward(y2, ga2, None, g2, mi2, sb2, tr2, relu=True)
+        del ga2
+        go = ops.pw_conv(gy2, w2, transposed=True, name="pw_conv<dgrad>")
+        gw2 = ops.pw_conv_wgrad(gy2, x, in_scale_bias=sb1, name="pw_conv_wgrad<bn+relu>").view(w2.shape) if need[3] else None
+        del gy2
+        gx, dg1, db1 = ops.bn_backward(x, go, g, g1, mi1, sb1, tr1, relu=True, need_dx=need[0])
+        return gx, dg1, db1, gw2, dg2, db2, gshift, gw3, None, None, None, None, None
+
+
+def rubiks_block_supported(block, x):
+    """True when `block` can run as the single fused Function: bf16 CUDA activations, identity shortcut, no SE,
+    plain conv2, as3 = _Rubiks3DWrap around a stride-1 / pad-0 / non-quantized RubiksShift3D with fp32 parameters."""
+    import torch.nn as nn
+    as3 = block.as3
+    r3 = getattr(as3, "rubiks3d", None)
+    if r3 is None or not x.is_cuda or x.dtype != torch.bfloat16 or x.dim() != 4:
+        return False
+    if not isinstance(block.shortcut, nn.Identity) or block.se is not None or not isinstance(block.conv2, nn.Conv2d):
+        return False
+    if tuple(r3.stride) != (1, 1, 1) or tuple(r3.padding) != (0, 0, 0) or r3.quantize:
+        return False
+    if not isinstance(r3.normalize_t_factor, (int, float)) or x.shape[0] % as3.n_segment != 0:
+        return False
+    params = (block.conv2.weight, block.conv3.weight, block.bn1.weight, block.bn2.weight, r3.shift)
+    if any(p is None or p.dtype != torch.float32 for p in params):
+        return False
+    return getattr(r3, "shift_function", None) is _default_shift_function()
+
+
+def _default_shift_function():
+    from .shiftlib.rubiks3d.primitive import rubiks_shift_3d
+    return rubiks_shift_3d
+
+
+def rubiks_block(block, x):
+    for bn in (block.bn1, block.bn2):
+        if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+    r3 = block.as3.rubiks3d
+    return _RubiksBlockFn.apply(x, block.bn1.weight, block.bn1.bias, block.conv2.weight, block.bn2.weight, block.bn2.bias,
+                                r3.shift, block.conv3.weight, block.bn1, block.bn2, block.as3.n_segment,
+                                bool(r3.normalize_grad), float(r3.normalize_t_factor))

@@ -1,0 +1,160 @@
+"""Raw (non-autograd) calls into librubiks_b200's block-level kernels: BatchNorm statistics / apply / backward, the
+tcgen05 pointwise-conv GEMMs (forward, input gradient, weight gradient) and the fused 3D-shift + conv3 launches.
+
+Everything here takes contiguous CUDA tensors [NI, C, H, W] (NI = clips * frames), launches on torch's current
+stream and returns torch tensors; there is no fallback.  When ``timing.enabled`` every call is bracketed by CUDA
+events on the launching stream so that bench.py can attribute time and algorithmic bytes to kernels.
+"""
+import torch
+
+from . import _lib
+from .rubiksnet_cuda import _on_device
+
+BF16 = torch.bfloat16
+
+
+timing = _lib.timing
+_timed = _lib.timed
+
+
+def _nbytes(*tensors):
+    return sum(t.numel() * t.element_size() for t in tensors if t is not None)
+
+
+def _wdt(w):
+    if w.dtype == torch.float32:
+        return _lib.RB_F32
+    if w.dtype == BF16:
+        return _lib.RB_BF16
+    raise ValueError("conv weight must be float32 or bfloat16, got %s" % w.dtype)
+
+
+# ------------------------------------------------------------------------------------------ BatchNorm
+
+def bn_forward(x, gamma, beta, running_mean, running_var, training, momentum, eps, relu=True, apply=True):
+    """Statistics (+ apply pass when `apply`) of BatchNorm2d(+ReLU).  Returns (y or None, mean_invstd, scale_bias)."""
+    ni, c = x.shape[0], x.shape[1]
+    hw = x.numel() // max(ni * c, 1)
+    y = torch.empty_like(x) if apply else None
+    mean_invstd = torch.empty(c, 2, dtype=torch.float32, device=x.device)
+    scale_bias = torch.empty(c, 2, dtype=torch.float32, device=x.device)
+    with _on_device(x.device):
+        L = _lib.lib()
+        nbytes = L.rb_bn_workspace_bytes(ni, c)
+        ws = _lib.workspace(nbytes, x.device)
+        with _timed("bn_forward<%s>" % ("stats+apply" if apply else "stats"), _nbytes(x) * (2 if apply else 1) + _nbytes(y)):
+            _lib.check(L.rb_bn_act_forward(
+                _lib.ptr(x), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(running_mean), _lib.ptr(running_var), _lib.ptr(y),
+                _lib.ptr(mean_invstd), _lib.ptr(scale_bias), _lib.dtype_code(x), ni, c, hw, int(training), float(momentum),
+                float(eps), int(relu), _lib.ptr(ws), nbytes, _lib.stream_handle(x.device)))
+    return y, mean_invstd, scale_bias
+
+
+def bn_backward(x, dy, residual, gamma, mean_invstd, scale_bias, training, relu=True, need_dx=True, need_params=True):
+    """dx (+ residual), dgamma, dbeta of BatchNorm2d(+ReLU); the ReLU mask is recomputed from x."""
+    ni, c = x.shape[0], x.shape[1]
+    hw = x.numel() // max(ni * c, 1)
+    dx = torch.empty_like(x) if need_dx else None
+    dgamma = torch.empty(c, dtype=torch.float32, device=x.device) if need_params else None
+    dbeta = torch.empty(c, dtype=torch.float32, device=x.device) if need_params else None
+    with _on_device(x.device):
+        L = _lib.lib()
+        nbytes = L.rb_bn_workspace_bytes(ni, c)
+        ws = _lib.workspace(nbytes, x.device)
+        with _timed("bn_backward", 2 * _nbytes(x, dy) + _nbytes(residual, dx)):
+            _lib.check(L.rb_bn_act_backward(
+                _lib.ptr(x), _lib.ptr(dy), _lib.ptr(residual), _lib.ptr(gamma), _lib.ptr(mean_invstd), _lib.ptr(scale_bias),
+                _lib.ptr(dx), _lib.ptr(dgamma), _lib.ptr(dbeta), _lib.dtype_code(x), ni, c, hw, int(training), int(relu),
+                _lib.ptr(ws), nbytes, _lib.stream_handle(x.device)))
+    return dx, dgamma, dbeta
+
+
+# ------------------------------------------------------------------------------------------ pointwise convs
+
+def pw_conv(x, weight, residual=None, in_scale_bias=None, transposed=False, name="pw_conv"):
+    """out[i,n,p] = sum_k W[n,k] A[i,k,p] (+ residual).  weight: Conv2d parameter [N,K,1,1] / [N,K] (fp32 or bf16);
+    transposed=True reads it as [K,N] (input gradient of that conv).  A = relu(x*scale+bias) with in_scale_bias."""
+    assert x.dtype == BF16 and x.is_contiguous()
+    ni, k = x.shape[0], x.shape[1]
+    n = weight.shape[1] if transposed else weight.shape[0]
+    assert (weight.shape[0] if transposed else weight.shape[1]) == k, "channel mismatch"
+    hw = x.numel() // max(ni * k, 1)
+    out = torch.empty((ni, n) + tuple(x.shape[2:]), dtype=BF16, device=x.device)
+    if residual is not None:
+        assert residual.dtype == BF16 and residual.is_contiguous() and residual.shape == out.shape
+    with _on_device(x.device):
+        with _timed(name, _nbytes(x, residual, out), 2 * ni * hw * k * n):
+            _lib.check(_lib.lib().rb_pw_conv_forward(
+                _lib.ptr(x), _lib.ptr(weight), _wdt(weight), int(transposed), _lib.ptr(residual), _lib.ptr(out), _lib.RB_BF16,
+                ni, k, n, hw, _lib.ptr(in_scale_bias), _lib.stream_handle(x.device)))
+    return out
+
+
+def pw_conv_wgrad(out_grad, x, in_scale_bias=None, name="pw_conv_wgrad"):
+    """fp32 [N,K] weight gradient of the conv whose forward was pw_conv(x, W, in_scale_bias=...)."""
+    assert x.dtype == BF16 and out_grad.dtype == BF16 and x.is_contiguous() and out_grad.is_contiguous()
+    ni, k, n = x.shape[0], x.shape[1], out_grad.shape[1]
+    hw = x.numel() // max(ni * k, 1)
+    dw = torch.empty(n, k, dtype=torch.float32, device=x.device)
+    with _on_device(x.device):
+        L = _lib.lib()
+        nbytes = L.rb_pw_conv_wgrad_workspace_bytes(ni, k, n, hw)
+        ws = _lib.workspace(nbytes, x.device)
+        with _timed(name, _nbytes(x, out_grad), 2 * ni * hw * k * n):
+            _lib.check(L.rb_pw_conv_wgrad(_lib.ptr(out_grad), _lib.ptr(x), _lib.ptr(dw), _lib.RB_BF16, ni, k, n, hw,
+                                          _lib.ptr(in_scale_bias), _lib.ptr(ws), nbytes, _lib.stream_handle(x.device)))
+    return dw
+
+
+def shift3d_pw_conv(x, shift, weight, residual, frames):
+    """conv3(RubiksShift3D(x)) + residual in one launch.  x [N*T, C, H, W] bf16 (viewed [N,T,C,H,W])."""
+    assert x.dtype == BF16 and x.is_contiguous() and x.dim() == 4
+    nt, c, h, w = x.shape
+    assert nt % frames == 0
+    cout = weight.shape[0]
+    out = torch.empty(nt, cout, h, w, dtype=BF16, device=x.device)
+    if residual is not None:
+        assert residual.dtype == BF16 and residual.is_contiguous() and residual.shape == out.shape
+    with _on_device(x.device):
+        with _timed("shift3d_pw_conv", _nbytes(x, residual, out), 2 * nt * h * w * c * cout):
+            _lib.check(_lib.lib().rb_shift3d_pw_conv_forward(
+                _lib.ptr(x), _lib.ptr(shift), _lib.ptr(weight), _wdt(weight), _lib.ptr(residual), _lib.ptr(out), _lib.RB_BF16,
+                _lib.dtype_code(shift), nt // frames, frames, c, h, w, cout, _lib.stream_handle(x.device)))
+    return out
+
+
+def shift3d_pw_conv_wgrad(out_grad, x, shift, frames):
+    """fp32 [Cout, C] weight gradient of conv3 in shift3d_pw_conv (the shift is recomputed inside the kernel)."""
+    assert x.dtype == BF16 and out_grad.dtype == BF16 and x.is_contiguous() and out_grad.is_contiguous()
+    nt, c, h, w = x.shape
+    cout = out_grad.shape[1]
+    dw = torch.empty(cout, c, dtype=torch.float32, device=x.device)
+    with _on_device(x.device):
+        L = _lib.lib()
+        nbytes = L.rb_pw_conv_wgrad_workspace_bytes(nt, c, cout, h * w)
+        ws = _lib.workspace(nbytes, x.device)
+        with _timed("shift3d_pw_conv_wgrad", _nbytes(x, out_grad), 2 * nt * h * w * c * cout):
+            _lib.check(L.rb_shift3d_pw_conv_wgrad(
+                _lib.ptr(out_grad), _lib.ptr(x), _lib.ptr(shift), _lib.ptr(dw), _lib.RB_BF16, _lib.dtype_code(shift),
+                nt // frames, frames, c, h, w, cout, _lib.ptr(ws), nbytes, _lib.stream_handle(x.device)))
+    return dw
+
+
+def shift3d_backward(x, shift, out_grad, frames, normalize_grad, normalize_t_factor, need_x=True, need_shift=True):
+    """x_grad / shift_grad of the stride-1 3D shift over x [N*T, C, H, W] (rb_shift3d_backward)."""
+    nt, c, h, w = x.shape
+    n = nt // frames
+    x_grad = torch.empty_like(x) if need_x else None
+    shift_grad = torch.empty_like(shift) if need_shift else None
+    dt = _lib.dtype_code(x)
+    geo = (n, frames, c, h, w, 1, 1, 1, 0, 0, 0)
+    with _on_device(x.device):
+        L = _lib.lib()
+        nbytes = L.rb_shift3d_backward_workspace_bytes(dt, *geo) if need_shift else 0
+        ws = _lib.workspace(nbytes, x.device)
+        with _timed("shift3d_backward", _nbytes(x, out_grad, x_grad)):
+            _lib.check(L.rb_shift3d_backward(
+                _lib.ptr(x), _lib.ptr(shift), _lib.ptr(out_grad), _lib.ptr(x_grad), _lib.ptr(shift_grad), dt,
+                _lib.dtype_code(shift), *geo, int(bool(normalize_grad)), float(normalize_t_factor), 0, _lib.ptr(ws), nbytes,
+                _lib.stream_handle(x.device)))
+    return x_grad, shift_grad

@@ -113,7 +113,7 @@ def rubiks_shift_3d_forward(input, shift, strides, paddings, quantize, output, _
     _assert_contiguous(shift, "shift_tensor_ptr")
     _assert_contiguous(output, "output_tensor_ptr")
     N, T, C, H, W = input.shape
-    with _on_device(input.device):
+    with _on_device(input.device), _lib.timed("shift3d_forward", _lib.nbytes(input, output)):
         _lib.check(_lib.lib().rb_shift3d_forward(
             _lib.ptr(input), _lib.ptr(shift), _lib.ptr(output), _lib.dtype_code(input), _lib.dtype_code(shift),
             N, T, C, H, W, int(strides[0]), int(strides[1]), int(strides[2]),
@@ -137,10 +137,11 @@ def rubiks_shift_3d_backward(input, shift, output_grad, strides, paddings, input
         L = _lib.lib()
         nbytes = L.rb_shift3d_backward_workspace_bytes(dt, *geo) if shift_grad is not None else 0
         ws = _lib.workspace(nbytes, input.device)
-        _lib.check(L.rb_shift3d_backward(
-            _lib.ptr(input), _lib.ptr(shift), _lib.ptr(output_grad), _lib.ptr(input_grad), _lib.ptr(shift_grad),
-            dt, _lib.dtype_code(shift), *geo, int(bool(normalize_grad)), float(normalize_t_factor),
-            int(bool(quantize)), _lib.ptr(ws), nbytes, _lib.stream_handle(input.device)))
+        with _lib.timed("shift3d_backward", _lib.nbytes(input, output_grad, input_grad)):
+            _lib.check(L.rb_shift3d_backward(
+                _lib.ptr(input), _lib.ptr(shift), _lib.ptr(output_grad), _lib.ptr(input_grad), _lib.ptr(shift_grad),
+                dt, _lib.dtype_code(shift), *geo, int(bool(normalize_grad)), float(normalize_t_factor),
+                int(bool(quantize)), _lib.ptr(ws), nbytes, _lib.stream_handle(input.device)))
     return 0
 
 

@@ -1,0 +1,192 @@
+"""GPU parity tests of the tcgen05 pointwise-conv kernels (pw_conv.cu) through the C ABI:
+forward / input gradient / weight gradient against fp32 torch matmuls on the same bf16 inputs, the fused
+3D-shift + conv3 launch against rb_shift3d_forward followed by the GEMM, and
+the single-Function RubiksShiftBlock against the module graph.  Tolerance: 1e-2 relative (bf16, north_star)."""
+import os
+import sys
+
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+import rubiksnet_b200 as rb  # noqa: E402
+from rubiksnet_b200 import _lib, backbone, ops  # noqa: E402
+from rubiksnet_b200.shiftlib.rubiks3d.primitive import rubiks_shift_3d_forward  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+# (NI, K, N, HW): every RubiksNet-Large / -Tiny block geometry class + ragged cases (HW not a multiple of 2/4/8,
+# channels not a multiple of 8/16, N > 256 (two MMA column blocks), N split over CTAs (576), single pixel)
+SHAPES = [(8, 72, 72, 12544), (8, 72, 72, 3136), (8, 144, 144, 784), (16, 288, 288, 196), (16, 576, 576, 49),
+          (8, 72, 144, 784), (8, 288, 576, 49), (4, 54, 54, 3136), (4, 108, 216, 196), (4, 432, 432, 49),
+          (3, 17, 23, 75), (2, 8, 300, 130), (1, 16, 16, 1), (5, 40, 24, 127)]
+
+
+def _rel(a, b):
+    return (a.double() - b.double()).abs().max().item() / max(1.0, b.double().abs().max().item())
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("wdtype", [torch.float32, BF])
+def test_pw_conv_forward(shape, wdtype):
+    ni, k, n, hw = shape
+    torch.manual_seed(0)
+    x = torch.randn(ni, k, hw, device="cuda").to(BF)
+    w = (torch.randn(n, k, device="cuda") / k ** 0.5).to(wdtype)
+    res = torch.randn(ni, n, hw, device="cuda").to(BF)
+    ref = torch.matmul(w.to(BF).float(), x.float())
+    out = ops.pw_conv(x, w)
+    assert out.shape == (ni, n, hw) and out.dtype == BF
+    assert _rel(out, ref) <= 1e-2
+    out = ops.pw_conv(x, w, residual=res)
+    assert _rel(out, ref + res.float()) <= 1e-2
+    # input gradient = same kernel on the transposed weight buffer
+    g = torch.randn(ni, n, hw, device="cuda").to(BF)
+    gx = ops.pw_conv(g, w, transposed=True)
+    assert gx.shape == x.shape
+    assert _rel(gx, torch.matmul(w.to(BF).float().t(), g.float())) <= 1e-2
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_pw_conv_bn_relu_producer(shape):
+    ni, k, n, hw = shape
+    torch.manual_seed(1)
+    x = torch.randn(ni, k, hw, device="cuda").to(BF)
+    w = torch.randn(n, k, device="cuda") / k ** 0.5
+    sb = torch.stack([torch.rand(k, device="cuda") + 0.5, torch.randn(k, device="cuda")], dim=1).contiguous()
+    a = torch.relu(x.float() * sb[:, 0].view(1, k, 1) + sb[:, 1].view(1, k, 1)).to(BF)
+    ref = torch.matmul(w.to(BF).float(), a.float())
+    assert _rel(ops.pw_conv(x, w, in_scale_bias=sb), ref) <= 1e-2
+    g = torch.randn(ni, n, hw, device="cuda").to(BF)
+    dw = ops.pw_conv_wgrad(g, x, in_scale_bias=sb)
+    assert _rel(dw, torch.einsum("inp,ikp->nk", g.float(), a.float())) <= 1e-3
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_pw_conv_wgrad(shape):
+    ni, k, n, hw = shape
+    torch.manual_seed(2)
+    x = torch.randn(ni, k, hw, device="cuda").to(BF)
+    g = torch.randn(ni, n, hw, device="cuda").to(BF)
+    dw = ops.pw_conv_wgrad(g, x)
+    assert dw.shape == (n, k) and dw.dtype == torch.float32
+    assert _rel(dw, torch.einsum("inp,ikp->nk", g.float(), x.float())) <= 1e-4
+    dw2 = ops.pw_conv_wgrad(g, x)
+    assert torch.equal(dw, dw2), "weight gradient must be deterministic (fixed-order reduction)"
+
+
+# (clips, T, C, H, W, Cout)
+SHIFT_SHAPES = [(2, 8, 72, 56, 56, 72), (2, 8, 144, 28, 28, 144), (2, 8, 288, 14, 14, 288), (2, 8, 576, 7, 7, 576),
+                (1, 8, 54, 28, 28, 54), (2, 3, 10, 9, 11, 20), (1, 1, 16, 14, 14, 16), (1, 8, 24, 5, 3, 24)]
+
+
+@pytest.mark.parametrize("shape", SHIFT_SHAPES)
+@pytest.mark.parametrize("shift_kind", ["uniform1", "uniform3", "integer", "large"])
+def test_shift3d_pw_conv(shape, shift_kind):
+    n, t, c, h, w, cout = shape
+    torch.manual_seed(3)
+    x = torch.randn(n * t, c, h, w, device="cuda").to(BF)
+    if shift_kind == "uniform1":
+        shift = torch.rand(3, c, device="cuda") * 2 - 1
+    elif shift_kind == "uniform3":
+        shift = torch.rand(3, c, device="cuda") * 6 - 3
+    elif shift_kind == "integer":
+        shift = torch.randint(-2, 3, (3, c), device="cuda").float()
+        shift[:, ::3] += 0.5
+    else:
+        shift = torch.rand(3, c, device="cuda") * 30 - 15
+    wgt = torch.randn(cout, c, device="cuda") / c ** 0.5
+    res = torch.randn(n * t, cout, h, w, device="cuda").to(BF)
+    # the stand-alone sm_100a shift kernel (itself parity-tested against the oracle / reference goldens)
+    shifted = rubiks_shift_3d_forward(x.view(n, t, c, h, w), shift, (1, 1, 1), 0).view(n * t, c, h, w)
+    ref = ops.pw_conv(shifted, wgt, residual=res)
+    out = ops.shift3d_pw_conv(x, shift, wgt, res, t)
+    # same arithmetic (fp32 trilinear interpolation in the reference's association order, one rounding to bf16, then
+    # the GEMM); only the compiler's FMA contraction inside the interpolation may differ between the two kernels
+    assert _rel(out, ref) <= 4e-3, "fused shift+conv3 differs from shift kernel -> GEMM kernel"
+    assert (out == ref).float().mean().item() >= 0.99
+    assert _rel(out, torch.matmul(wgt.to(BF).float(), shifted.float().view(n * t, c, -1)).view_as(out) + res.float()) <= 1e-2
+    g = torch.randn(n * t, cout, h, w, device="cuda").to(BF)
+    dw = ops.shift3d_pw_conv_wgrad(g, x, shift, t)
+    assert _rel(dw, torch.einsum("inp,ikp->nk", g.float().flatten(2), shifted.float().flatten(2))) <= 1e-4
+
+
+def test_errors_are_reported():
+    L = _lib.lib()
+    x = torch.zeros(1, 8, 4, device="cuda", dtype=BF)
+    w = torch.zeros(8, 8, device="cuda")
+    out = torch.zeros(1, 8, 4, device="cuda", dtype=BF)
+    rc = L.rb_pw_conv_forward(_lib.ptr(x), _lib.ptr(w), _lib.RB_F32, 0, None, _lib.ptr(out), _lib.RB_F32, 1, 8, 8, 4, None, None)
+    assert rc == 2 and b"bf16" in L.rb_last_error()
+    rc = L.rb_pw_conv_forward(_lib.ptr(x), _lib.ptr(w), _lib.RB_F16, 0, None, _lib.ptr(out), _lib.RB_BF16, 1, 8, 8, 4, None, None)
+    assert rc == 1
+    rc = L.rb_pw_conv_forward(None, _lib.ptr(w), _lib.RB_F32, 0, None, _lib.ptr(out), _lib.RB_BF16, 1, 8, 8, 4, None, None)
+    assert rc == 1
+    # empty batch is a no-op
+    assert L.rb_pw_conv_forward(None, None, _lib.RB_F32, 0, None, None, _lib.RB_BF16, 0, 8, 8, 4, None, None) == 0
+    dw = torch.ones(8, 8, device="cuda")
+    assert L.rb_pw_conv_wgrad(None, None, _lib.ptr(dw), _lib.RB_BF16, 0, 8, 8, 4, None, None, 0, None) == 0
+    torch.cuda.synchronize()
+    assert float(dw.abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_whole_block_function_equals_module_graph(training):
+    """Identity-shortcut blocks as ONE autograd Function (shift fused into conv3, bn1 folded into conv2) vs the
+    per-op fused path, same bf16 inputs: outputs, input gradient and every parameter gradient."""
+    torch.manual_seed(5)
+    net = rb.RubiksNet(tier="tiny", num_classes=7, num_frames=8).cuda()
+    block = net.backbone.layer2[1]
+    block.train(training)
+    with torch.no_grad():
+        for bn in (block.bn1, block.bn2):
+            bn.weight.uniform_(0.5, 1.5)
+            bn.bias.uniform_(-0.3, 0.3)
+            bn.running_mean.uniform_(-0.2, 0.2)
+            bn.running_var.uniform_(0.5, 1.5)
+    x0 = torch.randn(16, block.conv2.in_channels, 28, 28, device="cuda").to(BF)
+    g = torch.randn(16, block.conv3.out_channels, 28, 28, device="cuda").to(BF)
+    results = []
+    for flag in (True, False):
+        backbone.FUSED_WHOLE_BLOCK = flag
+        try:
+            sd = {k: v.clone() for k, v in block.state_dict().items()}
+            block.zero_grad(set_to_none=True)
+            x = x0.clone().requires_grad_()
+            launches0 = _lib.launch_count()
+            out = block(x)
+            out.backward(g)
+            n_launch = _lib.launch_count() - launches0
+            results.append((out.detach().float(), x.grad.float(), {n: p.grad.float().clone() for n, p in block.named_parameters()},
+                            block.bn2.running_var.clone(), n_launch))
+            block.load_state_dict(sd)
+        finally:
+            backbone.FUSED_WHOLE_BLOCK = True
+    (o1, gx1, gp1, rv1, n1), (o0, gx0, gp0, rv0, n0) = results
+    assert n1 < n0, "the whole-block Function must launch fewer kernels than the per-op path"
+    assert _rel(o1, o0) <= 1e-2 and _rel(gx1, gx0) <= 2e-2
+    assert _rel(rv1, rv0) <= 1e-3
+    for name in gp0:
+        if name.endswith("shift"):
+            d = (gp1[name] - gp0[name]).abs()
+            assert d.mean().item() <= 5e-3 and d.max().item() <= 0.25, (name, d.mean().item(), d.max().item())
+        else:
+            assert _rel(gp1[name], gp0[name]) <= 2e-2, name
+
+
+def test_training_step_uses_tensor_core_blocks():
+    """A bf16 autocast training step of RubiksNet-Tiny routes its identity-shortcut blocks through the fused launch."""
+    torch.manual_seed(6)
+    net = rb.RubiksNet(tier="tiny", num_classes=5, num_frames=8).cuda().train()
+    clips = torch.randn(1, 8, 3, 224, 224, device="cuda")
+    _lib.timing.start()
+    with torch.autocast("cuda", dtype=BF):
+        loss = net(clips).float().square().mean()
+    loss.backward()
+    agg = _lib.timing.stop()
+    assert agg["shift3d_pw_conv"]["launches"] == 13            # 17 blocks - 4 down-sampling blocks
+    assert agg["shift3d_pw_conv_wgrad"]["launches"] == 13
+    assert torch.isfinite(loss).item()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
