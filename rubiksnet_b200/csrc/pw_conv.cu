@@ -1,24 +1,31 @@
-// Pointwise (1x1) convolution of RubiksShiftBlock as a tcgen05 tensor-core GEMM on NCHW bf16 activations, with the
-// operation in front of the convolution folded into the kernel's A-operand producer:
+// Pointwise (1x1) convolutions of RubiksShiftBlock as tcgen05 tensor-core GEMMs on NCHW bf16 activations, with the
+// operation in front of the convolution folded into the kernel's activation-operand producer:
 //
 //     out[i, n, p] = sum_k  W[n, k] * A(i, k, p)   (+ residual[i, n, p])          i = image (clip*T + t), p = pixel
 //
-//     PROD_PLAIN   A = x                                   conv2 / shortcut / the dgrad of any 1x1 conv
+//     PROD_PLAIN   A = x                                   conv2 / shortcut / the input gradient of any 1x1 conv
 //     PROD_BNRELU  A = relu(x * scale[k] + bias[k])          bn1 -> relu -> conv2          (backbone.py:123-128)
 //     PROD_SHIFT3D A = RubiksShift3D(x)[i, k, p]             as3 -> conv3 -> += shortcut   (backbone.py:129-135)
-//                  trilinear gather of cuda_src/rubiks3d_kernels.cu:54-203 (stride 1, pad 0), rounded to bf16 once,
-//                  i.e. exactly what the stand-alone shift kernel would have stored: the shifted tensor never
+//                  trilinear gather of cuda_src/rubiks3d_kernels.cu:54-203 (stride 1, pad 0) in fp32, rounded to
+//                  bf16 once -- what the stand-alone shift kernel would have stored; the shifted tensor never
 //                  exists in HBM.
 //
-// One launch, persistent CTAs (one per SM), 13 warps with fixed roles:
-//     warp 0       allocates TMEM; one elected thread issues tcgen05.mma (M=128 pixels x N<=256 channels x K=16)
-//     warps 1-4    epilogue: tcgen05.ld the fp32 accumulator (thread = pixel row), add the residual, store bf16
-//     warps 5-12   producers: build the A tile [128 pixels x 64 channels] in shared memory in the UMMA canonical
-//                  MN-major (pixel-contiguous) no-swizzle layout, so global reads stay coalesced along pixels;
-//                  generic-proxy stores -> fence.proxy.async -> mbarrier, ring of up to 6 stages
-// The weight block B [Ncta x Kpad] stays resident in shared memory (K-major canonical layout) for the CTA's
-// lifetime.  GEMM view per tile: D[128 px, Ncta] = A[128 px, K] * B[Ncta, K]^T, accumulators in TMEM
-// (double-buffered when 2*Ncta <= 512 columns so the epilogue of tile i overlaps the MMAs of tile i+1).
+// k_pw_conv (forward / input gradient): GEMM view per tile  D[channel n, pixel p] = W[n, :] . A[:, p]
+//     M = output channels (TMEM lanes; the weight block [Ncta x Kpad] is the K-major MMA "A" operand and stays resident in
+//         shared memory for the CTA's lifetime), N = 64 or 128 pixels (TMEM columns; the activation tile is the MN-major,
+//         i.e. pixel-contiguous, MMA "B" operand), K = input channels.
+//     Pixels on the column axis mean that an epilogue thread owns one output channel and 16 CONSECUTIVE pixels per
+//     tcgen05.ld, so results (and the residual) move with 8/16-byte vector accesses along NCHW rows.
+//   persistent CTAs (one per SM), 17 warps with fixed roles:
+//     warp 0       allocates TMEM; one elected thread issues tcgen05.mma (128 x Npx x 16 per instruction)
+//     warps 1-8    epilogue: tcgen05.ld the fp32 accumulator, add the residual, store bf16
+//     warps 9-16   producers: build the activation tile in shared memory in the UMMA canonical no-swizzle layout
+//                  (generic-proxy stores -> fence.proxy.async -> mbarrier), ring of up to 6 stages of 16 KiB
+//   accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// k_pw_wgrad (weight gradient):  dW[m, n] = sum_{i,p} G[i, m, p] * A(i, n, p), both operands K-major (pixels are the
+//     reduction axis), 128-byte-swizzled canonical layout; split over pixel ranges, fp32 partial slices, fixed-order
+//     reduction (deterministic).
 #include "tc_common.cuh"
 
 namespace rb {
@@ -27,48 +34,18 @@ using namespace tc;
 
 namespace {
 
-constexpr int kProdWarp0 = 5;
+constexpr int kEpiWarp0 = 1;
+constexpr int kNumEpiWarps = 8;
+constexpr int kProdWarp0 = kEpiWarp0 + kNumEpiWarps;  // 9
 constexpr int kNumProdWarps = 8;
-constexpr int kThreads = (kProdWarp0 + kNumProdWarps) * 32;  // 416
-constexpr int kTileM = 128;
-constexpr int kStageK = 64;
-constexpr int kStageBytes = kStageK * kTileM * 2;  // 16 KiB
+constexpr int kProdThreads = kNumProdWarps * 32;
+constexpr int kThreads = (kProdWarp0 + kNumProdWarps) * 32;  // 544
+constexpr int kStageBytes = 16384;  // activation stage: Npx pixels x (8192 / Npx) channels
 constexpr int kMaxStages = 6;
 constexpr int kSmemLimit = 227 * 1024;
 constexpr int kHdrBytes = 256;
 
 enum { PROD_PLAIN = 0, PROD_BNRELU = 1, PROD_SHIFT3D = 2 };
-
-// what the shift producer reads (shared by the forward and the weight-gradient kernels)
-struct ShiftSrc {
-    const __nv_bfloat16 *x;  // [clips, T, K, H, W]
-    const void *shift;       // [3, K]
-    int shift_dt, T, H, W, HW, K;
-};
-
-struct PwArgs {
-    const __nv_bfloat16 *x;    // [NI, K, HW]
-    const void *w;             // [N, K] (w_trans: [K, N]), bf16 or fp32 (w_dt)
-    int w_dt, w_trans;
-    const __nv_bfloat16 *res;  // [NI, N, HW] or null
-    __nv_bfloat16 *out;        // [NI, N, HW]
-    const float *a_sb;              // PROD_BNRELU: per input channel (scale, bias) pairs [K, 2]
-    const void *shift;              // PROD_SHIFT3D: [3, K]
-    int shift_dt;
-    int T, H, W;                    // PROD_SHIFT3D: frames per clip, map size (HW = H*W)
-    int NI, K, N, HW;
-    int Kpad, Ncta, n_sub, sub_n, acc_stages, stages, tmem_cols;
-    int tiles_per_img, total_tiles, k_stages;
-    uint32_t off_b, off_a, off_sb;
-    uint32_t a_lbo, a_sbo, b_lbo, b_sbo;  // physical strides: 8-channel group / 8-row group
-    uint32_t ad_lbo, ad_sbo, bd_lbo, bd_sbo;  // the same, as written into the UMMA descriptors
-};
-
-struct Hdr {
-    uint64_t full[kMaxStages], empty[kMaxStages], tmem_full[2], tmem_empty[2];
-    uint32_t tmem_base;
-};
-static_assert(sizeof(Hdr) <= kHdrBytes, "header");
 
 __device__ __forceinline__ uint4 ldg16(const void *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
 __device__ __forceinline__ uint2 ldg8(const void *p) { return __ldg(reinterpret_cast<const uint2 *>(p)); }
@@ -108,81 +85,124 @@ template <int VEC> __device__ __forceinline__ void load_unit(const __nv_bfloat16
     }
 }
 
-__device__ __forceinline__ void bn_relu_unit(uint32_t (&r)[4], float sc, float bi) {
+// relu(x*sc + bi) on the first `nvalid` elements; the rest stay zero (padding must not become relu(bias))
+__device__ __forceinline__ void bn_relu_unit(uint32_t (&r)[4], float sc, float bi, int nvalid) {
 #pragma unroll
     for (int h = 0; h < 4; ++h) {
-        const float lo = fmaxf(fmaf(bf16_lo(r[h]), sc, bi), 0.f);
-        const float hi = fmaxf(fmaf(bf16_hi(r[h]), sc, bi), 0.f);
+        const float lo = (nvalid > 2 * h) ? fmaxf(fmaf(bf16_lo(r[h]), sc, bi), 0.f) : 0.f;
+        const float hi = (nvalid > 2 * h + 1) ? fmaxf(fmaf(bf16_hi(r[h]), sc, bi), 0.f) : 0.f;
         r[h] = pack_bf16x2(lo, hi);
     }
 }
 
-// RubiksShift3D forward for 8 consecutive output pixels p..p+7 of (image img = clip*T + t, channel k), stride 1 /
-// pad 0: out = (1-rT)((1-rH)(q111(1-rW)+q112 rW) + rH(q121(1-rW)+q122 rW)) + rT(...), zero outside the tensor
-// (cuda_src/rubiks3d_kernels.cu:54-74,97-203; same association order).  Walks the pixels left to right and reuses
-// the right-hand taps of pixel e as the left-hand taps of pixel e+1 inside an image row.
-__device__ __forceinline__ void shift3d_unit(const ShiftSrc &a, int img, int k, int p, uint32_t (&r)[4]) {
-    const int T = a.T, H = a.H, W = a.W, HW = a.HW;
-    const float sT = ld_param<float>(a.shift, a.shift_dt, k), sH = ld_param<float>(a.shift, a.shift_dt, a.K + k),
-                sW = ld_param<float>(a.shift, a.shift_dt, 2 * a.K + k);
-    const int fT = floor3d(sT), fH = floor3d(sH), fW = floor3d(sW);
-    const float rT = sT - fT, rH = sH - fH, rW = sW - fW;
-    const float wT0 = 1.f - rT, wH0 = 1.f - rH, wW0 = 1.f - rW;
-    const int clip = img / T, t = img - clip * T;
-    int h = p / W, w = p - h * W;
-    // tap rows c = 2*a + b  (a: frame ts = t+fT+a, b: row hs = h+fH+b)
-    const __nv_bfloat16 *rowp[4];
-    bool rowok[4];
-    auto set_rows = [&]() {
+// ---- 3D shift gather ---------------------------------------------------------------------------------------------
+struct ShiftSrc {
+    const __nv_bfloat16 *x;  // [clips, T, K, H, W]
+    const void *shift;       // [3, K] rows (T, H, W)
+    int shift_dt, T, H, W, HW, K;
+    int64_t last_word;       // index of the 32-bit word holding the tensor's last element
+};
+
+struct ShiftCh {  // per-channel constants: floors and the (1-r, r) weights of cuda_src/rubiks3d_kernels.cu:65-74
+    int fT, fH, fW;
+    float wT0, wT1, wH0, wH1, wW0, wW1;
+};
+
+__device__ __forceinline__ ShiftCh shift_channel(const ShiftSrc &s, int k) {
+    const float sT = ld_param<float>(s.shift, s.shift_dt, k), sH = ld_param<float>(s.shift, s.shift_dt, s.K + k),
+                sW = ld_param<float>(s.shift, s.shift_dt, 2 * s.K + k);
+    ShiftCh c;
+    c.fT = floor3d(sT); c.fH = floor3d(sH); c.fW = floor3d(sW);
+    c.wT1 = sT - c.fT; c.wH1 = sH - c.fH; c.wW1 = sW - c.fW;
+    c.wT0 = 1.f - c.wT1; c.wH0 = 1.f - c.wH1; c.wW0 = 1.f - c.wW1;
+    return c;
+}
+
+// RubiksShift3D forward (stride 1, pad 0; cuda_src/rubiks3d_kernels.cu:54-74,97-203) for the 8 output pixels
+// (row h, columns c0..c0+7) of channel k, frame t of clip `clip`:
+//     out[c] = sum_{a,b,d in {0,1}} wT[a] wH[b] wW[d] * X[t+fT+a, k, h+fH+b, c+fW+d],   X = 0 outside the tensor.
+// The 9 source columns needed from each of the 4 (frame, row) pairs are fetched as 5 aligned 32-bit words and realigned
+// with a funnel shift; the (frame, row) pairs are combined first, V[j] = sum_ab wT[a] wH[b] X_ab[j], then the two
+// column taps, out[i] = V[i] wW0 + V[i+1] wW1  (fp32 throughout; same taps and weights as the reference, summed in a
+// different order).  Columns outside [0, W) are zeroed after the combination, rows / frames outside are never loaded.
+__device__ __forceinline__ void shift3d_run(const ShiftSrc &s, const ShiftCh &ch, int clip, int t, int k, int h, int c0,
+                                            float (&o)[8]) {
+    const int ws = c0 + ch.fW;
+    float V[9];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int ts = t + fT + (c >> 1), hs = h + fH + (c & 1);
-            rowok[c] = ts >= 0 && ts < T && hs >= 0 && hs < H;
-            rowp[c] = a.x + ((int64_t)((clip * T + ts) * a.K + k) * HW + (int64_t)hs * W);
-        }
-    };
-    set_rows();
-    float right[4] = {0.f, 0.f, 0.f, 0.f};
-    bool cont = false;
-    float o[8];
+    for (int j = 0; j < 9; ++j) V[j] = 0.f;
+    const uint32_t *words = reinterpret_cast<const uint32_t *>(s.x);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        float left[4];
-        const int ws = w + fW;
-        if (p + e < HW) {
+    for (int a = 0; a < 2; ++a) {
+        const int ts = t + ch.fT + a;
+        const float wa = a ? ch.wT1 : ch.wT0;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                left[c] = cont ? right[c] : ((rowok[c] && ws >= 0 && ws < W) ? bf16_lo(ldg2(rowp[c] + ws)) : 0.f);
-                right[c] = (rowok[c] && ws + 1 >= 0 && ws + 1 < W) ? bf16_lo(ldg2(rowp[c] + ws + 1)) : 0.f;
+        for (int b = 0; b < 2; ++b) {
+            const int hs = h + ch.fH + b;
+            const float wab = wa * (b ? ch.wH1 : ch.wH0);
+            const bool rowok = ts >= 0 && ts < s.T && hs >= 0 && hs < s.H;
+            const int64_t e0 = ((int64_t)((clip * s.T + ts) * s.K + k) * s.H + hs) * s.W + ws;
+            const int64_t wi0 = e0 >> 1;  // floor: e0 may be slightly negative at the tensor's first row
+            const uint32_t sh = (uint32_t)(e0 & 1) * 16u;
+            uint32_t wd[5];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                const int64_t wi = wi0 + i;
+                wd[i] = (rowok && wi >= 0 && wi <= s.last_word) ? __ldg(words + wi) : 0u;
             }
-            const float l0 = left[0] * wW0 + right[0] * rW, l1 = left[1] * wW0 + right[1] * rW;
-            const float l2 = left[2] * wW0 + right[2] * rW, l3 = left[3] * wW0 + right[3] * rW;
-            o[e] = wT0 * (wH0 * l0 + rH * l1) + rT * (wH0 * l2 + rH * l3);
-            cont = true;
-            if (++w == W) {
-                w = 0;
-                ++h;
-                cont = false;
-                set_rows();
+            uint32_t nw[5];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) nw[i] = __funnelshift_r(wd[i], wd[i + 1], sh);
+            nw[4] = wd[4] >> sh;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                V[2 * i] = fmaf(wab, bf16_lo(nw[i]), V[2 * i]);
+                V[2 * i + 1] = fmaf(wab, bf16_hi(nw[i]), V[2 * i + 1]);
             }
-        } else {
-            o[e] = 0.f;
+            V[8] = fmaf(wab, bf16_lo(nw[4]), V[8]);
         }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) r[i] = pack_bf16x2(o[2 * i], o[2 * i + 1]);
+    for (int j = 0; j < 9; ++j)
+        if (ws + j < 0 || ws + j >= s.W) V[j] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = V[i] * ch.wW0 + V[i + 1] * ch.wW1;
 }
+
+// =====================================================================================================================
+struct PwArgs {
+    const __nv_bfloat16 *x;    // [NI, K, HW]
+    const void *w;             // [N, K] (w_trans: [K, N]), bf16 or fp32 (w_dt)
+    int w_dt, w_trans;
+    const __nv_bfloat16 *res;  // [NI, N, HW] or null
+    __nv_bfloat16 *out;        // [NI, N, HW]
+    const float *a_sb;         // PROD_BNRELU: per input channel (scale, bias) pairs [K, 2]
+    const void *shift;         // PROD_SHIFT3D: [3, K]
+    int shift_dt;
+    int T, H, W;               // PROD_SHIFT3D: frames per clip, map size (HW = H*W)
+    int NI, K, N, HW;
+    int Kpad, Ncta, Mt, Npx, kstage, acc_stages, stages, tmem_cols;
+    int tiles_per_img, total_tiles, k_stages;
+    uint32_t off_w, off_a, off_sb, w_lbo, a_lbo;
+};
+
+struct Hdr {
+    uint64_t full[kMaxStages], empty[kMaxStages], tmem_full[2], tmem_empty[2];
+    uint32_t tmem_base;
+};
+static_assert(sizeof(Hdr) <= kHdrBytes, "header");
 
 template <int PROD, int VEC>
 __global__ void __launch_bounds__(kThreads, 1) k_pw_conv(const PwArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     Hdr *hdr = reinterpret_cast<Hdr *>(smem);
-    unsigned char *smem_b = smem + a.off_b;
+    unsigned char *smem_w = smem + a.off_w;
     unsigned char *smem_a = smem + a.off_a;
     float *smem_sb = reinterpret_cast<float *>(smem + a.off_sb);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n0 = blockIdx.y * a.Ncta;
+    const int nrows = min(a.Ncta, a.N - n0);  // output channels owned by this CTA
 
     // ---- one-time setup: barriers, TMEM, resident weight block --------------------------------------------------
     if (tid == 0) {
@@ -192,7 +212,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_conv(const PwArgs a) {
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&hdr->tmem_full[i], 1);
-            mbar_init(&hdr->tmem_empty[i], 128);
+            mbar_init(&hdr->tmem_empty[i], kNumEpiWarps * 32);
         }
         mbar_fence_init();
     }
@@ -201,30 +221,44 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_conv(const PwArgs a) {
         tmem_alloc(&hdr->tmem_base, (uint32_t)a.tmem_cols);
     }
     {
-        // B[n, k] -> (k/8)*b_lbo + (n/8)*b_sbo + (n%8)*16 + (k%8)*2 ; rows n0+n >= N and columns k >= K are zero
-        const int kgroups = a.Kpad >> 3;
-        const bool fast = a.w_dt == RB_BF16 && !a.w_trans && (a.K & 7) == 0;
+        // W[n, k] -> (k/8)*w_lbo + (n/8)*128 + (n%8)*16 + (k%8)*2 (K-major core matrices; w_lbo is an odd multiple of 16
+        // bytes so that the 8 k-groups written by a quarter warp land in 8 different bank groups).  Rows beyond the
+        // CTA's channels and columns k >= K are zero.  Thread order follows the contiguous axis of the weight buffer.
+        const int kgroups = a.Kpad >> 3, rows8 = (a.Ncta + 7) & ~7;
         const __nv_bfloat16 *wb = reinterpret_cast<const __nv_bfloat16 *>(a.w);
         const float *wf = reinterpret_cast<const float *>(a.w);
-        for (int u = tid; u < a.Ncta * kgroups; u += kThreads) {
-            const int kg = u / a.Ncta, n = u - kg * a.Ncta;
+        const bool vec_ok = (a.K & 7) == 0 && !a.w_trans;
+        for (int u = tid; u < rows8 * kgroups; u += kThreads) {
+            int kg, n;
+            if (a.w_trans) { kg = u / rows8; n = u - kg * rows8; }
+            else { n = u / kgroups; kg = u - n * kgroups; }
             uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (n0 + n < a.N) {
-                if (fast) {
-                    if (kg * 8 < a.K) v = ldg16(wb + (int64_t)(n0 + n) * a.K + kg * 8);
+            if (n < nrows) {
+                const int64_t row = n0 + n;
+                if (vec_ok) {
+                    if (kg * 8 < a.K) {
+                        if (a.w_dt == RB_BF16) {
+                            v = ldg16(wb + row * a.K + kg * 8);
+                        } else {
+                            const float4 f0 = __ldg(reinterpret_cast<const float4 *>(wf + row * a.K + kg * 8));
+                            const float4 f1 = __ldg(reinterpret_cast<const float4 *>(wf + row * a.K + kg * 8 + 4));
+                            v = make_uint4(pack_bf16x2(f0.x, f0.y), pack_bf16x2(f0.z, f0.w), pack_bf16x2(f1.x, f1.y),
+                                           pack_bf16x2(f1.z, f1.w));
+                        }
+                    }
                 } else {
                     float f[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
                         const int k = kg * 8 + e;
-                        const int64_t idx = a.w_trans ? (int64_t)k * a.N + (n0 + n) : (int64_t)(n0 + n) * a.K + k;
+                        const int64_t idx = a.w_trans ? (int64_t)k * a.N + row : row * a.K + k;
                         f[e] = k < a.K ? (a.w_dt == RB_BF16 ? __bfloat162float(wb[idx]) : __ldg(wf + idx)) : 0.f;
                     }
                     v = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
                                    pack_bf16x2(f[6], f[7]));
                 }
             }
-            *reinterpret_cast<uint4 *>(smem_b + (size_t)kg * a.b_lbo + (size_t)(n >> 3) * a.b_sbo + (n & 7) * 16) = v;
+            *reinterpret_cast<uint4 *>(smem_w + (size_t)kg * a.w_lbo + (size_t)(n >> 3) * 128 + (n & 7) * 16) = v;
         }
         if (PROD == PROD_BNRELU)
             for (int k = tid; k < a.Kpad; k += kThreads) {
@@ -239,13 +273,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_conv(const PwArgs a) {
     const uint32_t tmem_base = hdr->tmem_base;
 
     const int tile0 = blockIdx.x, tstride = gridDim.x;
-    const ShiftSrc ssrc{a.x, a.shift, a.shift_dt, a.T, a.H, a.W, a.HW, a.K};
+    const int acc_cols = a.Mt * a.Npx;
 
     if (warp == 0) {
         // ===================================== MMA issuer ========================================================
         if (lane == 0) {
-            const uint32_t idesc = instr_desc_bf16(kTileM, a.sub_n, /*A MN-major*/ 1, /*B K-major*/ 0);
-            const uint32_t a_base = smem_u32(smem_a), b_base = smem_u32(smem_b);
+            const uint32_t idesc = instr_desc_bf16(128, a.Npx, /*weights K-major*/ 0, /*activations MN-major*/ 1);
+            const uint32_t a_base = smem_u32(smem_a), w_base = smem_u32(smem_w);
+            const int ksteps_per_stage = a.kstage >> 4;
             int slot = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -257,15 +292,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_conv(const PwArgs a) {
                 for (int st = 0; st < a.k_stages; ++st) {
                     mbar_wait(&hdr->full[slot], phase);
                     tc_fence_after();
-                    const int ksteps = min(kStageK / 16, (a.Kpad - st * kStageK) >> 4);
+                    const int ksteps = min(ksteps_per_stage, (a.Kpad - st * a.kstage) >> 4);
                     for (int ks = 0; ks < ksteps; ++ks) {
-                        const uint64_t adesc =
-                            smem_desc(a_base + slot * kStageBytes + ks * 2 * a.a_lbo, a.ad_lbo, a.ad_sbo, LAYOUT_NONE);
-                        const int kg = (st * kStageK >> 3) + ks * 2;
-                        for (int j = 0; j < a.n_sub; ++j) {
-                            const uint64_t bdesc = smem_desc(b_base + kg * a.b_lbo + j * (a.sub_n >> 3) * a.b_sbo, a.bd_lbo,
-                                                             a.bd_sbo, LAYOUT_NONE);
-                            mma_bf16(tmem_base + as * a.Ncta + j * a.sub_n, adesc, bdesc, idesc, (st | ks) ? 1u : 0u);
+                        const uint64_t bdesc = smem_desc(a_base + slot * kStageBytes + ks * 2 * a.a_lbo, a.a_lbo, 128, LAYOUT_NONE);
+                        const int kg = ((st * a.kstage) >> 3) + ks * 2;
+                        for (int mt = 0; mt < a.Mt; ++mt) {
+                            const uint64_t adesc = smem_desc(w_base + kg * a.w_lbo + mt * 2048, a.w_lbo, 128, LAYOUT_NONE);
+                            mma_bf16(tmem_base + as * acc_cols + mt * a.Npx, adesc, bdesc, idesc, (st | ks) ? 1u : 0u);
                         }
                     }
                     mma_commit(&hdr->empty[slot]);
@@ -277,55 +310,89 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_conv(const PwArgs a) {
         __syncwarp();
     } else if (warp < kProdWarp0) {
         // ===================================== epilogue ==========================================================
-        const int q = warp & 3, row = q * 32 + lane;
+        // warp -> TMEM lane quarter (hardware: warp id % 4) and one half of the tile's pixel columns
+        const int q = warp & 3, half = (warp - kEpiWarp0) >> 2;
+        const int cbeg = half * (a.Npx >> 1), cend = cbeg + (a.Npx >> 1);
         int it = 0;
         for (int tile = tile0; tile < a.total_tiles; tile += tstride, ++it) {
             const int as = it % a.acc_stages;
             const uint32_t aph = (uint32_t)(it / a.acc_stages) & 1u;
-            const int img = tile / a.tiles_per_img, p = (tile - img * a.tiles_per_img) * kTileM + row;
-            const bool valid = p < a.HW;
+            const int img = tile / a.tiles_per_img, p0 = (tile - img * a.tiles_per_img) * a.Npx;
             mbar_wait(&hdr->tmem_full[as], aph);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * a.Ncta;
-            const int64_t obase = ((int64_t)img * a.N + n0) * a.HW + p;
-            for (int c0 = 0; c0 < a.Ncta && n0 + c0 < a.N; c0 += 16) {
-                uint32_t v[16];
-                __syncwarp();
-                tmem_ld16(taddr + c0, v);
-                float rr[16];
+            for (int mt = 0; mt < a.Mt; ++mt) {
+                if (mt * 128 + q * 32 >= nrows) break;  // whole warp beyond the CTA's channels (warp-uniform)
+                const int nl = mt * 128 + q * 32 + lane;
+                const bool rowok = nl < nrows;
+                const int64_t rbase = ((int64_t)img * a.N + n0 + nl) * a.HW + p0;
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * acc_cols + mt * a.Npx;
+                for (int c0 = cbeg; c0 < cend && p0 + c0 < a.HW; c0 += 16) {
+                    uint32_t v[16];
+                    __syncwarp();
+                    tmem_ld16(taddr + c0, v);
+                    const int nv = rowok ? a.HW - (p0 + c0) : 0;  // valid pixels from this chunk's start (may exceed 16)
+                    uint32_t rr[8];
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    rr[j] = (a.res != nullptr && valid && n0 + c0 + j < a.N)
-                                ? __bfloat162float(a.res[obase + (int64_t)(c0 + j) * a.HW])
-                                : 0.f;
-                tmem_ld_wait();
+                    for (int i = 0; i < 8; ++i) rr[i] = 0u;
+                    if (a.res != nullptr) {
+                        const __nv_bfloat16 *rp = a.res + rbase + c0;
+                        uint32_t t4[4];
+                        load_unit<VEC>(rp, nv, t4);
+                        rr[0] = t4[0]; rr[1] = t4[1]; rr[2] = t4[2]; rr[3] = t4[3];
+                        load_unit<VEC>(rp + 8, nv - 8, t4);
+                        rr[4] = t4[0]; rr[5] = t4[1]; rr[6] = t4[2]; rr[7] = t4[3];
+                    }
+                    tmem_ld_wait();
+                    uint32_t ov[8];
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (valid && n0 + c0 + j < a.N)
-                        a.out[obase + (int64_t)(c0 + j) * a.HW] = __float2bfloat16_rn(__uint_as_float(v[j]) + rr[j]);
+                    for (int i = 0; i < 8; ++i)
+                        ov[i] = pack_bf16x2(__uint_as_float(v[2 * i]) + bf16_lo(rr[i]), __uint_as_float(v[2 * i + 1]) + bf16_hi(rr[i]));
+                    __nv_bfloat16 *op = a.out + rbase + c0;
+                    if (VEC == 8) {
+                        if (nv >= 8) *reinterpret_cast<uint4 *>(op) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+                        if (nv >= 16) *reinterpret_cast<uint4 *>(op + 8) = make_uint4(ov[4], ov[5], ov[6], ov[7]);
+                    } else if (VEC == 4) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (nv >= 4 * i + 4) *reinterpret_cast<uint2 *>(op + 4 * i) = make_uint2(ov[2 * i], ov[2 * i + 1]);
+                    } else if (VEC == 2) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            if (nv >= 2 * i + 2) *reinterpret_cast<uint32_t *>(op + 2 * i) = ov[i];
+                    } else {
+                        unsigned short *os = reinterpret_cast<unsigned short *>(op);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            if (nv > 2 * i) os[2 * i] = (unsigned short)(ov[i] & 0xffffu);
+                            if (nv > 2 * i + 1) os[2 * i + 1] = (unsigned short)(ov[i] >> 16);
+                        }
+                    }
+                }
             }
+            __syncwarp();
             tc_fence_before();
             mbar_arrive(&hdr->tmem_empty[as]);
         }
     } else {
-        // ===================================== A producers =======================================================
+        // ===================================== activation producers ==============================================
         const int pw = warp - kProdWarp0;
-        const int mg = (pw & 3) * 4 + (lane >> 3);  // 8-pixel group inside the tile
-        const int kk0 = (pw >> 2) * 8 + (lane & 7);   // channel inside a 16-channel slab (+ j*16)
-        const uint32_t soff0 = (uint32_t)(pw >> 2) * a.a_lbo + (uint32_t)mg * a.a_sbo + (uint32_t)(lane & 7) * 16u;
+        const int kq = lane & 7, mgq = lane >> 3;
+        const int nq = a.Npx >> 5;  // quads of 8-pixel groups per tile
+        const ShiftSrc ssrc{a.x, a.shift, a.shift_dt, a.T, a.H, a.W, a.HW, a.K,
+                            ((int64_t)a.NI * a.K * a.HW - 1) >> 1};
+
+        // unit j of this thread inside a stage: channel kk (0..kstage-1), 8-pixel group mg
+        auto unit_kk = [&](int j) { return ((j * kNumProdWarps + pw) / nq) * 8 + kq; };
+        auto unit_mg = [&](int j) { return ((j * kNumProdWarps + pw) % nq) * 4 + mgq; };
 
         auto load_stage = [&](int tile, int st, uint32_t (&r)[4][4]) {
-            const int img = tile / a.tiles_per_img, p = (tile - img * a.tiles_per_img) * kTileM + mg * 8;
+            const int img = tile / a.tiles_per_img, p0 = (tile - img * a.tiles_per_img) * a.Npx;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int k = st * kStageK + j * 16 + kk0;
+                const int k = st * a.kstage + unit_kk(j), p = p0 + unit_mg(j) * 8;
                 if (k < a.K && p < a.HW) {
-                    if (PROD == PROD_SHIFT3D) {
-                        shift3d_unit(ssrc, img, k, p, r[j]);
-                    } else {
-                        load_unit<VEC>(a.x + ((int64_t)img * a.K + k) * a.HW + p, a.HW - p, r[j]);
-                        if (PROD == PROD_BNRELU) bn_relu_unit(r[j], smem_sb[k], smem_sb[a.Kpad + k]);
-                    }
+                    load_unit<VEC>(a.x + ((int64_t)img * a.K + k) * a.HW + p, a.HW - p, r[j]);
+                    if (PROD == PROD_BNRELU) bn_relu_unit(r[j], smem_sb[k], smem_sb[a.Kpad + k], a.HW - p);
                 } else {
                     r[j][0] = r[j][1] = r[j][2] = r[j][3] = 0u;
                 }
@@ -334,28 +401,78 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_conv(const PwArgs a) {
 
         int tile = tile0, st = 0, slot = 0;
         uint32_t phase = 0;
-        uint32_t cur[4][4];
-        if (tile < a.total_tiles) load_stage(tile, st, cur);
-        while (tile < a.total_tiles) {
-            int ntile = tile, nst = st + 1;
-            if (nst == a.k_stages) { nst = 0; ntile += tstride; }
-            uint32_t nxt[4][4];
-            if (ntile < a.total_tiles) load_stage(ntile, nst, nxt);
-            mbar_wait(&hdr->empty[slot], phase ^ 1u);
-            unsigned char *sp = smem_a + (size_t)slot * kStageBytes + soff0;
+        if (PROD != PROD_SHIFT3D) {
+            uint32_t cur[4][4];
+            if (tile < a.total_tiles) load_stage(tile, st, cur);
+            while (tile < a.total_tiles) {
+                int ntile = tile, nst = st + 1;
+                if (nst == a.k_stages) { nst = 0; ntile += tstride; }
+                uint32_t nxt[4][4];
+                if (ntile < a.total_tiles) load_stage(ntile, nst, nxt);
+                mbar_wait(&hdr->empty[slot], phase ^ 1u);
+                unsigned char *sp = smem_a + (size_t)slot * kStageBytes;
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                *reinterpret_cast<uint4 *>(sp + (size_t)j * 2 * a.a_lbo) = make_uint4(cur[j][0], cur[j][1], cur[j][2], cur[j][3]);
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&hdr->full[slot]);
+                for (int j = 0; j < 4; ++j) {
+                    const int kk = unit_kk(j);
+                    *reinterpret_cast<uint4 *>(sp + (size_t)(kk >> 3) * a.a_lbo + unit_mg(j) * 128 + (kk & 7) * 16) =
+                        make_uint4(cur[j][0], cur[j][1], cur[j][2], cur[j][3]);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&hdr->full[slot]);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+                for (int j = 0; j < 4; ++j)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) cur[j][i] = nxt[j][i];
-            tile = ntile;
-            st = nst;
-            if (++slot == a.stages) { slot = 0; phase ^= 1u; }
+                    for (int i = 0; i < 4; ++i) cur[j][i] = nxt[j][i];
+                tile = ntile;
+                st = nst;
+                if (++slot == a.stages) { slot = 0; phase ^= 1u; }
+            }
+        } else {
+            // 3D-shift gather: work items = (channel, row run of <= 8 pixels); results go to shared memory with 2-byte
+            // stores because a run need not be aligned to the 8-pixel groups of the operand layout
+            const int rpr = (a.W + 7) >> 3;  // runs per image row
+            for (; tile < a.total_tiles; tile += tstride) {
+                const int img = tile / a.tiles_per_img, p0 = (tile - img * a.tiles_per_img) * a.Npx;
+                const int pend = min(p0 + a.Npx, a.HW);
+                const int clip = img / a.T, t = img - clip * a.T;
+                const int h0 = p0 / a.W, ncand = ((pend - 1) / a.W - h0 + 1) * rpr;
+                for (st = 0; st < a.k_stages; ++st) {
+                    mbar_wait(&hdr->empty[slot], phase ^ 1u);
+                    unsigned char *sp = smem_a + (size_t)slot * kStageBytes;
+                    for (int kl = pw * 8 + kq; kl < a.kstage; kl += 64) {
+                        const int k = st * a.kstage + kl;
+                        if (k >= a.Kpad) break;
+                        const bool kreal = k < a.K;
+                        ShiftCh ch{};
+                        if (kreal) ch = shift_channel(ssrc, k);
+                        unsigned short *srow = reinterpret_cast<unsigned short *>(sp + (size_t)(kl >> 3) * a.a_lbo + (kl & 7) * 16);
+                        for (int r = mgq; r < ncand; r += 4) {
+                            const int rh = r / rpr, c0 = (r - rh * rpr) * 8, h = h0 + rh;
+                            const int pr0 = h * a.W + c0;
+                            const int lo = max(p0 - pr0, 0), hi = min(min(8, a.W - c0), pend - pr0);
+                            if (lo >= hi) continue;
+                            float o[8];
+                            if (kreal) {
+                                shift3d_run(ssrc, ch, clip, t, k, h, c0, o);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) o[i] = 0.f;
+                            }
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                if (i >= lo && i < hi) {
+                                    const int m = pr0 + i - p0;
+                                    srow[(m >> 3) * 64 + (m & 7)] = __bfloat16_as_ushort(__float2bfloat16_rn(o[i]));
+                                }
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&hdr->full[slot]);
+                    if (++slot == a.stages) { slot = 0; phase ^= 1u; }
+                }
+            }
         }
     }
 
@@ -371,43 +488,47 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_conv(const PwArgs a) {
 
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
-// splits N over grid.y so that the resident weight block fits shared memory and the accumulators fit TMEM
+// splits the output channels over grid.y so that the resident weight block fits shared memory, picks the pixel-tile width
+// so that two accumulator stages fit the 512 TMEM columns
 bool plan(PwArgs &a, int prod, dim3 *grid, size_t *smem_bytes) {
     a.Kpad = round_up(a.K, 16);
-    a.k_stages = cdiv(a.Kpad, kStageK);
     const int sb_bytes = prod == PROD_BNRELU ? round_up(2 * a.Kpad * 4, 128) : 0;
-    int gy = 0, Ncta = 0, n_sub = 0, stages = 0;
-    for (int cand = 1; cand <= 16; ++cand) {
-        int nc = round_up(cdiv(a.N, cand), 16);
-        const int ns = cdiv(nc, 256);
-        nc = round_up(nc, 16 * ns);
-        if (nc > 512) continue;
-        const int b_bytes = nc * a.Kpad * 2;
-        const int st = (kSmemLimit - kHdrBytes - sb_bytes - b_bytes) / kStageBytes;
+    int gy = 0;
+    for (int cand = 1; cand <= 16 && !gy; ++cand) {
+        const int nc = round_up(cdiv(a.N, cand), 8);
+        const int mt = cdiv(nc, 128);
+        if (mt > 4) continue;
+        const int w_lbo = nc * 16 + 16;
+        const int w_bytes = round_up((a.Kpad >> 3) * w_lbo, 128);
+        const int st = (kSmemLimit - kHdrBytes - sb_bytes - w_bytes) / kStageBytes;
         if (st < 2) continue;
-        gy = cand; Ncta = nc; n_sub = ns; stages = st < kMaxStages ? st : kMaxStages;
-        break;
+        // the last M tile reads (garbage, ignored) rows up to mt*128 of the last k-group: keep that inside the allocation
+        const int reach = ((a.Kpad >> 3) - 1) * w_lbo + mt * 2048;
+        const int stages = st < kMaxStages ? st : kMaxStages;
+        if (reach > w_bytes + stages * kStageBytes) continue;
+        gy = cand;
+        a.Ncta = nc; a.Mt = mt; a.w_lbo = (uint32_t)w_lbo; a.stages = stages;
+        a.off_sb = kHdrBytes;
+        a.off_w = kHdrBytes + sb_bytes;
+        a.off_a = a.off_w + w_bytes;
     }
     if (!gy) return false;
-    a.Ncta = Ncta; a.n_sub = n_sub; a.sub_n = Ncta / n_sub; a.stages = stages;
-    a.acc_stages = (2 * Ncta <= 512) ? 2 : 1;
+    a.Npx = (2 * a.Mt * 128 <= 512) ? 128 : 64;
+    a.kstage = kStageBytes / 2 / a.Npx;
+    a.a_lbo = (uint32_t)a.Npx * 16;
+    a.k_stages = cdiv(a.Kpad, a.kstage);
+    a.acc_stages = 2;
     int cols = 32;
-    while (cols < a.acc_stages * Ncta) cols <<= 1;
+    while (cols < a.acc_stages * a.Mt * a.Npx) cols <<= 1;
     a.tmem_cols = cols;
-    a.tiles_per_img = cdiv(a.HW, kTileM);
+    a.tiles_per_img = cdiv(a.HW, a.Npx);
     a.total_tiles = a.NI * a.tiles_per_img;
-    a.off_sb = kHdrBytes;
-    a.off_b = kHdrBytes + sb_bytes;
-    a.off_a = a.off_b + round_up(Ncta * a.Kpad * 2, 128);
-    // canonical no-swizzle layouts: 8 x 16-byte core matrices, contiguous along the non-strided direction
-    a.a_sbo = 128; a.a_lbo = (kTileM / 8) * 128;
-    a.b_sbo = 128; a.b_lbo = (uint32_t)Ncta * 16;
-    a.ad_lbo = a.a_lbo; a.ad_sbo = a.a_sbo; a.bd_lbo = a.b_lbo; a.bd_sbo = a.b_sbo;
-    *smem_bytes = (size_t)a.off_a + (size_t)stages * kStageBytes;
-    int ctas_x = sm_count() / gy;
+    *smem_bytes = (size_t)a.off_a + (size_t)a.stages * kStageBytes;
+    const int gy_real = cdiv(a.N, a.Ncta);
+    int ctas_x = sm_count() / gy_real;
     if (ctas_x < 1) ctas_x = 1;
     if (ctas_x > a.total_tiles) ctas_x = a.total_tiles;
-    *grid = dim3((unsigned)ctas_x, (unsigned)gy, 1);
+    *grid = dim3((unsigned)ctas_x, (unsigned)gy_real, 1);
     return true;
 }
 
@@ -425,16 +546,13 @@ template <int PROD, int VEC> int launch(const PwArgs &a, dim3 grid, size_t smem_
 }
 
 template <int PROD> int launch_vec(const PwArgs &a, dim3 grid, size_t smem_bytes, cudaStream_t s) {
-    if constexpr (PROD == PROD_SHIFT3D) return launch<PROD, 1>(a, grid, smem_bytes, s);
-    else {
-    const bool base16 = (reinterpret_cast<uintptr_t>(a.x) & 15) == 0;
+    uintptr_t align = reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.out) | reinterpret_cast<uintptr_t>(a.res);
+    const bool base16 = (align & 15) == 0;
     if (base16 && a.HW % 8 == 0) return launch<PROD, 8>(a, grid, smem_bytes, s);
     if (base16 && a.HW % 4 == 0) return launch<PROD, 4>(a, grid, smem_bytes, s);
     if (base16 && a.HW % 2 == 0) return launch<PROD, 2>(a, grid, smem_bytes, s);
     return launch<PROD, 1>(a, grid, smem_bytes, s);
-    }
 }
-
 
 // =====================================================================================================================
 // Weight gradient of the 1x1 convolution:  dW[m, n] = sum_{i, p} G[i, m, p] * A(i, n, p)      (A as in the forward)
@@ -444,7 +562,7 @@ template <int PROD> int launch_vec(const PwArgs &a, dim3 grid, size_t smem_bytes
 // grid = (pixel splits, N blocks, M blocks); every CTA reduces its pixel range into TMEM and writes one fp32
 // partial [M, N] slice; k_wg_reduce sums the slices in a fixed order (deterministic, unlike atomics).
 constexpr int kWgMaxStages = 4;
-constexpr int kWgChunk = 64;          // pixels per stage
+constexpr int kWgChunk = 64;             // pixels per stage
 constexpr int kWgTileBytes = 128 * 128;  // one 128-row operand tile
 
 struct WgArgs {
@@ -465,6 +583,11 @@ struct WgHdr {
     uint32_t tmem_base;
 };
 static_assert(sizeof(WgHdr) <= kHdrBytes, "header");
+
+// byte offset of (row r, 16-byte chunk c) inside a 128-byte-swizzled K-major operand block (8-row atoms of 1 KiB)
+__device__ __forceinline__ uint32_t sw128_off(int r, int c) {
+    return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+}
 
 template <int PROD, int VEC>
 __global__ void __launch_bounds__(kThreads, 1) k_pw_wgrad(const WgArgs a) {
@@ -531,15 +654,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_wgrad(const WgArgs a) {
         }
         __syncwarp();
     } else if (warp < kProdWarp0) {
-        const int q4 = warp & 3, row = q4 * 32 + lane;
+        // epilogue: warp -> TMEM lane quarter + every other 16-column chunk; fp32 partial slice of this pixel split
+        const int q4 = warp & 3, half = (warp - kEpiWarp0) >> 2, row = q4 * 32 + lane;
         mbar_wait(&hdr->tmem_full, 0);
         tc_fence_after();
         float *dst = a.partial + (int64_t)blockIdx.x * a.M * a.N;
+        const int nchunks = (nrows + 15) >> 4;
         for (int mt = 0; mt < a.Mt; ++mt) {
             const int ml = mt * 128 + row;
             const bool valid = ml < mrows;
             const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + mt * a.Nc;
-            for (int c0 = 0; c0 < nrows; c0 += 16) {
+            for (int ci = half; ci < nchunks; ci += 2) {
+                const int c0 = ci * 16;
                 uint32_t v[16];
                 __syncwarp();
                 tmem_ld16(taddr + c0, v);
@@ -553,9 +679,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_wgrad(const WgArgs a) {
             }
         }
     } else {
-        const int pt = tid - kProdWarp0 * 32;
-        const int total_units = (mrows + nrows) * 8;
-        const ShiftSrc ssrc{a.x, a.shift, a.shift_dt, a.T, a.H, a.W, a.HW, a.N};
+        const int pt = tid - kProdWarp0 * 32, pw = pt >> 5;
+        // operand rows loaded verbatim: G always, x unless it goes through the shift gather
+        const int unit_rows = (PROD == PROD_SHIFT3D) ? mrows : mrows + nrows;
+        const int total_units = unit_rows * 8;
+        const ShiftSrc ssrc{a.x, a.shift, a.shift_dt, a.T, a.H, a.W, a.HW, a.N, ((int64_t)a.NI * a.N * a.HW - 1) >> 1};
+        const int rpr = (a.W + 7) >> 3;
         int slot = 0;
         uint32_t phase = 0;
         for (int q = c_begin; q < c_end; ++q) {
@@ -565,11 +694,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_wgrad(const WgArgs a) {
             const int nchunks16 = ((kvalid + 15) >> 4) * 2;  // 16-byte chunks the MMAs of this stage will read
             mbar_wait(&hdr->empty[slot], phase ^ 1u);
             unsigned char *abase = stage0 + (size_t)slot * a.stage_bytes, *bbase = abase + (size_t)a.Mt * kWgTileBytes;
-            for (int u0 = pt; u0 < total_units; u0 += 8 * kNumProdWarps * 32) {
+            for (int u0 = pt; u0 < total_units; u0 += 8 * kProdThreads) {
                 uint32_t r[8][4];
 #pragma unroll
                 for (int b = 0; b < 8; ++b) {
-                    const int u = u0 + b * kNumProdWarps * 32;
+                    const int u = u0 + b * kProdThreads;
                     const int rowi = u >> 3, c = u & 7;
                     r[b][0] = r[b][1] = r[b][2] = r[b][3] = 0u;
                     if (u < total_units && c < nchunks16) {
@@ -578,40 +707,48 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_wgrad(const WgArgs a) {
                             load_unit<VEC>(a.g + ((int64_t)img * a.M + m0 + rowi) * a.HW + p, a.HW - p, r[b]);
                         } else {
                             const int k = n0 + rowi - mrows;
-                            if (PROD == PROD_SHIFT3D) {
-                                if (p < a.HW) shift3d_unit(ssrc, img, k, p, r[b]);
-                            } else {
-                                load_unit<VEC>(a.x + ((int64_t)img * a.N + k) * a.HW + p, a.HW - p, r[b]);
-                                if (PROD == PROD_BNRELU) {
-                                    // padding pixels must stay zero: relu(0*s + b) may not be
-                                    const int nv = a.HW - p;
-                                    bn_relu_unit(r[b], smem_sb[k], smem_sb[a.N + k]);
-                                    if (nv < 8) {
-#pragma unroll
-                                        for (int hh = 0; hh < 4; ++hh) {
-                                            if (nv <= 2 * hh) r[b][hh] = 0u;
-                                            else if (nv == 2 * hh + 1) r[b][hh] &= 0xffffu;
-                                        }
-                                    }
-                                }
-                            }
+                            load_unit<VEC>(a.x + ((int64_t)img * a.N + k) * a.HW + p, a.HW - p, r[b]);
+                            if (PROD == PROD_BNRELU) bn_relu_unit(r[b], smem_sb[k], smem_sb[a.N + k], a.HW - p);
                         }
                     }
                 }
 #pragma unroll
                 for (int b = 0; b < 8; ++b) {
-                    const int u = u0 + b * kNumProdWarps * 32;
+                    const int u = u0 + b * kProdThreads;
                     const int rowi = u >> 3, c = u & 7;
                     if (u < total_units && c < nchunks16) {
-                        unsigned char *d;
-                        if (rowi < mrows) {
-                            d = abase + (rowi >> 7) * kWgTileBytes + ((rowi & 127) >> 3) * 1024 + (rowi & 7) * 128 +
-                                ((c ^ (rowi & 7)) << 4);
-                        } else {
-                            const int rb = rowi - mrows;
-                            d = bbase + (rb >> 3) * 1024 + (rb & 7) * 128 + ((c ^ (rb & 7)) << 4);
-                        }
+                        unsigned char *d = (rowi < mrows) ? abase + (rowi >> 7) * kWgTileBytes + sw128_off(rowi & 127, c)
+                                                          : bbase + sw128_off(rowi - mrows, c);
                         *reinterpret_cast<uint4 *>(d) = make_uint4(r[b][0], r[b][1], r[b][2], r[b][3]);
+                    }
+                }
+            }
+            if (PROD == PROD_SHIFT3D) {
+                // shifted activations: (channel, row run) items, 2-byte stores into the swizzled K-major block
+                const int pend = p0 + kvalid, npad = nchunks16 * 8;
+                const int clip = img / a.T, t = img - clip * a.T;
+                const int h0 = p0 / a.W, ncand = ((pend - 1) / a.W - h0 + 1) * rpr;
+                const int kq = lane & 7, mgq = lane >> 3;
+                for (int rb = pw * 8 + kq; rb < nrows; rb += 64) {
+                    const int k = n0 + rb;
+                    const ShiftCh ch = shift_channel(ssrc, k);
+                    unsigned char *brow = bbase + (rb >> 3) * 1024 + (rb & 7) * 128;
+                    for (int m = kvalid + mgq; m < npad; m += 4)  // zero the reduction padding
+                        *reinterpret_cast<unsigned short *>(brow + (((m >> 3) ^ (rb & 7)) << 4) + (m & 7) * 2) = 0;
+                    for (int r = mgq; r < ncand; r += 4) {
+                        const int rh = r / rpr, c0 = (r - rh * rpr) * 8, h = h0 + rh;
+                        const int pr0 = h * a.W + c0;
+                        const int lo = max(p0 - pr0, 0), hi = min(min(8, a.W - c0), pend - pr0);
+                        if (lo >= hi) continue;
+                        float o[8];
+                        shift3d_run(ssrc, ch, clip, t, k, h, c0, o);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            if (i >= lo && i < hi) {
+                                const int m = pr0 + i - p0;
+                                *reinterpret_cast<unsigned short *>(brow + (((m >> 3) ^ (rb & 7)) << 4) + (m & 7) * 2) =
+                                    __bfloat16_as_ushort(__float2bfloat16_rn(o[i]));
+                            }
                     }
                 }
             }
@@ -639,8 +776,8 @@ __global__ void k_wg_reduce(const float *__restrict__ partial, float *__restrict
     out[i] = s;
 }
 
-bool wg_plan(WgArgs &a, int prod, dim3 *grid, size_t *smem_bytes) {
-    const int sb_bytes = prod == PROD_BNRELU ? round_up(2 * a.N * 4, 128) : 0;
+bool wg_plan(WgArgs &a, dim3 *grid, size_t *smem_bytes) {
+    const int sb_bytes = round_up(2 * a.N * 4, 128);
     a.off_sb = kHdrBytes;
     a.off_stage = (uint32_t)round_up(kHdrBytes + sb_bytes, 1024);
     int best = 1 << 30, bmb = 0, bnb = 0;
@@ -671,13 +808,13 @@ bool wg_plan(WgArgs &a, int prod, dim3 *grid, size_t *smem_bytes) {
     a.tmem_cols = cols;
     a.cpi = cdiv(a.HW, kWgChunk);
     a.total_chunks = a.NI * a.cpi;
-    int want = sm_count() / (bmb * bnb);
+    const int gy = cdiv(a.N, a.Nc), gz = cdiv(a.M, a.Mb);
+    int want = sm_count() / (gy * gz);
     if (want < 1) want = 1;
     if (want > a.total_chunks) want = a.total_chunks;
     a.chunks_per_split = cdiv(a.total_chunks, want);
     const int splits = cdiv(a.total_chunks, a.chunks_per_split);
-    // the last M / N block may be empty after rounding Mb / Nc up: shrink the grid to the blocks that own rows
-    *grid = dim3((unsigned)splits, (unsigned)cdiv(a.N, a.Nc), (unsigned)cdiv(a.M, a.Mb));
+    *grid = dim3((unsigned)splits, (unsigned)gy, (unsigned)gz);
     *smem_bytes = (size_t)a.off_stage + (size_t)a.stages * a.stage_bytes;
     return true;
 }
@@ -716,27 +853,19 @@ int pw_conv_forward(const void *x, const void *w, int w_dt, int w_trans, const v
     size_t smem_bytes = 0;
     if (!plan(a, prod, &grid, &smem_bytes))
         return fail(RB_ERR_UNSUPPORTED, "pw_conv: no tiling for K=%d N=%d (weight block does not fit shared memory)", K, N);
-    if (const char *dbg = getenv("RB_PW_SWAP")) {  // debug: swap leading/stride offsets of A (bit 0) / B (bit 1)
-        const int m = atoi(dbg);
-        if (m & 1) { uint32_t t = a.ad_lbo; a.ad_lbo = a.ad_sbo; a.ad_sbo = t; }
-        if (m & 2) { uint32_t t = a.bd_lbo; a.bd_lbo = a.bd_sbo; a.bd_sbo = t; }
-    }
+    if ((reinterpret_cast<uintptr_t>(x) & 3) != 0) return fail(RB_ERR_INVALID_ARGUMENT, "pw_conv: x must be 4-byte aligned");
     if (prod == PROD_SHIFT3D) return launch_vec<PROD_SHIFT3D>(a, grid, smem_bytes, s);
     if (prod == PROD_BNRELU) return launch_vec<PROD_BNRELU>(a, grid, smem_bytes, s);
     return launch_vec<PROD_PLAIN>(a, grid, smem_bytes, s);
 }
 
-}  // namespace rb
-
-namespace rb {
-
-// scratch floats needed by pw_conv_wgrad: [splits, M, N]
+// scratch bytes needed by pw_conv_wgrad: fp32 [splits, M, N]
 size_t pw_conv_wgrad_workspace(int NI, int M, int N, int HW) {
     WgArgs a{};
     a.NI = NI; a.M = M; a.N = N; a.HW = HW;
     dim3 grid;
     size_t smem_bytes = 0;
-    if (!wg_plan(a, PROD_BNRELU, &grid, &smem_bytes)) return 0;
+    if (!wg_plan(a, &grid, &smem_bytes)) return 0;
     return (size_t)grid.x * M * N * sizeof(float);
 }
 
@@ -749,8 +878,8 @@ int pw_conv_wgrad(const void *g, const void *x, float *dw, int NI, int M, int N,
     const int prod = shift ? PROD_SHIFT3D : (x_sb ? PROD_BNRELU : PROD_PLAIN);
     dim3 grid;
     size_t smem_bytes = 0;
-    if (!wg_plan(a, PROD_BNRELU, &grid, &smem_bytes))
-        return fail(RB_ERR_UNSUPPORTED, "pw_conv_wgrad: no tiling for M=%d N=%d", M, N);
+    if (!wg_plan(a, &grid, &smem_bytes)) return fail(RB_ERR_UNSUPPORTED, "pw_conv_wgrad: no tiling for M=%d N=%d", M, N);
+    if ((reinterpret_cast<uintptr_t>(x) & 3) != 0) return fail(RB_ERR_INVALID_ARGUMENT, "pw_conv_wgrad: x must be 4-byte aligned");
     int rc;
     if (prod == PROD_SHIFT3D) rc = wg_launch_vec<PROD_SHIFT3D>(a, grid, smem_bytes, s);
     else if (prod == PROD_BNRELU) rc = wg_launch_vec<PROD_BNRELU>(a, grid, smem_bytes, s);
