@@ -44,6 +44,7 @@ constexpr int kStageBytes = 16384;  // activation stage: Npx pixels x (8192 / Np
 constexpr int kMaxStages = 6;
 constexpr int kSmemLimit = 227 * 1024;
 constexpr int kHdrBytes = 256;
+constexpr int kStgBytes = kNumEpiWarps * 2048;  // epilogue staging: 32 channels x 64 B per warp
 
 enum { PROD_PLAIN = 0, PROD_BNRELU = 1, PROD_SHIFT3D = 2 };
 
@@ -100,73 +101,101 @@ struct ShiftSrc {
     const __nv_bfloat16 *x;  // [clips, T, K, H, W]
     const void *shift;       // [3, K] rows (T, H, W)
     int shift_dt, T, H, W, HW, K;
-    int64_t last_word;       // index of the 32-bit word holding the tensor's last element
+    int last_word;           // index of the 32-bit word holding the tensor's last element (< 2^30 elements pairs)
 };
 
-struct ShiftCh {  // per-channel constants: floors and the (1-r, r) weights of cuda_src/rubiks3d_kernels.cu:65-74
-    int fT, fH, fW;
-    float wT0, wT1, wH0, wH1, wW0, wW1;
+// per (channel, frame) constants: floors and (1-r, r) weights of cuda_src/rubiks3d_kernels.cu:65-74, folded with the frame
+struct ShiftCh {
+    int fH, fW;
+    int ebase[2];   // element index of (clip, t+fT+a, k, row 0, col 0); only used when tok[a]
+    bool tok[2];    // source frame t+fT+a exists
+    float wab[4];   // wT[a] * wH[b]
+    float wW0, wW1;
 };
 
-__device__ __forceinline__ ShiftCh shift_channel(const ShiftSrc &s, int k) {
+__device__ __forceinline__ ShiftCh shift_channel(const ShiftSrc &s, int k, int clip, int t) {
     const float sT = ld_param<float>(s.shift, s.shift_dt, k), sH = ld_param<float>(s.shift, s.shift_dt, s.K + k),
                 sW = ld_param<float>(s.shift, s.shift_dt, 2 * s.K + k);
     ShiftCh c;
-    c.fT = floor3d(sT); c.fH = floor3d(sH); c.fW = floor3d(sW);
-    c.wT1 = sT - c.fT; c.wH1 = sH - c.fH; c.wW1 = sW - c.fW;
-    c.wT0 = 1.f - c.wT1; c.wH0 = 1.f - c.wH1; c.wW0 = 1.f - c.wW1;
+    const int fT = floor3d(sT);
+    c.fH = floor3d(sH); c.fW = floor3d(sW);
+    const float rT = sT - fT, rH = sH - c.fH;
+    c.wW1 = sW - c.fW; c.wW0 = 1.f - c.wW1;
+    c.wab[0] = (1.f - rT) * (1.f - rH); c.wab[1] = (1.f - rT) * rH;
+    c.wab[2] = rT * (1.f - rH); c.wab[3] = rT * rH;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        const int ts = t + fT + a;
+        c.tok[a] = ts >= 0 && ts < s.T;
+        c.ebase[a] = ((clip * s.T + ts) * s.K + k) * s.HW;
+    }
     return c;
 }
 
 // RubiksShift3D forward (stride 1, pad 0; cuda_src/rubiks3d_kernels.cu:54-74,97-203) for the 8 output pixels
-// (row h, columns c0..c0+7) of channel k, frame t of clip `clip`:
+// (row h, columns c0..c0+7) of one (channel, frame):
 //     out[c] = sum_{a,b,d in {0,1}} wT[a] wH[b] wW[d] * X[t+fT+a, k, h+fH+b, c+fW+d],   X = 0 outside the tensor.
-// The 9 source columns needed from each of the 4 (frame, row) pairs are fetched as 5 aligned 32-bit words and realigned
-// with a funnel shift; the (frame, row) pairs are combined first, V[j] = sum_ab wT[a] wH[b] X_ab[j], then the two
-// column taps, out[i] = V[i] wW0 + V[i+1] wW1  (fp32 throughout; same taps and weights as the reference, summed in a
-// different order).  Columns outside [0, W) are zeroed after the combination, rows / frames outside are never loaded.
-__device__ __forceinline__ void shift3d_run(const ShiftSrc &s, const ShiftCh &ch, int clip, int t, int k, int h, int c0,
-                                            float (&o)[8]) {
+// shift3d_load fetches the 9 source columns needed from each of the 4 (frame, row) pairs as 5 aligned 32-bit words;
+// shift3d_compute realigns them with a funnel shift, combines the (frame, row) pairs first,
+// V[j] = sum_ab wT[a] wH[b] X_ab[j], then the two column taps, out[i] = V[i] wW0 + V[i+1] wW1  (fp32 throughout; same
+// taps and weights as the reference, summed in a different order).  Columns outside [0, W) are zeroed after the
+// combination, rows / frames outside are never loaded.  The split lets callers keep the loads of the next run in
+// flight while the current one is being combined.
+struct RunLoad {
+    uint32_t wd[4][5];
+    uint32_t shr[4];  // 0 or 16 per (frame, row): parity of the first source element
+};
+
+__device__ __forceinline__ void shift3d_load(const ShiftSrc &s, const ShiftCh &ch, int h, int c0, RunLoad &L) {
+    const int ws = c0 + ch.fW;
+    const uint32_t *words = reinterpret_cast<const uint32_t *>(s.x);
+#pragma unroll
+    for (int ab = 0; ab < 4; ++ab) {
+        const int hs = h + ch.fH + (ab & 1);
+        const bool rowok = ch.tok[ab >> 1] && (unsigned)hs < (unsigned)s.H;
+        const int e0 = ch.ebase[ab >> 1] + hs * s.W + ws;  // may be slightly negative on the tensor's first row
+        const int wi0 = e0 >> 1;                            // floor
+        L.shr[ab] = (uint32_t)(e0 & 1) * 16u;
+        if (wi0 >= 0 && wi0 + 4 <= s.last_word) {
+            const uint32_t *wp = words + wi0;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) L.wd[ab][i] = rowok ? __ldg(wp + i) : 0u;
+        } else {
+            // first / last row of the whole tensor: the words that fall outside hold only columns outside [0, W)
+#pragma unroll
+            for (int i = 0; i < 5; ++i) L.wd[ab][i] = rowok ? __ldg(words + min(max(wi0 + i, 0), s.last_word)) : 0u;
+        }
+    }
+}
+
+__device__ __forceinline__ void shift3d_compute(const ShiftSrc &s, const ShiftCh &ch, int c0, const RunLoad &L, float (&o)[8]) {
     const int ws = c0 + ch.fW;
     float V[9];
 #pragma unroll
     for (int j = 0; j < 9; ++j) V[j] = 0.f;
-    const uint32_t *words = reinterpret_cast<const uint32_t *>(s.x);
 #pragma unroll
-    for (int a = 0; a < 2; ++a) {
-        const int ts = t + ch.fT + a;
-        const float wa = a ? ch.wT1 : ch.wT0;
+    for (int ab = 0; ab < 4; ++ab) {
+        const float w = ch.wab[ab];
+        const uint32_t sh = L.shr[ab];
 #pragma unroll
-        for (int b = 0; b < 2; ++b) {
-            const int hs = h + ch.fH + b;
-            const float wab = wa * (b ? ch.wH1 : ch.wH0);
-            const bool rowok = ts >= 0 && ts < s.T && hs >= 0 && hs < s.H;
-            const int64_t e0 = ((int64_t)((clip * s.T + ts) * s.K + k) * s.H + hs) * s.W + ws;
-            const int64_t wi0 = e0 >> 1;  // floor: e0 may be slightly negative at the tensor's first row
-            const uint32_t sh = (uint32_t)(e0 & 1) * 16u;
-            uint32_t wd[5];
-#pragma unroll
-            for (int i = 0; i < 5; ++i) {
-                const int64_t wi = wi0 + i;
-                wd[i] = (rowok && wi >= 0 && wi <= s.last_word) ? __ldg(words + wi) : 0u;
-            }
-            uint32_t nw[5];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) nw[i] = __funnelshift_r(wd[i], wd[i + 1], sh);
-            nw[4] = wd[4] >> sh;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                V[2 * i] = fmaf(wab, bf16_lo(nw[i]), V[2 * i]);
-                V[2 * i + 1] = fmaf(wab, bf16_hi(nw[i]), V[2 * i + 1]);
-            }
-            V[8] = fmaf(wab, bf16_lo(nw[4]), V[8]);
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t nw = __funnelshift_r(L.wd[ab][i], L.wd[ab][i + 1], sh);
+            V[2 * i] = fmaf(w, bf16_lo(nw), V[2 * i]);
+            V[2 * i + 1] = fmaf(w, bf16_hi(nw), V[2 * i + 1]);
         }
+        V[8] = fmaf(w, bf16_lo(L.wd[ab][4] >> sh), V[8]);
     }
 #pragma unroll
     for (int j = 0; j < 9; ++j)
-        if (ws + j < 0 || ws + j >= s.W) V[j] = 0.f;
+        if ((unsigned)(ws + j) >= (unsigned)s.W) V[j] = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = V[i] * ch.wW0 + V[i + 1] * ch.wW1;
+}
+
+// run g of an image (rows of `rpr` runs of 8 columns) -> (row, first column)
+__device__ __forceinline__ void run_coords(int g, int rpr, uint32_t magic, int &h, int &c0) {
+    h = (int)(((uint32_t)g * magic) >> 16);
+    c0 = (g - h * rpr) * 8;
 }
 
 // =====================================================================================================================
@@ -183,7 +212,8 @@ struct PwArgs {
     int NI, K, N, HW;
     int Kpad, Ncta, Mt, Npx, kstage, acc_stages, stages, tmem_cols;
     int tiles_per_img, total_tiles, k_stages;
-    uint32_t off_w, off_a, off_sb, w_lbo, a_lbo;
+    uint32_t off_w, off_a, off_sb, off_stg, w_lbo, a_lbo;
+    uint32_t rpr, rpr_magic;   // runs of 8 columns per image row; (r * rpr_magic) >> 16 == r / rpr for r < 4096
 };
 
 struct Hdr {
@@ -313,6 +343,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_conv(const PwArgs a) {
         // warp -> TMEM lane quarter (hardware: warp id % 4) and one half of the tile's pixel columns
         const int q = warp & 3, half = (warp - kEpiWarp0) >> 2;
         const int cbeg = half * (a.Npx >> 1), cend = cbeg + (a.Npx >> 1);
+        unsigned char *stg = smem + a.off_stg + (warp - kEpiWarp0) * 2048;
         int it = 0;
         for (int tile = tile0; tile < a.total_tiles; tile += tstride, ++it) {
             const int as = it % a.acc_stages;
@@ -322,49 +353,61 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_conv(const PwArgs a) {
             tc_fence_after();
             for (int mt = 0; mt < a.Mt; ++mt) {
                 if (mt * 128 + q * 32 >= nrows) break;  // whole warp beyond the CTA's channels (warp-uniform)
-                const int nl = mt * 128 + q * 32 + lane;
-                const bool rowok = nl < nrows;
-                const int64_t rbase = ((int64_t)img * a.N + n0 + nl) * a.HW + p0;
+                const int r0 = mt * 128 + q * 32;       // first CTA-local channel of this warp's 32 TMEM lanes
+                const int64_t rb0 = ((int64_t)img * a.N + n0 + r0) * a.HW + p0;
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * acc_cols + mt * a.Npx;
-                for (int c0 = cbeg; c0 < cend && p0 + c0 < a.HW; c0 += 16) {
-                    uint32_t v[16];
+                // rounds of 32 pixels: TMEM -> registers (thread = channel) -> bf16 -> per-warp staging tile in shared
+                // memory (32 channels x 64 B, 16-byte chunks XOR-swizzled) -> read back with 4 lanes per channel row, so
+                // every global access instruction touches 8 rows x 64 contiguous bytes instead of 32 rows x 16 bytes
+                for (int c0 = cbeg; c0 < cend && p0 + c0 < a.HW; c0 += 32) {
+                    uint32_t v[2][16];
                     __syncwarp();
-                    tmem_ld16(taddr + c0, v);
-                    const int nv = rowok ? a.HW - (p0 + c0) : 0;  // valid pixels from this chunk's start (may exceed 16)
-                    uint32_t rr[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) rr[i] = 0u;
-                    if (a.res != nullptr) {
-                        const __nv_bfloat16 *rp = a.res + rbase + c0;
-                        uint32_t t4[4];
-                        load_unit<VEC>(rp, nv, t4);
-                        rr[0] = t4[0]; rr[1] = t4[1]; rr[2] = t4[2]; rr[3] = t4[3];
-                        load_unit<VEC>(rp + 8, nv - 8, t4);
-                        rr[4] = t4[0]; rr[5] = t4[1]; rr[6] = t4[2]; rr[7] = t4[3];
-                    }
+                    tmem_ld16(taddr + c0, v[0]);
+                    tmem_ld16(taddr + c0 + 16, v[1]);
                     tmem_ld_wait();
-                    uint32_t ov[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        ov[i] = pack_bf16x2(__uint_as_float(v[2 * i]) + bf16_lo(rr[i]), __uint_as_float(v[2 * i + 1]) + bf16_hi(rr[i]));
-                    __nv_bfloat16 *op = a.out + rbase + c0;
-                    if (VEC == 8) {
-                        if (nv >= 8) *reinterpret_cast<uint4 *>(op) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
-                        if (nv >= 16) *reinterpret_cast<uint4 *>(op + 8) = make_uint4(ov[4], ov[5], ov[6], ov[7]);
-                    } else if (VEC == 4) {
+                    for (int c = 0; c < 4; ++c) {
+                        const uint32_t *vv = &v[c >> 1][(c & 1) * 8];
+                        *reinterpret_cast<uint4 *>(stg + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) =
+                            make_uint4(pack_bf16x2(__uint_as_float(vv[0]), __uint_as_float(vv[1])),
+                                       pack_bf16x2(__uint_as_float(vv[2]), __uint_as_float(vv[3])),
+                                       pack_bf16x2(__uint_as_float(vv[4]), __uint_as_float(vv[5])),
+                                       pack_bf16x2(__uint_as_float(vv[6]), __uint_as_float(vv[7])));
+                    }
+                    __syncwarp();
 #pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            if (nv >= 4 * i + 4) *reinterpret_cast<uint2 *>(op + 4 * i) = make_uint2(ov[2 * i], ov[2 * i + 1]);
-                    } else if (VEC == 2) {
+                    for (int i = 0; i < 4; ++i) {
+                        const int row = (lane >> 2) + 8 * i, ch = lane & 3;
+                        const uint4 sv = *reinterpret_cast<const uint4 *>(stg + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4));
+                        uint32_t ov[4] = {sv.x, sv.y, sv.z, sv.w};
+                        const int pl = c0 + ch * 8;
+                        const int nv = (r0 + row < nrows) ? a.HW - (p0 + pl) : 0;  // valid pixels from this chunk's start
+                        const int64_t off = rb0 + (row * a.HW + pl);
+                        if (a.res != nullptr) {
+                            // `out += shortcut` on the bf16 conv result (the rounding order of conv3 followed by the add)
+                            uint32_t t4[4];
+                            load_unit<VEC>(a.res + off, nv, t4);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            if (nv >= 2 * i + 2) *reinterpret_cast<uint32_t *>(op + 2 * i) = ov[i];
-                    } else {
-                        unsigned short *os = reinterpret_cast<unsigned short *>(op);
+                            for (int e = 0; e < 4; ++e)
+                                ov[e] = pack_bf16x2(bf16_lo(ov[e]) + bf16_lo(t4[e]), bf16_hi(ov[e]) + bf16_hi(t4[e]));
+                        }
+                        __nv_bfloat16 *op = a.out + off;
+                        if (VEC == 8) {
+                            if (nv >= 8) *reinterpret_cast<uint4 *>(op) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+                        } else if (VEC == 4) {
+                            if (nv >= 4) *reinterpret_cast<uint2 *>(op) = make_uint2(ov[0], ov[1]);
+                            if (nv >= 8) *reinterpret_cast<uint2 *>(op + 4) = make_uint2(ov[2], ov[3]);
+                        } else if (VEC == 2) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            if (nv > 2 * i) os[2 * i] = (unsigned short)(ov[i] & 0xffffu);
-                            if (nv > 2 * i + 1) os[2 * i + 1] = (unsigned short)(ov[i] >> 16);
+                            for (int e = 0; e < 4; ++e)
+                                if (nv >= 2 * e + 2) *reinterpret_cast<uint32_t *>(op + 2 * e) = ov[e];
+                        } else {
+                            unsigned short *os = reinterpret_cast<unsigned short *>(op);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                if (nv > 2 * e) os[2 * e] = (unsigned short)(ov[e] & 0xffffu);
+                                if (nv > 2 * e + 1) os[2 * e + 1] = (unsigned short)(ov[e] >> 16);
+                            }
                         }
                     }
                 }
@@ -379,20 +422,27 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_conv(const PwArgs a) {
         const int kq = lane & 7, mgq = lane >> 3;
         const int nq = a.Npx >> 5;  // quads of 8-pixel groups per tile
         const ShiftSrc ssrc{a.x, a.shift, a.shift_dt, a.T, a.H, a.W, a.HW, a.K,
-                            ((int64_t)a.NI * a.K * a.HW - 1) >> 1};
+                            (int)(((int64_t)a.NI * a.K * a.HW - 1) >> 1)};
 
         // unit j of this thread inside a stage: channel kk (0..kstage-1), 8-pixel group mg
         auto unit_kk = [&](int j) { return ((j * kNumProdWarps + pw) / nq) * 8 + kq; };
         auto unit_mg = [&](int j) { return ((j * kNumProdWarps + pw) % nq) * 4 + mgq; };
 
+        // per-thread constants of the 4 units it owns in every stage
+        int ukk[4], usm[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            ukk[j] = unit_kk(j);
+            usm[j] = (ukk[j] >> 3) * (int)a.a_lbo + unit_mg(j) * 128 + (ukk[j] & 7) * 16;
+        }
         auto load_stage = [&](int tile, int st, uint32_t (&r)[4][4]) {
             const int img = tile / a.tiles_per_img, p0 = (tile - img * a.tiles_per_img) * a.Npx;
+            const __nv_bfloat16 *xb = a.x + (int64_t)img * a.K * a.HW + p0;  // element indices below fit 32 bits
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int k = st * a.kstage + unit_kk(j), p = p0 + unit_mg(j) * 8;
-                if (k < a.K && p < a.HW) {
-                    load_unit<VEC>(a.x + ((int64_t)img * a.K + k) * a.HW + p, a.HW - p, r[j]);
-                    if (PROD == PROD_BNRELU) bn_relu_unit(r[j], smem_sb[k], smem_sb[a.Kpad + k], a.HW - p);
+                const int k = st * a.kstage + ukk[j], pl = unit_mg(j) * 8;
+                if (k < a.K && p0 + pl < a.HW) {
+                    load_unit<VEC>(xb + (k * a.HW + pl), a.HW - p0 - pl, r[j]);
                 } else {
                     r[j][0] = r[j][1] = r[j][2] = r[j][3] = 0u;
                 }
@@ -402,69 +452,110 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_conv(const PwArgs a) {
         int tile = tile0, st = 0, slot = 0;
         uint32_t phase = 0;
         if (PROD != PROD_SHIFT3D) {
-            uint32_t cur[4][4];
-            if (tile < a.total_tiles) load_stage(tile, st, cur);
+            // register ring: the loads of the next kDepth-1 stages are in flight while one stage is written to shared memory
+            constexpr int kDepth = 4;
+            uint32_t buf[kDepth][4][4];
+            int ltile = tile0, lst = 0;  // load cursor, runs kDepth-1 stages ahead of (tile, st)
+            auto advance = [&](int &tl, int &s_) { if (++s_ == a.k_stages) { s_ = 0; tl += tstride; } };
+#pragma unroll
+            for (int d = 0; d < kDepth - 1; ++d) {
+                if (ltile < a.total_tiles) load_stage(ltile, lst, buf[d]);
+                advance(ltile, lst);
+            }
             while (tile < a.total_tiles) {
-                int ntile = tile, nst = st + 1;
-                if (nst == a.k_stages) { nst = 0; ntile += tstride; }
-                uint32_t nxt[4][4];
-                if (ntile < a.total_tiles) load_stage(ntile, nst, nxt);
-                mbar_wait(&hdr->empty[slot], phase ^ 1u);
-                unsigned char *sp = smem_a + (size_t)slot * kStageBytes;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int kk = unit_kk(j);
-                    *reinterpret_cast<uint4 *>(sp + (size_t)(kk >> 3) * a.a_lbo + unit_mg(j) * 128 + (kk & 7) * 16) =
-                        make_uint4(cur[j][0], cur[j][1], cur[j][2], cur[j][3]);
+                for (int d = 0; d < kDepth; ++d) {
+                    if (tile >= a.total_tiles) break;
+                    if (ltile < a.total_tiles) load_stage(ltile, lst, buf[(d + kDepth - 1) % kDepth]);
+                    advance(ltile, lst);
+                    mbar_wait(&hdr->empty[slot], phase ^ 1u);
+                    unsigned char *sp = smem_a + (size_t)slot * kStageBytes;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (st * a.kstage + ukk[j] >= a.Kpad) continue;  // beyond the last K step: never read
+                        if (PROD == PROD_BNRELU) {  // applied only now: the loads of this stage had kDepth-1 stages to land
+                            const int k = st * a.kstage + ukk[j];
+                            const int p0 = (tile % a.tiles_per_img) * a.Npx;
+                            if (k < a.K) bn_relu_unit(buf[d][j], smem_sb[k], smem_sb[a.Kpad + k], a.HW - p0 - unit_mg(j) * 8);
+                        }
+                        *reinterpret_cast<uint4 *>(sp + usm[j]) = make_uint4(buf[d][j][0], buf[d][j][1], buf[d][j][2], buf[d][j][3]);
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&hdr->full[slot]);
+                    advance(tile, st);
+                    if (++slot == a.stages) { slot = 0; phase ^= 1u; }
                 }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&hdr->full[slot]);
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) cur[j][i] = nxt[j][i];
-                tile = ntile;
-                st = nst;
-                if (++slot == a.stages) { slot = 0; phase ^= 1u; }
             }
         } else {
             // 3D-shift gather: work items = (channel, row run of <= 8 pixels); results go to shared memory with 2-byte
             // stores because a run need not be aligned to the 8-pixel groups of the operand layout
-            const int rpr = (a.W + 7) >> 3;  // runs per image row
+            const int rpr = (int)a.rpr;  // runs of 8 columns per image row
             for (; tile < a.total_tiles; tile += tstride) {
                 const int img = tile / a.tiles_per_img, p0 = (tile - img * a.tiles_per_img) * a.Npx;
                 const int pend = min(p0 + a.Npx, a.HW);
                 const int clip = img / a.T, t = img - clip * a.T;
-                const int h0 = p0 / a.W, ncand = ((pend - 1) / a.W - h0 + 1) * rpr;
+                const int h0 = p0 / a.W, h1 = (pend - 1) / a.W;
+                const int g0 = h0 * rpr + ((p0 - h0 * a.W) >> 3), g1 = h1 * rpr + ((pend - 1 - h1 * a.W) >> 3);
                 for (st = 0; st < a.k_stages; ++st) {
                     mbar_wait(&hdr->empty[slot], phase ^ 1u);
                     unsigned char *sp = smem_a + (size_t)slot * kStageBytes;
                     for (int kl = pw * 8 + kq; kl < a.kstage; kl += 64) {
                         const int k = st * a.kstage + kl;
                         if (k >= a.Kpad) break;
-                        const bool kreal = k < a.K;
-                        ShiftCh ch{};
-                        if (kreal) ch = shift_channel(ssrc, k);
-                        unsigned short *srow = reinterpret_cast<unsigned short *>(sp + (size_t)(kl >> 3) * a.a_lbo + (kl & 7) * 16);
-                        for (int r = mgq; r < ncand; r += 4) {
-                            const int rh = r / rpr, c0 = (r - rh * rpr) * 8, h = h0 + rh;
-                            const int pr0 = h * a.W + c0;
-                            const int lo = max(p0 - pr0, 0), hi = min(min(8, a.W - c0), pend - pr0);
-                            if (lo >= hi) continue;
-                            float o[8];
-                            if (kreal) {
-                                shift3d_run(ssrc, ch, clip, t, k, h, c0, o);
+                        unsigned char *srow = sp + (size_t)(kl >> 3) * a.a_lbo + (kl & 7) * 16;
+                        // results of run g (tile-relative pixels m0 .. m0+7, clipped to the tile and the row) -> shared memory
+                        auto store_run = [&](int h, int c0, const float (&o)[8]) {
+                            const int m0 = h * a.W + c0 - p0;
+                            const int lo = max(-m0, 0), hi = min(min(8, a.W - c0), pend - p0 - m0);
+                            if (((m0 & 7) | lo) == 0 && hi == 8) {  // whole, group-aligned run: one 16-byte store
+                                *reinterpret_cast<uint4 *>(srow + (m0 >> 3) * 128) =
+                                    make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
+                                               pack_bf16x2(o[6], o[7]));
                             } else {
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) o[i] = 0.f;
+                                for (int i = 0; i < 8; ++i)
+                                    if ((unsigned)(i - lo) < (unsigned)(hi - lo)) {
+                                        const int m = m0 + i;
+                                        *reinterpret_cast<unsigned short *>(srow + (m >> 3) * 128 + (m & 7) * 2) =
+                                            __bfloat16_as_ushort(__float2bfloat16_rn(o[i]));
+                                    }
                             }
-#pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                if (i >= lo && i < hi) {
-                                    const int m = pr0 + i - p0;
-                                    srow[(m >> 3) * 64 + (m & 7)] = __bfloat16_as_ushort(__float2bfloat16_rn(o[i]));
-                                }
+                        };
+                        if (k >= a.K) {  // channel padding of the last K step: zeros
+                            const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                            for (int g = g0 + mgq; g <= g1; g += 4) {
+                                int h, c0;
+                                run_coords(g, rpr, a.rpr_magic, h, c0);
+                                store_run(h, c0, z);
+                            }
+                            continue;
+                        }
+                        const ShiftCh ch = shift_channel(ssrc, k, clip, t);
+                        // two runs in flight: the loads of run g+4 are issued before run g is combined
+                        RunLoad LA, LB;
+                        int g = g0 + mgq, hA = 0, cA = 0, hB = 0, cB = 0;
+                        if (g <= g1) {
+                            run_coords(g, rpr, a.rpr_magic, hA, cA);
+                            shift3d_load(ssrc, ch, hA, cA, LA);
+                        }
+                        while (g <= g1) {
+                            float o[8];
+                            const bool hasB = g + 4 <= g1;
+                            if (hasB) {
+                                run_coords(g + 4, rpr, a.rpr_magic, hB, cB);
+                                shift3d_load(ssrc, ch, hB, cB, LB);
+                            }
+                            shift3d_compute(ssrc, ch, cA, LA, o);
+                            store_run(hA, cA, o);
+                            if (!hasB) break;
+                            if (g + 8 <= g1) {
+                                run_coords(g + 8, rpr, a.rpr_magic, hA, cA);
+                                shift3d_load(ssrc, ch, hA, cA, LA);
+                            }
+                            shift3d_compute(ssrc, ch, cB, LB, o);
+                            store_run(hB, cB, o);
+                            g += 8;
                         }
                     }
                     fence_proxy_async_smem();
@@ -500,7 +591,7 @@ bool plan(PwArgs &a, int prod, dim3 *grid, size_t *smem_bytes) {
         if (mt > 4) continue;
         const int w_lbo = nc * 16 + 16;
         const int w_bytes = round_up((a.Kpad >> 3) * w_lbo, 128);
-        const int st = (kSmemLimit - kHdrBytes - sb_bytes - w_bytes) / kStageBytes;
+        const int st = (kSmemLimit - kHdrBytes - sb_bytes - kStgBytes - w_bytes) / kStageBytes;
         if (st < 2) continue;
         // the last M tile reads (garbage, ignored) rows up to mt*128 of the last k-group: keep that inside the allocation
         const int reach = ((a.Kpad >> 3) - 1) * w_lbo + mt * 2048;
@@ -509,7 +600,8 @@ bool plan(PwArgs &a, int prod, dim3 *grid, size_t *smem_bytes) {
         gy = cand;
         a.Ncta = nc; a.Mt = mt; a.w_lbo = (uint32_t)w_lbo; a.stages = stages;
         a.off_sb = kHdrBytes;
-        a.off_w = kHdrBytes + sb_bytes;
+        a.off_stg = kHdrBytes + sb_bytes;
+        a.off_w = a.off_stg + kStgBytes;
         a.off_a = a.off_w + w_bytes;
     }
     if (!gy) return false;
@@ -523,6 +615,10 @@ bool plan(PwArgs &a, int prod, dim3 *grid, size_t *smem_bytes) {
     a.tmem_cols = cols;
     a.tiles_per_img = cdiv(a.HW, a.Npx);
     a.total_tiles = a.NI * a.tiles_per_img;
+    a.rpr = (uint32_t)(a.W > 0 ? (a.W + 7) / 8 : 1);
+    a.rpr_magic = 65536u / a.rpr + 1u;
+    for (uint32_t r = 0; r < 4096; ++r)
+        if (((r * a.rpr_magic) >> 16) != r / a.rpr) return false;
     *smem_bytes = (size_t)a.off_a + (size_t)a.stages * kStageBytes;
     const int gy_real = cdiv(a.N, a.Ncta);
     int ctas_x = sm_count() / gy_real;
@@ -576,6 +672,7 @@ struct WgArgs {
     int Mb, Mt, Nc, n_sub, sub_n, stages, tmem_cols;
     int cpi, total_chunks, chunks_per_split;
     uint32_t off_sb, off_stage, stage_bytes;
+    uint32_t rpr, rpr_magic;
 };
 
 struct WgHdr {
@@ -683,8 +780,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_wgrad(const WgArgs a) {
         // operand rows loaded verbatim: G always, x unless it goes through the shift gather
         const int unit_rows = (PROD == PROD_SHIFT3D) ? mrows : mrows + nrows;
         const int total_units = unit_rows * 8;
-        const ShiftSrc ssrc{a.x, a.shift, a.shift_dt, a.T, a.H, a.W, a.HW, a.N, ((int64_t)a.NI * a.N * a.HW - 1) >> 1};
-        const int rpr = (a.W + 7) >> 3;
+        const ShiftSrc ssrc{a.x, a.shift, a.shift_dt, a.T, a.H, a.W, a.HW, a.N, (int)(((int64_t)a.NI * a.N * a.HW - 1) >> 1)};
+        const int rpr = (int)a.rpr;
         int slot = 0;
         uint32_t phase = 0;
         for (int q = c_begin; q < c_end; ++q) {
@@ -727,28 +824,56 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_wgrad(const WgArgs a) {
                 // shifted activations: (channel, row run) items, 2-byte stores into the swizzled K-major block
                 const int pend = p0 + kvalid, npad = nchunks16 * 8;
                 const int clip = img / a.T, t = img - clip * a.T;
-                const int h0 = p0 / a.W, ncand = ((pend - 1) / a.W - h0 + 1) * rpr;
+                const int h0 = p0 / a.W, h1 = (pend - 1) / a.W;
+                const int g0 = h0 * rpr + ((p0 - h0 * a.W) >> 3), g1 = h1 * rpr + ((pend - 1 - h1 * a.W) >> 3);
                 const int kq = lane & 7, mgq = lane >> 3;
                 for (int rb = pw * 8 + kq; rb < nrows; rb += 64) {
                     const int k = n0 + rb;
-                    const ShiftCh ch = shift_channel(ssrc, k);
+                    const ShiftCh ch = shift_channel(ssrc, k, clip, t);
                     unsigned char *brow = bbase + (rb >> 3) * 1024 + (rb & 7) * 128;
+                    const int sw = rb & 7;
                     for (int m = kvalid + mgq; m < npad; m += 4)  // zero the reduction padding
-                        *reinterpret_cast<unsigned short *>(brow + (((m >> 3) ^ (rb & 7)) << 4) + (m & 7) * 2) = 0;
-                    for (int r = mgq; r < ncand; r += 4) {
-                        const int rh = r / rpr, c0 = (r - rh * rpr) * 8, h = h0 + rh;
-                        const int pr0 = h * a.W + c0;
-                        const int lo = max(p0 - pr0, 0), hi = min(min(8, a.W - c0), pend - pr0);
-                        if (lo >= hi) continue;
-                        float o[8];
-                        shift3d_run(ssrc, ch, clip, t, k, h, c0, o);
+                        *reinterpret_cast<unsigned short *>(brow + (((m >> 3) ^ sw) << 4) + (m & 7) * 2) = 0;
+                    auto store_run = [&](int h, int c0, const float (&o)[8]) {
+                        const int m0 = h * a.W + c0 - p0;
+                        const int lo = max(-m0, 0), hi = min(min(8, a.W - c0), kvalid - m0);
+                        if (((m0 & 7) | lo) == 0 && hi == 8) {
+                            *reinterpret_cast<uint4 *>(brow + (((m0 >> 3) ^ sw) << 4)) =
+                                make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
+                                           pack_bf16x2(o[6], o[7]));
+                        } else {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            if (i >= lo && i < hi) {
-                                const int m = pr0 + i - p0;
-                                *reinterpret_cast<unsigned short *>(brow + (((m >> 3) ^ (rb & 7)) << 4) + (m & 7) * 2) =
-                                    __bfloat16_as_ushort(__float2bfloat16_rn(o[i]));
-                            }
+                            for (int i = 0; i < 8; ++i)
+                                if ((unsigned)(i - lo) < (unsigned)(hi - lo)) {
+                                    const int m = m0 + i;
+                                    *reinterpret_cast<unsigned short *>(brow + (((m >> 3) ^ sw) << 4) + (m & 7) * 2) =
+                                        __bfloat16_as_ushort(__float2bfloat16_rn(o[i]));
+                                }
+                        }
+                    };
+                    RunLoad LA, LB;
+                    int g = g0 + mgq, hA = 0, cA = 0, hB = 0, cB = 0;
+                    if (g <= g1) {
+                        run_coords(g, rpr, a.rpr_magic, hA, cA);
+                        shift3d_load(ssrc, ch, hA, cA, LA);
+                    }
+                    while (g <= g1) {
+                        float o[8];
+                        const bool hasB = g + 4 <= g1;
+                        if (hasB) {
+                            run_coords(g + 4, rpr, a.rpr_magic, hB, cB);
+                            shift3d_load(ssrc, ch, hB, cB, LB);
+                        }
+                        shift3d_compute(ssrc, ch, cA, LA, o);
+                        store_run(hA, cA, o);
+                        if (!hasB) break;
+                        if (g + 8 <= g1) {
+                            run_coords(g + 8, rpr, a.rpr_magic, hA, cA);
+                            shift3d_load(ssrc, ch, hA, cA, LA);
+                        }
+                        shift3d_compute(ssrc, ch, cB, LB, o);
+                        store_run(hB, cB, o);
+                        g += 8;
                     }
                 }
             }
@@ -808,6 +933,8 @@ bool wg_plan(WgArgs &a, dim3 *grid, size_t *smem_bytes) {
     a.tmem_cols = cols;
     a.cpi = cdiv(a.HW, kWgChunk);
     a.total_chunks = a.NI * a.cpi;
+    a.rpr = (uint32_t)(a.W > 0 ? (a.W + 7) / 8 : 1);
+    a.rpr_magic = 65536u / a.rpr + 1u;
     const int gy = cdiv(a.N, a.Nc), gz = cdiv(a.M, a.Mb);
     int want = sm_count() / (gy * gz);
     if (want < 1) want = 1;
