@@ -86,6 +86,74 @@ template <int VEC> __device__ __forceinline__ void load_unit(const __nv_bfloat16
     }
 }
 
+// A "unit" is 8 consecutive positions of the flattened (image, pixel) axis of one channel row of an NCHW tensor
+// [NI, C, HW].  It starts at pixel p of some image (p % VEC == 0, HW % VEC == 0) and may run into the next image, whose
+// same channel row lies (C-1)*HW elements further than the plain continuation.  piece_offsets gives, for each VEC-wide
+// piece, its element offset relative to the unit's first element.
+template <int VEC> __device__ __forceinline__ void piece_offsets(int p, int HW, int wrap, int (&o)[8 / VEC]) {
+#pragma unroll
+    for (int s_ = 0; s_ < 8 / VEC; ++s_) {
+        int po = p + s_ * VEC, w = 0;
+        while (po >= HW) { po -= HW; w += wrap; }
+        o[s_] = s_ * VEC + w;
+    }
+}
+
+// loads the unit at element offset `off` of `base`; pieces at or beyond `nleft` positions read as zero
+template <int VEC>
+__device__ __forceinline__ void load_unit_flat(const __nv_bfloat16 *base, int off, const int (&o)[8 / VEC], int nleft, uint32_t (&r)[4]) {
+    if (VEC == 8) {
+        if (nleft >= 8) {
+            const uint4 v = ldg16(base + off);
+            r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+        } else {
+            r[0] = r[1] = r[2] = r[3] = 0u;
+        }
+    } else if (VEC == 4) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (nleft >= 4 * h + 4) {
+                const uint2 v = ldg8(base + off + o[h]);
+                r[2 * h] = v.x; r[2 * h + 1] = v.y;
+            } else {
+                r[2 * h] = r[2 * h + 1] = 0u;
+            }
+        }
+    } else if (VEC == 2) {
+#pragma unroll
+        for (int h = 0; h < 4; ++h) r[h] = (nleft >= 2 * h + 2) ? ldg4(base + off + o[h]) : 0u;
+    } else {
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            const uint32_t lo = (nleft > 2 * h) ? ldg2(base + off + o[2 * h]) : 0u;
+            const uint32_t hi = (nleft > 2 * h + 1) ? ldg2(base + off + o[2 * h + 1]) : 0u;
+            r[h] = lo | (hi << 16);
+        }
+    }
+}
+
+template <int VEC>
+__device__ __forceinline__ void store_unit_flat(__nv_bfloat16 *base, int off, const int (&o)[8 / VEC], int nleft, const uint32_t (&v)[4]) {
+    if (VEC == 8) {
+        if (nleft >= 8) *reinterpret_cast<uint4 *>(base + off) = make_uint4(v[0], v[1], v[2], v[3]);
+    } else if (VEC == 4) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+            if (nleft >= 4 * h + 4) *reinterpret_cast<uint2 *>(base + off + o[h]) = make_uint2(v[2 * h], v[2 * h + 1]);
+    } else if (VEC == 2) {
+#pragma unroll
+        for (int h = 0; h < 4; ++h)
+            if (nleft >= 2 * h + 2) *reinterpret_cast<uint32_t *>(base + off + o[h]) = v[h];
+    } else {
+        unsigned short *us = reinterpret_cast<unsigned short *>(base);
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            if (nleft > 2 * h) us[off + o[2 * h]] = (unsigned short)(v[h] & 0xffffu);
+            if (nleft > 2 * h + 1) us[off + o[2 * h + 1]] = (unsigned short)(v[h] >> 16);
+        }
+    }
+}
+
 // relu(x*sc + bi) on the first `nvalid` elements; the rest stay zero (padding must not become relu(bias))
 __device__ __forceinline__ void bn_relu_unit(uint32_t (&r)[4], float sc, float bi, int nvalid) {
 #pragma unroll
@@ -211,7 +279,7 @@ struct PwArgs {
     int T, H, W;               // PROD_SHIFT3D: frames per clip, map size (HW = H*W)
     int NI, K, N, HW;
     int Kpad, Ncta, Mt, Npx, kstage, acc_stages, stages, tmem_cols;
-    int tiles_per_img, total_tiles, k_stages;
+    int NP, total_tiles, k_stages;  // NP = NI*HW positions on the flattened (image, pixel) axis, tiled by Npx
     uint32_t off_w, off_a, off_sb, off_stg, w_lbo, a_lbo;
     uint32_t rpr, rpr_magic;   // runs of 8 columns per image row; (r * rpr_magic) >> 16 == r / rpr for r < 4096
 };
@@ -250,57 +318,79 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_conv(const PwArgs a) {
         __syncwarp();
         tmem_alloc(&hdr->tmem_base, (uint32_t)a.tmem_cols);
     }
-    {
-        // W[n, k] -> (k/8)*w_lbo + (n/8)*128 + (n%8)*16 + (k%8)*2 (K-major core matrices; w_lbo is an odd multiple of 16
-        // bytes so that the 8 k-groups written by a quarter warp land in 8 different bank groups).  Rows beyond the
-        // CTA's channels and columns k >= K are zero.  Thread order follows the contiguous axis of the weight buffer.
-        const int kgroups = a.Kpad >> 3, rows8 = (a.Ncta + 7) & ~7;
-        const __nv_bfloat16 *wb = reinterpret_cast<const __nv_bfloat16 *>(a.w);
-        const float *wf = reinterpret_cast<const float *>(a.w);
-        const bool vec_ok = (a.K & 7) == 0 && !a.w_trans;
-        for (int u = tid; u < rows8 * kgroups; u += kThreads) {
-            int kg, n;
-            if (a.w_trans) { kg = u / rows8; n = u - kg * rows8; }
-            else { n = u / kgroups; kg = u - n * kgroups; }
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (n < nrows) {
-                const int64_t row = n0 + n;
-                if (vec_ok) {
-                    if (kg * 8 < a.K) {
-                        if (a.w_dt == RB_BF16) {
-                            v = ldg16(wb + row * a.K + kg * 8);
-                        } else {
-                            const float4 f0 = __ldg(reinterpret_cast<const float4 *>(wf + row * a.K + kg * 8));
-                            const float4 f1 = __ldg(reinterpret_cast<const float4 *>(wf + row * a.K + kg * 8 + 4));
-                            v = make_uint4(pack_bf16x2(f0.x, f0.y), pack_bf16x2(f0.z, f0.w), pack_bf16x2(f1.x, f1.y),
-                                           pack_bf16x2(f1.z, f1.w));
-                        }
-                    }
-                } else {
-                    float f[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int k = kg * 8 + e;
-                        const int64_t idx = a.w_trans ? (int64_t)k * a.N + row : row * a.K + k;
-                        f[e] = k < a.K ? (a.w_dt == RB_BF16 ? __bfloat162float(wb[idx]) : __ldg(wf + idx)) : 0.f;
-                    }
-                    v = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                                   pack_bf16x2(f[6], f[7]));
-                }
-            }
-            *reinterpret_cast<uint4 *>(smem_w + (size_t)kg * a.w_lbo + (size_t)(n >> 3) * 128 + (n & 7) * 16) = v;
+    if (PROD == PROD_BNRELU)
+        for (int k = tid; k < a.Kpad; k += kThreads) {
+            smem_sb[k] = k < a.K ? a.a_sb[2 * k] : 0.f;
+            smem_sb[a.Kpad + k] = k < a.K ? a.a_sb[2 * k + 1] : 0.f;
         }
-        if (PROD == PROD_BNRELU)
-            for (int k = tid; k < a.Kpad; k += kThreads) {
-                smem_sb[k] = k < a.K ? a.a_sb[2 * k] : 0.f;
-                smem_sb[a.Kpad + k] = k < a.K ? a.a_sb[2 * k + 1] : 0.f;
-            }
-        fence_proxy_async_smem();
-    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = hdr->tmem_base;
+
+    if (warp < kProdWarp0) {
+        // Resident weight block, staged by the MMA + epilogue warps while the producer warps already fetch activations.
+        // W[n, k] -> (k/8)*w_lbo + (n/8)*128 + (n%8)*16 + (k%8)*2 (K-major core matrices; w_lbo is an odd multiple of 16
+        // bytes so that the 8 k-groups written by a quarter warp land in 8 different bank groups).  Rows beyond the
+        // CTA's channels and columns k >= K are zero.  Thread order follows the contiguous axis of the weight buffer;
+        // four units per thread are in flight at a time.
+        constexpr int kWThreads = kProdWarp0 * 32;
+        const int kgroups = a.Kpad >> 3, rows8 = (a.Ncta + 7) & ~7, total = rows8 * kgroups;
+        const __nv_bfloat16 *wb = reinterpret_cast<const __nv_bfloat16 *>(a.w);
+        const float *wf = reinterpret_cast<const float *>(a.w);
+        const bool vec_ok = (a.K & 7) == 0 && !a.w_trans;
+        for (int u0 = tid; u0 < total; u0 += 4 * kWThreads) {
+            uint4 v[4];
+            float4 f0[4], f1[4];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int u = u0 + b * kWThreads;
+                int kg, n;
+                if (a.w_trans) { kg = u / rows8; n = u - kg * rows8; }
+                else { n = u / kgroups; kg = u - n * kgroups; }
+                v[b] = make_uint4(0u, 0u, 0u, 0u);
+                f0[b] = f1[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (u < total && n < nrows) {
+                    const int64_t row = n0 + n;
+                    if (vec_ok) {
+                        if (kg * 8 < a.K) {
+                            if (a.w_dt == RB_BF16) {
+                                v[b] = ldg16(wb + row * a.K + kg * 8);
+                            } else {
+                                f0[b] = __ldg(reinterpret_cast<const float4 *>(wf + row * a.K + kg * 8));
+                                f1[b] = __ldg(reinterpret_cast<const float4 *>(wf + row * a.K + kg * 8 + 4));
+                            }
+                        }
+                    } else {
+                        float f[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int k = kg * 8 + e;
+                            const int64_t idx = a.w_trans ? (int64_t)k * a.N + row : row * a.K + k;
+                            f[e] = k < a.K ? (a.w_dt == RB_BF16 ? __bfloat162float(wb[idx]) : __ldg(wf + idx)) : 0.f;
+                        }
+                        f0[b] = make_float4(f[0], f[1], f[2], f[3]);
+                        f1[b] = make_float4(f[4], f[5], f[6], f[7]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int u = u0 + b * kWThreads;
+                if (u >= total) continue;
+                int kg, n;
+                if (a.w_trans) { kg = u / rows8; n = u - kg * rows8; }
+                else { n = u / kgroups; kg = u - n * kgroups; }
+                uint4 o = v[b];
+                if (!(vec_ok && a.w_dt == RB_BF16))
+                    o = make_uint4(pack_bf16x2(f0[b].x, f0[b].y), pack_bf16x2(f0[b].z, f0[b].w), pack_bf16x2(f1[b].x, f1[b].y),
+                                   pack_bf16x2(f1[b].z, f1[b].w));
+                *reinterpret_cast<uint4 *>(smem_w + (size_t)kg * a.w_lbo + (size_t)(n >> 3) * 128 + (n & 7) * 16) = o;
+            }
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, %0;" ::"n"(kProdWarp0 * 32) : "memory");
+    }
 
     const int tile0 = blockIdx.x, tstride = gridDim.x;
     const int acc_cols = a.Mt * a.Npx;
@@ -348,18 +438,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_conv(const PwArgs a) {
         for (int tile = tile0; tile < a.total_tiles; tile += tstride, ++it) {
             const int as = it % a.acc_stages;
             const uint32_t aph = (uint32_t)(it / a.acc_stages) & 1u;
-            const int img = tile / a.tiles_per_img, p0 = (tile - img * a.tiles_per_img) * a.Npx;
+            const int P0 = tile * a.Npx;  // first position of the tile on the flattened (image, pixel) axis
             mbar_wait(&hdr->tmem_full[as], aph);
             tc_fence_after();
             for (int mt = 0; mt < a.Mt; ++mt) {
                 if (mt * 128 + q * 32 >= nrows) break;  // whole warp beyond the CTA's channels (warp-uniform)
                 const int r0 = mt * 128 + q * 32;       // first CTA-local channel of this warp's 32 TMEM lanes
-                const int64_t rb0 = ((int64_t)img * a.N + n0 + r0) * a.HW + p0;
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * acc_cols + mt * a.Npx;
                 // rounds of 32 pixels: TMEM -> registers (thread = channel) -> bf16 -> per-warp staging tile in shared
                 // memory (32 channels x 64 B, 16-byte chunks XOR-swizzled) -> read back with 4 lanes per channel row, so
                 // every global access instruction touches 8 rows x 64 contiguous bytes instead of 32 rows x 16 bytes
-                for (int c0 = cbeg; c0 < cend && p0 + c0 < a.HW; c0 += 32) {
+                for (int c0 = cbeg; c0 < cend && P0 + c0 < a.NP; c0 += 32) {
                     uint32_t v[2][16];
                     __syncwarp();
                     tmem_ld16(taddr + c0, v[0]);
@@ -380,35 +469,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_conv(const PwArgs a) {
                         const int row = (lane >> 2) + 8 * i, ch = lane & 3;
                         const uint4 sv = *reinterpret_cast<const uint4 *>(stg + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4));
                         uint32_t ov[4] = {sv.x, sv.y, sv.z, sv.w};
-                        const int pl = c0 + ch * 8;
-                        const int nv = (r0 + row < nrows) ? a.HW - (p0 + pl) : 0;  // valid pixels from this chunk's start
-                        const int64_t off = rb0 + (row * a.HW + pl);
+                        // this lane's 8 positions: image / pixel of the first one, then pieces that may wrap into the next image
+                        const int P = P0 + c0 + ch * 8;
+                        const int img = P / a.HW, pp = P - img * a.HW;
+                        const int nv = (r0 + row < nrows) ? a.NP - P : 0;
+                        const int off = ((img * a.N + n0 + r0 + row) * a.HW) + pp;
+                        int po[8 / VEC];
+                        piece_offsets<VEC>(pp, a.HW, (a.N - 1) * a.HW, po);
                         if (a.res != nullptr) {
                             // `out += shortcut` on the bf16 conv result (the rounding order of conv3 followed by the add)
                             uint32_t t4[4];
-                            load_unit<VEC>(a.res + off, nv, t4);
+                            load_unit_flat<VEC>(a.res, off, po, nv, t4);
 #pragma unroll
                             for (int e = 0; e < 4; ++e)
                                 ov[e] = pack_bf16x2(bf16_lo(ov[e]) + bf16_lo(t4[e]), bf16_hi(ov[e]) + bf16_hi(t4[e]));
                         }
-                        __nv_bfloat16 *op = a.out + off;
-                        if (VEC == 8) {
-                            if (nv >= 8) *reinterpret_cast<uint4 *>(op) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
-                        } else if (VEC == 4) {
-                            if (nv >= 4) *reinterpret_cast<uint2 *>(op) = make_uint2(ov[0], ov[1]);
-                            if (nv >= 8) *reinterpret_cast<uint2 *>(op + 4) = make_uint2(ov[2], ov[3]);
-                        } else if (VEC == 2) {
-#pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                if (nv >= 2 * e + 2) *reinterpret_cast<uint32_t *>(op + 2 * e) = ov[e];
-                        } else {
-                            unsigned short *os = reinterpret_cast<unsigned short *>(op);
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                if (nv > 2 * e) os[2 * e] = (unsigned short)(ov[e] & 0xffffu);
-                                if (nv > 2 * e + 1) os[2 * e + 1] = (unsigned short)(ov[e] >> 16);
-                            }
-                        }
+                        store_unit_flat<VEC>(a.out, off, po, nv, ov);
                     }
                 }
             }
@@ -435,14 +511,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_conv(const PwArgs a) {
             ukk[j] = unit_kk(j);
             usm[j] = (ukk[j] >> 3) * (int)a.a_lbo + unit_mg(j) * 128 + (ukk[j] & 7) * 16;
         }
+        // every unit of a thread has the same 8-pixel group of the tile: one (image, pixel) decomposition per tile
+        const int umg = unit_mg(0);
         auto load_stage = [&](int tile, int st, uint32_t (&r)[4][4]) {
-            const int img = tile / a.tiles_per_img, p0 = (tile - img * a.tiles_per_img) * a.Npx;
-            const __nv_bfloat16 *xb = a.x + (int64_t)img * a.K * a.HW + p0;  // element indices below fit 32 bits
+            const int P = tile * a.Npx + umg * 8;
+            const int img = P / a.HW, pp = P - img * a.HW;
+            const int offb = img * a.K * a.HW + pp, nleft = a.NP - P;
+            int po[8 / VEC];
+            piece_offsets<VEC>(pp, a.HW, (a.K - 1) * a.HW, po);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int k = st * a.kstage + ukk[j], pl = unit_mg(j) * 8;
-                if (k < a.K && p0 + pl < a.HW) {
-                    load_unit<VEC>(xb + (k * a.HW + pl), a.HW - p0 - pl, r[j]);
+                const int k = st * a.kstage + ukk[j];
+                if (k < a.K) {
+                    load_unit_flat<VEC>(a.x, offb + k * a.HW, po, nleft, r[j]);
                 } else {
                     r[j][0] = r[j][1] = r[j][2] = r[j][3] = 0u;
                 }
@@ -475,8 +556,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_conv(const PwArgs a) {
                         if (st * a.kstage + ukk[j] >= a.Kpad) continue;  // beyond the last K step: never read
                         if (PROD == PROD_BNRELU) {  // applied only now: the loads of this stage had kDepth-1 stages to land
                             const int k = st * a.kstage + ukk[j];
-                            const int p0 = (tile % a.tiles_per_img) * a.Npx;
-                            if (k < a.K) bn_relu_unit(buf[d][j], smem_sb[k], smem_sb[a.Kpad + k], a.HW - p0 - unit_mg(j) * 8);
+                            if (k < a.K) bn_relu_unit(buf[d][j], smem_sb[k], smem_sb[a.Kpad + k], a.NP - tile * a.Npx - umg * 8);
                         }
                         *reinterpret_cast<uint4 *>(sp + usm[j]) = make_uint4(buf[d][j][0], buf[d][j][1], buf[d][j][2], buf[d][j][3]);
                     }
@@ -492,11 +572,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_conv(const PwArgs a) {
             // stores because a run need not be aligned to the 8-pixel groups of the operand layout
             const int rpr = (int)a.rpr;  // runs of 8 columns per image row
             for (; tile < a.total_tiles; tile += tstride) {
-                const int img = tile / a.tiles_per_img, p0 = (tile - img * a.tiles_per_img) * a.Npx;
-                const int pend = min(p0 + a.Npx, a.HW);
-                const int clip = img / a.T, t = img - clip * a.T;
-                const int h0 = p0 / a.W, h1 = (pend - 1) / a.W;
-                const int g0 = h0 * rpr + ((p0 - h0 * a.W) >> 3), g1 = h1 * rpr + ((pend - 1 - h1 * a.W) >> 3);
+                const int Plo = tile * a.Npx, Phi = min(Plo + a.Npx, a.NP);  // flattened (image, pixel) range of the tile
+                const int img_lo = Plo / a.HW, img_hi = (Phi - 1) / a.HW;
                 for (st = 0; st < a.k_stages; ++st) {
                     mbar_wait(&hdr->empty[slot], phase ^ 1u);
                     unsigned char *sp = smem_a + (size_t)slot * kStageBytes;
@@ -504,58 +581,65 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_conv(const PwArgs a) {
                         const int k = st * a.kstage + kl;
                         if (k >= a.Kpad) break;
                         unsigned char *srow = sp + (size_t)(kl >> 3) * a.a_lbo + (kl & 7) * 16;
-                        // results of run g (tile-relative pixels m0 .. m0+7, clipped to the tile and the row) -> shared memory
-                        auto store_run = [&](int h, int c0, const float (&o)[8]) {
-                            const int m0 = h * a.W + c0 - p0;
-                            const int lo = max(-m0, 0), hi = min(min(8, a.W - c0), pend - p0 - m0);
-                            if (((m0 & 7) | lo) == 0 && hi == 8) {  // whole, group-aligned run: one 16-byte store
-                                *reinterpret_cast<uint4 *>(srow + (m0 >> 3) * 128) =
-                                    make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
-                                               pack_bf16x2(o[6], o[7]));
-                            } else {
+                        for (int img = img_lo; img <= img_hi; ++img) {
+                            // the part of this image inside the tile: pixels [p0, pend), tile-relative base mb
+                            const int ib = img * a.HW, p0 = max(Plo - ib, 0), pend = min(Phi - ib, a.HW), mb = ib - Plo;
+                            const int clip = img / a.T, t = img - clip * a.T;
+                            const int h0 = p0 / a.W, h1 = (pend - 1) / a.W;
+                            const int g0 = h0 * rpr + ((p0 - h0 * a.W) >> 3), g1 = h1 * rpr + ((pend - 1 - h1 * a.W) >> 3);
+                            // results of a run (pixels pr0 .. pr0+7 of the image, clipped to [p0, pend) and to the row)
+                            auto store_run = [&](int h, int c0, const float (&o)[8]) {
+                                const int pr0 = h * a.W + c0, m0 = mb + pr0;
+                                const int lo = max(p0 - pr0, 0), hi = min(min(8, a.W - c0), pend - pr0);
+                                if (((m0 & 7) | lo) == 0 && hi == 8) {  // whole, group-aligned run: one 16-byte store
+                                    *reinterpret_cast<uint4 *>(srow + (m0 >> 3) * 128) =
+                                        make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
+                                                   pack_bf16x2(o[6], o[7]));
+                                } else {
 #pragma unroll
-                                for (int i = 0; i < 8; ++i)
-                                    if ((unsigned)(i - lo) < (unsigned)(hi - lo)) {
-                                        const int m = m0 + i;
-                                        *reinterpret_cast<unsigned short *>(srow + (m >> 3) * 128 + (m & 7) * 2) =
-                                            __bfloat16_as_ushort(__float2bfloat16_rn(o[i]));
-                                    }
+                                    for (int i = 0; i < 8; ++i)
+                                        if ((unsigned)(i - lo) < (unsigned)(hi - lo)) {
+                                            const int m = m0 + i;
+                                            *reinterpret_cast<unsigned short *>(srow + (m >> 3) * 128 + (m & 7) * 2) =
+                                                __bfloat16_as_ushort(__float2bfloat16_rn(o[i]));
+                                        }
+                                }
+                            };
+                            if (k >= a.K) {  // channel padding of the last K step: zeros
+                                const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                                for (int g = g0 + mgq; g <= g1; g += 4) {
+                                    int h, c0;
+                                    run_coords(g, rpr, a.rpr_magic, h, c0);
+                                    store_run(h, c0, z);
+                                }
+                                continue;
                             }
-                        };
-                        if (k >= a.K) {  // channel padding of the last K step: zeros
-                            const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                            for (int g = g0 + mgq; g <= g1; g += 4) {
-                                int h, c0;
-                                run_coords(g, rpr, a.rpr_magic, h, c0);
-                                store_run(h, c0, z);
-                            }
-                            continue;
-                        }
-                        const ShiftCh ch = shift_channel(ssrc, k, clip, t);
-                        // two runs in flight: the loads of run g+4 are issued before run g is combined
-                        RunLoad LA, LB;
-                        int g = g0 + mgq, hA = 0, cA = 0, hB = 0, cB = 0;
-                        if (g <= g1) {
-                            run_coords(g, rpr, a.rpr_magic, hA, cA);
-                            shift3d_load(ssrc, ch, hA, cA, LA);
-                        }
-                        while (g <= g1) {
-                            float o[8];
-                            const bool hasB = g + 4 <= g1;
-                            if (hasB) {
-                                run_coords(g + 4, rpr, a.rpr_magic, hB, cB);
-                                shift3d_load(ssrc, ch, hB, cB, LB);
-                            }
-                            shift3d_compute(ssrc, ch, cA, LA, o);
-                            store_run(hA, cA, o);
-                            if (!hasB) break;
-                            if (g + 8 <= g1) {
-                                run_coords(g + 8, rpr, a.rpr_magic, hA, cA);
+                            const ShiftCh ch = shift_channel(ssrc, k, clip, t);
+                            // two runs in flight: the loads of run g+4 are issued before run g is combined
+                            RunLoad LA, LB;
+                            int g = g0 + mgq, hA = 0, cA = 0, hB = 0, cB = 0;
+                            if (g <= g1) {
+                                run_coords(g, rpr, a.rpr_magic, hA, cA);
                                 shift3d_load(ssrc, ch, hA, cA, LA);
                             }
-                            shift3d_compute(ssrc, ch, cB, LB, o);
-                            store_run(hB, cB, o);
-                            g += 8;
+                            while (g <= g1) {
+                                float o[8];
+                                const bool hasB = g + 4 <= g1;
+                                if (hasB) {
+                                    run_coords(g + 4, rpr, a.rpr_magic, hB, cB);
+                                    shift3d_load(ssrc, ch, hB, cB, LB);
+                                }
+                                shift3d_compute(ssrc, ch, cA, LA, o);
+                                store_run(hA, cA, o);
+                                if (!hasB) break;
+                                if (g + 8 <= g1) {
+                                    run_coords(g + 8, rpr, a.rpr_magic, hA, cA);
+                                    shift3d_load(ssrc, ch, hA, cA, LA);
+                                }
+                                shift3d_compute(ssrc, ch, cB, LB, o);
+                                store_run(hB, cB, o);
+                                g += 8;
+                            }
                         }
                     }
                     fence_proxy_async_smem();
@@ -613,8 +697,8 @@ bool plan(PwArgs &a, int prod, dim3 *grid, size_t *smem_bytes) {
     int cols = 32;
     while (cols < a.acc_stages * a.Mt * a.Npx) cols <<= 1;
     a.tmem_cols = cols;
-    a.tiles_per_img = cdiv(a.HW, a.Npx);
-    a.total_tiles = a.NI * a.tiles_per_img;
+    a.NP = a.NI * a.HW;
+    a.total_tiles = cdiv(a.NP, a.Npx);
     a.rpr = (uint32_t)(a.W > 0 ? (a.W + 7) / 8 : 1);
     a.rpr_magic = 65536u / a.rpr + 1u;
     for (uint32_t r = 0; r < 4096; ++r)

@@ -160,6 +160,21 @@ def _bn_cfg(bn):
     return training, momentum, bn.eps, (bn.running_mean if track else None), (bn.running_var if track else None)
 
 
+# True: as3 -> conv3 -> += shortcut run as ONE launch (the shift is the operand producer of the tensor-core GEMM and is
+# recomputed by the conv3 weight-gradient kernel; the shifted tensor never exists in HBM).  False: the stand-alone strip
+# shift kernel writes the shifted tensor, which conv3 and its weight gradient then read.  Measured on B200 at 32 clips
+# (tools/bench_pw.py, profiles/): the per-element gather inside the GEMM producer costs more issue slots than the strip
+# kernel's shared-memory staging saves in HBM traffic, so the two-launch schedule is the faster one on every
+# RubiksNet-Large geometry today and is the default.
+FUSE_SHIFT_CONV3 = False
+
+
+def _shift3d_forward(x, shift, frames):
+    from .shiftlib.rubiks3d.primitive import rubiks_shift_3d_forward
+    nt, c, h, w = x.shape
+    return rubiks_shift_3d_forward(x.view(nt // frames, frames, c, h, w), shift, (1, 1, 1), 0).view(nt, c, h, w)
+
+
 class _RubiksBlockFn(torch.autograd.Function):
     """Identity-shortcut RubiksShiftBlock with a 3D shift (backbone.py:109-135 + models.py:128-145), bf16."""
 
@@ -172,20 +187,28 @@ class _RubiksBlockFn(torch.autograd.Function):
         _, mi1, sb1 = ops.bn_forward(x, g1, b1, rm1, rv1, tr1, mom1, eps1, relu=True, apply=False)
         y2 = ops.pw_conv(x, w2, in_scale_bias=sb1, name="pw_conv<bn+relu>")
         a2, mi2, sb2 = ops.bn_forward(y2, g2, b2, rm2, rv2, tr2, mom2, eps2, relu=True, apply=True)
-        out = ops.shift3d_pw_conv(a2, shift, w3, x, frames)
-        ctx.save_for_backward(x, y2, a2, mi1, sb1, mi2, sb2, g1, g2, w2, w3, shift)
+        if FUSE_SHIFT_CONV3:
+            s3 = None
+            out = ops.shift3d_pw_conv(a2, shift, w3, x, frames)
+        else:
+            s3 = _shift3d_forward(a2, shift, frames)
+            out = ops.pw_conv(s3, w3, residual=x, name="pw_conv<+residual>")
+        ctx.save_for_backward(x, y2, a2, s3, mi1, sb1, mi2, sb2, g1, g2, w2, w3, shift)
         ctx.cfg = (tr1, tr2, frames, normalize_grad, normalize_t_factor)
         return out
 
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, g):
-        x, y2, a2, mi1, sb1, mi2, sb2, g1, g2, w2, w3, shift = ctx.saved_tensors
+        x, y2, a2, s3, mi1, sb1, mi2, sb2, g1, g2, w2, w3, shift = ctx.saved_tensors
         tr1, tr2, frames, normalize_grad, normalize_t_factor = ctx.cfg
         g = g.contiguous()
         need = ctx.needs_input_grad
         gs = ops.pw_conv(g, w3, transposed=True, name="pw_conv<dgrad>")
-        gw3 = ops.shift3d_pw_conv_wgrad(g, a2, shift, frames).view(w3.shape) if need[7] else None
+        gw3 = None
+        if need[7]:
+            gw3 = (ops.shift3d_pw_conv_wgrad(g, a2, shift, frames) if s3 is None else ops.pw_conv_wgrad(g, s3)).view(w3.shape)
+        del s3
         ga2, gshift = ops.shift3d_backward(a2, shift, gs, frames, normalize_grad, normalize_t_factor, need_shift=need[6])
         del gs
         gy2, dg2, db2 = ops.bn_backward(y2, ga2, None, g2, mi2, sb2, tr2, relu=True)

@@ -134,8 +134,9 @@ def test_errors_are_reported():
     assert float(dw.abs().sum()) == 0.0
 
 
+@pytest.mark.parametrize("fuse_shift", [False, True])
 @pytest.mark.parametrize("training", [True, False])
-def test_whole_block_function_equals_module_graph(training):
+def test_whole_block_function_equals_module_graph(training, fuse_shift):
     """Identity-shortcut blocks as ONE autograd Function (shift fused into conv3, bn1 folded into conv2) vs the
     per-op fused path, same bf16 inputs: outputs, input gradient and every parameter gradient."""
     torch.manual_seed(5)
@@ -151,8 +152,10 @@ def test_whole_block_function_equals_module_graph(training):
     x0 = torch.randn(16, block.conv2.in_channels, 28, 28, device="cuda").to(BF)
     g = torch.randn(16, block.conv3.out_channels, 28, 28, device="cuda").to(BF)
     results = []
+    from rubiksnet_b200 import fused
     for flag in (True, False):
         backbone.FUSED_WHOLE_BLOCK = flag
+        fused.FUSE_SHIFT_CONV3 = fuse_shift
         try:
             sd = {k: v.clone() for k, v in block.state_dict().items()}
             block.zero_grad(set_to_none=True)
@@ -166,6 +169,7 @@ def test_whole_block_function_equals_module_graph(training):
             block.load_state_dict(sd)
         finally:
             backbone.FUSED_WHOLE_BLOCK = True
+            fused.FUSE_SHIFT_CONV3 = False
     (o1, gx1, gp1, rv1, n1), (o0, gx0, gp0, rv0, n0) = results
     assert n1 < n0, "the whole-block Function must launch fewer kernels than the per-op path"
     assert _rel(o1, o0) <= 1e-2 and _rel(gx1, gx0) <= 2e-2
@@ -178,17 +182,27 @@ def test_whole_block_function_equals_module_graph(training):
             assert _rel(gp1[name], gp0[name]) <= 2e-2, name
 
 
-def test_training_step_uses_tensor_core_blocks():
-    """A bf16 autocast training step of RubiksNet-Tiny routes its identity-shortcut blocks through the fused launch."""
+@pytest.mark.parametrize("fuse_shift", [False, True])
+def test_training_step_uses_tensor_core_blocks(fuse_shift):
+    """A bf16 autocast training step of RubiksNet-Tiny routes its identity-shortcut blocks through the tcgen05 kernels
+    (and, with FUSE_SHIFT_CONV3, through the single shift+conv3 launch)."""
+    from rubiksnet_b200 import fused
     torch.manual_seed(6)
     net = rb.RubiksNet(tier="tiny", num_classes=5, num_frames=8).cuda().train()
     clips = torch.randn(1, 8, 3, 224, 224, device="cuda")
-    _lib.timing.start()
-    with torch.autocast("cuda", dtype=BF):
-        loss = net(clips).float().square().mean()
-    loss.backward()
-    agg = _lib.timing.stop()
-    assert agg["shift3d_pw_conv"]["launches"] == 13            # 17 blocks - 4 down-sampling blocks
-    assert agg["shift3d_pw_conv_wgrad"]["launches"] == 13
+    fused.FUSE_SHIFT_CONV3 = fuse_shift
+    try:
+        _lib.timing.start()
+        with torch.autocast("cuda", dtype=BF):
+            loss = net(clips).float().square().mean()
+        loss.backward()
+        agg = _lib.timing.stop()
+    finally:
+        fused.FUSE_SHIFT_CONV3 = False
+    assert agg["pw_conv<bn+relu>"]["launches"] == 13             # 17 blocks - 4 down-sampling blocks
+    if fuse_shift:
+        assert agg["shift3d_pw_conv"]["launches"] == 13 and agg["shift3d_pw_conv_wgrad"]["launches"] == 13
+    else:
+        assert agg["pw_conv<+residual>"]["launches"] == 13 and "shift3d_pw_conv" not in agg
     assert torch.isfinite(loss).item()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
