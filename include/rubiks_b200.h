@@ -198,6 +198,10 @@ int rb_shift3d_pw_conv_wgrad(const void *out_grad, const void *x, const void *sh
                              int dtype, int shift_dtype, int N, int T, int C, int H, int W, int Cout,
                              void *workspace, size_t workspace_bytes, void *stream);
 
+/* Debug aid (tools/trace_pw.py): when non-NULL, every k_pw_conv CTA writes globaltimer stamps of its pipeline events
+ * (64 x uint64 per CTA) into this device buffer.  NULL switches tracing off (default). */
+void rb_debug_pw_trace(void *device_buffer);
+
 #ifdef __cplusplus
 }
 #endif

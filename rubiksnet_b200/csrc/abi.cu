@@ -50,6 +50,7 @@ int shift2d_bwd_shift_generic(const void *, const void *, const void *, void *, 
 int pw_conv_forward(const void *x, const void *w, int w_dt, int w_trans, const void *residual, void *out, int NI, int K,
                     int N, int HW, const float *a_sb, const void *shift, int shift_dt, int T, int H, int W, cudaStream_t s);
 size_t pw_conv_wgrad_workspace(int NI, int M, int N, int HW);
+void pw_conv_set_trace(void *p);
 int pw_conv_wgrad(const void *g, const void *x, float *dw, int NI, int M, int N, int HW, const float *x_sb,
                   const void *shift, int shift_dt, int T, int H, int W, void *workspace, cudaStream_t s);
 
@@ -331,5 +332,8 @@ int rb_shift3d_pw_conv_wgrad(const void *out_grad, const void *x, const void *sh
     return wgrad_common(out_grad, x, weight_grad, dtype, N * T, C, Cout, H * W, nullptr, shift, shift_dtype, T, H, W,
                         workspace, workspace_bytes, stream);
 }
+
+/* debug: device buffer (64 x uint64 per CTA) receiving globaltimer stamps of k_pw_conv; NULL switches tracing off */
+void rb_debug_pw_trace(void *device_buffer) { pw_conv_set_trace(device_buffer); }
 
 }  // extern "C"

@@ -38,7 +38,6 @@ constexpr int kEpiWarp0 = 1;
 constexpr int kNumEpiWarps = 8;
 constexpr int kProdWarp0 = kEpiWarp0 + kNumEpiWarps;  // 9
 constexpr int kNumProdWarps = 8;
-constexpr int kProdThreads = kNumProdWarps * 32;
 constexpr int kThreads = (kProdWarp0 + kNumProdWarps) * 32;  // 544
 constexpr int kStageBytes = 16384;  // activation stage: Npx pixels x (8192 / Npx) channels
 constexpr int kMaxStages = 6;
@@ -282,13 +281,130 @@ struct PwArgs {
     int NP, total_tiles, k_stages;  // NP = NI*HW positions on the flattened (image, pixel) axis, tiled by Npx
     uint32_t off_w, off_a, off_sb, off_stg, w_lbo, a_lbo;
     uint32_t rpr, rpr_magic;   // runs of 8 columns per image row; (r * rpr_magic) >> 16 == r / rpr for r < 4096
+    unsigned long long *trace; // debug: per-CTA event timestamps (globaltimer ns), 64 slots per CTA; null = off
 };
+
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define PW_TRACE(slot) do { if (a.trace) a.trace[(blockIdx.y * gridDim.x + blockIdx.x) * 64 + (slot)] = gtime(); } while (0)
 
 struct Hdr {
     uint64_t full[kMaxStages], empty[kMaxStages], tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
 };
 static_assert(sizeof(Hdr) <= kHdrBytes, "header");
+
+// Resident weight block of a CTA: W[n0 + n, k] (n < nrows) -> shared memory at
+//     (k/8)*w_lbo + (n/8)*128 + (n%8)*16 + (k%8)*2
+// (K-major 8x16-byte core matrices; w_lbo is an odd multiple of 16 bytes so that consecutive k-groups fall into different
+// bank groups).  Rows n >= nrows and columns k >= K are zero.  Threads follow the contiguous axis of the weight buffer
+// ([N,K]: 8 consecutive k = one 16-byte shared store; transposed [K,N]: 8 consecutive n = eight 2-byte stores), keep 8
+// units in flight each, and every CTA starts at a different offset so that the grid does not walk the same L2 lines in
+// lockstep.
+__device__ __forceinline__ void stage_weights(const PwArgs &a, unsigned char *smem_w, int n0, int nrows, int tid) {
+    const int kgroups = a.Kpad >> 3, rows8 = (a.Ncta + 7) & ~7;
+    const __nv_bfloat16 *wb = reinterpret_cast<const __nv_bfloat16 *>(a.w);
+    const float *wf = reinterpret_cast<const float *>(a.w);
+    const bool f32 = a.w_dt != RB_BF16;
+    constexpr int UB = 8;
+    if (!a.w_trans) {
+        const bool vec_ok = (a.K & 7) == 0;
+        const int total = rows8 * kgroups;
+        const int rot = (int)(((int64_t)blockIdx.x * total) / gridDim.x);
+        for (int u0 = tid; u0 < total; u0 += UB * kThreads) {
+            uint4 lo[UB], hi[UB];  // fp32: two float4 (as bits); bf16: lo only
+#pragma unroll
+            for (int b = 0; b < UB; ++b) {
+                const int ul = u0 + b * kThreads;
+                const int u = ul + rot < total ? ul + rot : ul + rot - total;
+                const int n = u / kgroups, kg = u - n * kgroups;
+                lo[b] = hi[b] = make_uint4(0u, 0u, 0u, 0u);
+                if (ul < total && n < nrows && kg * 8 < a.K) {
+                    const int64_t e = (int64_t)(n0 + n) * a.K + kg * 8;
+                    if (vec_ok) {
+                        if (f32) { lo[b] = ldg16(wf + e); hi[b] = ldg16(wf + e + 4); }
+                        else lo[b] = ldg16(wb + e);
+                    } else {
+                        float f[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            f[i] = kg * 8 + i < a.K ? (f32 ? __ldg(wf + e + i) : __bfloat162float(wb[e + i])) : 0.f;
+                        lo[b] = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+                        hi[b] = make_uint4(__float_as_uint(f[4]), __float_as_uint(f[5]), __float_as_uint(f[6]), __float_as_uint(f[7]));
+                    }
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < UB; ++b) {
+                const int ul = u0 + b * kThreads;
+                if (ul >= total) continue;
+                const int u = ul + rot < total ? ul + rot : ul + rot - total;
+                const int n = u / kgroups, kg = u - n * kgroups;
+                uint4 o = lo[b];
+                if (f32 || !vec_ok)
+                    o = make_uint4(pack_bf16x2(__uint_as_float(lo[b].x), __uint_as_float(lo[b].y)),
+                                   pack_bf16x2(__uint_as_float(lo[b].z), __uint_as_float(lo[b].w)),
+                                   pack_bf16x2(__uint_as_float(hi[b].x), __uint_as_float(hi[b].y)),
+                                   pack_bf16x2(__uint_as_float(hi[b].z), __uint_as_float(hi[b].w)));
+                *reinterpret_cast<uint4 *>(smem_w + (size_t)kg * a.w_lbo + (size_t)(n >> 3) * 128 + (n & 7) * 16) = o;
+            }
+        }
+    } else {
+        // buffer is [K, N]: unit = (k, group of 8 consecutive rows n); consecutive threads take consecutive k
+        const bool vec_ok = (a.N & 7) == 0;  // then n0 and the row groups are 8-aligned as well (Ncta % 8 == 0)
+        const int ngroups = rows8 >> 3, total = ngroups * a.Kpad;
+        const int rot = (int)(((int64_t)blockIdx.x * total) / gridDim.x);
+        for (int u0 = tid; u0 < total; u0 += UB * kThreads) {
+            uint4 lo[UB], hi[UB];
+#pragma unroll
+            for (int b = 0; b < UB; ++b) {
+                const int ul = u0 + b * kThreads;
+                const int u = ul + rot < total ? ul + rot : ul + rot - total;
+                const int ng = u / a.Kpad, k = u - ng * a.Kpad;
+                lo[b] = hi[b] = make_uint4(0u, 0u, 0u, 0u);
+                if (ul < total && k < a.K && ng * 8 < nrows) {
+                    const int64_t e = (int64_t)k * a.N + n0 + ng * 8;
+                    if (vec_ok) {  // rows beyond nrows inside the group belong to the next CTA or do not exist: masked below
+                        if (f32) { lo[b] = ldg16(wf + e); hi[b] = ldg16(wf + e + 4); }
+                        else lo[b] = ldg16(wb + e);
+                    } else {
+                        float f[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            f[i] = ng * 8 + i < nrows ? (f32 ? __ldg(wf + e + i) : __bfloat162float(wb[e + i])) : 0.f;
+                        lo[b] = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+                        hi[b] = make_uint4(__float_as_uint(f[4]), __float_as_uint(f[5]), __float_as_uint(f[6]), __float_as_uint(f[7]));
+                    }
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < UB; ++b) {
+                const int ul = u0 + b * kThreads;
+                if (ul >= total) continue;
+                const int u = ul + rot < total ? ul + rot : ul + rot - total;
+                const int ng = u / a.Kpad, k = u - ng * a.Kpad;
+                uint32_t w[4];  // 8 bf16 values: rows ng*8 .. ng*8+7 at column k
+                if (f32 || !vec_ok) {
+                    w[0] = pack_bf16x2(__uint_as_float(lo[b].x), __uint_as_float(lo[b].y));
+                    w[1] = pack_bf16x2(__uint_as_float(lo[b].z), __uint_as_float(lo[b].w));
+                    w[2] = pack_bf16x2(__uint_as_float(hi[b].x), __uint_as_float(hi[b].y));
+                    w[3] = pack_bf16x2(__uint_as_float(hi[b].z), __uint_as_float(hi[b].w));
+                } else {
+                    w[0] = lo[b].x; w[1] = lo[b].y; w[2] = lo[b].z; w[3] = lo[b].w;
+                }
+                unsigned short *d = reinterpret_cast<unsigned short *>(smem_w + (size_t)(k >> 3) * a.w_lbo + (size_t)ng * 128 + (k & 7) * 2);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const uint32_t v = (i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xffffu);
+                    d[i * 8] = (ng * 8 + i < nrows) ? (unsigned short)v : (unsigned short)0;
+                }
+            }
+        }
+    }
+}
 
 template <int PROD, int VEC>
 __global__ void __launch_bounds__(kThreads, 1) k_pw_conv(const PwArgs a) {
@@ -304,6 +420,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_conv(const PwArgs a) {
 
     // ---- one-time setup: barriers, TMEM, resident weight block --------------------------------------------------
     if (tid == 0) {
+        PW_TRACE(0);
         for (int i = 0; i < kMaxStages; ++i) {
             mbar_init(&hdr->full[i], kNumProdWarps);
             mbar_init(&hdr->empty[i], 1);
@@ -323,111 +440,73 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_conv(const PwArgs a) {
             smem_sb[k] = k < a.K ? a.a_sb[2 * k] : 0.f;
             smem_sb[a.Kpad + k] = k < a.K ? a.a_sb[2 * k + 1] : 0.f;
         }
+    stage_weights(a, smem_w, n0, nrows, tid);
+    fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = hdr->tmem_base;
+    if (tid == 0) PW_TRACE(2);
 
-    if (warp < kProdWarp0) {
-        // Resident weight block, staged by the MMA + epilogue warps while the producer warps already fetch activations.
-        // W[n, k] -> (k/8)*w_lbo + (n/8)*128 + (n%8)*16 + (k%8)*2 (K-major core matrices; w_lbo is an odd multiple of 16
-        // bytes so that the 8 k-groups written by a quarter warp land in 8 different bank groups).  Rows beyond the
-        // CTA's channels and columns k >= K are zero.  Thread order follows the contiguous axis of the weight buffer;
-        // four units per thread are in flight at a time.
-        constexpr int kWThreads = kProdWarp0 * 32;
-        const int kgroups = a.Kpad >> 3, rows8 = (a.Ncta + 7) & ~7, total = rows8 * kgroups;
-        const __nv_bfloat16 *wb = reinterpret_cast<const __nv_bfloat16 *>(a.w);
-        const float *wf = reinterpret_cast<const float *>(a.w);
-        const bool vec_ok = (a.K & 7) == 0 && !a.w_trans;
-        for (int u0 = tid; u0 < total; u0 += 4 * kWThreads) {
-            uint4 v[4];
-            float4 f0[4], f1[4];
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int u = u0 + b * kWThreads;
-                int kg, n;
-                if (a.w_trans) { kg = u / rows8; n = u - kg * rows8; }
-                else { n = u / kgroups; kg = u - n * kgroups; }
-                v[b] = make_uint4(0u, 0u, 0u, 0u);
-                f0[b] = f1[b] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (u < total && n < nrows) {
-                    const int64_t row = n0 + n;
-                    if (vec_ok) {
-                        if (kg * 8 < a.K) {
-                            if (a.w_dt == RB_BF16) {
-                                v[b] = ldg16(wb + row * a.K + kg * 8);
-                            } else {
-                                f0[b] = __ldg(reinterpret_cast<const float4 *>(wf + row * a.K + kg * 8));
-                                f1[b] = __ldg(reinterpret_cast<const float4 *>(wf + row * a.K + kg * 8 + 4));
-                            }
-                        }
-                    } else {
-                        float f[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const int k = kg * 8 + e;
-                            const int64_t idx = a.w_trans ? (int64_t)k * a.N + row : row * a.K + k;
-                            f[e] = k < a.K ? (a.w_dt == RB_BF16 ? __bfloat162float(wb[idx]) : __ldg(wf + idx)) : 0.f;
-                        }
-                        f0[b] = make_float4(f[0], f[1], f[2], f[3]);
-                        f1[b] = make_float4(f[4], f[5], f[6], f[7]);
-                    }
-                }
-            }
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int u = u0 + b * kWThreads;
-                if (u >= total) continue;
-                int kg, n;
-                if (a.w_trans) { kg = u / rows8; n = u - kg * rows8; }
-                else { n = u / kgroups; kg = u - n * kgroups; }
-                uint4 o = v[b];
-                if (!(vec_ok && a.w_dt == RB_BF16))
-                    o = make_uint4(pack_bf16x2(f0[b].x, f0[b].y), pack_bf16x2(f0[b].z, f0[b].w), pack_bf16x2(f1[b].x, f1[b].y),
-                                   pack_bf16x2(f1[b].z, f1[b].w));
-                *reinterpret_cast<uint4 *>(smem_w + (size_t)kg * a.w_lbo + (size_t)(n >> 3) * 128 + (n & 7) * 16) = o;
-            }
-        }
-        fence_proxy_async_smem();
-        asm volatile("bar.sync 1, %0;" ::"n"(kProdWarp0 * 32) : "memory");
-    }
+    if (tid == kProdWarp0 * 32) PW_TRACE(1);
 
     const int tile0 = blockIdx.x, tstride = gridDim.x;
     const int acc_cols = a.Mt * a.Npx;
 
     if (warp == 0) {
         // ===================================== MMA issuer ========================================================
-        if (lane == 0) {
-            const uint32_t idesc = instr_desc_bf16(128, a.Npx, /*weights K-major*/ 0, /*activations MN-major*/ 1);
-            const uint32_t a_base = smem_u32(smem_a), w_base = smem_u32(smem_w);
-            const int ksteps_per_stage = a.kstage >> 4;
-            int slot = 0;
-            uint32_t phase = 0;
-            int it = 0;
-            for (int tile = tile0; tile < a.total_tiles; tile += tstride, ++it) {
-                const int as = it % a.acc_stages;
-                const uint32_t aph = (uint32_t)(it / a.acc_stages) & 1u;
-                mbar_wait(&hdr->tmem_empty[as], aph ^ 1u);
+        // The whole warp runs the loop so that barrier phases, descriptors and TMEM addresses are warp-uniform values
+        // (uniform registers: tcgen05.mma takes its operands from them); one elected lane issues the instructions.
+        const bool leader = elect_one();
+        const uint32_t idesc = instr_desc_bf16(128, a.Npx, /*weights K-major*/ 0, /*activations MN-major*/ 1);
+        // descriptors advance by adding (bytes >> 4) to the start-address field (all addresses stay below 256 KiB)
+        const uint64_t adesc0 = smem_desc(smem_u32(smem_w), a.w_lbo, 128, LAYOUT_NONE);
+        const uint64_t bdesc0 = smem_desc(smem_u32(smem_a), a.a_lbo, 128, LAYOUT_NONE);
+        const uint32_t a_kstep = (2 * a.w_lbo) >> 4, b_kstep = (2 * a.a_lbo) >> 4;
+        const int ksteps_per_stage = a.kstage >> 4;
+        int slot = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int tile = tile0; tile < a.total_tiles; tile += tstride, ++it) {
+            const int as = it % a.acc_stages;
+            const uint32_t aph = (uint32_t)(it / a.acc_stages) & 1u;
+            const uint32_t tacc = tmem_base + as * acc_cols;
+            mbar_wait(&hdr->tmem_empty[as], aph ^ 1u);
+            tc_fence_after();
+            if (leader && it < 7) PW_TRACE(8 + it * 8);
+            uint64_t adesc_st = adesc0;  // weights: first k-group of the current stage
+            for (int st = 0; st < a.k_stages; ++st) {
+                mbar_wait(&hdr->full[slot], phase);
                 tc_fence_after();
-                for (int st = 0; st < a.k_stages; ++st) {
-                    mbar_wait(&hdr->full[slot], phase);
-                    tc_fence_after();
-                    const int ksteps = min(ksteps_per_stage, (a.Kpad - st * a.kstage) >> 4);
-                    for (int ks = 0; ks < ksteps; ++ks) {
-                        const uint64_t bdesc = smem_desc(a_base + slot * kStageBytes + ks * 2 * a.a_lbo, a.a_lbo, 128, LAYOUT_NONE);
-                        const int kg = ((st * a.kstage) >> 3) + ks * 2;
-                        for (int mt = 0; mt < a.Mt; ++mt) {
-                            const uint64_t adesc = smem_desc(w_base + kg * a.w_lbo + mt * 2048, a.w_lbo, 128, LAYOUT_NONE);
-                            mma_bf16(tmem_base + as * acc_cols + mt * a.Npx, adesc, bdesc, idesc, (st | ks) ? 1u : 0u);
+                if (leader && it < 7 && st == 0) PW_TRACE(9 + it * 8);
+                if (leader && it < 7 && st == a.k_stages - 1) PW_TRACE(10 + it * 8);
+                const int ksteps = min(ksteps_per_stage, (a.Kpad - st * a.kstage) >> 4);
+                uint64_t bdesc = bdesc0 + (uint64_t)((slot * kStageBytes) >> 4);
+                uint64_t adesc_k = adesc_st;
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    uint64_t adesc = adesc_k;
+                    uint32_t tcol = tacc;
+                    const bool first = (st | ks) == 0;
+                    for (int mt = 0; mt < a.Mt; ++mt, adesc += 2048 >> 4, tcol += a.Npx) {
+                        if (leader) {
+                            if (first) mma_bf16_first(tcol, adesc, bdesc, idesc);
+                            else mma_bf16_acc(tcol, adesc, bdesc, idesc);
                         }
                     }
-                    mma_commit(&hdr->empty[slot]);
-                    if (++slot == a.stages) { slot = 0; phase ^= 1u; }
+                    adesc_k += a_kstep;
+                    bdesc += b_kstep;
                 }
-                mma_commit(&hdr->tmem_full[as]);
+                adesc_st += (uint64_t)ksteps_per_stage * a_kstep;
+                if (leader) mma_commit(&hdr->empty[slot]);
+                __syncwarp();
+                if (++slot == a.stages) { slot = 0; phase ^= 1u; }
             }
+            if (leader) {
+                mma_commit(&hdr->tmem_full[as]);
+                if (it < 7) PW_TRACE(4 + it * 8);
+            }
+            __syncwarp();
         }
-        __syncwarp();
     } else if (warp < kProdWarp0) {
         // ===================================== epilogue ==========================================================
         // warp -> TMEM lane quarter (hardware: warp id % 4) and one half of the tile's pixel columns
@@ -441,6 +520,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_conv(const PwArgs a) {
             const int P0 = tile * a.Npx;  // first position of the tile on the flattened (image, pixel) axis
             mbar_wait(&hdr->tmem_full[as], aph);
             tc_fence_after();
+            if (tid == kEpiWarp0 * 32 && it < 7) PW_TRACE(5 + it * 8);
             for (int mt = 0; mt < a.Mt; ++mt) {
                 if (mt * 128 + q * 32 >= nrows) break;  // whole warp beyond the CTA's channels (warp-uniform)
                 const int r0 = mt * 128 + q * 32;       // first CTA-local channel of this warp's 32 TMEM lanes
@@ -491,6 +571,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_conv(const PwArgs a) {
             __syncwarp();
             tc_fence_before();
             mbar_arrive(&hdr->tmem_empty[as]);
+            if (tid == kEpiWarp0 * 32 && it < 7) PW_TRACE(6 + it * 8);
         }
     } else {
         // ===================================== activation producers ==============================================
@@ -563,6 +644,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_conv(const PwArgs a) {
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&hdr->full[slot]);
+                    if (tid == kProdWarp0 * 32 && st == a.k_stages - 1 && (tile - tile0) / tstride < 7) PW_TRACE(7 + ((tile - tile0) / tstride) * 8);
                     advance(tile, st);
                     if (++slot == a.stages) { slot = 0; phase ^= 1u; }
                 }
@@ -655,6 +737,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_conv(const PwArgs a) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (tid == 0) PW_TRACE(3);
     if (warp == 0) {
         __syncwarp();
         tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
@@ -690,10 +773,17 @@ bool plan(PwArgs &a, int prod, dim3 *grid, size_t *smem_bytes) {
     }
     if (!gy) return false;
     a.Npx = (2 * a.Mt * 128 <= 512) ? 128 : 64;
+    a.acc_stages = 2;
+    if (const char *dbg = getenv("RB_PW_NPX")) {  // experiment: wider pixel tile with a single accumulator stage
+        const int npx = atoi(dbg);
+        if ((npx == 64 || npx == 128) && a.Mt * npx <= 512) {
+            a.Npx = npx;
+            a.acc_stages = (2 * a.Mt * npx <= 512) ? 2 : 1;
+        }
+    }
     a.kstage = kStageBytes / 2 / a.Npx;
     a.a_lbo = (uint32_t)a.Npx * 16;
     a.k_stages = cdiv(a.Kpad, a.kstage);
-    a.acc_stages = 2;
     int cols = 32;
     while (cols < a.acc_stages * a.Mt * a.Npx) cols <<= 1;
     a.tmem_cols = cols;
@@ -744,6 +834,8 @@ template <int PROD> int launch_vec(const PwArgs &a, dim3 grid, size_t smem_bytes
 constexpr int kWgMaxStages = 4;
 constexpr int kWgChunk = 64;             // pixels per stage
 constexpr int kWgTileBytes = 128 * 128;  // one 128-row operand tile
+constexpr int kWgProdWarps = kNumEpiWarps + kNumProdWarps;  // the epilogue warps also produce during the main loop
+constexpr int kWgProdThreads = kWgProdWarps * 32;
 
 struct WgArgs {
     const __nv_bfloat16 *g;  // [NI, M, HW]
@@ -785,7 +877,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_wgrad(const WgArgs a) {
 
     if (tid == 0) {
         for (int i = 0; i < kWgMaxStages; ++i) {
-            mbar_init(&hdr->full[i], kNumProdWarps);
+            mbar_init(&hdr->full[i], kWgProdWarps);
             mbar_init(&hdr->empty[i], 1);
         }
         mbar_init(&hdr->tmem_full, 1);
@@ -806,61 +898,44 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_wgrad(const WgArgs a) {
     const uint32_t tmem_base = hdr->tmem_base;
 
     if (warp == 0) {
-        if (lane == 0) {
-            const uint32_t idesc = instr_desc_bf16(128, a.sub_n, 0, 0);
-            const uint32_t sbase = smem_u32(stage0);
-            int slot = 0;
-            uint32_t phase = 0, acc = 0;
-            for (int q = c_begin; q < c_end; ++q) {
-                const int pc = q % a.cpi;
-                const int kvalid = min(kWgChunk, a.HW - pc * kWgChunk);
-                const int ksteps = (kvalid + 15) >> 4;
-                mbar_wait(&hdr->full[slot], phase);
-                tc_fence_after();
-                const uint32_t abase = sbase + slot * a.stage_bytes, bbase = abase + a.Mt * kWgTileBytes;
-                for (int ks = 0; ks < ksteps; ++ks) {
-                    for (int mt = 0; mt < a.Mt; ++mt) {
-                        const uint64_t adesc = smem_desc(abase + mt * kWgTileBytes + ks * 32, 16, 1024, LAYOUT_SW128);
-                        for (int j = 0; j < a.n_sub; ++j) {
-                            const uint64_t bdesc = smem_desc(bbase + j * a.sub_n * 128 + ks * 32, 16, 1024, LAYOUT_SW128);
-                            mma_bf16(tmem_base + mt * a.Nc + j * a.sub_n, adesc, bdesc, idesc, acc);
+        // whole warp runs the loop (warp-uniform descriptors), one elected lane issues
+        const bool leader = elect_one();
+        const uint32_t idesc = instr_desc_bf16(128, a.sub_n, 0, 0);
+        const uint64_t desc0 = smem_desc(smem_u32(stage0), 16, 1024, LAYOUT_SW128);
+        int slot = 0;
+        uint32_t phase = 0;
+        bool first = true;
+        for (int q = c_begin; q < c_end; ++q) {
+            const int pc = q % a.cpi;
+            const int kvalid = min(kWgChunk, a.HW - pc * kWgChunk);
+            const int ksteps = (kvalid + 15) >> 4;
+            mbar_wait(&hdr->full[slot], phase);
+            tc_fence_after();
+            const uint64_t adesc_s = desc0 + (uint64_t)((slot * a.stage_bytes) >> 4);
+            const uint64_t bdesc_s = adesc_s + (uint64_t)((a.Mt * kWgTileBytes) >> 4);
+            for (int ks = 0; ks < ksteps; ++ks) {
+                uint64_t adesc = adesc_s + (uint64_t)(ks * 2);  // 32 bytes per K step inside the 128-byte swizzle atom
+                uint32_t tcol = tmem_base;
+                for (int mt = 0; mt < a.Mt; ++mt, adesc += kWgTileBytes >> 4) {
+                    uint64_t bdesc = bdesc_s + (uint64_t)(ks * 2);
+                    for (int j = 0; j < a.n_sub; ++j, bdesc += (a.sub_n * 128) >> 4, tcol += a.sub_n) {
+                        if (leader) {
+                            if (first) mma_bf16_first(tcol, adesc, bdesc, idesc);
+                            else mma_bf16_acc(tcol, adesc, bdesc, idesc);
                         }
                     }
-                    acc = 1u;
                 }
-                mma_commit(&hdr->empty[slot]);
-                if (++slot == a.stages) { slot = 0; phase ^= 1u; }
+                first = false;
             }
-            mma_commit(&hdr->tmem_full);
+            if (leader) mma_commit(&hdr->empty[slot]);
+            __syncwarp();
+            if (++slot == a.stages) { slot = 0; phase ^= 1u; }
         }
+        if (leader) mma_commit(&hdr->tmem_full);
         __syncwarp();
-    } else if (warp < kProdWarp0) {
-        // epilogue: warp -> TMEM lane quarter + every other 16-column chunk; fp32 partial slice of this pixel split
-        const int q4 = warp & 3, half = (warp - kEpiWarp0) >> 2, row = q4 * 32 + lane;
-        mbar_wait(&hdr->tmem_full, 0);
-        tc_fence_after();
-        float *dst = a.partial + (int64_t)blockIdx.x * a.M * a.N;
-        const int nchunks = (nrows + 15) >> 4;
-        for (int mt = 0; mt < a.Mt; ++mt) {
-            const int ml = mt * 128 + row;
-            const bool valid = ml < mrows;
-            const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + mt * a.Nc;
-            for (int ci = half; ci < nchunks; ci += 2) {
-                const int c0 = ci * 16;
-                uint32_t v[16];
-                __syncwarp();
-                tmem_ld16(taddr + c0, v);
-                tmem_ld_wait();
-                if (valid) {
-                    float *o = dst + (int64_t)(m0 + ml) * a.N + n0 + c0;
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (c0 + j < nrows) o[j] = __uint_as_float(v[j]);
-                }
-            }
-        }
     } else {
-        const int pt = tid - kProdWarp0 * 32, pw = pt >> 5;
+        // all 16 non-MMA warps build the operand stages; warps 1-8 drain the accumulators afterwards
+        const int pt = tid - 32, pw = pt >> 5;
         // operand rows loaded verbatim: G always, x unless it goes through the shift gather
         const int unit_rows = (PROD == PROD_SHIFT3D) ? mrows : mrows + nrows;
         const int total_units = unit_rows * 8;
@@ -875,11 +950,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_wgrad(const WgArgs a) {
             const int nchunks16 = ((kvalid + 15) >> 4) * 2;  // 16-byte chunks the MMAs of this stage will read
             mbar_wait(&hdr->empty[slot], phase ^ 1u);
             unsigned char *abase = stage0 + (size_t)slot * a.stage_bytes, *bbase = abase + (size_t)a.Mt * kWgTileBytes;
-            for (int u0 = pt; u0 < total_units; u0 += 8 * kProdThreads) {
+            for (int u0 = pt; u0 < total_units; u0 += 8 * kWgProdThreads) {
                 uint32_t r[8][4];
 #pragma unroll
                 for (int b = 0; b < 8; ++b) {
-                    const int u = u0 + b * kProdThreads;
+                    const int u = u0 + b * kWgProdThreads;
                     const int rowi = u >> 3, c = u & 7;
                     r[b][0] = r[b][1] = r[b][2] = r[b][3] = 0u;
                     if (u < total_units && c < nchunks16) {
@@ -895,7 +970,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_wgrad(const WgArgs a) {
                 }
 #pragma unroll
                 for (int b = 0; b < 8; ++b) {
-                    const int u = u0 + b * kProdThreads;
+                    const int u = u0 + b * kWgProdThreads;
                     const int rowi = u >> 3, c = u & 7;
                     if (u < total_units && c < nchunks16) {
                         unsigned char *d = (rowi < mrows) ? abase + (rowi >> 7) * kWgTileBytes + sw128_off(rowi & 127, c)
@@ -911,7 +986,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_wgrad(const WgArgs a) {
                 const int h0 = p0 / a.W, h1 = (pend - 1) / a.W;
                 const int g0 = h0 * rpr + ((p0 - h0 * a.W) >> 3), g1 = h1 * rpr + ((pend - 1 - h1 * a.W) >> 3);
                 const int kq = lane & 7, mgq = lane >> 3;
-                for (int rb = pw * 8 + kq; rb < nrows; rb += 64) {
+                for (int rb = pw * 8 + kq; rb < nrows; rb += 8 * kWgProdWarps) {
                     const int k = n0 + rb;
                     const ShiftCh ch = shift_channel(ssrc, k, clip, t);
                     unsigned char *brow = bbase + (rb >> 3) * 1024 + (rb & 7) * 128;
@@ -965,6 +1040,32 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_wgrad(const WgArgs a) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&hdr->full[slot]);
             if (++slot == a.stages) { slot = 0; phase ^= 1u; }
+        }
+        if (warp < kProdWarp0) {
+            // epilogue: warp -> TMEM lane quarter + every other 16-column chunk; fp32 partial slice of this pixel split
+            const int q4 = warp & 3, half = (warp - kEpiWarp0) >> 2, row = q4 * 32 + lane;
+            mbar_wait(&hdr->tmem_full, 0);
+            tc_fence_after();
+            float *dst = a.partial + (int64_t)blockIdx.x * a.M * a.N;
+            const int nchunks = (nrows + 15) >> 4;
+            for (int mt = 0; mt < a.Mt; ++mt) {
+                const int ml = mt * 128 + row;
+                const bool valid = ml < mrows;
+                const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + mt * a.Nc;
+                for (int ci = half; ci < nchunks; ci += 2) {
+                    const int c0 = ci * 16;
+                    uint32_t v[16];
+                    __syncwarp();
+                    tmem_ld16(taddr + c0, v);
+                    tmem_ld_wait();
+                    if (valid) {
+                        float *o = dst + (int64_t)(m0 + ml) * a.N + n0 + c0;
+    #pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (c0 + j < nrows) o[j] = __uint_as_float(v[j]);
+                    }
+                }
+            }
         }
     }
 
@@ -1053,12 +1154,16 @@ template <int PROD> int wg_launch_vec(const WgArgs &a, dim3 grid, size_t smem_by
 
 }  // namespace
 
+static unsigned long long *g_pw_trace = nullptr;
+void pw_conv_set_trace(void *p) { g_pw_trace = (unsigned long long *)p; }
+
 int pw_conv_forward(const void *x, const void *w, int w_dt, int w_trans, const void *residual, void *out, int NI, int K,
                     int N, int HW, const float *a_sb, const void *shift, int shift_dt, int T, int H, int W, cudaStream_t s) {
     PwArgs a{};
     a.x = (const __nv_bfloat16 *)x; a.w = w; a.w_dt = w_dt; a.w_trans = w_trans; a.res = (const __nv_bfloat16 *)residual;
     a.out = (__nv_bfloat16 *)out; a.a_sb = a_sb; a.shift = shift; a.shift_dt = shift_dt;
     a.T = T; a.H = H; a.W = W; a.NI = NI; a.K = K; a.N = N; a.HW = HW;
+    a.trace = g_pw_trace;
     const int prod = shift ? PROD_SHIFT3D : (a_sb ? PROD_BNRELU : PROD_PLAIN);
     dim3 grid;
     size_t smem_bytes = 0;

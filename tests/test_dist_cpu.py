@@ -34,8 +34,9 @@ def _worker(rank, world, port, out):
     red.zero_grad()
     # equal shard sizes => mean of shard-mean losses == full-batch mean loss
     nn.functional.cross_entropy(net(x[lo:hi]), y[lo:hi]).backward()
-    assert red.check_aliasing()
+    assert not red.check_aliasing()
     red.all_reduce()
+    assert red.check_aliasing()
     if rank == 0:
         torch.save(red.flat.clone(), out)
     dist.barrier()

@@ -1,0 +1,57 @@
+"""Pipeline timeline of one k_pw_conv launch (debug): per-CTA globaltimer stamps of setup / weights / per-tile
+producer-done, MMA-issued, epilogue start/end.   python tools/trace_pw.py [--C 288 --H 14 --batch 32 --mode fwd]"""
+import argparse
+import ctypes
+import os
+import sys
+
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+from rubiksnet_b200 import _lib, ops  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--C", type=int, default=288)
+    ap.add_argument("--H", type=int, default=14)
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--mode", default="fwd")
+    a = ap.parse_args()
+    L = _lib.lib()
+    L.rb_debug_pw_trace.argtypes = [ctypes.c_void_p]
+    L.rb_debug_pw_trace.restype = None
+    ni = a.batch * 8
+    x = torch.randn(ni, a.C, a.H, a.H, device="cuda").bfloat16()
+    w = torch.randn(a.C, a.C, device="cuda") / a.C ** 0.5
+    sb = torch.stack([torch.rand(a.C, device="cuda") + 0.5, torch.randn(a.C, device="cuda")], dim=1).contiguous()
+    fn = {"fwd": lambda: ops.pw_conv(x, w), "bn": lambda: ops.pw_conv(x, w, in_scale_bias=sb),
+          "dgrad": lambda: ops.pw_conv(x, w, transposed=True)}[a.mode]
+    for _ in range(3):
+        fn()
+    trace = torch.zeros(148 * 4 * 64, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    L.rb_debug_pw_trace(ctypes.c_void_p(trace.data_ptr()))
+    fn()
+    torch.cuda.synchronize()
+    L.rb_debug_pw_trace(None)
+    t = trace.view(-1, 64).cpu()
+    t = t[t[:, 0] > 0]
+    t0 = int(t[:, 0].min())
+    names = {0: "start", 1: "setup-done(prod)", 2: "weights-staged", 3: "end"}
+    print("CTAs traced:", t.shape[0], " kernel span %.1f us" % ((int(t[:, 3].max()) - t0) / 1e3))
+    for cta in (0, 1, t.shape[0] // 2, t.shape[0] - 1):
+        r = t[cta]
+        print("CTA %d:" % cta, " ".join("%s=%.1f" % (names[i], (int(r[i]) - t0) / 1e3) for i in (0, 1, 2, 3)))
+        for it in range(7):
+            ev = [int(r[4 + it * 8 + j]) for j in range(8)]
+            if not any(ev):
+                break
+            f = lambda v: "%.1f" % ((v - t0) / 1e3) if v else "-"
+            print("   tile %d: mma-start %s  stage0-full %s  last-stage-full %s  mma-issued %s | producer(w0)-done %s | epi-start %s  epi-end %s" % (
+                it, f(ev[4]), f(ev[5]), f(ev[6]), f(ev[0]), f(ev[3]), f(ev[1]), f(ev[2])))
+
+
+if __name__ == "__main__":
+    main()
