@@ -37,10 +37,12 @@ namespace {
 constexpr int kEpiWarp0 = 1;
 constexpr int kNumEpiWarps = 8;
 constexpr int kProdWarp0 = kEpiWarp0 + kNumEpiWarps;  // 9
-constexpr int kNumProdWarps = 8;
+constexpr int kNumProdWarps = 8;                             // gather (3D shift) producers, weight-gradient kernel
 constexpr int kThreads = (kProdWarp0 + kNumProdWarps) * 32;  // 544
-constexpr int kStageBytes = 16384;  // activation stage: Npx pixels x (8192 / Npx) channels
-constexpr int kMaxStages = 6;
+constexpr int kRowProdWarps = 7;                             // plain / BN+ReLU producers of k_pw_conv: 16 warps = 512 threads,
+constexpr int kRowThreads = (kProdWarp0 + kRowProdWarps) * 32;  // so that a thread may use up to 128 registers
+constexpr int kStageBytes = 16384;  // largest activation stage: Npx pixels x (8192 / Npx) channels
+constexpr int kMaxStages = 12;
 constexpr int kSmemLimit = 227 * 1024;
 constexpr int kHdrBytes = 256;
 constexpr int kStgBytes = kNumEpiWarps * 2048;  // epilogue staging: 32 channels x 64 B per warp
@@ -127,6 +129,27 @@ __device__ __forceinline__ void load_unit_flat(const __nv_bfloat16 *base, int of
             const uint32_t lo = (nleft > 2 * h) ? ldg2(base + off + o[2 * h]) : 0u;
             const uint32_t hi = (nleft > 2 * h + 1) ? ldg2(base + off + o[2 * h + 1]) : 0u;
             r[h] = lo | (hi << 16);
+        }
+    }
+}
+
+// the same unit, global -> shared (16 bytes at `dst`) with cp.async; pieces at or beyond `nleft` positions are zero-filled
+template <int VEC>
+__device__ __forceinline__ void cp_unit_flat(uint32_t dst, const __nv_bfloat16 *base, int off, const int (&o)[8 / VEC], int nleft) {
+    if (VEC == 8) {
+        const bool ok = nleft >= 8;
+        cp_async16(dst, ok ? base + off : base, ok ? 16u : 0u);
+    } else if (VEC == 4) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const bool ok = nleft >= 4 * h + 4;
+            cp_async8(dst + 8 * h, ok ? base + off + o[h] : base, ok ? 8u : 0u);
+        }
+    } else {
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            const bool ok = nleft >= 2 * h + 2;
+            cp_async4(dst + 4 * h, ok ? base + off + o[(VEC == 2) ? h : 0] : base, ok ? 4u : 0u);
         }
     }
 }
@@ -277,10 +300,12 @@ struct PwArgs {
     int shift_dt;
     int T, H, W;               // PROD_SHIFT3D: frames per clip, map size (HW = H*W)
     int NI, K, N, HW;
-    int Kpad, Ncta, Mt, Npx, kstage, acc_stages, stages, tmem_cols;
+    int Kpad, Ncta, Mt, Npx, kstage, acc_stages, stages, tmem_cols, stage_bytes, upt;
     int NP, total_tiles, k_stages;  // NP = NI*HW positions on the flattened (image, pixel) axis, tiled by Npx
     uint32_t off_w, off_a, off_sb, off_stg, w_lbo, a_lbo;
+    int b_rows;                // activation operand staged as 128-byte-swizzled pixel rows (cp.async path) instead of 8x16-byte core matrices
     uint32_t rpr, rpr_magic;   // runs of 8 columns per image row; (r * rpr_magic) >> 16 == r / rpr for r < 4096
+    int dbg;                   // debug: bit0 producers skip the global loads, bit1 epilogue skips global traffic, bit2 no MMAs
     unsigned long long *trace; // debug: per-CTA event timestamps (globaltimer ns), 64 slots per CTA; null = off
 };
 
@@ -289,7 +314,8 @@ __device__ __forceinline__ unsigned long long gtime() {
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
-#define PW_TRACE(slot) do { if (a.trace) a.trace[(blockIdx.y * gridDim.x + blockIdx.x) * 64 + (slot)] = gtime(); } while (0)
+#define PW_TRACE_IF(cond, slot) do { if (a.trace) { if (cond) a.trace[(blockIdx.y * gridDim.x + blockIdx.x) * 128 + (slot)] = gtime(); } } while (0)
+#define PW_TRACE(slot) do { if (a.trace) a.trace[(blockIdx.y * gridDim.x + blockIdx.x) * 128 + (slot)] = gtime(); } while (0)
 
 struct Hdr {
     uint64_t full[kMaxStages], empty[kMaxStages], tmem_full[2], tmem_empty[2];
@@ -305,7 +331,7 @@ static_assert(sizeof(Hdr) <= kHdrBytes, "header");
 // units in flight each, and every CTA starts at a different offset so that the grid does not walk the same L2 lines in
 // lockstep.
 __device__ __forceinline__ void stage_weights(const PwArgs &a, unsigned char *smem_w, int n0, int nrows, int tid) {
-    const int kgroups = a.Kpad >> 3, rows8 = (a.Ncta + 7) & ~7;
+    const int kgroups = a.Kpad >> 3, rows8 = (a.Ncta + 7) & ~7, nthreads = (int)blockDim.x;
     const __nv_bfloat16 *wb = reinterpret_cast<const __nv_bfloat16 *>(a.w);
     const float *wf = reinterpret_cast<const float *>(a.w);
     const bool f32 = a.w_dt != RB_BF16;
@@ -314,11 +340,11 @@ __device__ __forceinline__ void stage_weights(const PwArgs &a, unsigned char *sm
         const bool vec_ok = (a.K & 7) == 0;
         const int total = rows8 * kgroups;
         const int rot = (int)(((int64_t)blockIdx.x * total) / gridDim.x);
-        for (int u0 = tid; u0 < total; u0 += UB * kThreads) {
+        for (int u0 = tid; u0 < total; u0 += UB * nthreads) {
             uint4 lo[UB], hi[UB];  // fp32: two float4 (as bits); bf16: lo only
 #pragma unroll
             for (int b = 0; b < UB; ++b) {
-                const int ul = u0 + b * kThreads;
+                const int ul = u0 + b * nthreads;
                 const int u = ul + rot < total ? ul + rot : ul + rot - total;
                 const int n = u / kgroups, kg = u - n * kgroups;
                 lo[b] = hi[b] = make_uint4(0u, 0u, 0u, 0u);
@@ -339,7 +365,7 @@ __device__ __forceinline__ void stage_weights(const PwArgs &a, unsigned char *sm
             }
 #pragma unroll
             for (int b = 0; b < UB; ++b) {
-                const int ul = u0 + b * kThreads;
+                const int ul = u0 + b * nthreads;
                 if (ul >= total) continue;
                 const int u = ul + rot < total ? ul + rot : ul + rot - total;
                 const int n = u / kgroups, kg = u - n * kgroups;
@@ -357,11 +383,11 @@ __device__ __forceinline__ void stage_weights(const PwArgs &a, unsigned char *sm
         const bool vec_ok = (a.N & 7) == 0;  // then n0 and the row groups are 8-aligned as well (Ncta % 8 == 0)
         const int ngroups = rows8 >> 3, total = ngroups * a.Kpad;
         const int rot = (int)(((int64_t)blockIdx.x * total) / gridDim.x);
-        for (int u0 = tid; u0 < total; u0 += UB * kThreads) {
+        for (int u0 = tid; u0 < total; u0 += UB * nthreads) {
             uint4 lo[UB], hi[UB];
 #pragma unroll
             for (int b = 0; b < UB; ++b) {
-                const int ul = u0 + b * kThreads;
+                const int ul = u0 + b * nthreads;
                 const int u = ul + rot < total ? ul + rot : ul + rot - total;
                 const int ng = u / a.Kpad, k = u - ng * a.Kpad;
                 lo[b] = hi[b] = make_uint4(0u, 0u, 0u, 0u);
@@ -382,7 +408,7 @@ __device__ __forceinline__ void stage_weights(const PwArgs &a, unsigned char *sm
             }
 #pragma unroll
             for (int b = 0; b < UB; ++b) {
-                const int ul = u0 + b * kThreads;
+                const int ul = u0 + b * nthreads;
                 if (ul >= total) continue;
                 const int u = ul + rot < total ? ul + rot : ul + rot - total;
                 const int ng = u / a.Kpad, k = u - ng * a.Kpad;
@@ -406,8 +432,69 @@ __device__ __forceinline__ void stage_weights(const PwArgs &a, unsigned char *sm
     }
 }
 
+// MMA issue loop of k_pw_conv, run by one thread.  Per stage: wait for the producers, issue ksteps x MT instructions
+// (128 channels x Npx pixels x 16 input channels each), commit to the stage's `empty` barrier.
+template <int MT>
+__device__ __forceinline__ void mma_loop(const PwArgs &a, Hdr *hdr, unsigned char *smem_w, unsigned char *smem_a,
+                                         uint32_t tmem_base, int tile0, int tstride) {
+    const uint32_t idesc = instr_desc_bf16(128, a.Npx, /*weights K-major*/ 0, /*activations MN-major*/ 1);
+    const uint64_t adesc0 = smem_desc(smem_u32(smem_w), a.w_lbo, 128, LAYOUT_NONE);
+    // activations, MN-major.  Row layout: per 8-channel group 8 rows of 64 pixels (128 bytes, 16-byte chunks XOR-swizzled
+    // by the row), groups 1 KiB apart (SBO), the second 64-pixel half of a 128-pixel tile (kstage/8) KiB further (LBO)
+    const uint64_t bdesc0 = a.b_rows ? smem_desc(smem_u32(smem_a), (uint32_t)(a.kstage >> 3) * 1024u, 1024, LAYOUT_SW128)
+                                     : smem_desc(smem_u32(smem_a), a.a_lbo, 128, LAYOUT_NONE);
+    const uint32_t a_hi = (uint32_t)(adesc0 >> 32), b_hi = (uint32_t)(bdesc0 >> 32);
+    const uint32_t a_lo0 = (uint32_t)adesc0, b_lo0 = (uint32_t)bdesc0;
+    // descriptors advance by adding (bytes >> 4) to the start-address field (all addresses stay below 256 KiB)
+    const uint32_t a_kstep = (2 * a.w_lbo) >> 4, b_kstep = a.b_rows ? (2048u >> 4) : (2 * a.a_lbo) >> 4;
+    const int ksteps_per_stage = a.kstage >> 4;
+    const int acc_cols = a.Mt * a.Npx;
+    const uint32_t npx = (uint32_t)a.Npx, stage16 = (uint32_t)(a.stage_bytes >> 4);
+    const bool skip = (a.dbg & 4) != 0;
+    int slot = 0, it = 0;
+    uint32_t phase = 0;
+    for (int tile = tile0; tile < a.total_tiles; tile += tstride, ++it) {
+        const int as = it % a.acc_stages;
+        const uint32_t aph = (uint32_t)(it / a.acc_stages) & 1u;
+        const uint32_t tacc = tmem_base + as * acc_cols;
+        mbar_wait(&hdr->tmem_empty[as], aph ^ 1u);
+        tc_fence_after();
+        PW_TRACE_IF(it < 7, 8 + it * 8);
+        uint32_t a_lo = a_lo0;  // weights: first k-group of the current stage
+        uint32_t acc = 0u;
+        int kleft = a.Kpad >> 4;
+        for (int st = 0; st < a.k_stages; ++st) {
+            mbar_wait(&hdr->full[slot], phase);
+            tc_fence_after();
+            PW_TRACE_IF(it == 2 && st < 8, 64 + st * 8);
+            PW_TRACE_IF(it < 7 && st == 0, 9 + it * 8);
+            PW_TRACE_IF(it < 7 && st == a.k_stages - 1, 10 + it * 8);
+            const int ksteps = min(ksteps_per_stage, kleft);
+            kleft -= ksteps;
+            uint32_t b_lo = b_lo0 + (uint32_t)slot * stage16;
+            if (!skip) {
+                for (int ks = 0; ks < ksteps; ++ks) {
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt)
+                        mma_bf16_lohi(tacc + mt * npx, a_lo + mt * (2048 >> 4), a_hi, b_lo, b_hi, idesc, acc);
+                    acc = 1u;
+                    a_lo += a_kstep;
+                    b_lo += b_kstep;
+                }
+            } else {
+                a_lo += ksteps * a_kstep;
+            }
+            mma_commit(&hdr->empty[slot]);
+            PW_TRACE_IF(it == 2 && st < 8, 65 + st * 8);
+            if (++slot == a.stages) { slot = 0; phase ^= 1u; }
+        }
+        mma_commit(&hdr->tmem_full[as]);
+        PW_TRACE_IF(it < 7, 4 + it * 8);
+    }
+}
+
 template <int PROD, int VEC>
-__global__ void __launch_bounds__(kThreads, 1) k_pw_conv(const PwArgs a) {
+__global__ void __launch_bounds__(PROD == PROD_SHIFT3D ? kThreads : kRowThreads, 1) k_pw_conv(const PwArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     Hdr *hdr = reinterpret_cast<Hdr *>(smem);
     unsigned char *smem_w = smem + a.off_w;
@@ -422,7 +509,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_conv(const PwArgs a) {
     if (tid == 0) {
         PW_TRACE(0);
         for (int i = 0; i < kMaxStages; ++i) {
-            mbar_init(&hdr->full[i], kNumProdWarps);
+            mbar_init(&hdr->full[i], a.b_rows ? 1 : kNumProdWarps);
             mbar_init(&hdr->empty[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
@@ -436,7 +523,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_conv(const PwArgs a) {
         tmem_alloc(&hdr->tmem_base, (uint32_t)a.tmem_cols);
     }
     if (PROD == PROD_BNRELU)
-        for (int k = tid; k < a.Kpad; k += kThreads) {
+        for (int k = tid; k < a.Kpad; k += (int)blockDim.x) {
             smem_sb[k] = k < a.K ? a.a_sb[2 * k] : 0.f;
             smem_sb[a.Kpad + k] = k < a.K ? a.a_sb[2 * k + 1] : 0.f;
         }
@@ -455,58 +542,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_conv(const PwArgs a) {
 
     if (warp == 0) {
         // ===================================== MMA issuer ========================================================
-        // The whole warp runs the loop so that barrier phases, descriptors and TMEM addresses are warp-uniform values
-        // (uniform registers: tcgen05.mma takes its operands from them); one elected lane issues the instructions.
-        const bool leader = elect_one();
-        const uint32_t idesc = instr_desc_bf16(128, a.Npx, /*weights K-major*/ 0, /*activations MN-major*/ 1);
-        // descriptors advance by adding (bytes >> 4) to the start-address field (all addresses stay below 256 KiB)
-        const uint64_t adesc0 = smem_desc(smem_u32(smem_w), a.w_lbo, 128, LAYOUT_NONE);
-        const uint64_t bdesc0 = smem_desc(smem_u32(smem_a), a.a_lbo, 128, LAYOUT_NONE);
-        const uint32_t a_kstep = (2 * a.w_lbo) >> 4, b_kstep = (2 * a.a_lbo) >> 4;
-        const int ksteps_per_stage = a.kstage >> 4;
-        int slot = 0;
-        uint32_t phase = 0;
-        int it = 0;
-        for (int tile = tile0; tile < a.total_tiles; tile += tstride, ++it) {
-            const int as = it % a.acc_stages;
-            const uint32_t aph = (uint32_t)(it / a.acc_stages) & 1u;
-            const uint32_t tacc = tmem_base + as * acc_cols;
-            mbar_wait(&hdr->tmem_empty[as], aph ^ 1u);
-            tc_fence_after();
-            if (leader && it < 7) PW_TRACE(8 + it * 8);
-            uint64_t adesc_st = adesc0;  // weights: first k-group of the current stage
-            for (int st = 0; st < a.k_stages; ++st) {
-                mbar_wait(&hdr->full[slot], phase);
-                tc_fence_after();
-                if (leader && it < 7 && st == 0) PW_TRACE(9 + it * 8);
-                if (leader && it < 7 && st == a.k_stages - 1) PW_TRACE(10 + it * 8);
-                const int ksteps = min(ksteps_per_stage, (a.Kpad - st * a.kstage) >> 4);
-                uint64_t bdesc = bdesc0 + (uint64_t)((slot * kStageBytes) >> 4);
-                uint64_t adesc_k = adesc_st;
-                for (int ks = 0; ks < ksteps; ++ks) {
-                    uint64_t adesc = adesc_k;
-                    uint32_t tcol = tacc;
-                    const bool first = (st | ks) == 0;
-                    for (int mt = 0; mt < a.Mt; ++mt, adesc += 2048 >> 4, tcol += a.Npx) {
-                        if (leader) {
-                            if (first) mma_bf16_first(tcol, adesc, bdesc, idesc);
-                            else mma_bf16_acc(tcol, adesc, bdesc, idesc);
-                        }
-                    }
-                    adesc_k += a_kstep;
-                    bdesc += b_kstep;
-                }
-                adesc_st += (uint64_t)ksteps_per_stage * a_kstep;
-                if (leader) mma_commit(&hdr->empty[slot]);
-                __syncwarp();
-                if (++slot == a.stages) { slot = 0; phase ^= 1u; }
+        // ONE elected thread runs the whole loop (barrier waits included): no divergence inside it, descriptors stepped
+        // with 32-bit adds, the M tiles of a K step unrolled at compile time.
+        if (elect_one()) {
+            switch (a.Mt) {
+                case 1: mma_loop<1>(a, hdr, smem_w, smem_a, tmem_base, tile0, tstride); break;
+                case 2: mma_loop<2>(a, hdr, smem_w, smem_a, tmem_base, tile0, tstride); break;
+                case 3: mma_loop<3>(a, hdr, smem_w, smem_a, tmem_base, tile0, tstride); break;
+                default: mma_loop<4>(a, hdr, smem_w, smem_a, tmem_base, tile0, tstride); break;
             }
-            if (leader) {
-                mma_commit(&hdr->tmem_full[as]);
-                if (it < 7) PW_TRACE(4 + it * 8);
-            }
-            __syncwarp();
         }
+        __syncwarp();
     } else if (warp < kProdWarp0) {
         // ===================================== epilogue ==========================================================
         // warp -> TMEM lane quarter (hardware: warp id % 4) and one half of the tile's pixel columns
@@ -520,58 +566,75 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_conv(const PwArgs a) {
             const int P0 = tile * a.Npx;  // first position of the tile on the flattened (image, pixel) axis
             mbar_wait(&hdr->tmem_full[as], aph);
             tc_fence_after();
-            if (tid == kEpiWarp0 * 32 && it < 7) PW_TRACE(5 + it * 8);
-            for (int mt = 0; mt < a.Mt; ++mt) {
-                if (mt * 128 + q * 32 >= nrows) break;  // whole warp beyond the CTA's channels (warp-uniform)
-                const int r0 = mt * 128 + q * 32;       // first CTA-local channel of this warp's 32 TMEM lanes
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * acc_cols + mt * a.Npx;
-                // rounds of 32 pixels: TMEM -> registers (thread = channel) -> bf16 -> per-warp staging tile in shared
-                // memory (32 channels x 64 B, 16-byte chunks XOR-swizzled) -> read back with 4 lanes per channel row, so
-                // every global access instruction touches 8 rows x 64 contiguous bytes instead of 32 rows x 16 bytes
-                for (int c0 = cbeg; c0 < cend && P0 + c0 < a.NP; c0 += 32) {
-                    uint32_t v[2][16];
-                    __syncwarp();
-                    tmem_ld16(taddr + c0, v[0]);
-                    tmem_ld16(taddr + c0 + 16, v[1]);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const uint32_t *vv = &v[c >> 1][(c & 1) * 8];
-                        *reinterpret_cast<uint4 *>(stg + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) =
-                            make_uint4(pack_bf16x2(__uint_as_float(vv[0]), __uint_as_float(vv[1])),
-                                       pack_bf16x2(__uint_as_float(vv[2]), __uint_as_float(vv[3])),
-                                       pack_bf16x2(__uint_as_float(vv[4]), __uint_as_float(vv[5])),
-                                       pack_bf16x2(__uint_as_float(vv[6]), __uint_as_float(vv[7])));
-                    }
-                    __syncwarp();
+            PW_TRACE_IF(tid == kEpiWarp0 * 32 && it < 7, 5 + it * 8);
+            // rounds of (32 channels = this warp's TMEM lanes of one M tile) x (32 pixels): TMEM -> registers (thread =
+            // channel) -> bf16 -> per-warp staging tile in shared memory (32 channels x 64 B, 16-byte chunks
+            // XOR-swizzled) -> read back with 4 lanes per channel row, so every global access instruction touches 8 rows
+            // x 64 contiguous bytes instead of 32 rows x 16 bytes.  The TMEM load of round r+1 is in flight while round r
+            // goes through shared memory, and the accumulator stage is released as soon as the last load has landed.
+            const int ncr = (cend - cbeg) >> 5;                                  // column rounds per M tile
+            const int mts = nrows > q * 32 ? (nrows - q * 32 + 127) >> 7 : 0;    // M tiles holding channels of this warp
+            int nr = mts * ncr;
+            // One loop body for every round (the three roles of the CTA share the instruction caches: a second inlined
+            // copy of this body, tried for a software-pipelined TMEM load, cost more than the overlap gained).
+            for (int ridx = 0; ridx < nr; ++ridx) {
+                const int mt = ridx / ncr, c0 = cbeg + (ridx - mt * ncr) * 32;
+                const int r0 = mt * 128 + q * 32;  // first CTA-local channel of this warp's 32 TMEM lanes
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * acc_cols + mt * a.Npx + c0;
+                uint32_t v[2][16];
+                __syncwarp();
+                tmem_ld16(taddr, v[0]);
+                tmem_ld16(taddr + 16, v[1]);
+                // this lane's four (channel row, 8 positions) pieces of the round: addresses first, and the residual
+                // loads go out while the accumulator is being fetched
+                int off[4], nv[4], po[8 / VEC];
+                uint32_t rv[4][4];
+                {
+                    const int P = P0 + c0 + (lane & 3) * 8;
+                    const int img = P / a.HW, pp = P - img * a.HW;
+                    piece_offsets<VEC>(pp, a.HW, (a.N - 1) * a.HW, po);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const int row = (lane >> 2) + 8 * i, ch = lane & 3;
-                        const uint4 sv = *reinterpret_cast<const uint4 *>(stg + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4));
-                        uint32_t ov[4] = {sv.x, sv.y, sv.z, sv.w};
-                        // this lane's 8 positions: image / pixel of the first one, then pieces that may wrap into the next image
-                        const int P = P0 + c0 + ch * 8;
-                        const int img = P / a.HW, pp = P - img * a.HW;
-                        const int nv = (r0 + row < nrows) ? a.NP - P : 0;
-                        const int off = ((img * a.N + n0 + r0 + row) * a.HW) + pp;
-                        int po[8 / VEC];
-                        piece_offsets<VEC>(pp, a.HW, (a.N - 1) * a.HW, po);
-                        if (a.res != nullptr) {
-                            // `out += shortcut` on the bf16 conv result (the rounding order of conv3 followed by the add)
-                            uint32_t t4[4];
-                            load_unit_flat<VEC>(a.res, off, po, nv, t4);
-#pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                ov[e] = pack_bf16x2(bf16_lo(ov[e]) + bf16_lo(t4[e]), bf16_hi(ov[e]) + bf16_hi(t4[e]));
-                        }
-                        store_unit_flat<VEC>(a.out, off, po, nv, ov);
+                        const int row = (lane >> 2) + 8 * i;
+                        nv[i] = (r0 + row < nrows && !(a.dbg & 2)) ? a.NP - P : 0;  // <= 0 beyond the tensor: nothing moves
+                        off[i] = ((img * a.N + n0 + r0 + row) * a.HW) + pp;
+                        if (a.res != nullptr) load_unit_flat<VEC>(a.res, off[i], po, nv[i], rv[i]);
                     }
                 }
+                tmem_ld_wait();
+                if (ridx == nr - 1) {  // every TMEM load of this tile has landed: hand the accumulator stage back
+                    tc_fence_before();
+                    mbar_arrive(&hdr->tmem_empty[as]);
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const uint32_t *vv = &v[c >> 1][(c & 1) * 8];
+                    *reinterpret_cast<uint4 *>(stg + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) =
+                        make_uint4(pack_bf16x2(__uint_as_float(vv[0]), __uint_as_float(vv[1])),
+                                   pack_bf16x2(__uint_as_float(vv[2]), __uint_as_float(vv[3])),
+                                   pack_bf16x2(__uint_as_float(vv[4]), __uint_as_float(vv[5])),
+                                   pack_bf16x2(__uint_as_float(vv[6]), __uint_as_float(vv[7])));
+                }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int row = (lane >> 2) + 8 * i, ch = lane & 3;
+                    const uint4 sv = *reinterpret_cast<const uint4 *>(stg + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4));
+                    uint32_t ov[4] = {sv.x, sv.y, sv.z, sv.w};
+                    if (a.res != nullptr) {
+                        // `out += shortcut` on the bf16 conv result (the rounding order of conv3 followed by the add)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            ov[e] = pack_bf16x2(bf16_lo(ov[e]) + bf16_lo(rv[i][e]), bf16_hi(ov[e]) + bf16_hi(rv[i][e]));
+                    }
+                    store_unit_flat<VEC>(a.out, off[i], po, nv[i], ov);
+                }
             }
-            __syncwarp();
-            tc_fence_before();
-            mbar_arrive(&hdr->tmem_empty[as]);
-            if (tid == kEpiWarp0 * 32 && it < 7) PW_TRACE(6 + it * 8);
+            if (nr == 0) {
+                tc_fence_before();
+                mbar_arrive(&hdr->tmem_empty[as]);
+            }
+            PW_TRACE_IF(tid == kEpiWarp0 * 32 && it < 7, 6 + it * 8);
         }
     } else {
         // ===================================== activation producers ==============================================
@@ -603,7 +666,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_conv(const PwArgs a) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int k = st * a.kstage + ukk[j];
-                if (k < a.K) {
+                if (j < a.upt && k < a.K) {
                     load_unit_flat<VEC>(a.x, offb + k * a.HW, po, nleft, r[j]);
                 } else {
                     r[j][0] = r[j][1] = r[j][2] = r[j][3] = 0u;
@@ -613,41 +676,121 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_conv(const PwArgs a) {
 
         int tile = tile0, st = 0, slot = 0;
         uint32_t phase = 0;
-        if (PROD != PROD_SHIFT3D) {
-            // register ring: the loads of the next kDepth-1 stages are in flight while one stage is written to shared memory
-            constexpr int kDepth = 4;
-            uint32_t buf[kDepth][4][4];
-            int ltile = tile0, lst = 0;  // load cursor, runs kDepth-1 stages ahead of (tile, st)
-            auto advance = [&](int &tl, int &s_) { if (++s_ == a.k_stages) { s_ = 0; tl += tstride; } };
-#pragma unroll
-            for (int d = 0; d < kDepth - 1; ++d) {
-                if (ltile < a.total_tiles) load_stage(ltile, lst, buf[d]);
-                advance(ltile, lst);
-            }
+        if constexpr (PROD != PROD_SHIFT3D) {
+            // One warp per stage: producer warp w owns stages w, w+8, ... and moves a whole 8 KiB stage through its
+            // registers (64 per lane): all loads of the stage are issued back to back, then -- once the MMA warp has
+            // released the slot -- stored into the operand layout.  A warp's loads share one scoreboard, so a warp can
+            // only wait for ALL of its outstanding loads; giving every warp exactly one stage in flight makes that the
+            // right wait, and the eight warps keep eight stages (64 KiB per SM) in flight regardless of the depth of the
+            // shared-memory ring.  BN+ReLU is applied to the registers.
+            //
+            // A stage holds kstage channel rows per 64-pixel half: rows of 128 bytes, 16-byte chunks XOR-swizzled by
+            // the row (MN-major SWIZZLE_128B operand).  A piece is PB = 2*VEC bytes of one row; the lanes of a warp
+            // cover whole rows (RPI rows per instruction), so global reads are contiguous 128-byte segments and the
+            // shared-memory stores are conflict free.
+            // VEC == 1 (odd plane sizes, 7x7): pieces of two pixels, fetched with two 2-byte loads that may lie in
+            // different images
+            constexpr int EPP = VEC == 1 ? 2 : VEC;  // elements per piece
+            constexpr int PB = 2 * EPP, PPR = 128 / PB, RPI = 32 / PPR, NPIECE = 8192 / (32 * PB), WPP = PB / 4;
+            const int pc = lane % PPR, rl = lane / PPR;  // piece column, row inside one instruction
+            const uint32_t smem_a_u32 = smem_u32(smem_a);
+            const uint32_t chunk = (uint32_t)(pc * PB) >> 4, sub = (uint32_t)(pc * PB) & 15u;
+            const uint32_t sb_u32 = smem_u32(smem_sb);
+            // stage cursor of this warp
+            // Only min(7, stages) warps take part: a warp waiting for the slot of stage m has stored stage m - W, so
+            // m < c + stages + W (c = stage the MMA warp is consuming); W <= stages keeps every waiter less than two
+            // ring rounds ahead of the consumer, which is what the one-bit mbarrier phase parity can tell apart.
+            const int W = a.stages < kRowProdWarps ? a.stages : kRowProdWarps;
+            int n = pw;  // global stage index
+            st = pw % a.k_stages;
+            tile = pw < W ? tile0 + (pw / a.k_stages) * tstride : a.total_tiles;
             while (tile < a.total_tiles) {
+                slot = n % a.stages;
+                phase = (uint32_t)(n / a.stages) & 1u;
+                // pixel column of this lane in each 64-pixel half of the tile
+                int offb[2], offb1[2];  // offb1 / pvalid1: second pixel of the piece (VEC == 1 only)
+                bool pvalid[2], pvalid1[2];
 #pragma unroll
-                for (int d = 0; d < kDepth; ++d) {
-                    if (tile >= a.total_tiles) break;
-                    if (ltile < a.total_tiles) load_stage(ltile, lst, buf[(d + kDepth - 1) % kDepth]);
-                    advance(ltile, lst);
-                    mbar_wait(&hdr->empty[slot], phase ^ 1u);
-                    unsigned char *sp = smem_a + (size_t)slot * kStageBytes;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (st * a.kstage + ukk[j] >= a.Kpad) continue;  // beyond the last K step: never read
-                        if (PROD == PROD_BNRELU) {  // applied only now: the loads of this stage had kDepth-1 stages to land
-                            const int k = st * a.kstage + ukk[j];
-                            if (k < a.K) bn_relu_unit(buf[d][j], smem_sb[k], smem_sb[a.Kpad + k], a.NP - tile * a.Npx - umg * 8);
-                        }
-                        *reinterpret_cast<uint4 *>(sp + usm[j]) = make_uint4(buf[d][j][0], buf[d][j][1], buf[d][j][2], buf[d][j][3]);
-                    }
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&hdr->full[slot]);
-                    if (tid == kProdWarp0 * 32 && st == a.k_stages - 1 && (tile - tile0) / tstride < 7) PW_TRACE(7 + ((tile - tile0) / tstride) * 8);
-                    advance(tile, st);
-                    if (++slot == a.stages) { slot = 0; phase ^= 1u; }
+                for (int hf = 0; hf < 2; ++hf) {
+                    const int P = tile * a.Npx + hf * 64 + pc * EPP;
+                    pvalid[hf] = hf * 64 < a.Npx && P < a.NP;
+                    const int img = P / a.HW, pp = P - img * a.HW;
+                    offb[hf] = img * a.K * a.HW + pp;
+                    pvalid1[hf] = hf * 64 < a.Npx && P + 1 < a.NP;
+                    offb1[hf] = pp + 1 < a.HW ? offb[hf] + 1 : (img + 1) * a.K * a.HW;
                 }
+                const int kbase = st * a.kstage;
+                uint32_t r[NPIECE][WPP];
+#pragma unroll
+                for (int i = 0; i < NPIECE; ++i) {
+                    const int R = i * RPI + rl;
+                    const int hf = R >= a.kstage ? 1 : 0;
+                    const int k = kbase + R - hf * a.kstage;
+                    const bool ok = pvalid[hf] && k < a.K;
+                    // uniform 64-bit base + 32-bit byte offset: one register per address (tensors stay below 4 GiB)
+                    const __nv_bfloat16 *src = reinterpret_cast<const __nv_bfloat16 *>(
+                        reinterpret_cast<const char *>(a.x) + (uint32_t)(offb[hf] + k * a.HW) * 2u);
+                    if (VEC == 8) {
+                        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                        if (ok) v = ldg16(src);
+                        r[i][0] = v.x; r[i][WPP > 1 ? 1 : 0] = v.y; r[i][WPP > 2 ? 2 : 0] = v.z; r[i][WPP > 3 ? 3 : 0] = v.w;
+                    } else if (VEC == 4) {
+                        uint2 v = make_uint2(0u, 0u);
+                        if (ok) v = ldg8(src);
+                        r[i][0] = v.x; r[i][WPP > 1 ? 1 : 0] = v.y;
+                    } else if (VEC == 2) {
+                        r[i][0] = ok ? ldg4(src) : 0u;
+                    } else {
+                        const uint32_t lo = ok ? ldg2(src) : 0u;
+                        const uint32_t hi = (pvalid1[hf] && k < a.K) ? ldg2(reinterpret_cast<const char *>(a.x) + (uint32_t)(offb1[hf] + k * a.HW) * 2u) : 0u;
+                        r[i][0] = lo | (hi << 16);
+                    }
+                }
+                if (PROD == PROD_BNRELU) {
+                    // rows of a half are valid up to a per-lane limit (k < K), so validity is a compare against the
+                    // unrolled index; the coefficient loads are volatile so that they are not hoisted into 2 x NPIECE
+                    // live registers
+                    const int half_i = a.kstage / RPI;  // pieces per half
+                    const int lim0 = pvalid[0] ? (a.K - kbase - rl + RPI - 1) / RPI : 0;
+                    const int lim1 = pvalid[1] ? half_i + (a.K - kbase - rl + RPI - 1) / RPI : 0;
+                    uint32_t sbp = sb_u32 + (uint32_t)(kbase + rl) * 4u;
+#pragma unroll
+                    for (int i = 0; i < NPIECE; ++i) {
+                        const bool second = i >= half_i;
+                        const bool valid = second ? i < lim1 : i < lim0;
+                        if (valid) {
+                            const uint32_t ap = sbp + (uint32_t)((second ? i - half_i : i) * RPI) * 4u;
+                            float sc, bi;
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sc) : "r"(ap));
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(bi) : "r"(ap + (uint32_t)a.Kpad * 4u));
+#pragma unroll
+                            for (int e = 0; e < WPP; ++e)
+                                r[i][e] = pack_bf16x2(fmaxf(fmaf(bf16_lo(r[i][e]), sc, bi), 0.f),
+                                                      (VEC > 1 || pvalid1[second ? 1 : 0]) ? fmaxf(fmaf(bf16_hi(r[i][e]), sc, bi), 0.f) : 0.f);
+                        }
+                    }
+                }
+                mbar_wait(&hdr->empty[slot], phase ^ 1u);
+                const uint32_t sp = smem_a_u32 + (uint32_t)(slot * a.stage_bytes);
+#pragma unroll
+                for (int i = 0; i < NPIECE; ++i) {
+                    const int R = i * RPI + rl;
+                    const uint32_t d = sp + (uint32_t)((R >> 3) * 1024 + (R & 7) * 128) + ((chunk ^ (uint32_t)(R & 7)) << 4) + sub;
+                    if (VEC == 8)
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d), "r"(r[i][0]), "r"(r[i][WPP > 1 ? 1 : 0]),
+                                     "r"(r[i][WPP > 2 ? 2 : 0]), "r"(r[i][WPP > 3 ? 3 : 0]) : "memory");
+                    else if (VEC == 4)
+                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(d), "r"(r[i][0]), "r"(r[i][WPP > 1 ? 1 : 0]) : "memory");
+                    else
+                        asm volatile("st.shared.b32 [%0], %1;" ::"r"(d), "r"(r[i][0]) : "memory");
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&hdr->full[slot]);
+                PW_TRACE_IF(lane == 0 && st == a.k_stages - 1 && (tile - tile0) / tstride < 7, 7 + ((tile - tile0) / tstride) * 8);
+                n += W;
+                st += W;
+                while (st >= a.k_stages) { st -= a.k_stages; tile += tstride; }
             }
         } else {
             // 3D-shift gather: work items = (channel, row run of <= 8 pixels); results go to shared memory with 2-byte
@@ -658,7 +801,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_conv(const PwArgs a) {
                 const int img_lo = Plo / a.HW, img_hi = (Phi - 1) / a.HW;
                 for (st = 0; st < a.k_stages; ++st) {
                     mbar_wait(&hdr->empty[slot], phase ^ 1u);
-                    unsigned char *sp = smem_a + (size_t)slot * kStageBytes;
+                    unsigned char *sp = smem_a + (size_t)slot * a.stage_bytes;
                     for (int kl = pw * 8 + kq; kl < a.kstage; kl += 64) {
                         const int k = st * a.kstage + kl;
                         if (k >= a.Kpad) break;
@@ -748,24 +891,30 @@ int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 // splits the output channels over grid.y so that the resident weight block fits shared memory, picks the pixel-tile width
 // so that two accumulator stages fit the 512 TMEM columns
-bool plan(PwArgs &a, int prod, dim3 *grid, size_t *smem_bytes) {
+bool plan(PwArgs &a, int prod, int vec, dim3 *grid, size_t *smem_bytes) {
+    a.b_rows = prod != PROD_SHIFT3D ? 1 : 0;
     a.Kpad = round_up(a.K, 16);
     const int sb_bytes = prod == PROD_BNRELU ? round_up(2 * a.Kpad * 4, 128) : 0;
     int gy = 0;
-    for (int cand = 1; cand <= 16 && !gy; ++cand) {
+    int cand0 = 1;
+    if (const char *dbg = getenv("RB_PW_GY")) cand0 = atoi(dbg) > 0 ? atoi(dbg) : 1;
+    for (int cand = cand0; cand <= 16 && !gy; ++cand) {
         const int nc = round_up(cdiv(a.N, cand), 8);
         const int mt = cdiv(nc, 128);
         if (mt > 4) continue;
         const int w_lbo = nc * 16 + 16;
-        const int w_bytes = round_up((a.Kpad >> 3) * w_lbo, 128);
-        const int st = (kSmemLimit - kHdrBytes - sb_bytes - kStgBytes - w_bytes) / kStageBytes;
-        if (st < 2) continue;
+        const int w_bytes = round_up(kHdrBytes + sb_bytes + kStgBytes + (a.Kpad >> 3) * w_lbo, 1024) - (kHdrBytes + sb_bytes + kStgBytes);  // stages start 1 KiB aligned
+        const int room = kSmemLimit - kHdrBytes - sb_bytes - kStgBytes - w_bytes;
+        if (room / kStageBytes < 2) continue;
+        // little room next to a large weight block: halve the stages so that more of them are in flight
+        const int stage_bytes = a.b_rows ? 8192 : kStageBytes;  // row path: one stage = one warp's registers
+        const int st = room / stage_bytes;
         // the last M tile reads (garbage, ignored) rows up to mt*128 of the last k-group: keep that inside the allocation
         const int reach = ((a.Kpad >> 3) - 1) * w_lbo + mt * 2048;
         const int stages = st < kMaxStages ? st : kMaxStages;
-        if (reach > w_bytes + stages * kStageBytes) continue;
+        if (reach > w_bytes + stages * stage_bytes) continue;
         gy = cand;
-        a.Ncta = nc; a.Mt = mt; a.w_lbo = (uint32_t)w_lbo; a.stages = stages;
+        a.Ncta = nc; a.Mt = mt; a.w_lbo = (uint32_t)w_lbo; a.stages = stages; a.stage_bytes = stage_bytes;
         a.off_sb = kHdrBytes;
         a.off_stg = kHdrBytes + sb_bytes;
         a.off_w = a.off_stg + kStgBytes;
@@ -781,7 +930,8 @@ bool plan(PwArgs &a, int prod, dim3 *grid, size_t *smem_bytes) {
             a.acc_stages = (2 * a.Mt * npx <= 512) ? 2 : 1;
         }
     }
-    a.kstage = kStageBytes / 2 / a.Npx;
+    a.kstage = a.stage_bytes / 2 / a.Npx;
+    a.upt = a.stage_bytes / 4096;  // 16-byte units per producer thread and stage
     a.a_lbo = (uint32_t)a.Npx * 16;
     a.k_stages = cdiv(a.Kpad, a.kstage);
     int cols = 32;
@@ -793,7 +943,7 @@ bool plan(PwArgs &a, int prod, dim3 *grid, size_t *smem_bytes) {
     a.rpr_magic = 65536u / a.rpr + 1u;
     for (uint32_t r = 0; r < 4096; ++r)
         if (((r * a.rpr_magic) >> 16) != r / a.rpr) return false;
-    *smem_bytes = (size_t)a.off_a + (size_t)a.stages * kStageBytes;
+    *smem_bytes = (size_t)a.off_a + (size_t)a.stages * a.stage_bytes;
     const int gy_real = cdiv(a.N, a.Ncta);
     int ctas_x = sm_count() / gy_real;
     if (ctas_x < 1) ctas_x = 1;
@@ -811,16 +961,24 @@ template <int PROD, int VEC> int launch(const PwArgs &a, dim3 grid, size_t smem_
         if (e != cudaSuccess) return fail(RB_ERR_CUDA, "cudaFuncSetAttribute(k_pw_conv): %s", cudaGetErrorString(e));
         configured_dev = dev;
     }
-    k_pw_conv<PROD, VEC><<<grid, kThreads, smem_bytes, s>>>(a);
+    k_pw_conv<PROD, VEC><<<grid, PROD == PROD_SHIFT3D ? kThreads : kRowThreads, smem_bytes, s>>>(a);
     return launched("k_pw_conv");
 }
 
-template <int PROD> int launch_vec(const PwArgs &a, dim3 grid, size_t smem_bytes, cudaStream_t s) {
+// widest alignment granule (elements) shared by the tensors' base addresses and the plane size
+int pick_vec(const PwArgs &a) {
     uintptr_t align = reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.out) | reinterpret_cast<uintptr_t>(a.res);
     const bool base16 = (align & 15) == 0;
-    if (base16 && a.HW % 8 == 0) return launch<PROD, 8>(a, grid, smem_bytes, s);
-    if (base16 && a.HW % 4 == 0) return launch<PROD, 4>(a, grid, smem_bytes, s);
-    if (base16 && a.HW % 2 == 0) return launch<PROD, 2>(a, grid, smem_bytes, s);
+    if (base16 && a.HW % 8 == 0) return 8;
+    if (base16 && a.HW % 4 == 0) return 4;
+    if (base16 && a.HW % 2 == 0) return 2;
+    return 1;
+}
+
+template <int PROD> int launch_vec(const PwArgs &a, int vec, dim3 grid, size_t smem_bytes, cudaStream_t s) {
+    if (vec == 8) return launch<PROD, 8>(a, grid, smem_bytes, s);
+    if (vec == 4) return launch<PROD, 4>(a, grid, smem_bytes, s);
+    if (vec == 2) return launch<PROD, 2>(a, grid, smem_bytes, s);
     return launch<PROD, 1>(a, grid, smem_bytes, s);
 }
 
@@ -1164,15 +1322,17 @@ int pw_conv_forward(const void *x, const void *w, int w_dt, int w_trans, const v
     a.out = (__nv_bfloat16 *)out; a.a_sb = a_sb; a.shift = shift; a.shift_dt = shift_dt;
     a.T = T; a.H = H; a.W = W; a.NI = NI; a.K = K; a.N = N; a.HW = HW;
     a.trace = g_pw_trace;
+    if (const char *dbg = getenv("RB_PW_DBG")) a.dbg = atoi(dbg);
     const int prod = shift ? PROD_SHIFT3D : (a_sb ? PROD_BNRELU : PROD_PLAIN);
     dim3 grid;
     size_t smem_bytes = 0;
-    if (!plan(a, prod, &grid, &smem_bytes))
+    const int vec = pick_vec(a);
+    if (!plan(a, prod, vec, &grid, &smem_bytes))
         return fail(RB_ERR_UNSUPPORTED, "pw_conv: no tiling for K=%d N=%d (weight block does not fit shared memory)", K, N);
     if ((reinterpret_cast<uintptr_t>(x) & 3) != 0) return fail(RB_ERR_INVALID_ARGUMENT, "pw_conv: x must be 4-byte aligned");
-    if (prod == PROD_SHIFT3D) return launch_vec<PROD_SHIFT3D>(a, grid, smem_bytes, s);
-    if (prod == PROD_BNRELU) return launch_vec<PROD_BNRELU>(a, grid, smem_bytes, s);
-    return launch_vec<PROD_PLAIN>(a, grid, smem_bytes, s);
+    if (prod == PROD_SHIFT3D) return launch_vec<PROD_SHIFT3D>(a, vec, grid, smem_bytes, s);
+    if (prod == PROD_BNRELU) return launch_vec<PROD_BNRELU>(a, vec, grid, smem_bytes, s);
+    return launch_vec<PROD_PLAIN>(a, vec, grid, smem_bytes, s);
 }
 
 // scratch bytes needed by pw_conv_wgrad: fp32 [splits, M, N]

@@ -30,13 +30,13 @@ def main():
           "dgrad": lambda: ops.pw_conv(x, w, transposed=True)}[a.mode]
     for _ in range(3):
         fn()
-    trace = torch.zeros(148 * 4 * 64, dtype=torch.int64, device="cuda")
+    trace = torch.zeros(148 * 4 * 128, dtype=torch.int64, device="cuda")
     torch.cuda.synchronize()
     L.rb_debug_pw_trace(ctypes.c_void_p(trace.data_ptr()))
     fn()
     torch.cuda.synchronize()
     L.rb_debug_pw_trace(None)
-    t = trace.view(-1, 64).cpu()
+    t = trace.view(-1, 128).cpu()
     t = t[t[:, 0] > 0]
     t0 = int(t[:, 0].min())
     names = {0: "start", 1: "setup-done(prod)", 2: "weights-staged", 3: "end"}
@@ -51,6 +51,14 @@ def main():
             f = lambda v: "%.1f" % ((v - t0) / 1e3) if v else "-"
             print("   tile %d: mma-start %s  stage0-full %s  last-stage-full %s  mma-issued %s | producer(w0)-done %s | epi-start %s  epi-end %s" % (
                 it, f(ev[4]), f(ev[5]), f(ev[6]), f(ev[0]), f(ev[3]), f(ev[1]), f(ev[2])))
+        if cta == 0:  # per-stage handoffs of tile 2
+            for st in range(8):
+                ev = [int(r[64 + st * 8 + j]) for j in range(6)]
+                if not any(ev):
+                    break
+                f = lambda v: "%.2f" % ((v - t0) / 1e3) if v else "-"
+                print("      tile 2 stage %d: mma full-seen %s  issued+commit %s | producer: enter %s  landed %s  arrived %s  next-issued %s" % (
+                    st, f(ev[0]), f(ev[1]), f(ev[2]), f(ev[3]), f(ev[4]), f(ev[5])))
 
 
 if __name__ == "__main__":
