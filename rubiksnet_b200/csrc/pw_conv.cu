@@ -691,7 +691,10 @@ __global__ void __launch_bounds__(PROD == PROD_SHIFT3D ? kThreads : kRowThreads,
             // VEC == 1 (odd plane sizes, 7x7): pieces of two pixels, fetched with two 2-byte loads that may lie in
             // different images
             constexpr int EPP = VEC == 1 ? 2 : VEC;  // elements per piece
-            constexpr int PB = 2 * EPP, PPR = 128 / PB, RPI = 32 / PPR, NPIECE = 8192 / (32 * PB), WPP = PB / 4;
+            // (their halves are merged only after every load has been issued -- a dependent OR between the loads would
+            // serialise them -- so VEC == 1 stages are 4 KiB to keep both halves of all pieces in registers)
+            constexpr int STAGE = VEC == 1 ? 4096 : 8192;
+            constexpr int PB = 2 * EPP, PPR = 128 / PB, RPI = 32 / PPR, NPIECE = STAGE / (32 * PB), WPP = PB / 4;
             const int pc = lane % PPR, rl = lane / PPR;  // piece column, row inside one instruction
             const uint32_t smem_a_u32 = smem_u32(smem_a);
             const uint32_t chunk = (uint32_t)(pc * PB) >> 4, sub = (uint32_t)(pc * PB) & 15u;
@@ -721,6 +724,7 @@ __global__ void __launch_bounds__(PROD == PROD_SHIFT3D ? kThreads : kRowThreads,
                 }
                 const int kbase = st * a.kstage;
                 uint32_t r[NPIECE][WPP];
+                uint32_t rhi[VEC == 1 ? NPIECE : 1];  // VEC == 1: second pixel of every piece
 #pragma unroll
                 for (int i = 0; i < NPIECE; ++i) {
                     const int R = i * RPI + rl;
@@ -741,10 +745,14 @@ __global__ void __launch_bounds__(PROD == PROD_SHIFT3D ? kThreads : kRowThreads,
                     } else if (VEC == 2) {
                         r[i][0] = ok ? ldg4(src) : 0u;
                     } else {
-                        const uint32_t lo = ok ? ldg2(src) : 0u;
-                        const uint32_t hi = (pvalid1[hf] && k < a.K) ? ldg2(reinterpret_cast<const char *>(a.x) + (uint32_t)(offb1[hf] + k * a.HW) * 2u) : 0u;
-                        r[i][0] = lo | (hi << 16);
+                        r[i][0] = ok ? ldg2(src) : 0u;
+                        rhi[VEC == 1 ? i : 0] = (pvalid1[hf] && k < a.K)
+                            ? ldg2(reinterpret_cast<const char *>(a.x) + (uint32_t)(offb1[hf] + k * a.HW) * 2u) : 0u;
                     }
+                }
+                if (VEC == 1) {
+#pragma unroll
+                    for (int i = 0; i < NPIECE; ++i) r[i][0] |= rhi[VEC == 1 ? i : 0] << 16;
                 }
                 if (PROD == PROD_BNRELU) {
                     // rows of a half are valid up to a per-lane limit (k < K), so validity is a compare against the
@@ -907,7 +915,7 @@ bool plan(PwArgs &a, int prod, int vec, dim3 *grid, size_t *smem_bytes) {
         const int room = kSmemLimit - kHdrBytes - sb_bytes - kStgBytes - w_bytes;
         if (room / kStageBytes < 2) continue;
         // little room next to a large weight block: halve the stages so that more of them are in flight
-        const int stage_bytes = a.b_rows ? 8192 : kStageBytes;  // row path: one stage = one warp's registers
+        const int stage_bytes = a.b_rows ? (vec == 1 ? 4096 : 8192) : kStageBytes;  // row path: one stage = one warp's registers
         const int st = room / stage_bytes;
         // the last M tile reads (garbage, ignored) rows up to mt*128 of the last k-group: keep that inside the allocation
         const int reach = ((a.Kpad >> 3) - 1) * w_lbo + mt * 2048;
@@ -1056,40 +1064,38 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_wgrad(const WgArgs a) {
     const uint32_t tmem_base = hdr->tmem_base;
 
     if (warp == 0) {
-        // whole warp runs the loop (warp-uniform descriptors), one elected lane issues
-        const bool leader = elect_one();
-        const uint32_t idesc = instr_desc_bf16(128, a.sub_n, 0, 0);
-        const uint64_t desc0 = smem_desc(smem_u32(stage0), 16, 1024, LAYOUT_SW128);
-        int slot = 0;
-        uint32_t phase = 0;
-        bool first = true;
-        for (int q = c_begin; q < c_end; ++q) {
-            const int pc = q % a.cpi;
-            const int kvalid = min(kWgChunk, a.HW - pc * kWgChunk);
-            const int ksteps = (kvalid + 15) >> 4;
-            mbar_wait(&hdr->full[slot], phase);
-            tc_fence_after();
-            const uint64_t adesc_s = desc0 + (uint64_t)((slot * a.stage_bytes) >> 4);
-            const uint64_t bdesc_s = adesc_s + (uint64_t)((a.Mt * kWgTileBytes) >> 4);
-            for (int ks = 0; ks < ksteps; ++ks) {
-                uint64_t adesc = adesc_s + (uint64_t)(ks * 2);  // 32 bytes per K step inside the 128-byte swizzle atom
-                uint32_t tcol = tmem_base;
-                for (int mt = 0; mt < a.Mt; ++mt, adesc += kWgTileBytes >> 4) {
-                    uint64_t bdesc = bdesc_s + (uint64_t)(ks * 2);
-                    for (int j = 0; j < a.n_sub; ++j, bdesc += (a.sub_n * 128) >> 4, tcol += a.sub_n) {
-                        if (leader) {
-                            if (first) mma_bf16_first(tcol, adesc, bdesc, idesc);
-                            else mma_bf16_acc(tcol, adesc, bdesc, idesc);
-                        }
+        // ONE elected thread runs the whole issue loop (see mma_loop of k_pw_conv): descriptors as 32-bit halves
+        if (elect_one()) {
+            const uint32_t idesc = instr_desc_bf16(128, a.sub_n, 0, 0);
+            const uint64_t desc0 = smem_desc(smem_u32(stage0), 16, 1024, LAYOUT_SW128);
+            const uint32_t d_hi = (uint32_t)(desc0 >> 32), d_lo0 = (uint32_t)desc0;
+            const uint32_t b_off = (uint32_t)((a.Mt * kWgTileBytes) >> 4), sub_step = (uint32_t)((a.sub_n * 128) >> 4);
+            int slot = 0;
+            uint32_t phase = 0, acc = 0u;
+            int pc = c_begin % a.cpi;
+            for (int q = c_begin; q < c_end; ++q) {
+                const int kvalid = min(kWgChunk, a.HW - pc * kWgChunk);
+                const int ksteps = (kvalid + 15) >> 4;
+                if (++pc == a.cpi) pc = 0;
+                mbar_wait(&hdr->full[slot], phase);
+                tc_fence_after();
+                const uint32_t a_lo_s = d_lo0 + (uint32_t)((slot * a.stage_bytes) >> 4);
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    // 32 bytes per K step inside the 128-byte swizzle atom
+                    uint32_t a_lo = a_lo_s + (uint32_t)(ks * 2);
+                    uint32_t tcol = tmem_base;
+                    for (int mt = 0; mt < a.Mt; ++mt, a_lo += kWgTileBytes >> 4) {
+                        uint32_t b_lo = a_lo_s + b_off + (uint32_t)(ks * 2);
+                        for (int j = 0; j < a.n_sub; ++j, b_lo += sub_step, tcol += a.sub_n)
+                            mma_bf16_lohi(tcol, a_lo, d_hi, b_lo, d_hi, idesc, acc);
                     }
+                    acc = 1u;
                 }
-                first = false;
+                mma_commit(&hdr->empty[slot]);
+                if (++slot == a.stages) { slot = 0; phase ^= 1u; }
             }
-            if (leader) mma_commit(&hdr->empty[slot]);
-            __syncwarp();
-            if (++slot == a.stages) { slot = 0; phase ^= 1u; }
+            mma_commit(&hdr->tmem_full);
         }
-        if (leader) mma_commit(&hdr->tmem_full);
         __syncwarp();
     } else {
         // all 16 non-MMA warps build the operand stages; warps 1-8 drain the accumulators afterwards
@@ -1217,10 +1223,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_wgrad(const WgArgs a) {
                     tmem_ld16(taddr + c0, v);
                     tmem_ld_wait();
                     if (valid) {
-                        float *o = dst + (int64_t)(m0 + ml) * a.N + n0 + c0;
-    #pragma unroll
+                        // slice layout [N, M]: for a fixed column the 32 lanes (= 32 consecutive rows m) write 128
+                        // contiguous bytes
+                        float *o = dst + (int64_t)(n0 + c0) * a.M + m0 + ml;
+#pragma unroll
                         for (int j = 0; j < 16; ++j)
-                            if (c0 + j < nrows) o[j] = __uint_as_float(v[j]);
+                            if (c0 + j < nrows) o[(int64_t)j * a.M] = __uint_as_float(v[j]);
                     }
                 }
             }
@@ -1236,12 +1244,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_wgrad(const WgArgs a) {
     }
 }
 
-__global__ void k_wg_reduce(const float *__restrict__ partial, float *__restrict__ out, int splits, int64_t count) {
+// partial: [splits][N][M] (M contiguous); out: [M][N].  Thread -> (n, m) with m fastest, so the slice reads are coalesced;
+// the transposed write of the small result is not, and does not matter.
+__global__ void k_wg_reduce(const float *__restrict__ partial, float *__restrict__ out, int splits, int M, int N) {
+    const int64_t count = (int64_t)M * N;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     float s = 0.f;
     for (int k = 0; k < splits; ++k) s += partial[(int64_t)k * count + i];
-    out[i] = s;
+    const int n = (int)(i / M), m = (int)(i - (int64_t)n * M);
+    out[(int64_t)m * N + n] = s;
 }
 
 bool wg_plan(WgArgs &a, dim3 *grid, size_t *smem_bytes) {
@@ -1362,7 +1374,7 @@ int pw_conv_wgrad(const void *g, const void *x, float *dw, int NI, int M, int N,
     else rc = wg_launch_vec<PROD_PLAIN>(a, grid, smem_bytes, s);
     if (rc) return rc;
     const int64_t count = (int64_t)M * N;
-    k_wg_reduce<<<(unsigned)cdiv64(count, 256), 256, 0, s>>>(a.partial, dw, (int)grid.x, count);
+    k_wg_reduce<<<(unsigned)cdiv64(count, 256), 256, 0, s>>>(a.partial, dw, (int)grid.x, M, N);
     return launched("k_wg_reduce");
 }
 
