@@ -171,6 +171,14 @@ int rb_pw_conv_forward(const void *x, const void *weight, int weight_dtype, int 
                        const void *residual, void *out, int dtype, int NI, int K, int N, int HW,
                        const float *in_scale_bias, void *stream);
 
+/* Per-step preparation of a conv weight for the two GEMMs above: the fp32 master [N, K] (nn.Conv2d(k=1).weight,
+ * backbone.py:45-47) is rounded to bf16 once, in both orientations -- weight_nk [N, K] for the forward
+ * (rb_pw_conv_forward(..., weight_nk, RB_BF16, 0, ...)) and weight_kn [K, N], which is the [N'=K, K'=N] weight
+ * matrix of the input gradient (rb_pw_conv_forward(out_grad, weight_kn, RB_BF16, 0, ..., K'=N, N'=K)).  Same
+ * rounding as the kernels apply when handed the fp32 master; saves every CTA the conversion (and, for the input
+ * gradient, a transposing scatter) of the whole weight block.  One launch. */
+int rb_pw_weight_pack(const float *weight, void *weight_nk, void *weight_kn, int N, int K, void *stream);
+
 /* as3 -> conv3 -> `out += shortcut` of RubiksShiftBlock.forward (backbone.py:129-135, with as3 the
  * _Rubiks3DWrap of rubiksnet/models.py:128-145) in ONE launch: the 3D learnable shift
  * (rubiks_shift_3d_forward_cuda, rubiks3d_kernels.cu:15-205; stride (1,1,1), padding 0, no quantize) is the

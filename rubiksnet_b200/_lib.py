@@ -61,6 +61,8 @@ def _declare(lib):
     lib.rb_bn_act_backward.restype = i
     lib.rb_pw_conv_forward.argtypes = [vp, vp, i, i, vp, vp, i, i, i, i, i, vp, vp]
     lib.rb_pw_conv_forward.restype = i
+    lib.rb_pw_weight_pack.argtypes = [vp, vp, vp, i, i, vp]
+    lib.rb_pw_weight_pack.restype = i
     lib.rb_shift3d_pw_conv_forward.argtypes = [vp, vp, vp, i, vp, vp] + [i] * 8 + [vp]
     lib.rb_shift3d_pw_conv_forward.restype = i
     lib.rb_pw_conv_wgrad_workspace_bytes.argtypes = [i, i, i, i]

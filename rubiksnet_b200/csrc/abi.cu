@@ -51,6 +51,7 @@ int pw_conv_forward(const void *x, const void *w, int w_dt, int w_trans, const v
                     int N, int HW, const float *a_sb, const void *shift, int shift_dt, int T, int H, int W, cudaStream_t s);
 size_t pw_conv_wgrad_workspace(int NI, int M, int N, int HW);
 void pw_conv_set_trace(void *p);
+int pw_weight_pack(const float *w, void *w_nk, void *w_kn, int N, int K, cudaStream_t s);
 int pw_conv_wgrad(const void *g, const void *x, float *dw, int NI, int M, int N, int HW, const float *x_sb,
                   const void *shift, int shift_dt, int T, int H, int W, void *workspace, cudaStream_t s);
 
@@ -270,6 +271,12 @@ int rb_pw_conv_forward(const void *x, const void *weight, int weight_dtype, int 
     if (!x || !weight || !out) return fail(RB_ERR_INVALID_ARGUMENT, "null pointer");
     return pw_conv_forward(x, weight, weight_dtype, weight_transposed != 0, residual, out, NI, K, N, HW, in_scale_bias,
                            nullptr, 0, 0, 0, 0, (cudaStream_t)stream);
+}
+
+int rb_pw_weight_pack(const float *weight, void *weight_nk, void *weight_kn, int N, int K, void *stream) {
+    if (N <= 0 || K <= 0) return fail(RB_ERR_INVALID_ARGUMENT, "bad extent [%d,%d]", N, K);
+    if (!weight || !weight_nk || !weight_kn) return fail(RB_ERR_INVALID_ARGUMENT, "null pointer");
+    return pw_weight_pack(weight, weight_nk, weight_kn, N, K, (cudaStream_t)stream);
 }
 
 int rb_shift3d_pw_conv_forward(const void *x, const void *shift, const void *weight, int weight_dtype, const void *residual,

@@ -330,12 +330,29 @@ static_assert(sizeof(Hdr) <= kHdrBytes, "header");
 // ([N,K]: 8 consecutive k = one 16-byte shared store; transposed [K,N]: 8 consecutive n = eight 2-byte stores), keep 8
 // units in flight each, and every CTA starts at a different offset so that the grid does not walk the same L2 lines in
 // lockstep.
-__device__ __forceinline__ void stage_weights(const PwArgs &a, unsigned char *smem_w, int n0, int nrows, int tid) {
-    const int kgroups = a.Kpad >> 3, rows8 = (a.Ncta + 7) & ~7, nthreads = (int)blockDim.x;
+__device__ __forceinline__ void stage_weights(const PwArgs &a, unsigned char *smem_w, int n0, int nrows, int tid, int nthreads) {
+    const int kgroups = a.Kpad >> 3, rows8 = (a.Ncta + 7) & ~7;
     const __nv_bfloat16 *wb = reinterpret_cast<const __nv_bfloat16 *>(a.w);
     const float *wf = reinterpret_cast<const float *>(a.w);
     const bool f32 = a.w_dt != RB_BF16;
     constexpr int UB = 8;
+    if (!a.w_trans && !f32 && (a.K & 7) == 0 && (reinterpret_cast<uintptr_t>(a.w) & 15) == 0) {
+        // packed bf16 [N, K] weights (rb_pw_weight_pack): every unit is one 16-byte cp.async straight into the operand
+        // layout; all of a thread's copies are in flight together, so the whole block costs about one memory latency
+        const int total = rows8 * kgroups;
+        const int rot = (int)(((int64_t)blockIdx.x * total) / gridDim.x);
+        const uint32_t sw = smem_u32(smem_w);
+        for (int ul = tid; ul < total; ul += nthreads) {
+            const int u = ul + rot < total ? ul + rot : ul + rot - total;
+            const int n = u / kgroups, kg = u - n * kgroups;
+            const bool ok = n < nrows && kg * 8 < a.K;
+            cp_async16(sw + (uint32_t)kg * a.w_lbo + (uint32_t)(n >> 3) * 128u + (uint32_t)(n & 7) * 16u,
+                       ok ? wb + (int64_t)(n0 + n) * a.K + kg * 8 : wb, ok ? 16u : 0u);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        return;
+    }
     if (!a.w_trans) {
         const bool vec_ok = (a.K & 7) == 0;
         const int total = rows8 * kgroups;
@@ -527,12 +544,18 @@ __global__ void __launch_bounds__(PROD == PROD_SHIFT3D ? kThreads : kRowThreads,
             smem_sb[k] = k < a.K ? a.a_sb[2 * k] : 0.f;
             smem_sb[a.Kpad + k] = k < a.K ? a.a_sb[2 * k + 1] : 0.f;
         }
-    stage_weights(a, smem_w, n0, nrows, tid);
-    fence_proxy_async_smem();
+    // barriers, TMEM address and BN coefficients are visible to everybody after this sync; the producer warps then start
+    // loading activations at once, while the MMA + epilogue warps (the only readers of the weight block, through the
+    // tensor core) stage the weights and meet again on a named barrier of their own
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = hdr->tmem_base;
+    if (warp < kProdWarp0) {
+        stage_weights(a, smem_w, n0, nrows, tid, kProdWarp0 * 32);
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, %0;" ::"n"(kProdWarp0 * 32) : "memory");
+    }
     if (tid == 0) PW_TRACE(2);
 
     if (tid == kProdWarp0 * 32) PW_TRACE(1);
@@ -1323,6 +1346,31 @@ template <int PROD> int wg_launch_vec(const WgArgs &a, dim3 grid, size_t smem_by
 }
 
 }  // namespace
+
+// fp32 [N, K] conv weight -> bf16 copies in both orientations, one launch: w_nk [N, K] (forward) and w_kn [K, N] (the
+// weight matrix of the input-gradient GEMM).  32x32 tiles through shared memory: reads and both writes are coalesced.
+__global__ void k_pw_weight_pack(const float *__restrict__ w, __nv_bfloat16 *__restrict__ w_nk, __nv_bfloat16 *__restrict__ w_kn,
+                                 int N, int K) {
+    __shared__ float tile[32][33];
+    const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8 threads
+    for (int r = ty; r < 32; r += 8) {
+        const int n = n0 + r, k = k0 + tx;
+        const float v = (n < N && k < K) ? w[(int64_t)n * K + k] : 0.f;
+        tile[r][tx] = v;
+        if (n < N && k < K) w_nk[(int64_t)n * K + k] = __float2bfloat16_rn(v);
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int k = k0 + r, n = n0 + tx;
+        if (n < N && k < K) w_kn[(int64_t)k * N + n] = __float2bfloat16_rn(tile[tx][r]);
+    }
+}
+
+int pw_weight_pack(const float *w, void *w_nk, void *w_kn, int N, int K, cudaStream_t s) {
+    dim3 grid((unsigned)cdiv(K, 32), (unsigned)cdiv(N, 32));
+    k_pw_weight_pack<<<grid, 256, 0, s>>>(w, (__nv_bfloat16 *)w_nk, (__nv_bfloat16 *)w_kn, N, K);
+    return launched("k_pw_weight_pack");
+}
 
 static unsigned long long *g_pw_trace = nullptr;
 void pw_conv_set_trace(void *p) { g_pw_trace = (unsigned long long *)p; }

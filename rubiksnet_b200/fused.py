@@ -88,16 +88,23 @@ class _Conv1x1TC(torch.autograd.Function):
         x = x.contiguous()
         if residual is not None:
             residual = residual.contiguous()
-        ctx.save_for_backward(x, weight)
         ctx.has_res = residual is not None
-        return ops.pw_conv(x, weight, residual=residual)
+        if weight.dtype == torch.float32 and weight.is_contiguous():
+            w_nk, w_kn = ops.pw_weight_pack(weight)
+        else:
+            w_nk, w_kn = weight, None
+        ctx.save_for_backward(x, weight, w_kn)
+        return ops.pw_conv(x, w_nk, residual=residual)
 
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, g):
-        x, weight = ctx.saved_tensors
+        x, weight, w_kn = ctx.saved_tensors
         g = g.contiguous()
-        gx = ops.pw_conv(g, weight, transposed=True, name="pw_conv<dgrad>") if ctx.needs_input_grad[0] else None
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = (ops.pw_conv(g, w_kn, name="pw_conv<dgrad>") if w_kn is not None
+                  else ops.pw_conv(g, weight, transposed=True, name="pw_conv<dgrad>"))
         gw = None
         if ctx.needs_input_grad[1]:
             gw = ops.pw_conv_wgrad(g, x).view(weight.shape).to(weight.dtype)
@@ -184,27 +191,30 @@ class _RubiksBlockFn(torch.autograd.Function):
         x = x.contiguous()
         tr1, mom1, eps1, rm1, rv1 = _bn_cfg(bn1)
         tr2, mom2, eps2, rm2, rv2 = _bn_cfg(bn2)
+        # conv weights: rounded to bf16 once per step, in both orientations (forward / input gradient)
+        w2_nk, w2_kn = ops.pw_weight_pack(w2)
+        w3_nk, w3_kn = ops.pw_weight_pack(w3)
         _, mi1, sb1 = ops.bn_forward(x, g1, b1, rm1, rv1, tr1, mom1, eps1, relu=True, apply=False)
-        y2 = ops.pw_conv(x, w2, in_scale_bias=sb1, name="pw_conv<bn+relu>")
+        y2 = ops.pw_conv(x, w2_nk, in_scale_bias=sb1, name="pw_conv<bn+relu>")
         a2, mi2, sb2 = ops.bn_forward(y2, g2, b2, rm2, rv2, tr2, mom2, eps2, relu=True, apply=True)
         if FUSE_SHIFT_CONV3:
             s3 = None
-            out = ops.shift3d_pw_conv(a2, shift, w3, x, frames)
+            out = ops.shift3d_pw_conv(a2, shift, w3_nk, x, frames)
         else:
             s3 = _shift3d_forward(a2, shift, frames)
-            out = ops.pw_conv(s3, w3, residual=x, name="pw_conv<+residual>")
-        ctx.save_for_backward(x, y2, a2, s3, mi1, sb1, mi2, sb2, g1, g2, w2, w3, shift)
+            out = ops.pw_conv(s3, w3_nk, residual=x, name="pw_conv<+residual>")
+        ctx.save_for_backward(x, y2, a2, s3, mi1, sb1, mi2, sb2, g1, g2, w2, w3, shift, w2_kn, w3_kn)
         ctx.cfg = (tr1, tr2, frames, normalize_grad, normalize_t_factor)
         return out
 
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, g):
-        x, y2, a2, s3, mi1, sb1, mi2, sb2, g1, g2, w2, w3, shift = ctx.saved_tensors
+        x, y2, a2, s3, mi1, sb1, mi2, sb2, g1, g2, w2, w3, shift, w2_kn, w3_kn = ctx.saved_tensors
         tr1, tr2, frames, normalize_grad, normalize_t_factor = ctx.cfg
         g = g.contiguous()
         need = ctx.needs_input_grad
-        gs = ops.pw_conv(g, w3, transposed=True, name="pw_conv<dgrad>")
+        gs = ops.pw_conv(g, w3_kn, name="pw_conv<dgrad>")
         gw3 = None
         if need[7]:
             gw3 = (ops.shift3d_pw_conv_wgrad(g, a2, shift, frames) if s3 is None else ops.pw_conv_wgrad(g, s3)).view(w3.shape)
@@ -213,7 +223,7 @@ class _RubiksBlockFn(torch.autograd.Function):
         del gs
         gy2, dg2, db2 = ops.bn_backward(y2, ga2, None, g2, mi2, sb2, tr2, relu=True)
         del ga2
-        go = ops.pw_conv(gy2, w2, transposed=True, name="pw_conv<dgrad>")
+        go = ops.pw_conv(gy2, w2_kn, name="pw_conv<dgrad>")
         gw2 = ops.pw_conv_wgrad(gy2, x, in_scale_bias=sb1, name="pw_conv_wgrad<bn+relu>").view(w2.shape) if need[3] else None
         del gy2
         gx, dg1, db1 = ops.bn_backward(x, go, g, g1, mi1, sb1, tr1, relu=True, need_dx=need[0])

@@ -90,6 +90,19 @@ def pw_conv(x, weight, residual=None, in_scale_bias=None, transposed=False, name
     return out
 
 
+def pw_weight_pack(weight):
+    """bf16 copies of a fp32 conv weight [N,K(,1,1)] in both orientations: (w_nk [N,K], w_kn [K,N]); one launch.
+    pw_conv(x, w_nk) is the forward, pw_conv(g, w_kn) the input gradient (no transposing weight staging)."""
+    assert weight.dtype == torch.float32 and weight.is_contiguous()
+    n, k = weight.shape[0], weight.shape[1]
+    packed = torch.empty(2, n * k, dtype=BF16, device=weight.device)
+    with _on_device(weight.device):
+        with _timed("pw_weight_pack", 4 * n * k + 4 * n * k):
+            _lib.check(_lib.lib().rb_pw_weight_pack(_lib.ptr(weight), _lib.ptr(packed[0]), _lib.ptr(packed[1]), n, k,
+                                                    _lib.stream_handle(weight.device)))
+    return packed[0].view(n, k), packed[1].view(k, n)
+
+
 def pw_conv_wgrad(out_grad, x, in_scale_bias=None, name="pw_conv_wgrad"):
     """fp32 [N,K] weight gradient of the conv whose forward was pw_conv(x, W, in_scale_bias=...)."""
     assert x.dtype == BF16 and out_grad.dtype == BF16 and x.is_contiguous() and out_grad.is_contiguous()

@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--H", type=int, default=14)
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--mode", default="fwd")
+    ap.add_argument("--wbf16", action="store_true", help="bf16 weights packed by rb_pw_weight_pack")
     a = ap.parse_args()
     L = _lib.lib()
     L.rb_debug_pw_trace.argtypes = [ctypes.c_void_p]
@@ -25,9 +26,11 @@ def main():
     ni = a.batch * 8
     x = torch.randn(ni, a.C, a.H, a.H, device="cuda").bfloat16()
     w = torch.randn(a.C, a.C, device="cuda") / a.C ** 0.5
+    if a.wbf16:
+        w, w_kn = ops.pw_weight_pack(w)
     sb = torch.stack([torch.rand(a.C, device="cuda") + 0.5, torch.randn(a.C, device="cuda")], dim=1).contiguous()
     fn = {"fwd": lambda: ops.pw_conv(x, w), "bn": lambda: ops.pw_conv(x, w, in_scale_bias=sb),
-          "dgrad": lambda: ops.pw_conv(x, w, transposed=True)}[a.mode]
+          "dgrad": (lambda: ops.pw_conv(x, w_kn)) if a.wbf16 else (lambda: ops.pw_conv(x, w, transposed=True))}[a.mode]
     for _ in range(3):
         fn()
     trace = torch.zeros(148 * 4 * 128, dtype=torch.int64, device="cuda")
