@@ -171,6 +171,28 @@ int rb_pw_conv_forward(const void *x, const void *weight, int weight_dtype, int 
                        const void *residual, void *out, int dtype, int NI, int K, int N, int HW,
                        const float *in_scale_bias, void *stream);
 
+/* rb_pw_conv_forward that also reduces the BatchNorm statistics of its own output in the GEMM epilogue (the block
+ * feeds every conv output into a BatchNorm: conv2 -> bn2, conv3 + shortcut -> the next block's bn1, backbone.py:123-135),
+ * so the separate statistics pass over the tensor disappears.  stats_partial receives per channel and split the fp64
+ * pair (sum, sum of squares) of the stored bf16 values, laid out [N][*stats_splits][2]; *stats_splits (<= 2 x SM count) is
+ * written by the call; stats_bytes >= N * 2 * 148 * 16 always suffices.  Feed both to rb_bn_stats_finalize. */
+int rb_pw_conv_forward_stats(const void *x, const void *weight, int weight_dtype, int weight_transposed,
+                             const void *residual, void *out, int dtype, int NI, int K, int N, int HW,
+                             const float *in_scale_bias, double *stats_partial, size_t stats_bytes, int *stats_splits,
+                             void *stream);
+
+/* Batch statistics -> (mean, invstd), (scale, bias) and the running-statistics update of nn.BatchNorm2d in training
+ * mode, from partial sums [C][splits][2] over `count` elements per channel (what rb_bn_act_forward does after its own
+ * reduction pass).  running_mean / running_var may be NULL. */
+int rb_bn_stats_finalize(const double *partial, int splits, int C, double count, const float *gamma, const float *beta,
+                         float *running_mean, float *running_var, float momentum, float eps, float *mean_invstd,
+                         float *scale_bias, void *stream);
+
+/* y = relu?(x * scale[c] + bias[c]): the apply pass of rb_bn_act_forward alone, for coefficients obtained from
+ * rb_bn_stats_finalize. */
+int rb_bn_apply_forward(const void *x, const float *scale_bias, void *y, int dtype, int NI, int C, int HW, int relu,
+                        void *stream);
+
 /* Per-step preparation of a conv weight for the two GEMMs above: the fp32 master [N, K] (nn.Conv2d(k=1).weight,
  * backbone.py:45-47) is rounded to bf16 once, in both orientations -- weight_nk [N, K] for the forward
  * (rb_pw_conv_forward(..., weight_nk, RB_BF16, 0, ...)) and weight_kn [K, N], which is the [N'=K, K'=N] weight

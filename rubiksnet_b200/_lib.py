@@ -61,6 +61,12 @@ def _declare(lib):
     lib.rb_bn_act_backward.restype = i
     lib.rb_pw_conv_forward.argtypes = [vp, vp, i, i, vp, vp, i, i, i, i, i, vp, vp]
     lib.rb_pw_conv_forward.restype = i
+    lib.rb_pw_conv_forward_stats.argtypes = [vp, vp, i, i, vp, vp, i, i, i, i, i, vp, vp, sz, ctypes.POINTER(ctypes.c_int), vp]
+    lib.rb_pw_conv_forward_stats.restype = i
+    lib.rb_bn_stats_finalize.argtypes = [vp, i, i, dbl, vp, vp, vp, vp, fl, fl, vp, vp, vp]
+    lib.rb_bn_stats_finalize.restype = i
+    lib.rb_bn_apply_forward.argtypes = [vp, vp, vp, i, i, i, i, i, vp]
+    lib.rb_bn_apply_forward.restype = i
     lib.rb_pw_weight_pack.argtypes = [vp, vp, vp, i, i, vp]
     lib.rb_pw_weight_pack.restype = i
     lib.rb_shift3d_pw_conv_forward.argtypes = [vp, vp, vp, i, vp, vp] + [i] * 8 + [vp]

@@ -48,7 +48,12 @@ int shift2d_bwd_shift_generic(const void *, const void *, const void *, void *, 
 
 // pw_conv.cu
 int pw_conv_forward(const void *x, const void *w, int w_dt, int w_trans, const void *residual, void *out, int NI, int K,
-                    int N, int HW, const float *a_sb, const void *shift, int shift_dt, int T, int H, int W, cudaStream_t s);
+                    int N, int HW, const float *a_sb, const void *shift, int shift_dt, int T, int H, int W, cudaStream_t s,
+                    double *stats = nullptr, size_t stats_bytes = 0, int *stats_splits = nullptr);
+int bn_stats_finalize(const double *partial, int splits, int C, double count, const float *gamma, const float *beta,
+                      float *running_mean, float *running_var, float momentum, float eps, float *mean_invstd, float *scale_bias,
+                      cudaStream_t s);
+int bn_apply_forward(const void *x, const float *scale_bias, void *y, int dtype, int NI, int C, int HW, int relu, cudaStream_t s);
 size_t pw_conv_wgrad_workspace(int NI, int M, int N, int HW);
 void pw_conv_set_trace(void *p);
 int pw_weight_pack(const float *w, void *w_nk, void *w_kn, int N, int K, cudaStream_t s);
@@ -271,6 +276,37 @@ int rb_pw_conv_forward(const void *x, const void *weight, int weight_dtype, int 
     if (!x || !weight || !out) return fail(RB_ERR_INVALID_ARGUMENT, "null pointer");
     return pw_conv_forward(x, weight, weight_dtype, weight_transposed != 0, residual, out, NI, K, N, HW, in_scale_bias,
                            nullptr, 0, 0, 0, 0, (cudaStream_t)stream);
+}
+
+int rb_pw_conv_forward_stats(const void *x, const void *weight, int weight_dtype, int weight_transposed, const void *residual,
+                             void *out, int dtype, int NI, int K, int N, int HW, const float *in_scale_bias,
+                             double *stats_partial, size_t stats_bytes, int *stats_splits, void *stream) {
+    if (dtype != RB_BF16) return fail(RB_ERR_UNSUPPORTED, "rb_pw_conv_forward_stats: bf16 activations only (got dtype %d)", dtype);
+    int rc = check_weight_dtype(weight_dtype);
+    if (rc) return rc;
+    if (NI <= 0 || K <= 0 || N <= 0 || HW <= 0) return fail(RB_ERR_INVALID_ARGUMENT, "bad extent [%d,%d,%d,%d]", NI, K, N, HW);
+    if ((int64_t)NI * K * HW > 0x7fffffffLL || (int64_t)NI * N * HW > 0x7fffffffLL)
+        return fail(RB_ERR_UNSUPPORTED, "tensors with more than 2^31-1 elements are not supported");
+    if (!x || !weight || !out || !stats_partial || !stats_splits) return fail(RB_ERR_INVALID_ARGUMENT, "null pointer");
+    return pw_conv_forward(x, weight, weight_dtype, weight_transposed != 0, residual, out, NI, K, N, HW, in_scale_bias,
+                           nullptr, 0, 0, 0, 0, (cudaStream_t)stream, stats_partial, stats_bytes, stats_splits);
+}
+
+int rb_bn_stats_finalize(const double *partial, int splits, int C, double count, const float *gamma, const float *beta,
+                         float *running_mean, float *running_var, float momentum, float eps, float *mean_invstd,
+                         float *scale_bias, void *stream) {
+    if (splits <= 0 || C <= 0 || !(count > 0)) return fail(RB_ERR_INVALID_ARGUMENT, "bad extent");
+    if (!partial || !mean_invstd || !scale_bias) return fail(RB_ERR_INVALID_ARGUMENT, "null pointer");
+    return bn_stats_finalize(partial, splits, C, count, gamma, beta, running_mean, running_var, momentum, eps, mean_invstd,
+                             scale_bias, (cudaStream_t)stream);
+}
+
+int rb_bn_apply_forward(const void *x, const float *scale_bias, void *y, int dtype, int NI, int C, int HW, int relu, void *stream) {
+    if (NI < 0 || C < 0 || HW < 0) return fail(RB_ERR_INVALID_ARGUMENT, "negative extent");
+    if ((int64_t)NI * C * HW == 0) return RB_OK;
+    if ((int64_t)NI * C * HW > 0x7fffffffLL) return fail(RB_ERR_UNSUPPORTED, "bn: tensor too large");
+    if (!x || !scale_bias || !y) return fail(RB_ERR_INVALID_ARGUMENT, "null pointer");
+    return bn_apply_forward(x, scale_bias, y, dtype, NI, C, HW, relu, (cudaStream_t)stream);
 }
 
 int rb_pw_weight_pack(const float *weight, void *weight_nk, void *weight_kn, int N, int K, void *stream) {

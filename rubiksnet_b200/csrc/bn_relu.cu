@@ -290,6 +290,10 @@ static int bn_splits(int NI, int C) {
     if (want < 1) want = 1;
     return want < NI ? want : NI;
 }
+int bn_stats_finalize(const double *partial, int splits, int C, double count, const float *gamma, const float *beta,
+                      float *running_mean, float *running_var, float momentum, float eps, float *mean_invstd, float *scale_bias,
+                      cudaStream_t s);
+int bn_apply_forward(const void *x, const float *scale_bias, void *y, int dtype, int NI, int C, int HW, int relu, cudaStream_t s);
 static size_t bn_ws_bytes(int NI, int C) {
     return ((size_t)C * bn_splits(NI, C) * 2 * sizeof(double) + (size_t)C * 4 * sizeof(float) + 255) & ~(size_t)255;
 }
@@ -297,6 +301,33 @@ static size_t bn_ws_bytes(int NI, int C) {
 }  // namespace rb
 
 using namespace rb;
+
+// statistics reduced elsewhere (the epilogue of the producing GEMM, pw_conv.cu): partial[(c * splits + sp) * 2 + {0,1}]
+int rb::bn_stats_finalize(const double *partial, int splits, int C, double count, const float *gamma, const float *beta,
+                          float *running_mean, float *running_var, float momentum, float eps, float *mean_invstd,
+                          float *scale_bias, cudaStream_t s) {
+    k_bn_stats_finalize<<<cdiv(C, 4), 128, 0, s>>>(partial, splits, C, count, gamma, beta, running_mean, running_var, momentum,
+                                                   eps, mean_invstd, scale_bias);
+    return launched("k_bn_stats_finalize");
+}
+
+// y = act(x * scale + bias) with given per-channel coefficients (the apply pass alone)
+int rb::bn_apply_forward(const void *x, const float *scale_bias, void *y, int dtype, int NI, int C, int HW, int relu,
+                         cudaStream_t s) {
+    if (dtype_size(dtype) == 0 || dtype == RB_F64) return fail(RB_ERR_INVALID_ARGUMENT, "bn: dtype %d not supported", dtype);
+    if (C > 65535) return fail(RB_ERR_UNSUPPORTED, "bn: C > 65535");
+    const int64_t total = (int64_t)NI * C * HW;
+    const FastDiv hw = make_fastdiv((uint32_t)HW);
+    RB_DISPATCH_DTYPE(dtype, {
+        const int64_t nvec = total / Vec<T>::N;
+        int blocks = (int)((nvec + kBT - 1) / kBT);
+        const int cap = sm_count() * 16;
+        if (blocks > cap) blocks = cap;
+        if (blocks < 1) blocks = 1;
+        k_bn_apply<T, 0><<<blocks, kBT, 0, s>>>((const T *)x, nullptr, nullptr, scale_bias, nullptr, (T *)y, total, C, hw, relu);
+    });
+    return launched("k_bn_apply<fwd>");
+}
 
 extern "C" size_t rb_bn_workspace_bytes(int NI, int C) {
     if (NI <= 0 || C <= 0) return 0;

@@ -305,6 +305,8 @@ struct PwArgs {
     uint32_t off_w, off_a, off_sb, off_stg, w_lbo, a_lbo;
     int b_rows;                // activation operand staged as 128-byte-swizzled pixel rows (cp.async path) instead of 8x16-byte core matrices
     uint32_t rpr, rpr_magic;   // runs of 8 columns per image row; (r * rpr_magic) >> 16 == r / rpr for r < 4096
+    double *stats;             // non-null: per-channel (sum, sum of squares) of `out` -> stats[(c * stats_splits + split) * 2 + {0,1}]
+    int stats_splits;          // = 2 * gridDim.x (every CTA column and pixel half is one split)
     int dbg;                   // debug: bit0 producers skip the global loads, bit1 epilogue skips global traffic, bit2 no MMAs
     unsigned long long *trace; // debug: per-CTA event timestamps (globaltimer ns), 64 slots per CTA; null = off
 };
@@ -582,6 +584,13 @@ __global__ void __launch_bounds__(PROD == PROD_SHIFT3D ? kThreads : kRowThreads,
         const int q = warp & 3, half = (warp - kEpiWarp0) >> 2;
         const int cbeg = half * (a.Npx >> 1), cend = cbeg + (a.Npx >> 1);
         unsigned char *stg = smem + a.off_stg + (warp - kEpiWarp0) * 2048;
+        // BatchNorm statistics of the output (a.stats): every lane owns the same 4 channel rows of each M tile for the
+        // whole kernel, so the sums stay in registers until the end
+        float st_s[4][4], st_q[4][4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) st_s[m][i] = st_q[m][i] = 0.f;
         int it = 0;
         for (int tile = tile0; tile < a.total_tiles; tile += tstride, ++it) {
             const int as = it % a.acc_stages;
@@ -651,6 +660,18 @@ __global__ void __launch_bounds__(PROD == PROD_SHIFT3D ? kThreads : kRowThreads,
                             ov[e] = pack_bf16x2(bf16_lo(ov[e]) + bf16_lo(rv[i][e]), bf16_hi(ov[e]) + bf16_hi(rv[i][e]));
                     }
                     store_unit_flat<VEC>(a.out, off[i], po, nv[i], ov);
+                    if (a.stats != nullptr) {  // of the stored (bf16-rounded) values, as BatchNorm would read them back
+                        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float lo = 2 * e < nv[i] ? bf16_lo(ov[e]) : 0.f, hi = 2 * e + 1 < nv[i] ? bf16_hi(ov[e]) : 0.f;
+                            s1 += lo + hi;
+                            s2 = fmaf(lo, lo, fmaf(hi, hi, s2));
+                        }
+#pragma unroll
+                        for (int m = 0; m < 4; ++m)
+                            if (m == mt) { st_s[m][i] += s1; st_q[m][i] += s2; }
+                    }
                 }
             }
             if (nr == 0) {
@@ -658,6 +679,23 @@ __global__ void __launch_bounds__(PROD == PROD_SHIFT3D ? kThreads : kRowThreads,
                 mbar_arrive(&hdr->tmem_empty[as]);
             }
             PW_TRACE_IF(tid == kEpiWarp0 * 32 && it < 7, 6 + it * 8);
+        }
+        if (a.stats != nullptr) {
+            const int sp = blockIdx.x * 2 + half;
+#pragma unroll
+            for (int m = 0; m < 4; ++m)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float s1 = st_s[m][i], s2 = st_q[m][i];  // the 4 lanes of a row hold its 4 groups of 8 pixels
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, 2); s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+                    const int chl = m * 128 + q * 32 + (lane >> 2) + 8 * i;
+                    if ((lane & 3) == 0 && m < a.Mt && chl < nrows) {
+                        double *o = a.stats + ((int64_t)(n0 + chl) * a.stats_splits + sp) * 2;
+                        o[0] = (double)s1;
+                        o[1] = (double)s2;
+                    }
+                }
         }
     } else {
         // ===================================== activation producers ==============================================
@@ -1376,7 +1414,8 @@ static unsigned long long *g_pw_trace = nullptr;
 void pw_conv_set_trace(void *p) { g_pw_trace = (unsigned long long *)p; }
 
 int pw_conv_forward(const void *x, const void *w, int w_dt, int w_trans, const void *residual, void *out, int NI, int K,
-                    int N, int HW, const float *a_sb, const void *shift, int shift_dt, int T, int H, int W, cudaStream_t s) {
+                    int N, int HW, const float *a_sb, const void *shift, int shift_dt, int T, int H, int W, cudaStream_t s,
+                    double *stats, size_t stats_bytes, int *stats_splits) {
     PwArgs a{};
     a.x = (const __nv_bfloat16 *)x; a.w = w; a.w_dt = w_dt; a.w_trans = w_trans; a.res = (const __nv_bfloat16 *)residual;
     a.out = (__nv_bfloat16 *)out; a.a_sb = a_sb; a.shift = shift; a.shift_dt = shift_dt;
@@ -1390,6 +1429,13 @@ int pw_conv_forward(const void *x, const void *w, int w_dt, int w_trans, const v
     if (!plan(a, prod, vec, &grid, &smem_bytes))
         return fail(RB_ERR_UNSUPPORTED, "pw_conv: no tiling for K=%d N=%d (weight block does not fit shared memory)", K, N);
     if ((reinterpret_cast<uintptr_t>(x) & 3) != 0) return fail(RB_ERR_INVALID_ARGUMENT, "pw_conv: x must be 4-byte aligned");
+    if (stats != nullptr) {
+        a.stats = stats;
+        a.stats_splits = 2 * (int)grid.x;
+        if (stats_bytes < (size_t)N * a.stats_splits * 2 * sizeof(double))
+            return fail(RB_ERR_WORKSPACE, "pw_conv: statistics need %zu bytes", (size_t)N * a.stats_splits * 2 * sizeof(double));
+        if (stats_splits) *stats_splits = a.stats_splits;
+    }
     if (prod == PROD_SHIFT3D) return launch_vec<PROD_SHIFT3D>(a, vec, grid, smem_bytes, s);
     if (prod == PROD_BNRELU) return launch_vec<PROD_BNRELU>(a, vec, grid, smem_bytes, s);
     return launch_vec<PROD_PLAIN>(a, vec, grid, smem_bytes, s);

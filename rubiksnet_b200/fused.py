@@ -175,6 +175,10 @@ def _bn_cfg(bn):
 # RubiksNet-Large geometry today and is the default.
 FUSE_SHIFT_CONV3 = False
 
+# True: the per-channel sums BatchNorm needs are reduced in the epilogue of the GEMM that produces the tensor (conv2 ->
+# bn2 inside a block, conv3 + shortcut -> bn1 of the next block) instead of by a separate pass over it.
+EPILOGUE_BN_STATS = True
+
 
 def _shift3d_forward(x, shift, frames):
     from .shiftlib.rubiks3d.primitive import rubiks_shift_3d_forward
@@ -187,29 +191,47 @@ class _RubiksBlockFn(torch.autograd.Function):
 
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda")
-    def forward(ctx, x, g1, b1, w2, g2, b2, shift, w3, bn1, bn2, frames, normalize_grad, normalize_t_factor):
+    def forward(ctx, x, g1, b1, w2, g2, b2, shift, w3, bn1, bn2, frames, normalize_grad, normalize_t_factor, x_stats):
         x = x.contiguous()
         tr1, mom1, eps1, rm1, rv1 = _bn_cfg(bn1)
         tr2, mom2, eps2, rm2, rv2 = _bn_cfg(bn2)
+        count = x.shape[0] * x.shape[2] * x.shape[3]
         # conv weights: rounded to bf16 once per step, in both orientations (forward / input gradient)
         w2_nk, w2_kn = ops.pw_weight_pack(w2)
         w3_nk, w3_kn = ops.pw_weight_pack(w3)
-        _, mi1, sb1 = ops.bn_forward(x, g1, b1, rm1, rv1, tr1, mom1, eps1, relu=True, apply=False)
-        y2 = ops.pw_conv(x, w2_nk, in_scale_bias=sb1, name="pw_conv<bn+relu>")
-        a2, mi2, sb2 = ops.bn_forward(y2, g2, b2, rm2, rv2, tr2, mom2, eps2, relu=True, apply=True)
+        # BatchNorm statistics come out of the epilogue of the GEMM that produced the tensor (x: the previous block's
+        # conv3, handed over as x_stats; y2: conv2 below) -- no separate reduction pass in training mode
+        if x_stats is not None and tr1:
+            mi1, sb1 = ops.bn_finalize(x_stats, count, g1, b1, rm1, rv1, mom1, eps1)
+        else:
+            _, mi1, sb1 = ops.bn_forward(x, g1, b1, rm1, rv1, tr1, mom1, eps1, relu=True, apply=False)
+        if tr2 and EPILOGUE_BN_STATS:
+            y2, st2 = ops.pw_conv(x, w2_nk, in_scale_bias=sb1, name="pw_conv<bn+relu>", stats=True)
+            mi2, sb2 = ops.bn_finalize(st2, count, g2, b2, rm2, rv2, mom2, eps2)
+            a2 = ops.bn_apply(y2, sb2, relu=True)
+        else:
+            y2 = ops.pw_conv(x, w2_nk, in_scale_bias=sb1, name="pw_conv<bn+relu>")
+            a2, mi2, sb2 = ops.bn_forward(y2, g2, b2, rm2, rv2, tr2, mom2, eps2, relu=True, apply=True)
+        out_stats = None
         if FUSE_SHIFT_CONV3:
             s3 = None
             out = ops.shift3d_pw_conv(a2, shift, w3_nk, x, frames)
         else:
             s3 = _shift3d_forward(a2, shift, frames)
-            out = ops.pw_conv(s3, w3_nk, residual=x, name="pw_conv<+residual>")
+            if EPILOGUE_BN_STATS:
+                out, out_stats = ops.pw_conv(s3, w3_nk, residual=x, name="pw_conv<+residual>", stats=True)
+            else:
+                out = ops.pw_conv(s3, w3_nk, residual=x, name="pw_conv<+residual>")
         ctx.save_for_backward(x, y2, a2, s3, mi1, sb1, mi2, sb2, g1, g2, w2, w3, shift, w2_kn, w3_kn)
         ctx.cfg = (tr1, tr2, frames, normalize_grad, normalize_t_factor)
-        return out
+        if out_stats is None:
+            return out, None, 0
+        ctx.mark_non_differentiable(out_stats[0])
+        return out, out_stats[0], out_stats[1]
 
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
-    def backward(ctx, g):
+    def backward(ctx, g, _g_stats=None, _g_splits=None):
         x, y2, a2, s3, mi1, sb1, mi2, sb2, g1, g2, w2, w3, shift, w2_kn, w3_kn = ctx.saved_tensors
         tr1, tr2, frames, normalize_grad, normalize_t_factor = ctx.cfg
         g = g.contiguous()
@@ -227,7 +249,7 @@ class _RubiksBlockFn(torch.autograd.Function):
         gw2 = ops.pw_conv_wgrad(gy2, x, in_scale_bias=sb1, name="pw_conv_wgrad<bn+relu>").view(w2.shape) if need[3] else None
         del gy2
         gx, dg1, db1 = ops.bn_backward(x, go, g, g1, mi1, sb1, tr1, relu=True, need_dx=need[0])
-        return gx, dg1, db1, gw2, dg2, db2, gshift, gw3, None, None, None, None, None
+        return gx, dg1, db1, gw2, dg2, db2, gshift, gw3, None, None, None, None, None, None
 
 
 def rubiks_block_supported(block, x):
@@ -260,6 +282,12 @@ def rubiks_block(block, x):
         if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
             bn.num_batches_tracked.add_(1)
     r3 = block.as3.rubiks3d
-    return _RubiksBlockFn.apply(x, block.bn1.weight, block.bn1.bias, block.conv2.weight, block.bn2.weight, block.bn2.bias,
-                                r3.shift, block.conv3.weight, block.bn1, block.bn2, block.as3.n_segment,
-                                bool(r3.normalize_grad), float(r3.normalize_t_factor))
+    # statistics of x reduced by the conv3 epilogue of the block that produced it (attached to the tensor below)
+    x_stats = getattr(x, "_rb_bn_stats", None) if EPILOGUE_BN_STATS else None
+    out, partial, splits = _RubiksBlockFn.apply(
+        x, block.bn1.weight, block.bn1.bias, block.conv2.weight, block.bn2.weight, block.bn2.bias, r3.shift,
+        block.conv3.weight, block.bn1, block.bn2, block.as3.n_segment, bool(r3.normalize_grad),
+        float(r3.normalize_t_factor), x_stats)
+    if partial is not None:
+        out._rb_bn_stats = (partial, splits)
+    return out

@@ -71,7 +71,39 @@ def bn_backward(x, dy, residual, gamma, mean_invstd, scale_bias, training, relu=
 
 # ------------------------------------------------------------------------------------------ pointwise convs
 
-def pw_conv(x, weight, residual=None, in_scale_bias=None, transposed=False, name="pw_conv"):
+def bn_finalize(stats, count, gamma, beta, running_mean, running_var, momentum, eps):
+    """(mean_invstd, scale_bias) of training-mode BatchNorm2d from the partial sums a GEMM epilogue produced
+    (`stats` = (partial fp64 [C, splits, 2], splits) as returned by pw_conv(..., stats=True)); updates the running
+    statistics like nn.BatchNorm2d."""
+    partial, splits = stats
+    c = gamma.shape[0]
+    mean_invstd = torch.empty(c, 2, dtype=torch.float32, device=partial.device)
+    scale_bias = torch.empty(c, 2, dtype=torch.float32, device=partial.device)
+    with _on_device(partial.device):
+        with _timed("bn_finalize", 0):
+            _lib.check(_lib.lib().rb_bn_stats_finalize(
+                _lib.ptr(partial), int(splits), c, float(count), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(running_mean),
+                _lib.ptr(running_var), float(momentum), float(eps), _lib.ptr(mean_invstd), _lib.ptr(scale_bias),
+                _lib.stream_handle(partial.device)))
+    return mean_invstd, scale_bias
+
+
+def bn_apply(x, scale_bias, relu=True):
+    """y = relu(x * scale + bias) with given per-channel coefficients [C, 2] (one streaming pass)."""
+    ni, c = x.shape[0], x.shape[1]
+    hw = x.numel() // max(ni * c, 1)
+    y = torch.empty_like(x)
+    with _on_device(x.device):
+        with _timed("bn_apply", _nbytes(x, y)):
+            _lib.check(_lib.lib().rb_bn_apply_forward(_lib.ptr(x), _lib.ptr(scale_bias), _lib.ptr(y), _lib.dtype_code(x), ni, c, hw,
+                                                      int(relu), _lib.stream_handle(x.device)))
+    return y
+
+
+_MAX_STAT_SPLITS = 2 * 148
+
+
+def pw_conv(x, weight, residual=None, in_scale_bias=None, transposed=False, name="pw_conv", stats=False):
     """out[i,n,p] = sum_k W[n,k] A[i,k,p] (+ residual).  weight: Conv2d parameter [N,K,1,1] / [N,K] (fp32 or bf16);
     transposed=True reads it as [K,N] (input gradient of that conv).  A = relu(x*scale+bias) with in_scale_bias."""
     assert x.dtype == BF16 and x.is_contiguous()
@@ -84,6 +116,17 @@ def pw_conv(x, weight, residual=None, in_scale_bias=None, transposed=False, name
         assert residual.dtype == BF16 and residual.is_contiguous() and residual.shape == out.shape
     with _on_device(x.device):
         with _timed(name, _nbytes(x, residual, out), 2 * ni * hw * k * n):
+            if stats:
+                # stats=True: also returns (partial, splits), the per-channel (sum, sum of squares) of `out` reduced in
+                # the GEMM epilogue -- input of bn_finalize for the BatchNorm that consumes `out`
+                import ctypes
+                partial = torch.empty(n * _MAX_STAT_SPLITS * 2, dtype=torch.float64, device=x.device)
+                splits = ctypes.c_int(0)
+                _lib.check(_lib.lib().rb_pw_conv_forward_stats(
+                    _lib.ptr(x), _lib.ptr(weight), _wdt(weight), int(transposed), _lib.ptr(residual), _lib.ptr(out),
+                    _lib.RB_BF16, ni, k, n, hw, _lib.ptr(in_scale_bias), _lib.ptr(partial), partial.numel() * 8,
+                    ctypes.byref(splits), _lib.stream_handle(x.device)))
+                return out, (partial, splits.value)
             _lib.check(_lib.lib().rb_pw_conv_forward(
                 _lib.ptr(x), _lib.ptr(weight), _wdt(weight), int(transposed), _lib.ptr(residual), _lib.ptr(out), _lib.RB_BF16,
                 ni, k, n, hw, _lib.ptr(in_scale_bias), _lib.stream_handle(x.device)))

@@ -50,6 +50,42 @@ def test_pw_conv_forward(shape, wdtype):
 
 
 @pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("with_res", [False, True])
+def test_pw_conv_epilogue_bn_statistics(shape, with_res):
+    """rb_pw_conv_forward_stats: same output as rb_pw_conv_forward, and the per-channel sums reduced in the epilogue give
+    -- through rb_bn_stats_finalize / rb_bn_apply_forward -- what torch's training-mode BatchNorm2d computes on that
+    output (batch mean / biased variance, running statistics with the unbiased variance)."""
+    ni, k, n, hw = shape
+    torch.manual_seed(7)
+    x = torch.randn(ni, k, hw, device="cuda").to(BF)
+    w_nk, w_kn = ops.pw_weight_pack((torch.randn(n, k, device="cuda") / k ** 0.5).contiguous())
+    res = torch.randn(ni, n, hw, device="cuda").to(BF) if with_res else None
+    ref_out = ops.pw_conv(x, w_nk, residual=res)
+    out, stats = ops.pw_conv(x, w_nk, residual=res, stats=True)
+    assert torch.equal(out, ref_out)
+    partial, splits = stats
+    assert 1 <= splits <= 2 * 148
+    sums = partial[:n * splits * 2].view(n, splits, 2).sum(1)
+    o = out.double()
+    assert _rel(sums[:, 0], o.sum((0, 2))) <= 1e-4 and _rel(sums[:, 1], (o * o).sum((0, 2))) <= 1e-4
+    bn = torch.nn.BatchNorm2d(n).cuda().train()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.uniform_(-0.5, 0.5)
+    rm, rv = bn.running_mean.clone(), bn.running_var.clone()
+    mi, sb = ops.bn_finalize(stats, ni * hw, bn.weight, bn.bias, rm, rv, 0.1, bn.eps)
+    y = ops.bn_apply(out.view(ni, n, hw, 1), sb, relu=True)
+    want = torch.relu(bn(out.float().view(ni, n, hw, 1)))
+    assert _rel(y, want) <= 1e-2
+    if ni * hw > 1:
+        assert _rel(rm, bn.running_mean) <= 1e-4 and _rel(rv, bn.running_var) <= 1e-3
+    assert _rel(mi[:, 0], o.mean((0, 2))) <= 1e-4
+    # the packed transposed copy drives the input gradient
+    g = torch.randn(ni, n, hw, device="cuda").to(BF)
+    assert _rel(ops.pw_conv(g, w_kn), torch.matmul(w_nk.float().t(), g.float())) <= 1e-2
+
+
+@pytest.mark.parametrize("shape", SHAPES)
 def test_pw_conv_bn_relu_producer(shape):
     ni, k, n, hw = shape
     torch.manual_seed(1)
