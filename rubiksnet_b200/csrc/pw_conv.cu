@@ -648,6 +648,7 @@ __global__ void __launch_bounds__(PROD == PROD_SHIFT3D ? kThreads : kRowThreads,
                                    pack_bf16x2(__uint_as_float(vv[6]), __uint_as_float(vv[7])));
                 }
                 __syncwarp();
+                float rs1[4] = {0.f, 0.f, 0.f, 0.f}, rs2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int row = (lane >> 2) + 8 * i, ch = lane & 3;
@@ -662,15 +663,38 @@ __global__ void __launch_bounds__(PROD == PROD_SHIFT3D ? kThreads : kRowThreads,
                     store_unit_flat<VEC>(a.out, off[i], po, nv[i], ov);
                     if (a.stats != nullptr) {  // of the stored (bf16-rounded) values, as BatchNorm would read them back
                         float s1 = 0.f, s2 = 0.f;
+                        if (nv[i] >= 8) {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float lo = 2 * e < nv[i] ? bf16_lo(ov[e]) : 0.f, hi = 2 * e + 1 < nv[i] ? bf16_hi(ov[e]) : 0.f;
-                            s1 += lo + hi;
-                            s2 = fmaf(lo, lo, fmaf(hi, hi, s2));
+                            for (int e = 0; e < 4; ++e) {
+                                const float lo = bf16_lo(ov[e]), hi = bf16_hi(ov[e]);
+                                s1 += lo + hi;
+                                s2 = fmaf(lo, lo, fmaf(hi, hi, s2));
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float lo = 2 * e < nv[i] ? bf16_lo(ov[e]) : 0.f, hi = 2 * e + 1 < nv[i] ? bf16_hi(ov[e]) : 0.f;
+                                s1 += lo + hi;
+                                s2 = fmaf(lo, lo, fmaf(hi, hi, s2));
+                            }
                         }
+                        rs1[i] = s1;
+                        rs2[i] = s2;
+                    }
+                }
+                if (a.stats != nullptr) {  // warp-uniform choice of the M tile's accumulators
+                    if (mt == 0) {
 #pragma unroll
-                        for (int m = 0; m < 4; ++m)
-                            if (m == mt) { st_s[m][i] += s1; st_q[m][i] += s2; }
+                        for (int i = 0; i < 4; ++i) { st_s[0][i] += rs1[i]; st_q[0][i] += rs2[i]; }
+                    } else if (mt == 1) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { st_s[1][i] += rs1[i]; st_q[1][i] += rs2[i]; }
+                    } else if (mt == 2) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { st_s[2][i] += rs1[i]; st_q[2][i] += rs2[i]; }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { st_s[3][i] += rs1[i]; st_q[3][i] += rs2[i]; }
                     }
                 }
             }

@@ -176,8 +176,11 @@ def _bn_cfg(bn):
 FUSE_SHIFT_CONV3 = False
 
 # True: the per-channel sums BatchNorm needs are reduced in the epilogue of the GEMM that produces the tensor (conv2 ->
-# bn2 inside a block, conv3 + shortcut -> bn1 of the next block) instead of by a separate pass over it.
-EPILOGUE_BN_STATS = True
+# bn2 inside a block, conv3 + shortcut -> bn1 of the next block) instead of by a separate pass over it.  Parity-tested
+# (tests/test_gpu_pwconv.py::test_pw_conv_epilogue_bn_statistics) but OFF by default: measured on B200 at 32 clips
+# (gpurun_out/s27, round 1) it removes 2.6 ms of statistics passes per step and adds 3.0 ms to the two GEMMs, whose
+# epilogue warps -- not HBM -- are what bounds them (731 vs 756 clips/s).
+EPILOGUE_BN_STATS = False
 
 
 def _shift3d_forward(x, shift, frames):

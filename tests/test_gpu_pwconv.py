@@ -68,6 +68,8 @@ def test_pw_conv_epilogue_bn_statistics(shape, with_res):
     sums = partial[:n * splits * 2].view(n, splits, 2).sum(1)
     o = out.double()
     assert _rel(sums[:, 0], o.sum((0, 2))) <= 1e-4 and _rel(sums[:, 1], (o * o).sum((0, 2))) <= 1e-4
+    if ni * hw == 1:
+        return  # torch refuses training-mode BatchNorm on one value per channel
     bn = torch.nn.BatchNorm2d(n).cuda().train()
     with torch.no_grad():
         bn.weight.uniform_(0.5, 1.5)
@@ -168,6 +170,36 @@ def test_errors_are_reported():
     assert L.rb_pw_conv_wgrad(None, None, _lib.ptr(dw), _lib.RB_BF16, 0, 8, 8, 4, None, None, 0, None) == 0
     torch.cuda.synchronize()
     assert float(dw.abs().sum()) == 0.0
+
+
+def test_epilogue_bn_stats_block_chain():
+    """Two chained identity blocks with fused.EPILOGUE_BN_STATS: the second block takes its bn1 statistics from the first
+    block's conv3 epilogue; outputs, gradients and running statistics match the default schedule."""
+    from rubiksnet_b200 import fused
+    torch.manual_seed(11)
+    net = rb.RubiksNet(tier="tiny", num_classes=5, num_frames=8).cuda().train()
+    blocks = torch.nn.Sequential(net.backbone.layer3[1], net.backbone.layer3[2])
+    x0 = torch.randn(16, 216, 14, 14, device="cuda").to(BF)
+    res = []
+    for flag in (False, True):
+        fused.EPILOGUE_BN_STATS = flag
+        try:
+            sd = {k: v.clone() for k, v in blocks.state_dict().items()}
+            blocks.zero_grad(set_to_none=True)
+            x = x0.clone().requires_grad_()
+            out = blocks(x)
+            assert hasattr(out, "_rb_bn_stats") == flag
+            out.float().square().mean().backward()
+            res.append((out.detach().float(), x.grad.float(), {n: p.grad.float().clone() for n, p in blocks.named_parameters()},
+                        blocks[1].bn1.running_var.clone()))
+            blocks.load_state_dict(sd)
+        finally:
+            fused.EPILOGUE_BN_STATS = False
+    (o0, g0, p0, rv0), (o1, g1, p1, rv1) = res
+    assert _rel(o1, o0) <= 1e-2 and _rel(g1, g0) <= 2e-2 and _rel(rv1, rv0) <= 1e-3
+    for name in p0:
+        if not name.endswith("shift"):
+            assert _rel(p1[name], p0[name]) <= 2e-2, name
 
 
 @pytest.mark.parametrize("fuse_shift", [False, True])
