@@ -182,7 +182,9 @@ class Trainer:
 
     def runner(self, clips, labels):
         """The callable the timed loops drive: the CUDA-graph replay of `step` (ours, --graph on) or `step` itself."""
-        if self.kind != "ours" or self.args.graph != "on":
+        # N > 1: eager launches -- the NCCL all-reduce stays outside any capture (a whole-step capture that includes the
+        # collective hung on 2 GPUs, gpurun_out/s28)
+        if self.kind != "ours" or self.args.graph != "on" or (self.world > 1 and not os.environ.get("RB_GRAPH_MULTI")):
             return self.step
         if self.graphed is None:
             from rubiksnet_b200.graph import GraphedStep
@@ -360,7 +362,8 @@ def main():
                           % (args.tier.capitalize(), args.variant),
               "clips_per_gpu": args.batch, "frames": FRAMES, "num_classes": NUM_CLASSES,
               "parallelism": "dp%d (batch sharded, NCCL grad all-reduce)" % args.gpus,
-              "launch": "whole step replayed from one CUDA graph" if args.graph == "on" and args.impl == "ours" else "eager",
+              "launch": ("whole step replayed from one CUDA graph" if args.graph == "on" and args.impl == "ours" and args.gpus == 1
+                         else "eager"),
               "l2": "working set per step (>10 GB of activations) far exceeds the 126 MB L2; no flush needed"}
 
     if args.impl == "reference":
@@ -432,8 +435,9 @@ def main():
     else:
         line["impl"] = "rubiksnet_b200"
         line["gpu_launches"] = launches0
+        roof = kernel_roofline(tr, dclips, dlabels)  # every rank: the extra step contains the gradient all-reduce
         if rank == 0:
-            line["roofline"] = kernel_roofline(tr, dclips, dlabels)
+            line["roofline"] = roof
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             v, cores, dt = cpu_port_clips_per_s(args, args.cpu_sample_clips)
