@@ -307,6 +307,7 @@ struct PwArgs {
     uint32_t rpr, rpr_magic;   // runs of 8 columns per image row; (r * rpr_magic) >> 16 == r / rpr for r < 4096
     double *stats;             // non-null: per-channel (sum, sum of squares) of `out` -> stats[(c * stats_splits + split) * 2 + {0,1}]
     int stats_splits;          // = 2 * gridDim.x (every CTA column and pixel half is one split)
+    uint32_t hw_mul, hw_shr;   // exact division by HW for positions < 2^31: (umulhi(P, hw_mul) >> hw_shr), HW == 1: mul 0
     int dbg;                   // debug: bit0 producers skip the global loads, bit1 epilogue skips global traffic, bit2 no MMAs
     unsigned long long *trace; // debug: per-CTA event timestamps (globaltimer ns), 64 slots per CTA; null = off
 };
@@ -315,6 +316,10 @@ __device__ __forceinline__ unsigned long long gtime() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
+}
+// P / HW without the ~30-instruction runtime division (Granlund-Montgomery, exact for P < 2^31)
+__device__ __forceinline__ int div_hw(const PwArgs &a, int P) {
+    return a.hw_mul == 0u ? P : (int)(__umulhi((uint32_t)P, a.hw_mul) >> a.hw_shr);
 }
 #define PW_TRACE_IF(cond, slot) do { if (a.trace) { if (cond) a.trace[(blockIdx.y * gridDim.x + blockIdx.x) * 128 + (slot)] = gtime(); } } while (0)
 #define PW_TRACE(slot) do { if (a.trace) a.trace[(blockIdx.y * gridDim.x + blockIdx.x) * 128 + (slot)] = gtime(); } while (0)
@@ -610,7 +615,7 @@ __global__ void __launch_bounds__(PROD == PROD_SHIFT3D ? kThreads : kRowThreads,
             // One loop body for every round (the three roles of the CTA share the instruction caches: a second inlined
             // copy of this body, tried for a software-pipelined TMEM load, cost more than the overlap gained).
             for (int ridx = 0; ridx < nr; ++ridx) {
-                const int mt = ridx / ncr, c0 = cbeg + (ridx - mt * ncr) * 32;
+                const int mt = ncr == 2 ? ridx >> 1 : (ncr == 1 ? ridx : ridx / ncr), c0 = cbeg + (ridx - mt * ncr) * 32;
                 const int r0 = mt * 128 + q * 32;  // first CTA-local channel of this warp's 32 TMEM lanes
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * acc_cols + mt * a.Npx + c0;
                 uint32_t v[2][16];
@@ -623,7 +628,7 @@ __global__ void __launch_bounds__(PROD == PROD_SHIFT3D ? kThreads : kRowThreads,
                 uint32_t rv[4][4];
                 {
                     const int P = P0 + c0 + (lane & 3) * 8;
-                    const int img = P / a.HW, pp = P - img * a.HW;
+                    const int img = div_hw(a, P), pp = P - img * a.HW;
                     piece_offsets<VEC>(pp, a.HW, (a.N - 1) * a.HW, po);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -802,7 +807,7 @@ __global__ void __launch_bounds__(PROD == PROD_SHIFT3D ? kThreads : kRowThreads,
                 for (int hf = 0; hf < 2; ++hf) {
                     const int P = tile * a.Npx + hf * 64 + pc * EPP;
                     pvalid[hf] = hf * 64 < a.Npx && P < a.NP;
-                    const int img = P / a.HW, pp = P - img * a.HW;
+                    const int img = div_hw(a, P), pp = P - img * a.HW;
                     offb[hf] = img * a.K * a.HW + pp;
                     pvalid1[hf] = hf * 64 < a.Npx && P + 1 < a.NP;
                     offb1[hf] = pp + 1 < a.HW ? offb[hf] + 1 : (img + 1) * a.K * a.HW;
@@ -1032,6 +1037,14 @@ bool plan(PwArgs &a, int prod, int vec, dim3 *grid, size_t *smem_bytes) {
     a.tmem_cols = cols;
     a.NP = a.NI * a.HW;
     a.total_tiles = cdiv(a.NP, a.Npx);
+    if (a.HW <= 1) {
+        a.hw_mul = 0u; a.hw_shr = 0u;
+    } else {
+        uint32_t l = 0;
+        while ((1u << l) < (uint32_t)a.HW) ++l;  // ceil(log2 HW)
+        a.hw_mul = (uint32_t)(((uint64_t(1) << (31 + l)) + (uint32_t)a.HW - 1) / (uint32_t)a.HW);
+        a.hw_shr = l - 1;
+    }
     a.rpr = (uint32_t)(a.W > 0 ? (a.W + 7) / 8 : 1);
     a.rpr_magic = 65536u / a.rpr + 1u;
     for (uint32_t r = 0; r < 4096; ++r)
@@ -1085,8 +1098,11 @@ template <int PROD> int launch_vec(const PwArgs &a, int vec, dim3 grid, size_t s
 constexpr int kWgMaxStages = 4;
 constexpr int kWgChunk = 64;             // pixels per stage
 constexpr int kWgTileBytes = 128 * 128;  // one 128-row operand tile
-constexpr int kWgProdWarps = kNumEpiWarps + kNumProdWarps;  // the epilogue warps also produce during the main loop
-constexpr int kWgProdThreads = kWgProdWarps * 32;
+constexpr int kWgProdWarps = 14;  // producer warps (the first 8 also drain the accumulators at the end); with the MMA warp
+constexpr int kWgProdThreads = kWgProdWarps * 32;  // 480 threads, so that a thread may hold 16 units (64 registers) of a stage
+constexpr int kWgThreads = kWgProdThreads + 32;
+constexpr int kWgGroups = 2;      // plain / BN+ReLU producers: two groups of 7 warps fill alternate stages
+constexpr int kWgUB = 16;         // units a thread keeps in flight
 
 struct WgArgs {
     const __nv_bfloat16 *g;  // [NI, M, HW]
@@ -1114,7 +1130,7 @@ __device__ __forceinline__ uint32_t sw128_off(int r, int c) {
 }
 
 template <int PROD, int VEC>
-__global__ void __launch_bounds__(kThreads, 1) k_pw_wgrad(const WgArgs a) {
+__global__ void __launch_bounds__(kWgThreads, 1) k_pw_wgrad(const WgArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     WgHdr *hdr = reinterpret_cast<WgHdr *>(smem);
     float *smem_sb = reinterpret_cast<float *>(smem + a.off_sb);
@@ -1128,7 +1144,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_wgrad(const WgArgs a) {
 
     if (tid == 0) {
         for (int i = 0; i < kWgMaxStages; ++i) {
-            mbar_init(&hdr->full[i], kWgProdWarps);
+            mbar_init(&hdr->full[i], PROD == PROD_SHIFT3D ? kWgProdWarps : kWgProdWarps / kWgGroups);
             mbar_init(&hdr->empty[i], 1);
         }
         mbar_init(&hdr->tmem_full, 1);
@@ -1139,7 +1155,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_wgrad(const WgArgs a) {
         tmem_alloc(&hdr->tmem_base, (uint32_t)a.tmem_cols);
     }
     if (PROD == PROD_BNRELU)
-        for (int k = tid; k < a.N; k += kThreads) {
+        for (int k = tid; k < a.N; k += kWgThreads) {
             smem_sb[k] = a.x_sb[2 * k];
             smem_sb[a.N + k] = a.x_sb[2 * k + 1];
         }
@@ -1190,44 +1206,56 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_wgrad(const WgArgs a) {
         const int total_units = unit_rows * 8;
         const ShiftSrc ssrc{a.x, a.shift, a.shift_dt, a.T, a.H, a.W, a.HW, a.N, (int)(((int64_t)a.NI * a.N * a.HW - 1) >> 1)};
         const int rpr = (int)a.rpr;
-        int slot = 0;
-        uint32_t phase = 0;
-        for (int q = c_begin; q < c_end; ++q) {
+        // Plain / BN+ReLU operands: the warps form kWgGroups groups that fill alternate stages, each thread with all its
+        // units of the stage (<= kWgUB) in flight at once -- two stages are being loaded while a third is consumed.  (A
+        // warp's loads share one scoreboard: more than one batch per thread and stage would serialise on it.)  The shift
+        // gather keeps every warp on every stage.
+        constexpr int G = PROD == PROD_SHIFT3D ? 1 : kWgGroups;
+        constexpr int GT = kWgProdThreads / G;          // threads per group
+        const int grp = pt / GT, gt = pt - grp * GT;    // group, thread inside the group
+        for (int q = c_begin + grp; q < c_end; q += G) {
+            const int j = q - c_begin;                  // stage index of this CTA
+            const int slot = j % a.stages;
+            const uint32_t phase = (uint32_t)(j / a.stages) & 1u;
             const int img = q / a.cpi, pc = q - img * a.cpi;
             const int p0 = pc * kWgChunk;
             const int kvalid = min(kWgChunk, a.HW - p0);
             const int nchunks16 = ((kvalid + 15) >> 4) * 2;  // 16-byte chunks the MMAs of this stage will read
-            mbar_wait(&hdr->empty[slot], phase ^ 1u);
             unsigned char *abase = stage0 + (size_t)slot * a.stage_bytes, *bbase = abase + (size_t)a.Mt * kWgTileBytes;
-            for (int u0 = pt; u0 < total_units; u0 += 8 * kWgProdThreads) {
-                uint32_t r[8][4];
+            bool waited = false;
+            for (int u0 = gt; u0 < total_units; u0 += kWgUB * GT) {
+                uint32_t r[kWgUB][4];
 #pragma unroll
-                for (int b = 0; b < 8; ++b) {
-                    const int u = u0 + b * kWgProdThreads;
+                for (int b = 0; b < kWgUB; ++b) {
+                    const int u = u0 + b * GT;
                     const int rowi = u >> 3, c = u & 7;
                     r[b][0] = r[b][1] = r[b][2] = r[b][3] = 0u;
                     if (u < total_units && c < nchunks16) {
                         const int p = p0 + c * 8;
-                        if (rowi < mrows) {
-                            load_unit<VEC>(a.g + ((int64_t)img * a.M + m0 + rowi) * a.HW + p, a.HW - p, r[b]);
-                        } else {
-                            const int k = n0 + rowi - mrows;
-                            load_unit<VEC>(a.x + ((int64_t)img * a.N + k) * a.HW + p, a.HW - p, r[b]);
-                            if (PROD == PROD_BNRELU) bn_relu_unit(r[b], smem_sb[k], smem_sb[a.N + k], a.HW - p);
-                        }
+                        if (rowi < mrows) load_unit<VEC>(a.g + ((int64_t)img * a.M + m0 + rowi) * a.HW + p, a.HW - p, r[b]);
+                        else load_unit<VEC>(a.x + ((int64_t)img * a.N + n0 + rowi - mrows) * a.HW + p, a.HW - p, r[b]);
                     }
                 }
+                if (!waited) {  // the loads above do not need the slot: wait for it only now
+                    mbar_wait(&hdr->empty[slot], phase ^ 1u);
+                    waited = true;
+                }
 #pragma unroll
-                for (int b = 0; b < 8; ++b) {
-                    const int u = u0 + b * kWgProdThreads;
+                for (int b = 0; b < kWgUB; ++b) {
+                    const int u = u0 + b * GT;
                     const int rowi = u >> 3, c = u & 7;
                     if (u < total_units && c < nchunks16) {
+                        if (PROD == PROD_BNRELU && rowi >= mrows) {  // applied after all loads of the batch were issued
+                            const int k = n0 + rowi - mrows;
+                            bn_relu_unit(r[b], smem_sb[k], smem_sb[a.N + k], a.HW - (p0 + c * 8));
+                        }
                         unsigned char *d = (rowi < mrows) ? abase + (rowi >> 7) * kWgTileBytes + sw128_off(rowi & 127, c)
                                                           : bbase + sw128_off(rowi - mrows, c);
                         *reinterpret_cast<uint4 *>(d) = make_uint4(r[b][0], r[b][1], r[b][2], r[b][3]);
                     }
                 }
             }
+            if (!waited) mbar_wait(&hdr->empty[slot], phase ^ 1u);
             if (PROD == PROD_SHIFT3D) {
                 // shifted activations: (channel, row run) items, 2-byte stores into the swizzled K-major block
                 const int pend = p0 + kvalid, npad = nchunks16 * 8;
@@ -1288,7 +1316,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_pw_wgrad(const WgArgs a) {
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&hdr->full[slot]);
-            if (++slot == a.stages) { slot = 0; phase ^= 1u; }
         }
         if (warp < kProdWarp0) {
             // epilogue: warp -> TMEM lane quarter + every other 16-column chunk; fp32 partial slice of this pixel split
@@ -1395,7 +1422,7 @@ template <int PROD, int VEC> int wg_launch(const WgArgs &a, dim3 grid, size_t sm
         if (e != cudaSuccess) return fail(RB_ERR_CUDA, "cudaFuncSetAttribute(k_pw_wgrad): %s", cudaGetErrorString(e));
         configured_dev = dev;
     }
-    k_pw_wgrad<PROD, VEC><<<grid, kThreads, smem_bytes, s>>>(a);
+    k_pw_wgrad<PROD, VEC><<<grid, kWgThreads, smem_bytes, s>>>(a);
     return launched("k_pw_wgrad");
 }
 
