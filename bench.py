@@ -184,14 +184,29 @@ class Trainer:
         """The callable the timed loops drive: the CUDA-graph replay of `step` (ours, --graph on) or `step` itself."""
         # N > 1: eager launches -- the NCCL all-reduce stays outside any capture (a whole-step capture that includes the
         # collective hung on 2 GPUs, gpurun_out/s28)
-        if self.kind != "ours" or self.args.graph != "on" or (self.world > 1 and not os.environ.get("RB_GRAPH_MULTI")):
+        if self.kind != "ours" or self.args.graph != "on":
             return self.step
+        from rubiksnet_b200.graph import GraphedStep
+        if self.world == 1 or os.environ.get("RB_GRAPH_MULTI"):
+            if self.graphed is None:
+                self.graphed = GraphedStep(self.step, clips, labels, warmup=2)
+            return self.graphed
+        # N > 1: forward + backward replayed from a graph; the gradient all-reduce and the SGD update stay eager (a
+        # whole-step capture including the NCCL collective ran, but hung at process teardown: gpurun_out/s31)
         if self.graphed is None:
-            from rubiksnet_b200.graph import GraphedStep
-            self.graphed = GraphedStep(self.step, clips, labels, warmup=2)
-        return self.graphed
+            self.graphed = GraphedStep(self.fwd_bwd, clips, labels, warmup=2)
+            self.static_grads = [p.grad for p in self.reducer.params]  # where the captured backward writes
 
-    def step(self, clips, labels):
+        def run(c, l):
+            loss = self.graphed(c, l)
+            for p, g in zip(self.reducer.params, self.static_grads):
+                p.grad = g
+            self.reducer.all_reduce()
+            self.opt.step()
+            return loss
+        return run
+
+    def fwd_bwd(self, clips, labels):
         torch = self.torch
         if self.reducer is not None:
             self.reducer.zero_grad()
@@ -201,6 +216,10 @@ class Trainer:
             logits = self.fwd_net(clips)
         loss = self.loss_fn(logits.float(), labels)
         loss.backward()
+        return loss
+
+    def step(self, clips, labels):
+        loss = self.fwd_bwd(clips, labels)
         if self.reducer is not None:
             self.reducer.all_reduce()
         self.opt.step()
@@ -362,8 +381,9 @@ def main():
                           % (args.tier.capitalize(), args.variant),
               "clips_per_gpu": args.batch, "frames": FRAMES, "num_classes": NUM_CLASSES,
               "parallelism": "dp%d (batch sharded, NCCL grad all-reduce)" % args.gpus,
-              "launch": ("whole step replayed from one CUDA graph" if args.graph == "on" and args.impl == "ours" and args.gpus == 1
-                         else "eager"),
+              "launch": ("eager" if args.graph != "on" or args.impl != "ours" else
+                         "whole step replayed from one CUDA graph" if args.gpus == 1 else
+                         "forward + backward replayed from one CUDA graph, NCCL all-reduce + SGD eager"),
               "l2": "working set per step (>10 GB of activations) far exceeds the 126 MB L2; no flush needed"}
 
     if args.impl == "reference":
