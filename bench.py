@@ -321,6 +321,14 @@ def kernel_roofline(tr, clips, labels):
 
     out = {"bound": "hbm", "peak": peak, "unit": "GB/s", "traffic": None, "peak_source": peak_src}
     out.update(entry(top))
+    try:  # DRAM bytes of one launch of that kernel family from the committed ncu --set full capture
+        fam = "pw_conv_wgrad" if top.startswith("pw_conv_wgrad") else "pw_conv" if top.startswith("pw_conv") else None
+        t = json.load(open(os.path.join(REPO, "profiles", "r01g_traffic.json"))).get(fam)
+        if t:
+            out["traffic"] = t["dram_bytes_per_launch"]
+            out["traffic_detail"] = t
+    except Exception:  # noqa: BLE001
+        pass
     out["all_kernels"] = [entry(k) for k in sorted(agg, key=lambda k: -agg[k]["ms"]) if k != top]
     out["timed_ms_per_step"] = round(sum(d["ms"] for d in agg.values()), 3)
     return out
