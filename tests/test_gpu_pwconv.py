@@ -49,6 +49,37 @@ def test_pw_conv_forward(shape, wdtype):
     assert _rel(gx, torch.matmul(w.to(BF).float().t(), g.float())) <= 1e-2
 
 
+@pytest.mark.parametrize("geom", [(72, 112), (72, 56), (144, 28), (288, 14), (576, 7)])
+def test_pw_conv_full_size_block_geometries(geom):
+    """BASELINE C3 sizes (32 clips x 8 frames = 256 images, every RubiksNet-Large block geometry): forward with residual,
+    BN+ReLU producer, input gradient on the packed transposed weight and weight gradient, checked on a sample of images
+    against fp32 matmuls (weight gradient: all images), plus linearity of the forward in x (exact in the residual)."""
+    c, h = geom
+    ni, hw = 256, h * h
+    torch.manual_seed(3)
+    x = torch.randn(ni, c, hw, device="cuda").to(BF)
+    res = torch.randn(ni, c, hw, device="cuda").to(BF)
+    w = (torch.randn(c, c, device="cuda") / c ** 0.5).contiguous()
+    w_nk, w_kn = ops.pw_weight_pack(w)
+    sb = torch.stack([torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda")], dim=1).contiguous()
+    sample = [0, 1, 97, 254, 255]
+    wf = w_nk.float()
+    out = ops.pw_conv(x, w_nk, residual=res)
+    assert _rel(out[sample], torch.matmul(wf, x[sample].float()) + res[sample].float()) <= 1e-2
+    act = torch.relu(x.float() * sb[:, 0].view(1, c, 1) + sb[:, 1].view(1, c, 1)).to(BF)
+    assert _rel(ops.pw_conv(x, w_nk, in_scale_bias=sb)[sample], torch.matmul(wf, act[sample].float())) <= 1e-2
+    assert _rel(ops.pw_conv(x, w_kn)[sample], torch.matmul(wf.t(), x[sample].float())) <= 1e-2
+    assert torch.equal(ops.pw_conv(x, w_nk), ops.pw_conv(x, w))  # packed weights = what the kernel rounds itself
+    dw = ops.pw_conv_wgrad(res, x, in_scale_bias=sb)
+    ref = torch.zeros(c, c, device="cuda", dtype=torch.float64)
+    for i0 in range(0, ni, 32):
+        ref += torch.einsum("inp,ikp->nk", res[i0:i0 + 32].double(), act[i0:i0 + 32].double())
+    assert _rel(dw, ref) <= 1e-3
+    zero = torch.zeros_like(x)
+    assert torch.equal(ops.pw_conv(zero, w_nk, residual=res), res)  # W.0 + r == r exactly
+    assert torch.count_nonzero(ops.pw_conv(zero, w_nk)).item() == 0
+
+
 @pytest.mark.parametrize("shape", SHAPES)
 @pytest.mark.parametrize("with_res", [False, True])
 def test_pw_conv_epilogue_bn_statistics(shape, with_res):
