@@ -133,27 +133,6 @@ __device__ __forceinline__ void load_unit_flat(const __nv_bfloat16 *base, int of
     }
 }
 
-// the same unit, global -> shared (16 bytes at `dst`) with cp.async; pieces at or beyond `nleft` positions are zero-filled
-template <int VEC>
-__device__ __forceinline__ void cp_unit_flat(uint32_t dst, const __nv_bfloat16 *base, int off, const int (&o)[8 / VEC], int nleft) {
-    if (VEC == 8) {
-        const bool ok = nleft >= 8;
-        cp_async16(dst, ok ? base + off : base, ok ? 16u : 0u);
-    } else if (VEC == 4) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const bool ok = nleft >= 4 * h + 4;
-            cp_async8(dst + 8 * h, ok ? base + off + o[h] : base, ok ? 8u : 0u);
-        }
-    } else {
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-            const bool ok = nleft >= 2 * h + 2;
-            cp_async4(dst + 4 * h, ok ? base + off + o[(VEC == 2) ? h : 0] : base, ok ? 4u : 0u);
-        }
-    }
-}
-
 template <int VEC>
 __device__ __forceinline__ void store_unit_flat(__nv_bfloat16 *base, int off, const int (&o)[8 / VEC], int nleft, const uint32_t (&v)[4]) {
     if (VEC == 8) {
@@ -300,7 +279,7 @@ struct PwArgs {
     int shift_dt;
     int T, H, W;               // PROD_SHIFT3D: frames per clip, map size (HW = H*W)
     int NI, K, N, HW;
-    int Kpad, Ncta, Mt, Npx, kstage, acc_stages, stages, tmem_cols, stage_bytes, upt;
+    int Kpad, Ncta, Mt, Npx, kstage, acc_stages, stages, tmem_cols, stage_bytes, reserved0;
     int NP, total_tiles, k_stages;  // NP = NI*HW positions on the flattened (image, pixel) axis, tiled by Npx
     uint32_t off_w, off_a, off_sb, off_stg, w_lbo, a_lbo;
     int b_rows;                // activation operand staged as 128-byte-swizzled pixel rows (cp.async path) instead of 8x16-byte core matrices
@@ -729,40 +708,9 @@ __global__ void __launch_bounds__(PROD == PROD_SHIFT3D ? kThreads : kRowThreads,
     } else {
         // ===================================== activation producers ==============================================
         const int pw = warp - kProdWarp0;
-        const int kq = lane & 7, mgq = lane >> 3;
-        const int nq = a.Npx >> 5;  // quads of 8-pixel groups per tile
+        const int kq = lane & 7, mgq = lane >> 3;  // gather producer: channel / group-of-runs lanes
         const ShiftSrc ssrc{a.x, a.shift, a.shift_dt, a.T, a.H, a.W, a.HW, a.K,
                             (int)(((int64_t)a.NI * a.K * a.HW - 1) >> 1)};
-
-        // unit j of this thread inside a stage: channel kk (0..kstage-1), 8-pixel group mg
-        auto unit_kk = [&](int j) { return ((j * kNumProdWarps + pw) / nq) * 8 + kq; };
-        auto unit_mg = [&](int j) { return ((j * kNumProdWarps + pw) % nq) * 4 + mgq; };
-
-        // per-thread constants of the 4 units it owns in every stage
-        int ukk[4], usm[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            ukk[j] = unit_kk(j);
-            usm[j] = (ukk[j] >> 3) * (int)a.a_lbo + unit_mg(j) * 128 + (ukk[j] & 7) * 16;
-        }
-        // every unit of a thread has the same 8-pixel group of the tile: one (image, pixel) decomposition per tile
-        const int umg = unit_mg(0);
-        auto load_stage = [&](int tile, int st, uint32_t (&r)[4][4]) {
-            const int P = tile * a.Npx + umg * 8;
-            const int img = P / a.HW, pp = P - img * a.HW;
-            const int offb = img * a.K * a.HW + pp, nleft = a.NP - P;
-            int po[8 / VEC];
-            piece_offsets<VEC>(pp, a.HW, (a.K - 1) * a.HW, po);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int k = st * a.kstage + ukk[j];
-                if (j < a.upt && k < a.K) {
-                    load_unit_flat<VEC>(a.x, offb + k * a.HW, po, nleft, r[j]);
-                } else {
-                    r[j][0] = r[j][1] = r[j][2] = r[j][3] = 0u;
-                }
-            }
-        };
 
         int tile = tile0, st = 0, slot = 0;
         uint32_t phase = 0;
@@ -994,9 +942,7 @@ bool plan(PwArgs &a, int prod, int vec, dim3 *grid, size_t *smem_bytes) {
     a.Kpad = round_up(a.K, 16);
     const int sb_bytes = prod == PROD_BNRELU ? round_up(2 * a.Kpad * 4, 128) : 0;
     int gy = 0;
-    int cand0 = 1;
-    if (const char *dbg = getenv("RB_PW_GY")) cand0 = atoi(dbg) > 0 ? atoi(dbg) : 1;
-    for (int cand = cand0; cand <= 16 && !gy; ++cand) {
+    for (int cand = 1; cand <= 16 && !gy; ++cand) {
         const int nc = round_up(cdiv(a.N, cand), 8);
         const int mt = cdiv(nc, 128);
         if (mt > 4) continue;
@@ -1021,15 +967,7 @@ bool plan(PwArgs &a, int prod, int vec, dim3 *grid, size_t *smem_bytes) {
     if (!gy) return false;
     a.Npx = (2 * a.Mt * 128 <= 512) ? 128 : 64;
     a.acc_stages = 2;
-    if (const char *dbg = getenv("RB_PW_NPX")) {  // experiment: wider pixel tile with a single accumulator stage
-        const int npx = atoi(dbg);
-        if ((npx == 64 || npx == 128) && a.Mt * npx <= 512) {
-            a.Npx = npx;
-            a.acc_stages = (2 * a.Mt * npx <= 512) ? 2 : 1;
-        }
-    }
     a.kstage = a.stage_bytes / 2 / a.Npx;
-    a.upt = a.stage_bytes / 4096;  // 16-byte units per producer thread and stage
     a.a_lbo = (uint32_t)a.Npx * 16;
     a.k_stages = cdiv(a.Kpad, a.kstage);
     int cols = 32;

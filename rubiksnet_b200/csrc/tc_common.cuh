@@ -40,32 +40,8 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async8(uint32_t dst, const void *src, uint32_t src_bytes) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src, uint32_t src_bytes) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-// runtime N in [0, 11] (warp-uniform)
-__device__ __forceinline__ void cp_async_wait_dyn(int n) {
-    switch (n) {
-        case 0: cp_async_wait<0>(); break;
-        case 1: cp_async_wait<1>(); break;
-        case 2: cp_async_wait<2>(); break;
-        case 3: cp_async_wait<3>(); break;
-        case 4: cp_async_wait<4>(); break;
-        case 5: cp_async_wait<5>(); break;
-        case 6: cp_async_wait<6>(); break;
-        case 7: cp_async_wait<7>(); break;
-        case 8: cp_async_wait<8>(); break;
-        case 9: cp_async_wait<9>(); break;
-        case 10: cp_async_wait<10>(); break;
-        default: cp_async_wait<11>(); break;
-    }
-}
-
 // one lane of the (converged) warp gets true
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -87,32 +63,7 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
-// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulation; issued by ONE thread
-__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// variants with the accumulate predicate fixed at compile time (no setp in the single-thread issue loop)
-__device__ __forceinline__ void mma_bf16_first(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, 0, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc)
-        : "memory");
-}
-__device__ __forceinline__ void mma_bf16_acc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.eq.b32 p, 0, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc)
-        : "memory");
-}
+// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulation; issued by ONE thread.
 // Descriptors passed as (lo, hi) 32-bit halves: the start-address field lives in the low 14 bits of `lo`, so stepping
 // through K / M is a 32-bit add.  For the single elected thread of the issuing warp.
 __device__ __forceinline__ void mma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
@@ -124,27 +75,6 @@ __device__ __forceinline__ void mma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, ui
         "mov.b64 db, {%3, %4};\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
         ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// Predicated form for a converged warp: every lane executes the statement, the lane with `issue` != 0 issues the MMA.
-// No branch around the instruction, so the warp never diverges inside the issue loop and the operands stay in
-// uniform registers (a divergent `if (leader)` costs a BSSY / BRA / BSYNC round trip per MMA).
-__device__ __forceinline__ void mma_bf16_pred(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
-                                              uint32_t issue) {
-    asm volatile(
-        "{\n\t.reg .pred p, q;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "setp.ne.b32 q, %5, 0;\n\t"
-        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(issue)
-        : "memory");
-}
-__device__ __forceinline__ void mma_commit_pred(uint64_t *bar, uint32_t issue) {
-    asm volatile(
-        "{\n\t.reg .pred q;\n\t"
-        "setp.ne.b32 q, %1, 0;\n\t"
-        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
-        ::"r"(smem_u32(bar)), "r"(issue)
         : "memory");
 }
 // the mbarrier receives one arrival once every tcgen05.mma issued so far by this thread has completed
