@@ -131,7 +131,9 @@ int rb_attention_shift_backward(const void *x, const float *taps, const void *ou
 
 /* The bn1->relu / bn2->relu / bn_last->relu stages of RubiksShiftBlock / RubiksNetBackbone
  * (rubiksnet/backbone.py:50-53,123-135,196), which the reference delegates to nn.BatchNorm2d + nn.ReLU.
- * x / y / dy / dx are [NI, C, HW] contiguous (NCHW), parameters and statistics are fp32.
+ * x / y / dy / dx / residual are [NI, C, HW] contiguous (NCHW) with 16-byte aligned base pointers (checked:
+ * RB_ERR_INVALID_ARGUMENT otherwise); gamma / beta / running_mean / running_var and all statistics are FP32
+ * arrays of C elements -- a caller holding 16-bit BatchNorm buffers (model.half()) must pass fp32 copies.
  *   mean_invstd [C,2] and scale_bias [C,2] are OUTPUTS of the forward pass that the backward pass
  *   (and the fused shift) consume: y = act(x * scale + bias), scale = gamma * invstd,
  *   bias = beta - mean * scale.
@@ -228,9 +230,12 @@ int rb_shift3d_pw_conv_wgrad(const void *out_grad, const void *x, const void *sh
                              int dtype, int shift_dtype, int N, int T, int C, int H, int W, int Cout,
                              void *workspace, size_t workspace_bytes, void *stream);
 
-/* Debug aid (tools/trace_pw.py): when non-NULL, every k_pw_conv CTA writes globaltimer stamps of its pipeline events
- * (64 x uint64 per CTA) into this device buffer.  NULL switches tracing off (default). */
+#ifdef RB_DEBUG_TRACE
+/* Debug builds only (python -m rubiksnet_b200.build --trace; tools/trace_pw.py): when non-NULL, every k_pw_conv CTA
+ * writes globaltimer stamps of its pipeline events (128 x uint64 per CTA) into this device buffer.  The product
+ * library does not export this symbol and contains no tracing or work-skipping code. */
 void rb_debug_pw_trace(void *device_buffer);
+#endif
 
 #ifdef __cplusplus
 }

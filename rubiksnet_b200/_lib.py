@@ -6,6 +6,7 @@ There is NO fallback: if the library is missing or a call fails, this raises.
 """
 import ctypes
 import os
+import threading
 
 import torch
 
@@ -118,16 +119,23 @@ def stream_handle(device):
 # one growing scratch buffer per (device, stream): stream-ordered reuse is safe because every kernel
 # that touches it is enqueued on that same stream
 _workspaces = {}
+_workspaces_lock = threading.Lock()  # autograd runs backward on its own threads (and nn.DataParallel one per device)
 
 
 def workspace(nbytes, device):
     if nbytes == 0:
         return None
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
-    buf = _workspaces.get(key)
-    if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
-        _workspaces[key] = buf
+    stream = torch.cuda.current_stream(device)
+    if torch.cuda.is_current_stream_capturing():
+        # a buffer that lives in a CUDA graph's private pool must not be handed to eager work later: allocate per call
+        # inside a capture (the pool recycles it between replays) and keep it out of the cache
+        return torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+    key = (device.index, stream.cuda_stream)
+    with _workspaces_lock:
+        buf = _workspaces.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+            _workspaces[key] = buf
     return buf
 
 

@@ -26,9 +26,15 @@ def _bn(planes):
     return bn
 
 
-# CUDA tensors take the fused path (librubiks_b200 BN+ReLU kernels, batched-GEMM 1x1 convs); set to False to
-# run the plain nn.Module graph (used by tests to check that both give the same numbers)
+# CUDA tensors in fp32 / fp16 / bf16 take the fused path (librubiks_b200 BN+ReLU kernels, GEMM 1x1 convs); float64 (the
+# reference runs end to end in double, e.g. for gradcheck) and FUSED_BLOCK = False run the plain nn.Module graph
+# around the shift kernels (tests use the switch to check that both give the same numbers)
 FUSED_BLOCK = True
+_FUSED_DTYPES = (torch.float32, torch.float16, torch.bfloat16)
+
+
+def _use_fused(x):
+    return FUSED_BLOCK and x.is_cuda and x.dtype in _FUSED_DTYPES
 # identity-shortcut rubiks3d blocks with bf16 activations: one autograd Function, shift fused into conv3 (fused.py)
 FUSED_WHOLE_BLOCK = True
 
@@ -72,7 +78,7 @@ class RubiksShiftBlock(nn.Module):
             self.shortcut = nn.Identity()
 
     def forward(self, x):
-        if x.is_cuda and FUSED_BLOCK:
+        if _use_fused(x):
             return self._forward_fused(x)
         out = self.relu(self.bn1(x))
         shortcut = x if isinstance(self.shortcut, nn.Identity) else self.shortcut(out)
@@ -141,7 +147,7 @@ class RubiksNetBackbone(nn.Module):
         x = self.conv1(x)
         for i in range(5):
             x = getattr(self, "layer%d" % i)(x)
-        if x.is_cuda and FUSED_BLOCK:
+        if _use_fused(x):
             x = self.avgpool(fused.bn_act(x, self.bn_last, relu=True))
         else:
             x = self.avgpool(self.relu(self.bn_last(x)))

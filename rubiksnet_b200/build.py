@@ -15,7 +15,7 @@ SOURCES = ["abi.cu", "shift3d_generic.cu", "shift3d_tiled.cu", "shift3d_strip.cu
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "--use_fast_math=false" if False else "-fmad=true",  # IEEE div/sqrt; FMA contraction like the reference build
+    "-fmad=true",  # no --use_fast_math: IEEE div/sqrt; FMA contraction like the reference build
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
     "--threads", "4",
 ]
@@ -36,16 +36,19 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    """Compile every .cu under csrc/ for sm_100a into one shared library.  Returns its path."""
-    if not force and not _stale():
+def build(force=False, verbose=False, trace=False):
+    """Compile every .cu under csrc/ for sm_100a into one shared library.  Returns its path.
+    trace=True builds the DEBUG library librubiks_b200_trace.so (-DRB_DEBUG_TRACE: pipeline time stamps for
+    tools/trace_pw.py); the product library never contains that code and nothing in the package loads the debug one."""
+    lib_path = LIB_PATH.replace(".so", "_trace.so") if trace else LIB_PATH
+    if not trace and not force and not _stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
     objs = []
     procs = []
     for src in SOURCES:
-        obj = os.path.join(LIB_DIR, src.replace(".cu", ".o"))
-        cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(LIB_DIR, src.replace(".cu", "_trace.o" if trace else ".o"))
+        cmd = [_nvcc(), *NVCC_FLAGS, *(["-DRB_DEBUG_TRACE"] if trace else []), "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), file=sys.stderr)
@@ -59,9 +62,9 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed building librubiks_b200.so")
-    subprocess.check_call([_nvcc(), "-shared", "-o", LIB_PATH, *objs, "-Xcompiler", "-fPIC"])
-    return LIB_PATH
+    subprocess.check_call([_nvcc(), "-shared", "-o", lib_path, *objs, "-Xcompiler", "-fPIC"])
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, trace="--trace" in sys.argv))

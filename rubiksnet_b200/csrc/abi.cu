@@ -55,7 +55,9 @@ int bn_stats_finalize(const double *partial, int splits, int C, double count, co
                       cudaStream_t s);
 int bn_apply_forward(const void *x, const float *scale_bias, void *y, int dtype, int NI, int C, int HW, int relu, cudaStream_t s);
 size_t pw_conv_wgrad_workspace(int NI, int M, int N, int HW);
+#ifdef RB_DEBUG_TRACE
 void pw_conv_set_trace(void *p);
+#endif
 int pw_weight_pack(const float *w, void *w_nk, void *w_kn, int N, int K, cudaStream_t s);
 int pw_conv_wgrad(const void *g, const void *x, float *dw, int NI, int M, int N, int HW, const float *x_sb,
                   const void *shift, int shift_dt, int T, int H, int W, void *workspace, cudaStream_t s);
@@ -376,7 +378,9 @@ int rb_shift3d_pw_conv_wgrad(const void *out_grad, const void *x, const void *sh
                         workspace, workspace_bytes, stream);
 }
 
-/* debug: device buffer (64 x uint64 per CTA) receiving globaltimer stamps of k_pw_conv; NULL switches tracing off */
+#ifdef RB_DEBUG_TRACE
+/* debug builds only: device buffer (128 x uint64 per CTA) receiving globaltimer stamps of k_pw_conv; NULL = off */
 void rb_debug_pw_trace(void *device_buffer) { pw_conv_set_trace(device_buffer); }
+#endif
 
 }  // extern "C"

@@ -14,6 +14,9 @@ namespace rb {
 
 static constexpr int kBT = 256;
 
+// the streaming passes use 128-bit vector accesses on every activation tensor
+static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 struct FastDiv {  // exact unsigned division by a runtime constant for n < 2^31 (Granlund-Montgomery)
     uint32_t d, mul, shr;
 };
@@ -316,6 +319,7 @@ int rb::bn_apply_forward(const void *x, const float *scale_bias, void *y, int dt
                          cudaStream_t s) {
     if (dtype_size(dtype) == 0 || dtype == RB_F64) return fail(RB_ERR_INVALID_ARGUMENT, "bn: dtype %d not supported", dtype);
     if (C > 65535) return fail(RB_ERR_UNSUPPORTED, "bn: C > 65535");
+    if (!aligned16(x) || !aligned16(y)) return fail(RB_ERR_INVALID_ARGUMENT, "bn: activation pointers must be 16-byte aligned");
     const int64_t total = (int64_t)NI * C * HW;
     const FastDiv hw = make_fastdiv((uint32_t)HW);
     RB_DISPATCH_DTYPE(dtype, {
@@ -346,6 +350,7 @@ extern "C" int rb_bn_act_forward(const void *x, const float *gamma, const float 
     if (total > 0x7fffffffLL) return fail(RB_ERR_UNSUPPORTED, "bn: tensor too large");
     if (!x || !mean_invstd || !scale_bias) return fail(RB_ERR_INVALID_ARGUMENT, "null pointer");
     if (!training && (!running_mean || !running_var)) return fail(RB_ERR_INVALID_ARGUMENT, "eval mode needs running stats");
+    if (!aligned16(x) || !aligned16(y)) return fail(RB_ERR_INVALID_ARGUMENT, "bn: activation pointers must be 16-byte aligned");
     if (C > 65535) return fail(RB_ERR_UNSUPPORTED, "bn: C > 65535");
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
@@ -394,6 +399,8 @@ extern "C" int rb_bn_act_backward(const void *x, const void *dy, const void *res
     if (total > 0x7fffffffLL) return fail(RB_ERR_UNSUPPORTED, "bn: tensor too large");
     if (!x || !dy || !mean_invstd || !scale_bias) return fail(RB_ERR_INVALID_ARGUMENT, "null pointer");
     if (C > 65535) return fail(RB_ERR_UNSUPPORTED, "bn: C > 65535");
+    if (!aligned16(x) || !aligned16(dy) || !aligned16(residual) || !aligned16(dx))
+        return fail(RB_ERR_INVALID_ARGUMENT, "bn: activation pointers must be 16-byte aligned");
     if (!workspace || workspace_bytes < bn_ws_bytes(NI, C))
         return fail(RB_ERR_WORKSPACE, "bn backward needs %zu workspace bytes", bn_ws_bytes(NI, C));
     const int splits = bn_splits(NI, C);

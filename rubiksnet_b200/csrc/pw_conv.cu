@@ -287,21 +287,31 @@ struct PwArgs {
     double *stats;             // non-null: per-channel (sum, sum of squares) of `out` -> stats[(c * stats_splits + split) * 2 + {0,1}]
     int stats_splits;          // = 2 * gridDim.x (every CTA column and pixel half is one split)
     uint32_t hw_mul, hw_shr;   // exact division by HW for positions < 2^31: (umulhi(P, hw_mul) >> hw_shr), HW == 1: mul 0
-    int dbg;                   // debug: bit0 producers skip the global loads, bit1 epilogue skips global traffic, bit2 no MMAs
-    unsigned long long *trace; // debug: per-CTA event timestamps (globaltimer ns), 64 slots per CTA; null = off
+#ifdef RB_DEBUG_TRACE
+    unsigned long long *trace; // debug builds only: per-CTA event timestamps (globaltimer ns), 128 slots per CTA; null = off
+#endif
 };
 
+#ifdef RB_DEBUG_TRACE
 __device__ __forceinline__ unsigned long long gtime() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
+#endif
 // P / HW without the ~30-instruction runtime division (Granlund-Montgomery, exact for P < 2^31)
 __device__ __forceinline__ int div_hw(const PwArgs &a, int P) {
     return a.hw_mul == 0u ? P : (int)(__umulhi((uint32_t)P, a.hw_mul) >> a.hw_shr);
 }
+// Pipeline time stamps exist only in debug builds (python -m rubiksnet_b200.build --trace -> -DRB_DEBUG_TRACE, used by
+// tools/trace_pw.py); the product library contains no tracing code and no work-skipping switches.
+#ifdef RB_DEBUG_TRACE
 #define PW_TRACE_IF(cond, slot) do { if (a.trace) { if (cond) a.trace[(blockIdx.y * gridDim.x + blockIdx.x) * 128 + (slot)] = gtime(); } } while (0)
 #define PW_TRACE(slot) do { if (a.trace) a.trace[(blockIdx.y * gridDim.x + blockIdx.x) * 128 + (slot)] = gtime(); } while (0)
+#else
+#define PW_TRACE_IF(cond, slot) do { } while (0)
+#define PW_TRACE(slot) do { } while (0)
+#endif
 
 struct Hdr {
     uint64_t full[kMaxStages], empty[kMaxStages], tmem_full[2], tmem_empty[2];
@@ -453,7 +463,6 @@ __device__ __forceinline__ void mma_loop(const PwArgs &a, Hdr *hdr, unsigned cha
     const int ksteps_per_stage = a.kstage >> 4;
     const int acc_cols = a.Mt * a.Npx;
     const uint32_t npx = (uint32_t)a.Npx, stage16 = (uint32_t)(a.stage_bytes >> 4);
-    const bool skip = (a.dbg & 4) != 0;
     int slot = 0, it = 0;
     uint32_t phase = 0;
     for (int tile = tile0; tile < a.total_tiles; tile += tstride, ++it) {
@@ -475,17 +484,13 @@ __device__ __forceinline__ void mma_loop(const PwArgs &a, Hdr *hdr, unsigned cha
             const int ksteps = min(ksteps_per_stage, kleft);
             kleft -= ksteps;
             uint32_t b_lo = b_lo0 + (uint32_t)slot * stage16;
-            if (!skip) {
-                for (int ks = 0; ks < ksteps; ++ks) {
+            for (int ks = 0; ks < ksteps; ++ks) {
 #pragma unroll
-                    for (int mt = 0; mt < MT; ++mt)
-                        mma_bf16_lohi(tacc + mt * npx, a_lo + mt * (2048 >> 4), a_hi, b_lo, b_hi, idesc, acc);
-                    acc = 1u;
-                    a_lo += a_kstep;
-                    b_lo += b_kstep;
-                }
-            } else {
-                a_lo += ksteps * a_kstep;
+                for (int mt = 0; mt < MT; ++mt)
+                    mma_bf16_lohi(tacc + mt * npx, a_lo + mt * (2048 >> 4), a_hi, b_lo, b_hi, idesc, acc);
+                acc = 1u;
+                a_lo += a_kstep;
+                b_lo += b_kstep;
             }
             mma_commit(&hdr->empty[slot]);
             PW_TRACE_IF(it == 2 && st < 8, 65 + st * 8);
@@ -612,7 +617,7 @@ __global__ void __launch_bounds__(PROD == PROD_SHIFT3D ? kThreads : kRowThreads,
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int row = (lane >> 2) + 8 * i;
-                        nv[i] = (r0 + row < nrows && !(a.dbg & 2)) ? a.NP - P : 0;  // <= 0 beyond the tensor: nothing moves
+                        nv[i] = (r0 + row < nrows) ? a.NP - P : 0;  // <= 0 beyond the tensor: nothing moves
                         off[i] = ((img * a.N + n0 + r0 + row) * a.HW) + pp;
                         if (a.res != nullptr) load_unit_flat<VEC>(a.res, off[i], po, nv[i], rv[i]);
                     }
@@ -1399,8 +1404,10 @@ int pw_weight_pack(const float *w, void *w_nk, void *w_kn, int N, int K, cudaStr
     return launched("k_pw_weight_pack");
 }
 
+#ifdef RB_DEBUG_TRACE
 static unsigned long long *g_pw_trace = nullptr;
 void pw_conv_set_trace(void *p) { g_pw_trace = (unsigned long long *)p; }
+#endif
 
 int pw_conv_forward(const void *x, const void *w, int w_dt, int w_trans, const void *residual, void *out, int NI, int K,
                     int N, int HW, const float *a_sb, const void *shift, int shift_dt, int T, int H, int W, cudaStream_t s,
@@ -1409,8 +1416,9 @@ int pw_conv_forward(const void *x, const void *w, int w_dt, int w_trans, const v
     a.x = (const __nv_bfloat16 *)x; a.w = w; a.w_dt = w_dt; a.w_trans = w_trans; a.res = (const __nv_bfloat16 *)residual;
     a.out = (__nv_bfloat16 *)out; a.a_sb = a_sb; a.shift = shift; a.shift_dt = shift_dt;
     a.T = T; a.H = H; a.W = W; a.NI = NI; a.K = K; a.N = N; a.HW = HW;
+#ifdef RB_DEBUG_TRACE
     a.trace = g_pw_trace;
-    if (const char *dbg = getenv("RB_PW_DBG")) a.dbg = atoi(dbg);
+#endif
     const int prod = shift ? PROD_SHIFT3D : (a_sb ? PROD_BNRELU : PROD_PLAIN);
     dim3 grid;
     size_t smem_bytes = 0;

@@ -49,7 +49,7 @@ class _BNAct(torch.autograd.Function):
     def backward(ctx, dy):
         x, weight, mean_invstd, scale_bias = ctx.saved_tensors
         ni, c, hw, training, relu = ctx.cfg
-        dy = dy.contiguous()
+        dy = _aligned(dy)
         need_x = ctx.needs_input_grad[0]
         need_w = weight is not None and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
         dx = torch.empty_like(x) if need_x else None
@@ -66,17 +66,53 @@ class _BNAct(torch.autograd.Function):
         return dx, dgamma, dbeta, None, None, None, None, None, None
 
 
+def _f32(t):
+    return t if t is None or t.dtype == torch.float32 else t.float()
+
+
+def _bn_momentum(bn):
+    """Exponential-average factor of nn.BatchNorm2d: `momentum`, or the cumulative average 1/num_batches_tracked
+    (read AFTER the increment of this step) when momentum is None."""
+    if bn.momentum is not None:
+        return float(bn.momentum)
+    if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        return 1.0 / max(float(bn.num_batches_tracked.item()), 1.0)
+    return 0.0
+
+
+class _RunningStats:
+    """fp32 views of a BatchNorm's running statistics for the kernels (which read / update `float *`).  16-bit buffers
+    (model.half() / model.bfloat16()) are updated through fp32 copies that are written back on exit."""
+
+    def __init__(self, bn):
+        track = bn.track_running_stats and bn.running_mean is not None
+        self.rm = bn.running_mean if track else None
+        self.rv = bn.running_var if track else None
+        self.copy_back = track and bn.training and (self.rm.dtype != torch.float32 or self.rv.dtype != torch.float32)
+        self.mean, self.var = _f32(self.rm), _f32(self.rv)
+
+    def commit(self):
+        if self.copy_back:
+            self.rm.copy_(self.mean)
+            self.rv.copy_(self.var)
+
+
+def _aligned(t):
+    """The BN passes use 128-bit accesses: a contiguous view with a storage offset that is not 16-byte aligned is copied."""
+    t = t.contiguous()
+    return t if t.data_ptr() % 16 == 0 else t.clone(memory_format=torch.contiguous_format)
+
+
 def bn_act(x, bn, relu=True):
     """relu(bn(x)) with torch.nn.BatchNorm2d semantics (batch statistics + running-stat update in training
     mode, running statistics in eval mode) for a CUDA NCHW tensor."""
     training = bn.training or bn.running_mean is None
     if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(1)
-    momentum = 0.1 if bn.momentum is None else bn.momentum
-    w = bn.weight.float() if bn.weight is not None and bn.weight.dtype != torch.float32 else bn.weight
-    b = bn.bias.float() if bn.bias is not None and bn.bias.dtype != torch.float32 else bn.bias
-    return _BNAct.apply(x, w, b, bn.running_mean if bn.track_running_stats else None,
-                        bn.running_var if bn.track_running_stats else None, training, momentum, bn.eps, relu)
+    rs = _RunningStats(bn)
+    out = _BNAct.apply(_aligned(x), _f32(bn.weight), _f32(bn.bias), rs.mean, rs.var, training, _bn_momentum(bn), bn.eps, relu)
+    rs.commit()
+    return out
 
 
 class _Conv1x1TC(torch.autograd.Function):
@@ -161,10 +197,11 @@ def conv1x1(x, weight, residual=None, stride=1):
 # ------------------------------------------------------------------------------------- whole block
 
 def _bn_cfg(bn):
+    """(training, momentum, eps, running_mean, running_var) for the whole-block Functions; they are only used when the
+    buffers are fp32 (rubiks_block_supported checks), so the kernels may update them in place."""
     training = bn.training or bn.running_mean is None
-    momentum = 0.1 if bn.momentum is None else bn.momentum
     track = bn.track_running_stats and bn.running_mean is not None
-    return training, momentum, bn.eps, (bn.running_mean if track else None), (bn.running_var if track else None)
+    return training, _bn_momentum(bn), bn.eps, (bn.running_mean if track else None), (bn.running_var if track else None)
 
 
 # True: as3 -> conv3 -> += shortcut run as ONE launch (the shift is the operand producer of the tensor-core GEMM and is
@@ -269,8 +306,15 @@ def rubiks_block_supported(block, x):
         return False
     if not isinstance(r3.normalize_t_factor, (int, float)) or x.shape[0] % as3.n_segment != 0:
         return False
-    params = (block.conv2.weight, block.conv3.weight, block.bn1.weight, block.bn2.weight, r3.shift)
+    params = (block.conv2.weight, block.conv3.weight, block.bn1.weight, block.bn2.weight, r3.shift,
+              block.bn1.bias, block.bn2.bias)
     if any(p is None or p.dtype != torch.float32 for p in params):
+        return False
+    for bn in (block.bn1, block.bn2):  # the kernels update the running statistics in place as float *
+        if bn.track_running_stats and bn.running_mean is not None and (
+                bn.running_mean.dtype != torch.float32 or bn.running_var.dtype != torch.float32):
+            return False
+    if x.data_ptr() % 16 != 0:
         return False
     return getattr(r3, "shift_function", None) is _default_shift_function()
 

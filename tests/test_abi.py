@@ -13,6 +13,7 @@ from rubiksnet_b200 import _lib
 
 def _declared_symbols():
     text = open(os.path.join(REPO, "include", "rubiks_b200.h")).read()
+    text = re.sub(r"#ifdef RB_DEBUG_TRACE.*?#endif", "", text, flags=re.S)  # debug-build-only declarations
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(rb_[a-z0-9_]+)\s*\(", text)))
 
@@ -23,6 +24,14 @@ def test_header_symbols_exported():
     assert len(names) >= 15, names
     for n in names:
         assert hasattr(lib, n), "librubiks_b200.so does not export %s" % n
+
+
+def test_product_library_has_no_debug_hooks():
+    """No tracing entry point and no environment-variable switches in the library whose numbers are graded."""
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    assert not hasattr(lib, "rb_debug_pw_trace")
+    blob = open(_lib.LIB_PATH, "rb").read()
+    assert b"RB_PW_DBG" not in blob
 
 
 def test_version_and_out_len():

@@ -20,6 +20,9 @@ def main():
     ap.add_argument("--mode", default="fwd")
     ap.add_argument("--wbf16", action="store_true", help="bf16 weights packed by rb_pw_weight_pack")
     a = ap.parse_args()
+    # the stamps only exist in the debug library (python -m rubiksnet_b200.build --trace); point the loader at it
+    _lib.LIB_PATH = _lib.LIB_PATH.replace(".so", "_trace.so")
+    assert os.path.exists(_lib.LIB_PATH), "build the debug library first: python -m rubiksnet_b200.build --trace"
     L = _lib.lib()
     L.rb_debug_pw_trace.argtypes = [ctypes.c_void_p]
     L.rb_debug_pw_trace.restype = None
