@@ -47,6 +47,11 @@ def parse():
     ap.add_argument("--ref-device", default="auto", choices=["auto", "cuda", "cpu"])
     ap.add_argument("--cpu-sample-clips", type=int, default=2, help="clips per CPU-baseline pass")
     ap.add_argument("--cpu-sample-reps", type=int, default=10, help="passes of the CPU baseline (bounded sample: ~10-20 s)")
+    ap.add_argument("--infer", action="store_true",
+                    help="inference: eval-mode forward under no_grad (BASELINE C2 with --tier tiny --dtype fp32)")
+    ap.add_argument("--ref-autocast", action="store_true",
+                    help="--impl reference only: run the reference model under bf16 autocast with .float() casts around its "
+                         "(fp32-only) shift ops -- the like-for-like precision arm of SURVEY 8d(1)")
     ap.add_argument("--graph", default="on", choices=["on", "off"],
                     help="replay the whole step from a CUDA graph (rubiksnet_b200.graph.GraphedStep); off = eager launches")
     return ap.parse_args()
@@ -157,7 +162,7 @@ class Trainer:
             from rubiksnet_b200.dp import FlatGradAllReduce
             self.net = rb.RubiksNet(tier=args.tier, num_classes=NUM_CLASSES, num_frames=FRAMES,
                                     variant=args.variant).cuda().train()
-            self.reducer = FlatGradAllReduce(self.net)
+            self.reducer = None if args.infer else FlatGradAllReduce(self.net)
             self.fwd_net = self.net
             self.autocast = args.dtype == "bf16"
         else:
@@ -170,9 +175,29 @@ class Trainer:
                                      variant=args.variant).cuda().train()
             self.reducer = None
             self.fwd_net = self.net
-            if world > 1:
+            if world > 1 and not args.infer:
                 self.fwd_net = torch.nn.parallel.DistributedDataParallel(self.net, device_ids=[torch.cuda.current_device()])
-            self.autocast = False  # the reference's 3D shift is float/double only (primitive.py:66-75)
+            # the reference's 3D shift is float/double only (primitive.py:66-75) and its 2D shift has no bf16 path: stock
+            # = fp32 end to end.  --ref-autocast: bf16 autocast for the library ops with the shift ops computed in fp32
+            # between casts (the package itself stays unmodified: the casts are nn.Module forward hooks on its shift modules)
+            self.autocast = bool(args.ref_autocast) and args.dtype == "bf16"
+            if self.autocast:
+                def to_float(mod, inputs):
+                    mod._rb_in_dtype = inputs[0].dtype
+                    return (inputs[0].float(),) + tuple(inputs[1:])
+
+                def to_input_dtype(mod, inputs, output):
+                    return output.to(mod._rb_in_dtype)
+                for m in self.net.modules():
+                    if "shift" in m._parameters:  # RubiksShift3D / RubiksShift2D of the reference
+                        m.register_forward_pre_hook(to_float)
+                        m.register_forward_hook(to_input_dtype)
+        if args.infer:
+            self.net.eval()
+            self.opt = None
+            self.loss_fn = None
+            self.graphed = None
+            return
         shift_params = [p for n, p in self.net.named_parameters() if n.endswith("shift")]
         other = [p for n, p in self.net.named_parameters() if not n.endswith("shift")]
         # shift parameters get lr * 0.01 as in scripts/example_finetune.py:49-64
@@ -188,7 +213,7 @@ class Trainer:
         if self.kind != "ours" or self.args.graph != "on":
             return self.step
         from rubiksnet_b200.graph import GraphedStep
-        if self.world == 1 or os.environ.get("RB_GRAPH_MULTI"):
+        if self.world == 1 or self.args.infer or os.environ.get("RB_GRAPH_MULTI"):
             if self.graphed is None:
                 self.graphed = GraphedStep(self.step, clips, labels, warmup=2)
             return self.graphed
@@ -207,6 +232,12 @@ class Trainer:
             return loss
         return run
 
+    def infer(self, clips, labels):
+        torch = self.torch
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.autocast):
+            logits = self.fwd_net(clips)
+        return logits.float().logsumexp(1).mean()  # a scalar the e2e loop reads back (stands in for the loss)
+
     def fwd_bwd(self, clips, labels):
         torch = self.torch
         if self.reducer is not None:
@@ -220,6 +251,8 @@ class Trainer:
         return loss
 
     def step(self, clips, labels):
+        if self.args.infer:
+            return self.infer(clips, labels)
         loss = self.fwd_bwd(clips, labels)
         if self.reducer is not None:
             self.reducer.all_reduce()
@@ -344,14 +377,18 @@ def summarize_roofline(agg):
     out = {"bound": "hbm", "peak": peak, "unit": "GB/s", "traffic": None, "peak_source": peak_src}
     out.update(entry(top))
     try:  # DRAM bytes of one launch of that kernel family from the committed ncu --set full capture
-        t = json.load(open(os.path.join(REPO, "profiles", "r01g_traffic.json"))).get(top_family)
+        tf = [f for f in sorted(os.listdir(os.path.join(REPO, "profiles"))) if f.endswith("_traffic.json")][-1]
+        t = json.load(open(os.path.join(REPO, "profiles", tf))).get(top_family)
         if t:
             out["traffic"] = t["dram_bytes_per_launch"]
-            out["traffic_detail"] = t
+            out["traffic_detail"] = dict(t, source="profiles/" + tf)
     except Exception:  # noqa: BLE001
         pass
     out["all_kernels"] = [entry(k) for k in sorted(agg, key=lambda k: -agg[k]["ms"]) if k != top]
-    out["timed_ms_per_step"] = round(sum(d["ms"] for d in agg.values()), 3)
+    # sum over the individual calls only (the merged family entry added above is not a second kernel); these are
+    # event-bracketed EAGER launches, so the sum exceeds the graph-replayed step time
+    out["timed_ms_per_step"] = round(sum(d["ms"] for d in fam.values()), 3)
+    out["timed_note"] = "CUDA-event time of every librubiks_b200 call in ONE extra eager step (not the graph replay)"
     return out
 
 
@@ -408,9 +445,17 @@ def main():
     args = parse()
     import torch
     have_cuda = torch.cuda.is_available()
-    metric = "clips/sec (fwd+bwd) RubiksNet-%s 8x224^2" % args.tier.capitalize()
-    config = {"workload": "BASELINE C3: RubiksNet-%s %s, 8 frames x 224^2, fwd+bwd+SGD, synthetic clips, random init"
-                          % (args.tier.capitalize(), args.variant),
+    metric = "clips/sec (%s) RubiksNet-%s 8x224^2" % ("inference" if args.infer else "fwd+bwd", args.tier.capitalize())
+    if args.infer:
+        cfg_name = "C2" if (args.tier, args.variant, args.dtype) == ("tiny", "rubiks3d", "fp32") else "C2-like"
+        what = "eval-mode forward under no_grad"
+    else:
+        cfg_name = {"rubiks3d": "C3" if args.gpus == 1 else "C5", "rubiks3d-aq": "C4"}.get(args.variant, "C3")
+        if args.tier != "large" or args.dtype != "bf16":
+            cfg_name += "-like"
+        what = "fwd+bwd+SGD"
+    config = {"workload": "BASELINE %s: RubiksNet-%s %s, 8 frames x 224^2, %s, %s, synthetic clips, random init"
+                          % (cfg_name, args.tier.capitalize(), args.variant, args.dtype, what),
               "clips_per_gpu": args.batch, "frames": FRAMES, "num_classes": NUM_CLASSES,
               "parallelism": "dp%d (batch sharded, NCCL grad all-reduce)" % args.gpus,
               "launch": ("eager" if args.graph != "on" or args.impl != "ours" else
@@ -481,8 +526,10 @@ def main():
             "clocks": clocks, "e2e": e2e}
     if args.impl == "reference":
         line["impl"] = "reference"
-        line["config"]["reference"] = ("unmodified reference package + its CUDA extension (baseline/_ref, built for sm_100), "
-                                       "fp32: its 3D shift has no 16-bit path; DDP for n_gpus>1")
+        line["config"]["reference"] = (
+            "unmodified reference package + its CUDA extension (baseline/_ref, built for sm_100); " +
+            ("bf16 autocast for the library ops, its shift ops in fp32 between casts (--ref-autocast, SURVEY 8d(1))"
+             if tr.autocast else "stock path: fp32 end to end (its 3D shift has no 16-bit path)") + "; DDP for n_gpus>1")
         line["gpu_launches"] = None
     else:
         line["impl"] = "rubiksnet_b200"

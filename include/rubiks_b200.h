@@ -230,6 +230,12 @@ int rb_shift3d_pw_conv_wgrad(const void *out_grad, const void *x, const void *sh
                              int dtype, int shift_dtype, int N, int T, int C, int H, int W, int Cout,
                              void *workspace, size_t workspace_bytes, void *stream);
 
+/* Tiling override for rb_pw_conv_forward (process-global, like rb_set_impl): lower bound on the number of
+ * output-channel splits (grid.y); more splits = a smaller resident weight block and a deeper activation ring per CTA
+ * at the price of reading the activations once per split (from L2).  0 = automatic (default).  Changes the schedule
+ * only, never the arithmetic. */
+void rb_pw_conv_set_tuning(int min_n_splits);
+
 #ifdef RB_DEBUG_TRACE
 /* Debug builds only (python -m rubiksnet_b200.build --trace; tools/trace_pw.py): when non-NULL, every k_pw_conv CTA
  * writes globaltimer stamps of its pipeline events (128 x uint64 per CTA) into this device buffer.  The product

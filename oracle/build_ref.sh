@@ -23,6 +23,6 @@ cd "$WORK"
 export TORCH_CUDA_ARCH_LIST="10.0" MAX_JOBS="${MAX_JOBS:-8}"
 python -m pip install --no-index --no-build-isolation --no-deps --find-links /opt/wheelhouse \
     --upgrade --target "$DEST" "$WORK" 2>&1 | tail -n 5
-# one small checkpoint travels with the reference install for whole-model parity tests on the GPU box
-mkdir -p "$DEST/pretrained" && cp "$SRC/pretrained/ssv2_tiny.pth.tar" "$DEST/pretrained/"
+# the 9 shipped checkpoints (196 MB) travel with the reference install for whole-model parity tests on the GPU box
+mkdir -p "$DEST/pretrained" && cp -n "$SRC"/pretrained/*.pth.tar "$DEST/pretrained/"
 ls -la "$DEST"

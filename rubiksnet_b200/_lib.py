@@ -78,6 +78,8 @@ def _declare(lib):
     lib.rb_pw_conv_wgrad.restype = i
     lib.rb_shift3d_pw_conv_wgrad.argtypes = [vp] * 4 + [i] * 8 + [vp, sz, vp]
     lib.rb_shift3d_pw_conv_wgrad.restype = i
+    lib.rb_pw_conv_set_tuning.argtypes = [i]
+    lib.rb_pw_conv_set_tuning.restype = None
 
 
 def lib():

@@ -55,6 +55,7 @@ int bn_stats_finalize(const double *partial, int splits, int C, double count, co
                       cudaStream_t s);
 int bn_apply_forward(const void *x, const float *scale_bias, void *y, int dtype, int NI, int C, int HW, int relu, cudaStream_t s);
 size_t pw_conv_wgrad_workspace(int NI, int M, int N, int HW);
+void pw_conv_set_tuning(int min_n_splits);
 #ifdef RB_DEBUG_TRACE
 void pw_conv_set_trace(void *p);
 #endif
@@ -377,6 +378,8 @@ int rb_shift3d_pw_conv_wgrad(const void *out_grad, const void *x, const void *sh
     return wgrad_common(out_grad, x, weight_grad, dtype, N * T, C, Cout, H * W, nullptr, shift, shift_dtype, T, H, W,
                         workspace, workspace_bytes, stream);
 }
+
+void rb_pw_conv_set_tuning(int min_n_splits) { pw_conv_set_tuning(min_n_splits); }
 
 #ifdef RB_DEBUG_TRACE
 /* debug builds only: device buffer (128 x uint64 per CTA) receiving globaltimer stamps of k_pw_conv; NULL = off */

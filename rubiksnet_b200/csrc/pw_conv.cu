@@ -940,6 +940,9 @@ __global__ void __launch_bounds__(PROD == PROD_SHIFT3D ? kThreads : kRowThreads,
 
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
+// tiling override (rb_pw_conv_set_tuning): lower bound on the number of output-channel splits; 0 = automatic
+int g_min_n_splits = 0;
+
 // splits the output channels over grid.y so that the resident weight block fits shared memory, picks the pixel-tile width
 // so that two accumulator stages fit the 512 TMEM columns
 bool plan(PwArgs &a, int prod, int vec, dim3 *grid, size_t *smem_bytes) {
@@ -947,7 +950,7 @@ bool plan(PwArgs &a, int prod, int vec, dim3 *grid, size_t *smem_bytes) {
     a.Kpad = round_up(a.K, 16);
     const int sb_bytes = prod == PROD_BNRELU ? round_up(2 * a.Kpad * 4, 128) : 0;
     int gy = 0;
-    for (int cand = 1; cand <= 16 && !gy; ++cand) {
+    for (int cand = g_min_n_splits > 0 ? g_min_n_splits : 1; cand <= 16 && !gy; ++cand) {
         const int nc = round_up(cdiv(a.N, cand), 8);
         const int mt = cdiv(nc, 128);
         if (mt > 4) continue;
@@ -1408,6 +1411,8 @@ int pw_weight_pack(const float *w, void *w_nk, void *w_kn, int N, int K, cudaStr
 static unsigned long long *g_pw_trace = nullptr;
 void pw_conv_set_trace(void *p) { g_pw_trace = (unsigned long long *)p; }
 #endif
+
+void pw_conv_set_tuning(int min_n_splits) { g_min_n_splits = min_n_splits < 0 ? 0 : (min_n_splits > 16 ? 16 : min_n_splits); }
 
 int pw_conv_forward(const void *x, const void *w, int w_dt, int w_trans, const void *residual, void *out, int NI, int K,
                     int N, int HW, const float *a_sb, const void *shift, int shift_dt, int T, int H, int W, cudaStream_t s,

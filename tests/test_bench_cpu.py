@@ -29,6 +29,7 @@ def test_roofline_summary_merges_kernel_roles():
     assert abs(r["achieved"] - 1400.0) < 1e-6 and r["launches_per_step"] == 145
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-3
     assert {k["kernel"] for k in r["all_kernels"]} == set(agg)
+    assert abs(r["timed_ms_per_step"] - (6.0 + 4.0 + 6.3 + 4.4)) < 1e-6  # every call once (was double-counted)
     assert r["traffic"] is None or r["traffic"] > 0
     assert bench.summarize_roofline({}) is None
     r = bench.summarize_roofline({"bn_backward": agg["bn_backward"], "pw_conv": {"bytes": 1, "flops": 0, "ms": 0.1, "launches": 1}})

@@ -1,0 +1,207 @@
+"""Whole-model parity against the UNMODIFIED reference package + its CUDA extension (baseline/_ref) on the GPU box:
+
+  * all 9 shipped checkpoints: strict load into both packages, eval-mode logits on a seeded clip (fp32, TF32 off);
+  * the BENCHMARKED configurations -- RubiksNet-Large rubiks3d (BASELINE C3) and rubiks3d-aq (C4) under bf16 autocast,
+    training mode, the whole-block tcgen05 / BN / strip-shift graph -- against the fp32 reference on the same
+    parameters and clips: logits, loss and the gradients of conv / bn / shift parameters of a block in every stage;
+  * the same in fp32 (tight tolerance) so that a bf16 deviation can be told from a composition error.
+
+Tolerances are written in each test; the measured errors are also dumped to gpurun_out/model_parity.json."""
+import contextlib
+import io
+import json
+import os
+import sys
+
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from helpers import REPO  # noqa: E402
+
+import rubiksnet_b200 as rb  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+_REF = os.path.join(REPO, "baseline", "_ref")
+_CKPTS = ["ssv2_tiny", "ssv2_small", "ssv2_medium", "ssv2_large", "ssv2_large_aq_budget0.125",
+          "kinetics_tiny", "kinetics_small", "kinetics_medium", "kinetics_large"]
+_REPORT = {}
+
+
+def _ref_net_class():
+    if not os.path.isdir(os.path.join(_REF, "rubiksnet")):
+        pytest.skip("baseline/_ref (reference package) not on this box")
+    if _REF not in sys.path:
+        sys.path.insert(0, _REF)
+    with contextlib.redirect_stdout(io.StringIO()):
+        from rubiksnet.models import RubiksNet as RefNet
+    return RefNet
+
+
+def _relmax(a, b):
+    a, b = a.double(), b.double()
+    return (a - b).abs().max().item() / max(1e-12, b.abs().max().item())
+
+
+def _rel_l2(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _cos(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return (a @ b / (a.norm() * b.norm()).clamp_min(1e-30)).item()
+
+
+def _dump(key, value):
+    _REPORT[key] = value
+    try:
+        os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(REPO, "gpurun_out", "model_parity.json"), "w") as f:
+            json.dump(_REPORT, f, indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
+@contextlib.contextmanager
+def _no_tf32():
+    old = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        yield
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+
+
+@pytest.mark.parametrize("ckpt", _CKPTS)
+def test_checkpoint_eval_logits_match_reference(ckpt):
+    """logits of RubiksNet.load_pretrained(...) for all 9 checkpoints, reference ext vs this package.
+    fp32, eval mode (running statistics), TF32 off.  Tolerance 1e-3 of max|logit| and identical top-1."""
+    RefNet = _ref_net_class()
+    path = os.path.join(_REF, "pretrained", ckpt + ".pth.tar")
+    if not os.path.exists(path):
+        pytest.skip("checkpoint %s not on this box" % ckpt)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref = RefNet.load_pretrained(path).cuda().eval()
+    new = rb.RubiksNet.load_pretrained(path).cuda().eval()
+    assert set(new.state_dict().keys()) == set(ref.state_dict().keys())
+    g = torch.Generator(device="cuda").manual_seed(11)
+    clips = torch.randn(2, 8, 3, 224, 224, device="cuda", generator=g)
+    with _no_tf32(), torch.no_grad():
+        lr, ln = ref(clips), new(clips)
+    err = _relmax(ln, lr)
+    _dump("ckpt_eval/%s" % ckpt, {"relmax": err, "top1_equal": bool(torch.equal(ln.argmax(1), lr.argmax(1)))})
+    assert err <= 1e-3, "eval logits differ from the reference: %.3e" % err
+    assert torch.equal(ln.argmax(1), lr.argmax(1))
+
+
+def _pair(variant, tier="large", seed=5):
+    """(reference net, this package's net) with identical random-init parameters, both in training mode on cuda."""
+    RefNet = _ref_net_class()
+    torch.manual_seed(seed)
+    new = rb.RubiksNet(tier=tier, num_classes=174, num_frames=8, variant=variant).cuda().train()
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref = RefNet(tier=tier, num_classes=174, num_frames=8, variant=variant)  # AQ: dummy CUDA forward inside (models.py:100-104)
+    ref.load_state_dict(new.state_dict(), strict=True)
+    return ref.cuda().train(), new
+
+
+_GRAD_KEYS = {
+    "rubiks3d": ["backbone.conv1.weight", "new_fc.weight",
+                 "backbone.layer0.0.conv2.weight", "backbone.layer0.0.bn2.weight", "backbone.layer0.0.as3.rubiks3d.shift",
+                 "backbone.layer1.0.shortcut.weight", "backbone.layer1.1.conv3.weight", "backbone.layer1.1.bn1.bias",
+                 "backbone.layer1.1.as3.rubiks3d.shift",
+                 "backbone.layer2.3.conv2.weight", "backbone.layer2.3.bn2.bias", "backbone.layer2.3.as3.rubiks3d.shift",
+                 "backbone.layer3.17.conv3.weight", "backbone.layer3.17.bn1.weight", "backbone.layer3.17.as3.rubiks3d.shift",
+                 "backbone.layer4.1.conv2.weight", "backbone.layer4.1.bn2.weight", "backbone.layer4.1.as3.rubiks3d.shift"],
+    "rubiks3d-aq": ["backbone.conv1.weight", "new_fc.weight",
+                    "backbone.layer0.0.conv2.1.weight", "backbone.layer0.0.conv2.0.weight", "backbone.layer0.0.as3.shift",
+                    "backbone.layer1.1.conv3.weight", "backbone.layer1.1.conv2.0.weight", "backbone.layer1.1.as3.shift",
+                    "backbone.layer2.3.conv2.1.weight", "backbone.layer2.3.bn2.bias", "backbone.layer2.3.as3.shift",
+                    "backbone.layer3.17.conv3.weight", "backbone.layer3.17.conv2.0.weight", "backbone.layer3.17.as3.shift",
+                    "backbone.layer4.1.conv2.1.weight", "backbone.layer4.1.bn2.weight", "backbone.layer4.1.as3.shift"],
+}
+
+
+def _train_step(net, clips, labels, autocast):
+    net.zero_grad(set_to_none=True)
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+        logits = net(clips)
+    loss = torch.nn.functional.cross_entropy(logits.float(), labels)
+    loss.backward()
+    return logits.detach().float(), loss.detach().float(), {n: p.grad for n, p in net.named_parameters() if p.grad is not None}
+
+
+@pytest.mark.parametrize("variant", ["rubiks3d", "rubiks3d-aq"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_large_training_step_matches_fp32_reference(variant, precision):
+    """RubiksNet-Large fwd+bwd, training-mode BatchNorm, 4 clips (32 images per BN batch), same parameters:
+    this package (fp32, or bf16 autocast = the benchmarked graph) vs the reference in fp32.
+      fp32: logits 1e-3 of max|logit|, loss 1e-4, weight/bn gradients rel-L2 5e-3
+      bf16: logits 1e-2 of max|logit| + 1e-2 absolute, loss 1e-2 (north_star: 1e-2 bf16), gradients cosine >= 0.98
+      shift gradients (unit-normalised per channel, sign-sensitive for near-zero raw gradients): mean |diff| bound."""
+    ref, new = _pair(variant)
+    g = torch.Generator(device="cuda").manual_seed(17)
+    clips = torch.randn(4, 8, 3, 224, 224, device="cuda", generator=g)
+    labels = torch.tensor([3, 100, 42, 7], device="cuda")
+    with _no_tf32():
+        lr, lossr, gr = _train_step(ref, clips, labels, autocast=False)
+        ln, lossn, gn = _train_step(new, clips, labels, autocast=(precision == "bf16"))
+    rep = {"logits_relmax": _relmax(ln, lr), "logits_absmax": (ln - lr).abs().max().item(), "logit_scale": lr.abs().max().item(),
+           "loss_ref": lossr.item(), "loss_new": lossn.item(), "grads": {}}
+    for k in _GRAD_KEYS[variant]:
+        assert k in gr and k in gn, k
+        rep["grads"][k] = {"rel_l2": _rel_l2(gn[k], gr[k]), "cos": _cos(gn[k], gr[k]),
+                           "mean_abs": (gn[k].double() - gr[k].double()).abs().mean().item()}
+    _dump("train_step/%s/%s" % (variant, precision), rep)
+    if precision == "fp32":
+        assert rep["logits_relmax"] <= 1e-3, rep
+        assert abs(lossn.item() - lossr.item()) <= 1e-4 * max(1.0, abs(lossr.item())), rep
+    else:
+        assert rep["logits_absmax"] <= 1e-2 * rep["logit_scale"] + 1e-2, rep
+        assert abs(lossn.item() - lossr.item()) <= 1e-2 * max(1.0, abs(lossr.item())), rep
+    for k, e in rep["grads"].items():
+        if k.endswith("shift"):
+            assert e["mean_abs"] <= (5e-3 if precision == "fp32" else 0.15), (k, e)
+            assert e["cos"] >= (0.999 if precision == "fp32" else 0.9), (k, e)
+        elif precision == "fp32":
+            assert e["rel_l2"] <= 5e-3, (k, e)
+        else:
+            assert e["cos"] >= 0.98, (k, e)
+
+
+def test_bf16_model_with_16bit_bn_buffers():
+    """net.bfloat16() makes the BatchNorm buffers 16-bit; the kernels read/update float*, so the wrappers must
+    go through fp32 copies (no out-of-bounds writes, running statistics still updated like nn.BatchNorm2d)."""
+    torch.manual_seed(2)
+    net = rb.RubiksNet(tier="tiny", num_classes=5, num_frames=8).cuda().train()
+    ref_rm = net.backbone.layer2[1].bn2.running_mean.clone()
+    net16 = rb.RubiksNet(tier="tiny", num_classes=5, num_frames=8).cuda().train()
+    net16.load_state_dict(net.state_dict())
+    net16 = net16.bfloat16()
+    for m in net16.modules():  # shift parameters stay fp32 (the kernels take fp32 shifts with 16-bit activations)
+        if hasattr(m, "shift") and isinstance(m.shift, torch.nn.Parameter):
+            m.shift.data = m.shift.data.float()
+    clips = torch.randn(1, 8, 3, 224, 224, device="cuda")
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        net(clips)
+    out16 = net16(clips.bfloat16())
+    assert out16.dtype == torch.bfloat16 and torch.isfinite(out16.float()).all()
+    bn, bn16 = net.backbone.layer2[1].bn2, net16.backbone.layer2[1].bn2
+    assert bn16.running_mean.dtype == torch.bfloat16
+    assert not torch.equal(bn.running_mean, ref_rm)
+    assert (bn16.running_mean.float() - bn.running_mean).abs().max().item() <= 2e-2 * max(1.0, bn.running_mean.abs().max().item())
+    assert int(bn16.num_batches_tracked) == 1
+
+
+def test_float64_model_runs_through_module_graph():
+    """the reference runs end to end in double; float64 CUDA models take the plain nn.Module graph around the
+    (double-capable) shift kernels instead of raising in the fused BN path."""
+    torch.manual_seed(3)
+    net = rb.RubiksNet(tier="tiny", num_classes=5, num_frames=8).cuda().double().train()
+    clips = torch.randn(1, 8, 3, 224, 224, device="cuda", dtype=torch.float64)
+    out = net(clips)
+    out.sum().backward()
+    assert out.dtype == torch.float64 and torch.isfinite(out).all()
+    assert net.backbone.layer3[0].as3.rubiks3d.shift.grad is not None

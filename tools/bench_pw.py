@@ -12,7 +12,7 @@ import torch
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
-from rubiksnet_b200 import ops  # noqa: E402
+from rubiksnet_b200 import _lib, ops  # noqa: E402
 
 LAYERS = [("layer0", 72, 112), ("layer1.x", 72, 56), ("layer2.x", 144, 28), ("layer3.x", 288, 14), ("layer4.x", 576, 7)]
 BF = torch.bfloat16
@@ -49,8 +49,10 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--only", default=None)
-    ap.add_argument("--modes", default="fwd,bn,shift,dgrad,wgrad,wgrad_shift,cublas")
+    ap.add_argument("--modes", default="fwd,res,bn,shift,dgrad,wgrad,wgrad_shift,cublas")
+    ap.add_argument("--splits", type=int, default=0, help="rb_pw_conv_set_tuning: minimum output-channel splits (0 = auto)")
     a = ap.parse_args()
+    _lib.lib().rb_pw_conv_set_tuning(a.splits)
     modes = a.modes.split(",")
     T = 8
     print("device:", torch.cuda.get_device_name(0))
@@ -66,11 +68,13 @@ def main():
         sb = torch.stack([torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda")], dim=1).contiguous()
         unit = x.numel() * 2
         flush = unit * 3 < (300 << 20)
+        w_nk, w_kn = ops.pw_weight_pack(w)  # what the block path feeds the kernels (bf16, both orientations)
         cases = {
-            "fwd": (lambda: ops.pw_conv(x, w), 2 * unit),
-            "bn": (lambda: ops.pw_conv(x, w, in_scale_bias=sb), 2 * unit),
-            "shift": (lambda: ops.shift3d_pw_conv(x, shift, w, res, T), 3 * unit),
-            "dgrad": (lambda: ops.pw_conv(g, w, transposed=True), 2 * unit),
+            "fwd": (lambda: ops.pw_conv(x, w_nk), 2 * unit),
+            "res": (lambda: ops.pw_conv(x, w_nk, residual=res), 3 * unit),
+            "bn": (lambda: ops.pw_conv(x, w_nk, in_scale_bias=sb), 2 * unit),
+            "shift": (lambda: ops.shift3d_pw_conv(x, shift, w_nk, res, T), 3 * unit),
+            "dgrad": (lambda: ops.pw_conv(g, w_kn), 2 * unit),
             "wgrad": (lambda: ops.pw_conv_wgrad(g, x), 2 * unit),
             "wgrad_shift": (lambda: ops.shift3d_pw_conv_wgrad(g, x, shift, T), 2 * unit),
         }
