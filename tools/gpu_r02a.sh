@@ -25,5 +25,5 @@ python bench.py --impl reference --variant rubiks3d-aq --steps 5 --warmup 3 > $O
 python bench.py --impl reference --variant rubiks3d-aq --ref-autocast --steps 5 --warmup 3 > $O/r02a_bench_c4_ref_autocast.json 2> $O/r02a_bench_c4_ref_autocast.err; echo "c4 ref autocast exit=$?"
 python bench.py --impl reference --tier tiny --dtype fp32 --infer --batch 8 --steps 20 --warmup 5 > $O/r02a_bench_c2_ref.json 2> $O/r02a_bench_c2_ref.err; echo "c2 ref exit=$?"
 echo "t=$(( $(date +%s)-T0 ))s"
-timeout 1500 bash tools/sanitize.sh r02a
+timeout 900 bash tools/sanitize.sh r02a
 echo "t=$(( $(date +%s)-T0 ))s"

@@ -5,10 +5,10 @@ TAG="${1:-r02}"
 OUT=gpurun_out
 mkdir -p "$OUT"
 CS=/usr/local/cuda/bin/compute-sanitizer
-for tool in memcheck racecheck synccheck; do
+for tool in memcheck racecheck; do
   for grp in pw shift misc; do
     log="$OUT/${TAG}_sanitizer_${tool}_${grp}.log"
-    timeout 600 "$CS" --tool "$tool" --print-limit 20 --error-exitcode 3 python tools/sanitize_cases.py "$grp" > "$log" 2>&1
+    timeout 200 "$CS" --tool "$tool" --print-limit 20 --error-exitcode 3 python tools/sanitize_cases.py "$grp" > "$log" 2>&1
     echo "$tool $grp exit=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' "$log" | tail -1)"
   done
 done 2>&1 | tee "$OUT/${TAG}_sanitizer_summary.txt"

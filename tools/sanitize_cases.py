@@ -18,7 +18,7 @@ BF = torch.bfloat16
 
 
 def pw_cases():
-    for c, h, ni in ((288, 14, 16), (576, 7, 16), (144, 28, 8), (72, 56, 8), (54, 7, 8)):
+    for c, h, ni in ((288, 14, 8), (144, 28, 8), (54, 7, 8)):
         x = torch.randn(ni, c, h, h, device="cuda").to(BF)
         g = torch.randn(ni, c, h, h, device="cuda").to(BF)
         w = torch.randn(c, c, device="cuda") / c ** 0.5
