@@ -230,6 +230,23 @@ int rb_shift3d_pw_conv_wgrad(const void *out_grad, const void *x, const void *sh
                              int dtype, int shift_dtype, int N, int T, int C, int H, int W, int Cout,
                              void *workspace, size_t workspace_bytes, void *stream);
 
+/* Second-generation pointwise-conv path (csrc/pw_conv2.cu: all global traffic through TMA bulk copies, output channels
+ * split over grid.y, whole-image tiles on 14x14 / 7x7 maps).  The weight is handed over as a PACKED IMAGE -- the bf16
+ * shared-memory layout of every output-channel slice, so that a CTA fetches its slice with one bulk copy:
+ *   rb_pw_weight_image_bytes(rows, contraction)  size of the image of a [rows x contraction] matrix;
+ *   rb_pw_weight_image_pack(weight fp32 [N, K], N, K, transposed, image)
+ *        transposed == 0: image of W   (rows = N, contraction = K)  -> the forward GEMM of the conv;
+ *        transposed == 1: image of W^T (rows = K, contraction = N)  -> its input-gradient GEMM;
+ *   rb_pw_conv_forward(x, image, RB_W_IMAGE, 0, ...)  runs it: K = contraction, N = rows of the packed matrix;
+ *   rb_pw_conv_image_supported(NI, K, N, HW, has_in_scale_bias) != 0 tells whether this geometry has an image path
+ *        (K % 8 == 0, N % 8 == 0, HW <= 224 or HW % 8 == 0 with a divisor in [64, 256] that is a multiple of 8);
+ *        otherwise call rb_pw_conv_forward with a plain fp32 / bf16 weight.
+ * Same arithmetic as the plain path (bf16 operands, fp32 accumulation, bf16 result, `+= residual` on the rounded value). */
+#define RB_W_IMAGE 16
+size_t rb_pw_weight_image_bytes(int rows, int contraction);
+int rb_pw_weight_image_pack(const float *weight, int N, int K, int transposed, void *image, void *stream);
+int rb_pw_conv_image_supported(int NI, int K, int N, int HW, int has_in_scale_bias);
+
 /* Tiling override for rb_pw_conv_forward (process-global, like rb_set_impl): lower bound on the number of
  * output-channel splits (grid.y); more splits = a smaller resident weight block and a deeper activation ring per CTA
  * at the price of reading the activations once per split (from L2).  0 = automatic (default).  Changes the schedule

@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "librubiks_b200.so")
 
 RB_F32, RB_F64, RB_F16, RB_BF16 = 0, 1, 2, 3
+RB_W_IMAGE = 16  # weight argument of rb_pw_conv_forward is a packed image (rb_pw_weight_image_pack)
 RB_IMPL_AUTO, RB_IMPL_GENERIC, RB_IMPL_TILED, RB_IMPL_STRIP = 0, 1, 2, 3
 _DTYPES = {torch.float32: RB_F32, torch.float64: RB_F64, torch.float16: RB_F16, torch.bfloat16: RB_BF16}
 
@@ -78,6 +79,12 @@ def _declare(lib):
     lib.rb_pw_conv_wgrad.restype = i
     lib.rb_shift3d_pw_conv_wgrad.argtypes = [vp] * 4 + [i] * 8 + [vp, sz, vp]
     lib.rb_shift3d_pw_conv_wgrad.restype = i
+    lib.rb_pw_weight_image_bytes.argtypes = [i, i]
+    lib.rb_pw_weight_image_bytes.restype = sz
+    lib.rb_pw_weight_image_pack.argtypes = [vp, i, i, i, vp, vp]
+    lib.rb_pw_weight_image_pack.restype = i
+    lib.rb_pw_conv_image_supported.argtypes = [i, i, i, i, i]
+    lib.rb_pw_conv_image_supported.restype = i
     lib.rb_pw_conv_set_tuning.argtypes = [i]
     lib.rb_pw_conv_set_tuning.restype = None
 

@@ -56,6 +56,12 @@ int bn_stats_finalize(const double *partial, int splits, int C, double count, co
 int bn_apply_forward(const void *x, const float *scale_bias, void *y, int dtype, int NI, int C, int HW, int relu, cudaStream_t s);
 size_t pw_conv_wgrad_workspace(int NI, int M, int N, int HW);
 void pw_conv_set_tuning(int min_n_splits);
+// pw_conv2.cu
+size_t pw2_weight_image_bytes(int rows, int contraction);
+int pw2_weight_pack(const float *w, int N, int K, int trans, void *image, cudaStream_t s);
+bool pw2_supported(int NI, int K, int N, int HW, int has_bn);
+int pw2_forward(const void *x, const void *wimg, const void *residual, void *out, int NI, int K, int N, int HW,
+                const float *a_sb, cudaStream_t s);
 #ifdef RB_DEBUG_TRACE
 void pw_conv_set_trace(void *p);
 #endif
@@ -270,15 +276,33 @@ static int check_weight_dtype(int wdt) {
 int rb_pw_conv_forward(const void *x, const void *weight, int weight_dtype, int weight_transposed, const void *residual,
                        void *out, int dtype, int NI, int K, int N, int HW, const float *in_scale_bias, void *stream) {
     if (dtype != RB_BF16) return fail(RB_ERR_UNSUPPORTED, "rb_pw_conv_forward: bf16 activations only (got dtype %d)", dtype);
-    int rc = check_weight_dtype(weight_dtype);
+    int rc = weight_dtype == RB_W_IMAGE ? RB_OK : check_weight_dtype(weight_dtype);
     if (rc) return rc;
     if (NI < 0 || K <= 0 || N <= 0 || HW < 0) return fail(RB_ERR_INVALID_ARGUMENT, "bad extent [%d,%d,%d,%d]", NI, K, N, HW);
     if ((int64_t)NI * K * HW > 0x7fffffffLL || (int64_t)NI * N * HW > 0x7fffffffLL)
         return fail(RB_ERR_UNSUPPORTED, "tensors with more than 2^31-1 elements are not supported");
     if ((int64_t)NI * HW == 0) return RB_OK;
     if (!x || !weight || !out) return fail(RB_ERR_INVALID_ARGUMENT, "null pointer");
+    if (weight_dtype == RB_W_IMAGE) {
+        if (weight_transposed)
+            return fail(RB_ERR_INVALID_ARGUMENT, "a packed weight image carries its orientation (rb_pw_weight_image_pack)");
+        return pw2_forward(x, weight, residual, out, NI, K, N, HW, in_scale_bias, (cudaStream_t)stream);
+    }
     return pw_conv_forward(x, weight, weight_dtype, weight_transposed != 0, residual, out, NI, K, N, HW, in_scale_bias,
                            nullptr, 0, 0, 0, 0, (cudaStream_t)stream);
+}
+
+size_t rb_pw_weight_image_bytes(int rows, int contraction) { return pw2_weight_image_bytes(rows, contraction); }
+
+int rb_pw_weight_image_pack(const float *weight, int N, int K, int transposed, void *image, void *stream) {
+    if (N <= 0 || K <= 0) return fail(RB_ERR_INVALID_ARGUMENT, "bad extent [%d,%d]", N, K);
+    if (!weight || !image) return fail(RB_ERR_INVALID_ARGUMENT, "null pointer");
+    if (reinterpret_cast<uintptr_t>(image) & 15) return fail(RB_ERR_INVALID_ARGUMENT, "weight image must be 16-byte aligned");
+    return pw2_weight_pack(weight, N, K, transposed != 0, image, (cudaStream_t)stream);
+}
+
+int rb_pw_conv_image_supported(int NI, int K, int N, int HW, int has_in_scale_bias) {
+    return pw2_supported(NI, K, N, HW, has_in_scale_bias) ? 1 : 0;
 }
 
 int rb_pw_conv_forward_stats(const void *x, const void *weight, int weight_dtype, int weight_transposed, const void *residual,

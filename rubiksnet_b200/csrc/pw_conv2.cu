@@ -1,0 +1,657 @@
+// Pointwise (1x1) convolution of RubiksShiftBlock, second generation: every byte of global traffic moves through the
+// TMA unit (cp.async.bulk, SASS UBLKCP), warps only touch shared memory and tensor memory.
+//
+//     out[i, n, p] = sum_k W[n, k] * A(i, k, p)  (+ residual[i, n, p]),   A = x  or  relu(x * scale[k] + bias[k])
+//
+// (conv2 / conv3 / shortcut of rubiksnet/backbone.py:123-135 and, on the transposed weight image, their input gradients.)
+//
+// Why a second kernel (measured on B200, profiles/r01g_*): the first-generation k_pw_conv keeps the WHOLE [N x K] weight
+// block resident (166 KiB at 288 channels), which leaves a 44 KiB activation ring -- one tile deep -- and moves activations
+// with per-thread LDG/STG, so its producers and its epilogue (15 GB/s per SM), not HBM, set the pace.  Here:
+//   * output channels are split over grid.y so that a CTA owns <= 128 of them: ONE M tile, a weight slice of <= 112 KiB that
+//     arrives as a single bulk copy of a pre-packed shared-memory image (rb_pw2_weight_pack), and room for deep rings;
+//   * a tile is S segments of L consecutive pixels (S whole images when a map has <= 224 pixels -- 14x14: one image, 7x7: four
+//     -- else L = a 16-byte-multiple divisor of the map), N_mma = round_up(S*L, 16) <= 256 accumulator columns, double-buffered
+//     in tensor memory;
+//   * raw ring: the producer warp fetches the [channels x L] rows of a K chunk exactly as they lie in NCHW (whole-image
+//     chunks are ONE contiguous bulk copy) -- alignment rules of cp.async.bulk (16 bytes) are met by construction;
+//   * relayout warps turn a raw stage into the MN-major SWIZZLE_128B UMMA operand (and apply bn1+relu on the way): shared ->
+//     shared with 29-cycle loads instead of 600-cycle global loads, so 4 warps with a handful of registers keep up;
+//   * the epilogue writes bf16 rows into a staging block laid out exactly like the output rows in global memory, the
+//     residual block is bulk-loaded into the same staging buffer beforehand and added in place, and the tile leaves with
+//     bulk stores (one per image for whole-image tiles).
+// Arithmetic is the same as k_pw_conv: bf16 operands, fp32 accumulation in TMEM, result rounded to bf16, `+= shortcut` on
+// the rounded value.
+#include "tc_common.cuh"
+
+namespace rb {
+
+using namespace tc;
+
+namespace {
+
+constexpr int kP2Warps = 14;
+constexpr int kP2Threads = kP2Warps * 32;  // 448
+constexpr int kP2RelWarp0 = 2, kP2NumRel = 4;
+constexpr int kP2EpiWarp0 = 6, kP2NumEpi = 8;
+constexpr int kP2MaxRing = 8;
+constexpr int kP2Smem = 227 * 1024;
+constexpr int kP2Hdr = 512;
+constexpr int kP2MaxRows = 128;
+
+struct P2Args {
+    const __nv_bfloat16 *x;      // [NI, K, HW]
+    const unsigned char *wimg;   // packed weight image: gy slices of w_bytes
+    const __nv_bfloat16 *res;    // [NI, N, HW] or null
+    __nv_bfloat16 *out;          // [NI, N, HW]
+    const float *a_sb;           // bn+relu producer: (scale, bias) pairs [K, 2] or null
+    int NI, K, N, HW;
+    int Kpad, Ncta, gy;
+    int L, S, tpi, caseA;        // segment length, segments per tile, tiles per image (case B), whole-image segments?
+    int Nmma, atoms, kc, G, k_stages, raw_stages, op_stages, stg_bufs, total_tiles;
+    int V;                       // elements per relayout piece (8 / 4 / 2 / 1)
+    uint32_t ppr, ppr_mul, ppr_shr;  // pieces per row and its exact-division constants
+    uint32_t w_lbo, w_bytes, off_sb, off_w, off_raw, off_op, off_stg;
+    uint32_t raw_stage_bytes, op_stage_bytes, stg_buf_bytes, stg_pitch, stg_seg_stride;
+};
+
+struct P2Hdr {
+    uint64_t raw_full[kP2MaxRing], raw_empty[kP2MaxRing], op_full[kP2MaxRing], op_empty[kP2MaxRing];
+    uint64_t tmem_full[2], tmem_empty[2], res_full[2], stg_free, w_full;
+    uint32_t tmem_base;
+};
+static_assert(sizeof(P2Hdr) <= kP2Hdr, "header");
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// global -> shared bulk copy (TMA, 1-D); completion is counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// shared -> global bulk copy; completion through the issuing thread's bulk async-groups
+__device__ __forceinline__ void bulk_s2g(void *dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t a) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return (uint32_t)v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts64(uint32_t a, uint2 v) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+__device__ __forceinline__ uint32_t bnrelu2(uint32_t w, float sc, float bi) {
+    return pack_bf16x2(fmaxf(fmaf(bf16_lo(w), sc, bi), 0.f), fmaxf(fmaf(bf16_hi(w), sc, bi), 0.f));
+}
+
+// tile -> first image, pixel offset inside the image, number of valid segments
+__device__ __forceinline__ void p2_tile(const P2Args &a, int tile, int &img0, int &p0, int &nseg) {
+    if (a.caseA) {
+        img0 = tile * a.S;
+        p0 = 0;
+        nseg = min(a.S, a.NI - img0);
+    } else {
+        img0 = tile / a.tpi;
+        p0 = (tile - img0 * a.tpi) * a.L;
+        nseg = 1;
+    }
+}
+
+template <int V, bool BN>
+__device__ __forceinline__ void p2_relayout_stage(const P2Args &a, uint32_t raw, uint32_t op, const float *sb, int kbase,
+                                                  int rows_real, int rows_pad_shift, int nseg, int rt) {
+    // pieces of V elements, flattened over (segment, channel row, piece): consecutive threads read consecutive addresses of
+    // the raw stage (rows are dense) and write 16-byte-chunk-swizzled rows of the operand
+    const uint32_t rows_pad = 1u << rows_pad_shift;
+    const uint32_t total = (uint32_t)nseg * rows_pad * a.ppr;
+    const uint32_t Lb = (uint32_t)a.L * 2u;
+    for (uint32_t q = (uint32_t)rt; q < total; q += kP2NumRel * 32) {
+        const uint32_t rowid = a.ppr_mul ? (__umulhi(q, a.ppr_mul) >> a.ppr_shr) : q;
+        const uint32_t piece = q - rowid * a.ppr;
+        const uint32_t s = rowid >> rows_pad_shift, kl = rowid & (rows_pad - 1);
+        const uint32_t c = s * (uint32_t)a.L + piece * V;
+        const uint32_t dst = op + (((c >> 6) * (uint32_t)a.G + (kl >> 3)) << 10) + ((kl & 7) << 7) +
+                             ((((c & 63) >> 3) ^ (kl & 7)) << 4) + ((c & 7) << 1);
+        const bool real = (int)kl < rows_real;
+        const uint32_t src = raw + (s * (uint32_t)a.kc + kl) * Lb + piece * (V * 2);
+        float sc = 0.f, bi = 0.f;
+        if (BN && real) {
+            sc = sb[kbase + (int)kl];
+            bi = sb[a.Kpad + kbase + (int)kl];
+        }
+        if (V == 8) {
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (real) {
+                v = lds128(src);
+                if (BN) { v.x = bnrelu2(v.x, sc, bi); v.y = bnrelu2(v.y, sc, bi); v.z = bnrelu2(v.z, sc, bi); v.w = bnrelu2(v.w, sc, bi); }
+            }
+            sts128(dst, v);
+        } else if (V == 4) {
+            uint2 v = make_uint2(0u, 0u);
+            if (real) {
+                v = lds64(src);
+                if (BN) { v.x = bnrelu2(v.x, sc, bi); v.y = bnrelu2(v.y, sc, bi); }
+            }
+            sts64(dst, v);
+        } else if (V == 2) {
+            uint32_t v = 0u;
+            if (real) {
+                v = lds32(src);
+                if (BN) v = bnrelu2(v, sc, bi);
+            }
+            sts32(dst, v);
+        } else {
+            uint32_t v = 0u;
+            if (real) {
+                v = lds16(src);
+                if (BN) v = bnrelu2(v, sc, bi) & 0xffffu;
+            }
+            sts16(dst, v);
+        }
+    }
+}
+
+template <int V, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_pw2(const P2Args a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    P2Hdr *hdr = reinterpret_cast<P2Hdr *>(smem);
+    float *smem_sb = reinterpret_cast<float *>(smem + a.off_sb);
+    const uint32_t s_w = smem_u32(smem + a.off_w), s_raw = smem_u32(smem + a.off_raw), s_op = smem_u32(smem + a.off_op),
+                   s_stg = smem_u32(smem + a.off_stg);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n0 = blockIdx.y * a.Ncta;
+    const int nrows = min(a.Ncta, a.N - n0);
+    const int tile0 = blockIdx.x, tstride = gridDim.x;
+    const bool has_res = a.res != nullptr;
+
+    if (tid == 0) {
+        for (int i = 0; i < kP2MaxRing; ++i) {
+            mbar_init(&hdr->raw_full[i], 1);
+            mbar_init(&hdr->raw_empty[i], kP2NumRel);
+            mbar_init(&hdr->op_full[i], kP2NumRel);
+            mbar_init(&hdr->op_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&hdr->tmem_full[i], 1);
+            mbar_init(&hdr->tmem_empty[i], kP2NumEpi);
+            mbar_init(&hdr->res_full[i], 1);
+        }
+        mbar_init(&hdr->stg_free, 1);
+        mbar_init(&hdr->w_full, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        __syncwarp();
+        tmem_alloc(&hdr->tmem_base, 512u);
+    }
+    if (BN)
+        for (int k = tid; k < a.Kpad; k += kP2Threads) {
+            smem_sb[k] = k < a.K ? a.a_sb[2 * k] : 0.f;
+            smem_sb[a.Kpad + k] = k < a.K ? a.a_sb[2 * k + 1] : 0.f;
+        }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = hdr->tmem_base;
+
+    if (warp == 0) {
+        // ================================ MMA issuer: one thread ===================================================
+        if (elect_one()) {
+            const uint32_t idesc = instr_desc_bf16(128, a.Nmma, /*weights: K-major*/ 0, /*activations: MN-major*/ 1);
+            const uint64_t adesc0 = smem_desc(s_w, a.w_lbo, 128, LAYOUT_NONE);
+            // activations: per 8-channel group 8 rows of 64 pixels (128 B, chunks XOR-swizzled by the row), groups 1 KiB apart
+            // (SBO), the next 64 pixels G KiB further (LBO)
+            const uint64_t bdesc0 = smem_desc(s_op, (uint32_t)a.G * 1024u, 1024, LAYOUT_SW128);
+            const uint32_t a_hi = (uint32_t)(adesc0 >> 32), b_hi = (uint32_t)(bdesc0 >> 32);
+            const uint32_t a_lo0 = (uint32_t)adesc0, b_lo0 = (uint32_t)bdesc0;
+            const uint32_t a_kstep = (2 * a.w_lbo) >> 4, op16 = a.op_stage_bytes >> 4;
+            mbar_wait(&hdr->w_full, 0);
+            tc_fence_after();
+            int n = 0, it = 0;
+            for (int tile = tile0; tile < a.total_tiles; tile += tstride, ++it) {
+                const int as = it & 1;
+                mbar_wait(&hdr->tmem_empty[as], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + (uint32_t)as * 256u;
+                uint32_t a_lo = a_lo0, acc = 0u;
+                for (int st = 0; st < a.k_stages; ++st, ++n) {
+                    const int o = n % a.op_stages;
+                    mbar_wait(&hdr->op_full[o], (uint32_t)(n / a.op_stages) & 1u);
+                    tc_fence_after();
+                    const int ksteps = min(a.kc, a.Kpad - st * a.kc) >> 4;
+                    uint32_t b_lo = b_lo0 + (uint32_t)o * op16;
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        mma_bf16_lohi(tacc, a_lo, a_hi, b_lo, b_hi, idesc, acc);
+                        acc = 1u;
+                        a_lo += a_kstep;
+                        b_lo += 2048u >> 4;
+                    }
+                    mma_commit(&hdr->op_empty[o]);
+                }
+                mma_commit(&hdr->tmem_full[as]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ================================ TMA producer warp ========================================================
+        if (lane == 0) {
+            mbar_expect_tx(&hdr->w_full, a.w_bytes);
+            bulk_g2s(s_w, a.wimg + (size_t)blockIdx.y * a.w_bytes, a.w_bytes, &hdr->w_full);
+        }
+        const uint32_t Lb = (uint32_t)a.L * 2u;
+        int n = 0, it = 0;
+        for (int tile = tile0; tile < a.total_tiles; tile += tstride, ++it) {
+            int img0, p0, nseg;
+            p2_tile(a, tile, img0, p0, nseg);
+            bool res_pending = has_res;
+            auto issue_residual = [&]() {
+                const int buf = it % a.stg_bufs;
+                const uint32_t dst0 = s_stg + (uint32_t)buf * a.stg_buf_bytes;
+                if (a.caseA) {
+                    const uint32_t bytes = (uint32_t)nrows * Lb;
+                    if (lane == 0) mbar_expect_tx(&hdr->res_full[buf], bytes * (uint32_t)nseg);
+                    __syncwarp();
+                    if (lane < nseg)
+                        bulk_g2s(dst0 + (uint32_t)lane * a.stg_seg_stride,
+                                 a.res + ((size_t)(img0 + lane) * a.N + n0) * a.HW, bytes, &hdr->res_full[buf]);
+                } else {
+                    if (lane == 0) mbar_expect_tx(&hdr->res_full[buf], (uint32_t)nrows * Lb);
+                    __syncwarp();
+                    for (int m = lane; m < nrows; m += 32)
+                        bulk_g2s(dst0 + (uint32_t)m * a.stg_pitch, a.res + ((size_t)img0 * a.N + n0 + m) * a.HW + p0, Lb,
+                                 &hdr->res_full[buf]);
+                }
+                res_pending = false;
+            };
+            // the staging buffer of this tile is free once the store of tile it - stg_bufs has read it: the epilogue signals
+            // that at the end of tile it - 1 (arrival it - 1 on stg_free).  Every arrival is waited for, in order (also the
+            // ones a second staging buffer would let us skip), so that this warp is never two phases behind the barrier.
+            const bool need_free = it >= 1;
+            const uint32_t free_par = (uint32_t)(it - 1) & 1u;
+            for (int st = 0; st < a.k_stages; ++st, ++n) {
+                if (res_pending) {
+                    bool ok = !need_free;
+                    if (need_free) ok = __shfl_sync(0xffffffffu, (int)mbar_test(&hdr->stg_free, free_par), 0) != 0;
+                    if (ok) issue_residual();
+                }
+                const int r = n % a.raw_stages;
+                mbar_wait(&hdr->raw_empty[r], ((uint32_t)(n / a.raw_stages) & 1u) ^ 1u);
+                const int k0 = st * a.kc;
+                const int rows = min(a.kc, a.K - k0);
+                const uint32_t dst0 = s_raw + (uint32_t)r * a.raw_stage_bytes;
+                if (a.caseA) {
+                    const uint32_t bytes = (uint32_t)rows * Lb;
+                    if (lane == 0) mbar_expect_tx(&hdr->raw_full[r], bytes * (uint32_t)nseg);
+                    __syncwarp();
+                    if (lane < nseg)
+                        bulk_g2s(dst0 + (uint32_t)lane * (uint32_t)a.kc * Lb, a.x + ((size_t)(img0 + lane) * a.K + k0) * a.HW, bytes,
+                                 &hdr->raw_full[r]);
+                } else {
+                    if (lane == 0) mbar_expect_tx(&hdr->raw_full[r], (uint32_t)rows * Lb);
+                    __syncwarp();
+                    if (lane < rows)
+                        bulk_g2s(dst0 + (uint32_t)lane * Lb, a.x + ((size_t)img0 * a.K + k0 + lane) * a.HW + p0, Lb, &hdr->raw_full[r]);
+                }
+                __syncwarp();
+            }
+            if (res_pending) {
+                if (need_free) mbar_wait(&hdr->stg_free, free_par);
+                issue_residual();
+            }
+        }
+    } else if (warp < kP2EpiWarp0) {
+        // ================================ relayout warps: raw stage -> UMMA operand =================================
+        const int rt = (warp - kP2RelWarp0) * 32 + lane;
+        int n = 0;
+        for (int tile = tile0; tile < a.total_tiles; tile += tstride) {
+            int img0, p0, nseg;
+            p2_tile(a, tile, img0, p0, nseg);
+            for (int st = 0; st < a.k_stages; ++st, ++n) {
+                const int r = n % a.raw_stages, o = n % a.op_stages;
+                const int k0 = st * a.kc;
+                const int rows_real = min(a.kc, a.K - k0);
+                const int rows_pad = min(a.kc, a.Kpad - k0);  // 16 or 32
+                mbar_wait(&hdr->raw_full[r], (uint32_t)(n / a.raw_stages) & 1u);
+                mbar_wait(&hdr->op_empty[o], ((uint32_t)(n / a.op_stages) & 1u) ^ 1u);
+                p2_relayout_stage<V, BN>(a, s_raw + (uint32_t)r * a.raw_stage_bytes, s_op + (uint32_t)o * a.op_stage_bytes, smem_sb,
+                                         k0, rows_real, rows_pad == 32 ? 5 : 4, nseg, rt);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&hdr->op_full[o]);
+                    mbar_arrive(&hdr->raw_empty[r]);
+                }
+            }
+        }
+    } else {
+        // ================================ epilogue warps ==========================================================
+        const int e = warp - kP2EpiWarp0, q = warp & 3, half = e >> 2;
+        const int m = q * 32 + lane;  // output channel row (TMEM lane) of this thread inside the CTA's slice
+        const bool rowok = m < nrows;
+        const bool fast = (a.S == 1) && (a.L % 4 == 0);
+        int it = 0;
+        for (int tile = tile0; tile < a.total_tiles; tile += tstride, ++it) {
+            int img0, p0, nseg;
+            p2_tile(a, tile, img0, p0, nseg);
+            const int as = it & 1, buf = it % a.stg_bufs;
+            const uint32_t stg = s_stg + (uint32_t)buf * a.stg_buf_bytes;
+            const int ncols = nseg * a.L;
+            const int nch = (ncols + 15) >> 4, nch0 = (nch + 1) >> 1;
+            const int ch_lo = half ? nch0 : 0, ch_hi = half ? nch : nch0;
+            // (1) the staging buffer is free (warp kP2EpiWarp0 waited for the store that last read it at the end of the
+            //     previous tile) -- barrier 3 publishes that to the other epilogue warps
+            asm volatile("bar.sync 3, %0;" ::"n"(kP2NumEpi * 32) : "memory");
+            mbar_wait(&hdr->tmem_full[as], (uint32_t)(it >> 1) & 1u);
+            tc_fence_after();
+            if (has_res) mbar_wait(&hdr->res_full[buf], (uint32_t)(it / a.stg_bufs) & 1u);
+            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256u;
+            const uint32_t rowaddr = stg + (uint32_t)m * a.stg_pitch;
+            for (int ch = ch_lo; ch < ch_hi; ++ch) {
+                const int c0 = ch << 4;
+                uint32_t v[16];
+                __syncwarp();
+                tmem_ld16(tbase + (uint32_t)c0, v);
+                tmem_ld_wait();
+                if (ch == ch_hi - 1) {  // last TMEM read of this warp for the tile: hand the accumulator stage back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&hdr->tmem_empty[as]);
+                }
+                if (!rowok) continue;
+                if (fast) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int c = c0 + 4 * j;
+                        if (c < ncols) {
+                            uint2 o = make_uint2(pack_bf16x2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])),
+                                                 pack_bf16x2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+                            const uint32_t ad = rowaddr + (uint32_t)c * 2u;
+                            if (has_res) {
+                                const uint2 rr = lds64(ad);
+                                o.x = pack_bf16x2(bf16_lo(o.x) + bf16_lo(rr.x), bf16_hi(o.x) + bf16_hi(rr.x));
+                                o.y = pack_bf16x2(bf16_lo(o.y) + bf16_lo(rr.y), bf16_hi(o.y) + bf16_hi(rr.y));
+                            }
+                            sts64(ad, o);
+                        }
+                    }
+                } else {
+                    int sg = c0 / a.L, p = c0 - sg * a.L;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (c0 + j < ncols) {
+                            const uint32_t ad = stg + (uint32_t)sg * a.stg_seg_stride + (uint32_t)m * a.stg_pitch + (uint32_t)p * 2u;
+                            float f = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[j])));
+                            if (has_res) f += __uint_as_float(lds16(ad) << 16);
+                            sts16(ad, (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(f)));
+                        }
+                        if (++p == a.L) { p = 0; ++sg; }
+                    }
+                }
+            }
+            if (ch_lo >= ch_hi) {  // no column chunk for this warp (tiny tile): still release the accumulator
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&hdr->tmem_empty[as]);
+            }
+            // (2) staging complete -> visible to the async proxy -> bulk stores by the first epilogue warp
+            fence_proxy_async_smem();
+            asm volatile("bar.sync 2, %0;" ::"n"(kP2NumEpi * 32) : "memory");
+            if (e == 0) {
+                const uint32_t Lb = (uint32_t)a.L * 2u;
+                if (a.caseA) {
+                    if (lane < nseg)
+                        bulk_s2g(a.out + ((size_t)(img0 + lane) * a.N + n0) * a.HW, stg + (uint32_t)lane * a.stg_seg_stride,
+                                 (uint32_t)nrows * Lb);
+                } else {
+                    for (int mm = lane; mm < nrows; mm += 32)
+                        bulk_s2g(a.out + ((size_t)img0 * a.N + n0 + mm) * a.HW + p0, stg + (uint32_t)mm * a.stg_pitch, Lb);
+                }
+                bulk_commit();
+                // the buffer the NEXT tile writes (it + 1) was last read by the store of tile it + 1 - stg_bufs
+                if (a.stg_bufs == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
+                __syncwarp();
+                if (has_res && lane == 0) mbar_arrive(&hdr->stg_free);
+            }
+        }
+        if (e == 0) bulk_wait_all();  // global writes complete before the CTA exits
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 0) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, 512u);
+    }
+}
+
+int p2_round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// output-channel slicing shared by the weight packer and the kernel: <= 128 rows per slice (one M tile), slices of <= 112 KiB
+void p2_slices(int rows, int contraction, int *gy, int *ncta, int *kpad, uint32_t *w_lbo, uint32_t *w_bytes) {
+    const int Kpad = p2_round_up(contraction, 16);
+    int g = cdiv(rows, kP2MaxRows);
+    for (;; ++g) {
+        const int nc = p2_round_up(cdiv(rows, g), 8);
+        const size_t bytes = (size_t)(Kpad >> 3) * (nc * 16 + 16);
+        if (nc <= kP2MaxRows && (bytes <= 112 * 1024 || nc <= 8)) {
+            *gy = g; *ncta = nc; *kpad = Kpad;
+            *w_lbo = (uint32_t)(nc * 16 + 16);
+            *w_bytes = (uint32_t)bytes;
+            return;
+        }
+    }
+}
+
+bool p2_plan(P2Args &a, dim3 *grid, size_t *smem_bytes) {
+    if (a.NI <= 0 || a.K <= 0 || a.N <= 0 || a.HW <= 0) return false;
+    if (a.K % 8 != 0 || a.N % 8 != 0) return false;
+    if ((int64_t)a.NI * a.HW * (a.K > a.N ? a.K : a.N) >= (int64_t(1) << 31)) return false;
+    p2_slices(a.N, a.K, &a.gy, &a.Ncta, &a.Kpad, &a.w_lbo, &a.w_bytes);
+    if (a.gy > 148) return false;
+    if (a.HW <= 224) {  // whole images per tile
+        a.caseA = 1;
+        a.L = a.HW;
+        a.S = 224 / a.HW;
+        if (a.S > 32) a.S = 32;
+        a.tpi = 1;
+        a.total_tiles = cdiv(a.NI, a.S);
+        a.V = a.HW % 8 == 0 ? 8 : (a.HW % 4 == 0 ? 4 : (a.HW % 2 == 0 ? 2 : 1));
+        a.stg_pitch = (uint32_t)a.L * 2u;
+        a.stg_seg_stride = (uint32_t)a.Ncta * a.stg_pitch;
+    } else {  // L pixels of one image: the largest divisor of HW that is a multiple of 8 and <= 256
+        if (a.HW % 8 != 0) return false;
+        int L = 0;
+        for (int c = 256; c >= 64; c -= 8)
+            if (a.HW % c == 0) { L = c; break; }
+        if (!L) return false;
+        a.caseA = 0;
+        a.L = L;
+        a.S = 1;
+        a.tpi = a.HW / L;
+        a.total_tiles = a.NI * a.tpi;
+        a.V = 8;
+        a.stg_pitch = (uint32_t)L * 2u + 16u;
+        a.stg_seg_stride = 0;
+    }
+    a.Nmma = p2_round_up(a.S * a.L, 16);
+    if (a.Nmma > 256 || a.Nmma < 16) return false;
+    a.atoms = cdiv(a.Nmma, 64);
+    a.ppr = (uint32_t)(a.L / a.V);
+    if (a.ppr <= 1) { a.ppr_mul = 0; a.ppr_shr = 0; }
+    else {
+        uint32_t l = 0;
+        while ((1u << l) < a.ppr) ++l;
+        a.ppr_mul = (uint32_t)(((uint64_t(1) << (31 + l)) + a.ppr - 1) / a.ppr);
+        a.ppr_shr = l - 1;
+    }
+    const uint32_t sb_bytes = a.a_sb ? (uint32_t)p2_round_up(2 * a.Kpad * 4, 128) : 0u;
+    a.off_sb = kP2Hdr;
+    a.off_w = a.off_sb + sb_bytes;
+    const uint32_t w_alloc = (uint32_t)p2_round_up((int)a.w_bytes + 2048, 1024);  // the M = 128 tile reads up to 2 KiB per k-group
+    uint32_t fixed = (uint32_t)p2_round_up((int)(a.off_w + w_alloc), 1024);
+    const uint32_t stg1 = (uint32_t)p2_round_up(a.caseA ? a.S * (int)a.stg_seg_stride : a.Ncta * (int)a.stg_pitch, 128);
+    // K chunk: 32 channels (16 when shared memory is short); rings as deep as the room allows
+    for (int kc = 32; kc >= 16; kc -= 16) {
+        const uint32_t raw_b = (uint32_t)p2_round_up(a.S * kc * a.L * 2, 128);
+        const uint32_t op_b = (uint32_t)a.atoms * (uint32_t)(kc >> 3) * 1024u;
+        for (int bufs = 2; bufs >= 1; --bufs) {
+            const int64_t room = (int64_t)kP2Smem - fixed - (int64_t)bufs * stg1;
+            if (room < (int64_t)2 * (raw_b + op_b)) continue;
+            int stages = (int)(room / (raw_b + op_b));
+            if (stages > kP2MaxRing) stages = kP2MaxRing;
+            a.kc = kc; a.G = kc >> 3;
+            a.k_stages = cdiv(a.Kpad, kc);
+            a.raw_stages = a.op_stages = stages;
+            a.stg_bufs = bufs;
+            a.raw_stage_bytes = raw_b; a.op_stage_bytes = op_b; a.stg_buf_bytes = stg1;
+            a.off_op = fixed;                                    // 1 KiB aligned (SWIZZLE_128B atoms)
+            a.off_raw = a.off_op + (uint32_t)stages * op_b;
+            a.off_stg = a.off_raw + (uint32_t)stages * raw_b;
+            *smem_bytes = (size_t)a.off_stg + (size_t)bufs * stg1;
+            int gx = sm_count() / a.gy;
+            if (gx < 1) gx = 1;
+            if (gx > a.total_tiles) gx = a.total_tiles;
+            *grid = dim3((unsigned)gx, (unsigned)a.gy, 1);
+            return true;
+        }
+    }
+    return false;
+}
+
+template <int V, bool BN> int p2_launch(const P2Args &a, dim3 grid, size_t smem_bytes, cudaStream_t s) {
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (configured_dev != dev) {
+        cudaError_t e = cudaFuncSetAttribute(k_pw2<V, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kP2Smem);
+        if (e != cudaSuccess) return fail(RB_ERR_CUDA, "cudaFuncSetAttribute(k_pw2): %s", cudaGetErrorString(e));
+        configured_dev = dev;
+    }
+    k_pw2<V, BN><<<grid, kP2Threads, smem_bytes, s>>>(a);
+    return launched("k_pw2");
+}
+
+template <bool BN> int p2_launch_v(const P2Args &a, dim3 grid, size_t smem_bytes, cudaStream_t s) {
+    switch (a.V) {
+        case 8: return p2_launch<8, BN>(a, grid, smem_bytes, s);
+        case 4: return p2_launch<4, BN>(a, grid, smem_bytes, s);
+        case 2: return p2_launch<2, BN>(a, grid, smem_bytes, s);
+        default: return p2_launch<1, BN>(a, grid, smem_bytes, s);
+    }
+}
+
+// one thread per 16-byte unit (slice, k-group, row): 8 consecutive k of weight row n0 + n (zero beyond the matrix)
+__global__ void k_pw2_pack(const float *__restrict__ w, unsigned char *__restrict__ img, int rows, int contraction, int trans,
+                           int gy, int ncta, int kgroups, uint32_t w_lbo, uint32_t w_bytes) {
+    const int64_t total = (int64_t)gy * kgroups * (ncta + 1);
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= total) return;
+    const int n = (int)(u % (ncta + 1));
+    const int kg = (int)((u / (ncta + 1)) % kgroups);
+    const int sl = (int)(u / ((int64_t)(ncta + 1) * kgroups));
+    const int row = sl * ncta + n;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int k = kg * 8 + j;
+        f[j] = (n < ncta && row < rows && k < contraction) ? (trans ? w[(int64_t)k * rows + row] : w[(int64_t)row * contraction + k]) : 0.f;
+    }
+    *reinterpret_cast<uint4 *>(img + (size_t)sl * w_bytes + (size_t)kg * w_lbo + (size_t)n * 16) =
+        make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+
+}  // namespace
+
+// bytes of the packed image of a [rows x contraction] weight matrix (all slices)
+size_t pw2_weight_image_bytes(int rows, int contraction) {
+    if (rows <= 0 || contraction <= 0) return 0;
+    int gy, ncta, kpad;
+    uint32_t lbo, wb;
+    p2_slices(rows, contraction, &gy, &ncta, &kpad, &lbo, &wb);
+    return (size_t)gy * wb;
+}
+
+// w: fp32 conv weight [N, K].  trans == 0: image of W (rows = N, contraction = K: the forward GEMM); trans == 1: image of
+// W^T (rows = K, contraction = N: the input-gradient GEMM).
+int pw2_weight_pack(const float *w, int N, int K, int trans, void *image, cudaStream_t s) {
+    const int rows = trans ? K : N, contraction = trans ? N : K;
+    int gy, ncta, kpad;
+    uint32_t lbo, wb;
+    p2_slices(rows, contraction, &gy, &ncta, &kpad, &lbo, &wb);
+    const int64_t total = (int64_t)gy * (kpad >> 3) * (ncta + 1);
+    // `w` is indexed [N, K] in both cases: W^T[row = k, col = n] = w[n * K + k] = w[col * rows + row]
+    k_pw2_pack<<<(unsigned)cdiv64(total, 256), 256, 0, s>>>(w, (unsigned char *)image, rows, contraction, trans, gy, ncta, kpad >> 3,
+                                                          lbo, wb);
+    return launched("k_pw2_pack");
+}
+
+bool pw2_supported(int NI, int K, int N, int HW, int has_bn) {
+    P2Args a{};
+    a.NI = NI; a.K = K; a.N = N; a.HW = HW;
+    a.a_sb = has_bn ? reinterpret_cast<const float *>(uintptr_t(16)) : nullptr;
+    dim3 grid;
+    size_t smem = 0;
+    return p2_plan(a, &grid, &smem);
+}
+
+int pw2_forward(const void *x, const void *wimg, const void *residual, void *out, int NI, int K, int N, int HW,
+                const float *a_sb, cudaStream_t s) {
+    P2Args a{};
+    a.x = (const __nv_bfloat16 *)x; a.wimg = (const unsigned char *)wimg; a.res = (const __nv_bfloat16 *)residual;
+    a.out = (__nv_bfloat16 *)out; a.a_sb = a_sb;
+    a.NI = NI; a.K = K; a.N = N; a.HW = HW;
+    dim3 grid;
+    size_t smem = 0;
+    if (!p2_plan(a, &grid, &smem))
+        return fail(RB_ERR_UNSUPPORTED, "pw_conv (image weights): geometry NI=%d K=%d N=%d HW=%d not supported", NI, K, N, HW);
+    const uintptr_t al = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(residual) |
+                         reinterpret_cast<uintptr_t>(wimg);
+    if (al & 15) return fail(RB_ERR_INVALID_ARGUMENT, "pw_conv (image weights): pointers must be 16-byte aligned");
+    return a_sb ? p2_launch_v<true>(a, grid, smem, s) : p2_launch_v<false>(a, grid, smem, s);
+}
+
+}  // namespace rb

@@ -115,6 +115,31 @@ def bn_act(x, bn, relu=True):
     return out
 
 
+# True: 1x1 convolutions whose geometry has an image path run on the second-generation TMA kernel (csrc/pw_conv2.cu);
+# False: always the first-generation k_pw_conv.  Same arithmetic either way (tests/test_gpu_pwconv2.py).
+USE_IMAGE_KERNEL = True
+
+
+def _pack_weight(weight, ni, hw):
+    """bf16 operands of a fp32 conv weight [N,K,1,1] for the forward and the input-gradient GEMM: packed images for the
+    TMA kernel when both geometries have an image path, else the plain [N,K] / [K,N] copies."""
+    n, k = weight.shape[0], weight.shape[1]
+    if USE_IMAGE_KERNEL and ops.pw_image_supported(ni, k, n, hw, True) and ops.pw_image_supported(ni, n, k, hw, False):
+        return ops.pw_weight_images(weight)
+    return ops.pw_weight_pack(weight)
+
+
+def _wsave(w):
+    """(tensor to save for backward, metadata) of a packed weight operand."""
+    if isinstance(w, ops.WeightImage):
+        return w.image, (w.rows, w.contraction)
+    return w, None
+
+
+def _wload(t, meta):
+    return t if meta is None or t is None else ops.WeightImage(t, *meta)
+
+
 class _Conv1x1TC(torch.autograd.Function):
     """bf16 activations: tcgen05 kernels of librubiks_b200 (fp32 master weight read directly by the kernels)."""
 
@@ -126,16 +151,18 @@ class _Conv1x1TC(torch.autograd.Function):
             residual = residual.contiguous()
         ctx.has_res = residual is not None
         if weight.dtype == torch.float32 and weight.is_contiguous():
-            w_nk, w_kn = ops.pw_weight_pack(weight)
+            w_nk, w_kn = _pack_weight(weight, x.shape[0], x.shape[2] * x.shape[3])
         else:
             w_nk, w_kn = weight, None
-        ctx.save_for_backward(x, weight, w_kn)
+        w_kn_t, ctx.wmeta = _wsave(w_kn)
+        ctx.save_for_backward(x, weight, w_kn_t)
         return ops.pw_conv(x, w_nk, residual=residual)
 
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, g):
         x, weight, w_kn = ctx.saved_tensors
+        w_kn = _wload(w_kn, ctx.wmeta)
         g = g.contiguous()
         gx = None
         if ctx.needs_input_grad[0]:
@@ -237,15 +264,16 @@ class _RubiksBlockFn(torch.autograd.Function):
         tr2, mom2, eps2, rm2, rv2 = _bn_cfg(bn2)
         count = x.shape[0] * x.shape[2] * x.shape[3]
         # conv weights: rounded to bf16 once per step, in both orientations (forward / input gradient)
-        w2_nk, w2_kn = ops.pw_weight_pack(w2)
-        w3_nk, w3_kn = ops.pw_weight_pack(w3)
+        hw = x.shape[2] * x.shape[3]
+        w2_nk, w2_kn = _pack_weight(w2, x.shape[0], hw)
+        w3_nk, w3_kn = _pack_weight(w3, x.shape[0], hw)
         # BatchNorm statistics come out of the epilogue of the GEMM that produced the tensor (x: the previous block's
         # conv3, handed over as x_stats; y2: conv2 below) -- no separate reduction pass in training mode
         if x_stats is not None and tr1:
             mi1, sb1 = ops.bn_finalize(x_stats, count, g1, b1, rm1, rv1, mom1, eps1)
         else:
             _, mi1, sb1 = ops.bn_forward(x, g1, b1, rm1, rv1, tr1, mom1, eps1, relu=True, apply=False)
-        if tr2 and EPILOGUE_BN_STATS:
+        if tr2 and EPILOGUE_BN_STATS and not isinstance(w2_nk, ops.WeightImage):
             y2, st2 = ops.pw_conv(x, w2_nk, in_scale_bias=sb1, name="pw_conv<bn+relu>", stats=True)
             mi2, sb2 = ops.bn_finalize(st2, count, g2, b2, rm2, rv2, mom2, eps2)
             a2 = ops.bn_apply(y2, sb2, relu=True)
@@ -253,17 +281,20 @@ class _RubiksBlockFn(torch.autograd.Function):
             y2 = ops.pw_conv(x, w2_nk, in_scale_bias=sb1, name="pw_conv<bn+relu>")
             a2, mi2, sb2 = ops.bn_forward(y2, g2, b2, rm2, rv2, tr2, mom2, eps2, relu=True, apply=True)
         out_stats = None
-        if FUSE_SHIFT_CONV3:
+        if FUSE_SHIFT_CONV3 and not isinstance(w3_nk, ops.WeightImage):
             s3 = None
             out = ops.shift3d_pw_conv(a2, shift, w3_nk, x, frames)
         else:
             s3 = _shift3d_forward(a2, shift, frames)
-            if EPILOGUE_BN_STATS:
+            if EPILOGUE_BN_STATS and not isinstance(w3_nk, ops.WeightImage):
                 out, out_stats = ops.pw_conv(s3, w3_nk, residual=x, name="pw_conv<+residual>", stats=True)
             else:
                 out = ops.pw_conv(s3, w3_nk, residual=x, name="pw_conv<+residual>")
-        ctx.save_for_backward(x, y2, a2, s3, mi1, sb1, mi2, sb2, g1, g2, w2, w3, shift, w2_kn, w3_kn)
+        w2_kn_t, m2 = _wsave(w2_kn)
+        w3_kn_t, m3 = _wsave(w3_kn)
+        ctx.save_for_backward(x, y2, a2, s3, mi1, sb1, mi2, sb2, g1, g2, w2, w3, shift, w2_kn_t, w3_kn_t)
         ctx.cfg = (tr1, tr2, frames, normalize_grad, normalize_t_factor)
+        ctx.wmeta = (m2, m3)
         if out_stats is None:
             return out, None, 0
         ctx.mark_non_differentiable(out_stats[0])
@@ -274,6 +305,7 @@ class _RubiksBlockFn(torch.autograd.Function):
     def backward(ctx, g, _g_stats=None, _g_splits=None):
         x, y2, a2, s3, mi1, sb1, mi2, sb2, g1, g2, w2, w3, shift, w2_kn, w3_kn = ctx.saved_tensors
         tr1, tr2, frames, normalize_grad, normalize_t_factor = ctx.cfg
+        w2_kn, w3_kn = _wload(w2_kn, ctx.wmeta[0]), _wload(w3_kn, ctx.wmeta[1])
         g = g.contiguous()
         need = ctx.needs_input_grad
         gs = ops.pw_conv(g, w3_kn, name="pw_conv<dgrad>")

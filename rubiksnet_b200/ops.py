@@ -103,10 +103,55 @@ def bn_apply(x, scale_bias, relu=True):
 _MAX_STAT_SPLITS = 2 * 148
 
 
+class WeightImage:
+    """Packed shared-memory image of a [rows x contraction] bf16 weight matrix (rb_pw_weight_image_pack): what the
+    second-generation kernel (csrc/pw_conv2.cu) bulk-copies per output-channel slice."""
+
+    __slots__ = ("image", "rows", "contraction")
+
+    def __init__(self, image, rows, contraction):
+        self.image, self.rows, self.contraction = image, rows, contraction
+
+
+def pw_image_supported(ni, k, n, hw, has_bn=False):
+    """True when rb_pw_conv_forward has an image path for [ni, k, hw] -> [ni, n, hw]."""
+    return bool(_lib.lib().rb_pw_conv_image_supported(int(ni), int(k), int(n), int(hw), int(bool(has_bn))))
+
+
+def pw_weight_images(weight):
+    """(forward image, input-gradient image) of a fp32 conv weight [N,K(,1,1)]: pw_conv(x, fwd) is the convolution,
+    pw_conv(g, dgrad) its input gradient."""
+    assert weight.dtype == torch.float32 and weight.is_contiguous()
+    n, k = weight.shape[0], weight.shape[1]
+    L = _lib.lib()
+    fwd = torch.empty(L.rb_pw_weight_image_bytes(n, k), dtype=torch.uint8, device=weight.device)
+    bwd = torch.empty(L.rb_pw_weight_image_bytes(k, n), dtype=torch.uint8, device=weight.device)
+    with _on_device(weight.device):
+        with _timed("pw_weight_pack", 8 * n * k + fwd.numel() + bwd.numel()):
+            _lib.check(L.rb_pw_weight_image_pack(_lib.ptr(weight), n, k, 0, _lib.ptr(fwd), _lib.stream_handle(weight.device)))
+            _lib.check(L.rb_pw_weight_image_pack(_lib.ptr(weight), n, k, 1, _lib.ptr(bwd), _lib.stream_handle(weight.device)))
+    return WeightImage(fwd, n, k), WeightImage(bwd, k, n)
+
+
 def pw_conv(x, weight, residual=None, in_scale_bias=None, transposed=False, name="pw_conv", stats=False):
-    """out[i,n,p] = sum_k W[n,k] A[i,k,p] (+ residual).  weight: Conv2d parameter [N,K,1,1] / [N,K] (fp32 or bf16);
-    transposed=True reads it as [K,N] (input gradient of that conv).  A = relu(x*scale+bias) with in_scale_bias."""
+    """out[i,n,p] = sum_k W[n,k] A[i,k,p] (+ residual).  weight: Conv2d parameter [N,K,1,1] / [N,K] (fp32 or bf16), or a
+    WeightImage (second-generation TMA kernel); transposed=True reads a plain weight as [K,N] (input gradient of that
+    conv).  A = relu(x*scale+bias) with in_scale_bias."""
     assert x.dtype == BF16 and x.is_contiguous()
+    if isinstance(weight, WeightImage):
+        assert not transposed and not stats
+        ni, k, n = x.shape[0], x.shape[1], weight.rows
+        assert weight.contraction == k, "channel mismatch"
+        hw = x.numel() // max(ni * k, 1)
+        out = torch.empty((ni, n) + tuple(x.shape[2:]), dtype=BF16, device=x.device)
+        if residual is not None:
+            assert residual.dtype == BF16 and residual.is_contiguous() and residual.shape == out.shape
+        with _on_device(x.device):
+            with _timed(name, _nbytes(x, residual, out), 2 * ni * hw * k * n):
+                _lib.check(_lib.lib().rb_pw_conv_forward(
+                    _lib.ptr(x), _lib.ptr(weight.image), _lib.RB_W_IMAGE, 0, _lib.ptr(residual), _lib.ptr(out), _lib.RB_BF16,
+                    ni, k, n, hw, _lib.ptr(in_scale_bias), _lib.stream_handle(x.device)))
+        return out
     ni, k = x.shape[0], x.shape[1]
     n = weight.shape[1] if transposed else weight.shape[0]
     assert (weight.shape[0] if transposed else weight.shape[1]) == k, "channel mismatch"

@@ -49,7 +49,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--only", default=None)
-    ap.add_argument("--modes", default="fwd,res,bn,shift,dgrad,wgrad,wgrad_shift,cublas")
+    ap.add_argument("--modes", default="fwd,fwd2,res,res2,bn,bn2,dgrad,dgrad2,shift,wgrad,wgrad_shift,cublas")
     ap.add_argument("--splits", type=int, default=0, help="rb_pw_conv_set_tuning: minimum output-channel splits (0 = auto)")
     a = ap.parse_args()
     _lib.lib().rb_pw_conv_set_tuning(a.splits)
@@ -78,11 +78,21 @@ def main():
             "wgrad": (lambda: ops.pw_conv_wgrad(g, x), 2 * unit),
             "wgrad_shift": (lambda: ops.shift3d_pw_conv_wgrad(g, x, shift, T), 2 * unit),
         }
+        if ops.pw_image_supported(ni, c, c, h * h, True):
+            img_f, img_b = ops.pw_weight_images(w)
+            cases.update({
+                "fwd2": (lambda: ops.pw_conv(x, img_f), 2 * unit),
+                "res2": (lambda: ops.pw_conv(x, img_f, residual=res), 3 * unit),
+                "bn2": (lambda: ops.pw_conv(x, img_f, in_scale_bias=sb), 2 * unit),
+                "dgrad2": (lambda: ops.pw_conv(g, img_b), 2 * unit),
+            })
         wb = w.to(BF)
         xb = x.view(ni, c, -1)
         cases["cublas"] = (lambda: torch.matmul(wb, xb), 2 * unit)
         msg = "%-9s C=%-3d H=%-3d unit %.1f MB |" % (name, c, h, unit / 1e6)
         for m in modes:
+            if m not in cases:
+                continue
             fn, nbytes = cases[m]
             ms = timeit(fn, a.iters, flush)
             msg += " %s %.3f ms %.0f GB/s |" % (m, ms, nbytes / ms / 1e6)
