@@ -59,7 +59,7 @@ void pw_conv_set_tuning(int min_n_splits);
 // pw_conv2.cu
 size_t pw2_weight_image_bytes(int rows, int contraction);
 int pw2_weight_pack(const float *w, int N, int K, int trans, void *image, cudaStream_t s);
-bool pw2_supported(int NI, int K, int N, int HW, int has_bn);
+int pw2_supported(int NI, int K, int N, int HW, int has_bn);
 int pw2_forward(const void *x, const void *wimg, const void *residual, void *out, int NI, int K, int N, int HW,
                 const float *a_sb, cudaStream_t s);
 #ifdef RB_DEBUG_TRACE
@@ -302,7 +302,7 @@ int rb_pw_weight_image_pack(const float *weight, int N, int K, int transposed, v
 }
 
 int rb_pw_conv_image_supported(int NI, int K, int N, int HW, int has_in_scale_bias) {
-    return pw2_supported(NI, K, N, HW, has_in_scale_bias) ? 1 : 0;
+    return pw2_supported(NI, K, N, HW, has_in_scale_bias);
 }
 
 int rb_pw_conv_forward_stats(const void *x, const void *weight, int weight_dtype, int weight_transposed, const void *residual,

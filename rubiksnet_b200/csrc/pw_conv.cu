@@ -1410,6 +1410,7 @@ int pw_weight_pack(const float *w, void *w_nk, void *w_kn, int N, int K, cudaStr
 #ifdef RB_DEBUG_TRACE
 static unsigned long long *g_pw_trace = nullptr;
 void pw_conv_set_trace(void *p) { g_pw_trace = (unsigned long long *)p; }
+unsigned long long *pw_conv_get_trace() { return g_pw_trace; }
 #endif
 
 void pw_conv_set_tuning(int min_n_splits) { g_min_n_splits = min_n_splits < 0 ? 0 : (min_n_splits > 16 ? 16 : min_n_splits); }

@@ -53,7 +53,21 @@ struct P2Args {
     uint32_t ppr, ppr_mul, ppr_shr;  // pieces per row and its exact-division constants
     uint32_t w_lbo, w_bytes, off_sb, off_w, off_raw, off_op, off_stg;
     uint32_t raw_stage_bytes, op_stage_bytes, stg_buf_bytes, stg_pitch, stg_seg_stride;
+#ifdef RB_DEBUG_TRACE
+    unsigned long long *trace;  // debug builds only: 128 globaltimer stamps per CTA (tools/trace_pw.py --v2)
+#endif
 };
+
+#ifdef RB_DEBUG_TRACE
+__device__ __forceinline__ unsigned long long p2_gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define P2_TRACE(cond, slot) do { if (a.trace && (cond)) a.trace[(blockIdx.y * gridDim.x + blockIdx.x) * 128 + (slot)] = p2_gtime(); } while (0)
+#else
+#define P2_TRACE(cond, slot) do { } while (0)
+#endif
 
 struct P2Hdr {
     uint64_t raw_full[kP2MaxRing], raw_empty[kP2MaxRing], op_full[kP2MaxRing], op_empty[kP2MaxRing];
@@ -140,61 +154,110 @@ __device__ __forceinline__ void p2_tile(const P2Args &a, int tile, int &img0, in
     }
 }
 
-template <int V, bool BN>
+// byte offset of tile column c (first column of a piece) inside the operand row of channel kl = 8 g + r:
+//     (atom(c) * G + g) * 1024 + r * 128 + ((chunk(c) ^ r) << 4) + sub(c)
+// split into a part that only depends on the column (high bits: atom and sub-chunk offset, low 3 bits: chunk index) ...
+__device__ __forceinline__ uint32_t p2_col_part(uint32_t c, uint32_t G) { return ((((c >> 6) * G) << 10) + ((c & 7u) << 1)) | 0u; }
+__device__ __forceinline__ uint32_t p2_col_chunk(uint32_t c) { return (c & 63u) >> 3; }
+// ... and the row part
+__device__ __forceinline__ uint32_t p2_dst(uint32_t op, uint32_t colpart, uint32_t chunk, uint32_t kl) {
+    const uint32_t r = kl & 7u;
+    return op + colpart + ((kl >> 3) << 10) + (r << 7) + ((chunk ^ r) << 4);
+}
+
+// Relayout of one raw stage: ONE WARP PER OPERAND ROW (segment s, channel kl), lanes along the row.  Column-dependent
+// address parts are lane constants per segment; rows are processed four at a time with all shared-memory loads issued
+// before the first store (the first version -- one flattened piece per thread and iteration, load -> store -- was bound
+// by the 29-cycle shared-memory latency: 4-13 us per tile instead of the 1-2 us of the MMAs).
+//   MODE 16 / 8: pieces of 16 / 8 bytes (L % 8 == 0 / L % 4 == 0): source and destination pieces are equally aligned.
+//   MODE 4: any L (7x7 maps: rows of 49 elements start on odd elements): 4-byte destination words; the source pair of a
+//           word is either one aligned word or two 2-byte halves (uniform per row), row ends are written as 2-byte halves so
+//           that the neighbouring segment's columns in the same operand row are never touched.
+template <int MODE, bool BN>
 __device__ __forceinline__ void p2_relayout_stage(const P2Args &a, uint32_t raw, uint32_t op, const float *sb, int kbase,
-                                                  int rows_real, int rows_pad_shift, int nseg, int rt) {
-    // pieces of V elements, flattened over (segment, channel row, piece): consecutive threads read consecutive addresses of
-    // the raw stage (rows are dense) and write 16-byte-chunk-swizzled rows of the operand
-    const uint32_t rows_pad = 1u << rows_pad_shift;
-    const uint32_t total = (uint32_t)nseg * rows_pad * a.ppr;
-    const uint32_t Lb = (uint32_t)a.L * 2u;
-    for (uint32_t q = (uint32_t)rt; q < total; q += kP2NumRel * 32) {
-        const uint32_t rowid = a.ppr_mul ? (__umulhi(q, a.ppr_mul) >> a.ppr_shr) : q;
-        const uint32_t piece = q - rowid * a.ppr;
-        const uint32_t s = rowid >> rows_pad_shift, kl = rowid & (rows_pad - 1);
-        const uint32_t c = s * (uint32_t)a.L + piece * V;
-        const uint32_t dst = op + (((c >> 6) * (uint32_t)a.G + (kl >> 3)) << 10) + ((kl & 7) << 7) +
-                             ((((c & 63) >> 3) ^ (kl & 7)) << 4) + ((c & 7) << 1);
-        const bool real = (int)kl < rows_real;
-        const uint32_t src = raw + (s * (uint32_t)a.kc + kl) * Lb + piece * (V * 2);
-        float sc = 0.f, bi = 0.f;
-        if (BN && real) {
-            sc = sb[kbase + (int)kl];
-            bi = sb[a.Kpad + kbase + (int)kl];
+                                                  int rows_real, int rows_pad, int nseg, int rw, int lane) {
+    const uint32_t Lb = (uint32_t)a.L * 2u, G = (uint32_t)a.G;
+    constexpr int RU = 4;  // rows in flight per warp
+    if (MODE == 16 || MODE == 8) {
+        constexpr uint32_t EPP = MODE / 2;  // elements per piece
+        const uint32_t ppr = (uint32_t)a.L / EPP;
+        for (int s = 0; s < nseg; ++s) {
+            for (uint32_t pc = (uint32_t)lane; pc < ppr; pc += 32) {
+                const uint32_t c = (uint32_t)s * (uint32_t)a.L + pc * EPP;
+                const uint32_t colpart = p2_col_part(c, G), chunk = p2_col_chunk(c);
+                const uint32_t src0 = raw + (uint32_t)s * (uint32_t)a.kc * Lb + pc * MODE;
+                for (int k0 = rw; k0 < rows_pad; k0 += kP2NumRel * RU) {
+                    uint4 v[RU];
+#pragma unroll
+                    for (int u = 0; u < RU; ++u) {
+                        const int kl = k0 + u * kP2NumRel;
+                        v[u] = make_uint4(0u, 0u, 0u, 0u);
+                        if (kl < rows_real) {
+                            if (MODE == 16) v[u] = lds128(src0 + (uint32_t)kl * Lb);
+                            else { const uint2 t = lds64(src0 + (uint32_t)kl * Lb); v[u].x = t.x; v[u].y = t.y; }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < RU; ++u) {
+                        const int kl = k0 + u * kP2NumRel;
+                        if (kl >= rows_pad) continue;
+                        if (BN && kl < rows_real) {
+                            const float sc = sb[kbase + kl], bi = sb[a.Kpad + kbase + kl];
+                            v[u].x = bnrelu2(v[u].x, sc, bi); v[u].y = bnrelu2(v[u].y, sc, bi);
+                            if (MODE == 16) { v[u].z = bnrelu2(v[u].z, sc, bi); v[u].w = bnrelu2(v[u].w, sc, bi); }
+                        }
+                        const uint32_t d = p2_dst(op, colpart, chunk, (uint32_t)kl);
+                        if (MODE == 16) sts128(d, v[u]); else sts64(d, make_uint2(v[u].x, v[u].y));
+                    }
+                }
+            }
         }
-        if (V == 8) {
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (real) {
-                v = lds128(src);
-                if (BN) { v.x = bnrelu2(v.x, sc, bi); v.y = bnrelu2(v.y, sc, bi); v.z = bnrelu2(v.z, sc, bi); v.w = bnrelu2(v.w, sc, bi); }
+    } else {
+        for (int s = 0; s < nseg; ++s) {
+            const uint32_t c0 = (uint32_t)s * (uint32_t)a.L, dpar = c0 & 1u, u0 = c0 >> 1;
+            const uint32_t nwords = ((c0 + (uint32_t)a.L - 1u) >> 1) - u0 + 1u;
+            for (uint32_t w = (uint32_t)lane; w < nwords; w += 32) {
+                const uint32_t c = 2u * (u0 + w);
+                const int p_lo = (int)c - (int)c0;  // -1 for the first word of a segment that starts on an odd column
+                const bool ok_lo = p_lo >= 0, ok_hi = p_lo + 1 < a.L;
+                const uint32_t colpart = p2_col_part(c, G), chunk = p2_col_chunk(c);
+                for (int k0 = rw; k0 < rows_pad; k0 += kP2NumRel * RU) {
+                    uint32_t lo[RU], hi[RU];
+#pragma unroll
+                    for (int u = 0; u < RU; ++u) {
+                        const int kl = k0 + u * kP2NumRel;
+                        lo[u] = hi[u] = 0u;
+                        if (kl < rows_real) {
+                            // element index of column p_lo in the raw stage; its parity is the same for every lane of the row
+                            const int e = (s * a.kc + kl) * a.L + p_lo;
+                            const uint32_t ad = raw + (uint32_t)(e * 2);
+                            if (((uint32_t)e & 1u) == 0u) {
+                                const uint32_t t = lds32(ad);
+                                lo[u] = t & 0xffffu; hi[u] = t >> 16;
+                            } else {
+                                lo[u] = lds16(ad); hi[u] = lds16(ad + 2u);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < RU; ++u) {
+                        const int kl = k0 + u * kP2NumRel;
+                        if (kl >= rows_pad) continue;
+                        uint32_t v = lo[u] | (hi[u] << 16);
+                        if (BN && kl < rows_real) v = bnrelu2(v, sb[kbase + kl], sb[a.Kpad + kbase + kl]);
+                        const uint32_t d = p2_dst(op, colpart, chunk, (uint32_t)kl);
+                        if (ok_lo && ok_hi) sts32(d, v);
+                        else if (ok_lo) sts16(d, v & 0xffffu);
+                        else if (ok_hi) sts16(d + 2u, v >> 16);
+                    }
+                }
             }
-            sts128(dst, v);
-        } else if (V == 4) {
-            uint2 v = make_uint2(0u, 0u);
-            if (real) {
-                v = lds64(src);
-                if (BN) { v.x = bnrelu2(v.x, sc, bi); v.y = bnrelu2(v.y, sc, bi); }
-            }
-            sts64(dst, v);
-        } else if (V == 2) {
-            uint32_t v = 0u;
-            if (real) {
-                v = lds32(src);
-                if (BN) v = bnrelu2(v, sc, bi);
-            }
-            sts32(dst, v);
-        } else {
-            uint32_t v = 0u;
-            if (real) {
-                v = lds16(src);
-                if (BN) v = bnrelu2(v, sc, bi) & 0xffffu;
-            }
-            sts16(dst, v);
+            (void)dpar;
         }
     }
 }
 
-template <int V, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_pw2(const P2Args a) {
+template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_pw2(const P2Args a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     P2Hdr *hdr = reinterpret_cast<P2Hdr *>(smem);
     float *smem_sb = reinterpret_cast<float *>(smem + a.off_sb);
@@ -206,6 +269,7 @@ template <int V, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_pw2
     const int nrows = min(a.Ncta, a.N - n0);
     const int tile0 = blockIdx.x, tstride = gridDim.x;
     const bool has_res = a.res != nullptr;
+    P2_TRACE(tid == 0, 0);
 
     if (tid == 0) {
         for (int i = 0; i < kP2MaxRing; ++i) {
@@ -248,8 +312,10 @@ template <int V, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_pw2
             const uint32_t a_hi = (uint32_t)(adesc0 >> 32), b_hi = (uint32_t)(bdesc0 >> 32);
             const uint32_t a_lo0 = (uint32_t)adesc0, b_lo0 = (uint32_t)bdesc0;
             const uint32_t a_kstep = (2 * a.w_lbo) >> 4, op16 = a.op_stage_bytes >> 4;
+            P2_TRACE(true, 1);
             mbar_wait(&hdr->w_full, 0);
             tc_fence_after();
+            P2_TRACE(true, 2);
             int n = 0, it = 0;
             for (int tile = tile0; tile < a.total_tiles; tile += tstride, ++it) {
                 const int as = it & 1;
@@ -257,10 +323,13 @@ template <int V, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_pw2
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)as * 256u;
                 uint32_t a_lo = a_lo0, acc = 0u;
+                P2_TRACE(it < 8, 8 + it * 12 + 0);
                 for (int st = 0; st < a.k_stages; ++st, ++n) {
                     const int o = n % a.op_stages;
                     mbar_wait(&hdr->op_full[o], (uint32_t)(n / a.op_stages) & 1u);
                     tc_fence_after();
+                    P2_TRACE(it < 8 && st == 0, 8 + it * 12 + 1);
+                    P2_TRACE(it < 8 && st == a.k_stages - 1, 8 + it * 12 + 2);
                     const int ksteps = min(a.kc, a.Kpad - st * a.kc) >> 4;
                     uint32_t b_lo = b_lo0 + (uint32_t)o * op16;
                     for (int ks = 0; ks < ksteps; ++ks) {
@@ -312,6 +381,8 @@ template <int V, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_pw2
             const bool need_free = it >= 1;
             const uint32_t free_par = (uint32_t)(it - 1) & 1u;
             for (int st = 0; st < a.k_stages; ++st, ++n) {
+                P2_TRACE(lane == 0 && it < 8 && st == 0, 8 + it * 12 + 6);
+                P2_TRACE(lane == 0 && it < 8 && st == a.k_stages - 1, 8 + it * 12 + 7);
                 if (res_pending) {
                     bool ok = !need_free;
                     if (need_free) ok = __shfl_sync(0xffffffffu, (int)mbar_test(&hdr->stg_free, free_par), 0) != 0;
@@ -344,7 +415,7 @@ template <int V, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_pw2
         }
     } else if (warp < kP2EpiWarp0) {
         // ================================ relayout warps: raw stage -> UMMA operand =================================
-        const int rt = (warp - kP2RelWarp0) * 32 + lane;
+        const int rw = warp - kP2RelWarp0;
         int n = 0;
         for (int tile = tile0; tile < a.total_tiles; tile += tstride) {
             int img0, p0, nseg;
@@ -355,15 +426,17 @@ template <int V, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_pw2
                 const int rows_real = min(a.kc, a.K - k0);
                 const int rows_pad = min(a.kc, a.Kpad - k0);  // 16 or 32
                 mbar_wait(&hdr->raw_full[r], (uint32_t)(n / a.raw_stages) & 1u);
+                P2_TRACE(rw == 0 && lane == 0 && (tile - tile0) / tstride < 8 && st == 0, 8 + ((tile - tile0) / tstride) * 12 + 8);
                 mbar_wait(&hdr->op_empty[o], ((uint32_t)(n / a.op_stages) & 1u) ^ 1u);
-                p2_relayout_stage<V, BN>(a, s_raw + (uint32_t)r * a.raw_stage_bytes, s_op + (uint32_t)o * a.op_stage_bytes, smem_sb,
-                                         k0, rows_real, rows_pad == 32 ? 5 : 4, nseg, rt);
+                p2_relayout_stage<MODE, BN>(a, s_raw + (uint32_t)r * a.raw_stage_bytes, s_op + (uint32_t)o * a.op_stage_bytes,
+                                            smem_sb, k0, rows_real, rows_pad, nseg, rw, lane);
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
                     mbar_arrive(&hdr->op_full[o]);
                     mbar_arrive(&hdr->raw_empty[r]);
                 }
+                P2_TRACE(rw == 0 && lane == 0 && (tile - tile0) / tstride < 8 && st == a.k_stages - 1, 8 + ((tile - tile0) / tstride) * 12 + 9);
             }
         }
     } else {
@@ -386,7 +459,9 @@ template <int V, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_pw2
             asm volatile("bar.sync 3, %0;" ::"n"(kP2NumEpi * 32) : "memory");
             mbar_wait(&hdr->tmem_full[as], (uint32_t)(it >> 1) & 1u);
             tc_fence_after();
+            P2_TRACE(e == 0 && lane == 0 && it < 8, 8 + it * 12 + 3);
             if (has_res) mbar_wait(&hdr->res_full[buf], (uint32_t)(it / a.stg_bufs) & 1u);
+            P2_TRACE(e == 0 && lane == 0 && it < 8, 8 + it * 12 + 10);
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256u;
             const uint32_t rowaddr = stg + (uint32_t)m * a.stg_pitch;
             for (int ch = ch_lo; ch < ch_hi; ++ch) {
@@ -439,6 +514,7 @@ template <int V, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_pw2
             // (2) staging complete -> visible to the async proxy -> bulk stores by the first epilogue warp
             fence_proxy_async_smem();
             asm volatile("bar.sync 2, %0;" ::"n"(kP2NumEpi * 32) : "memory");
+            P2_TRACE(e == 0 && lane == 0 && it < 8, 8 + it * 12 + 4);
             if (e == 0) {
                 const uint32_t Lb = (uint32_t)a.L * 2u;
                 if (a.caseA) {
@@ -454,6 +530,7 @@ template <int V, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_pw2
                 if (a.stg_bufs == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
                 __syncwarp();
                 if (has_res && lane == 0) mbar_arrive(&hdr->stg_free);
+                P2_TRACE(lane == 0 && it < 8, 8 + it * 12 + 5);
             }
         }
         if (e == 0) bulk_wait_all();  // global writes complete before the CTA exits
@@ -462,6 +539,7 @@ template <int V, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_pw2
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    P2_TRACE(tid == 0, 3);
     if (warp == 0) {
         __syncwarp();
         tmem_dealloc(tmem_base, 512u);
@@ -534,54 +612,59 @@ bool p2_plan(P2Args &a, dim3 *grid, size_t *smem_bytes) {
     const uint32_t w_alloc = (uint32_t)p2_round_up((int)a.w_bytes + 2048, 1024);  // the M = 128 tile reads up to 2 KiB per k-group
     uint32_t fixed = (uint32_t)p2_round_up((int)(a.off_w + w_alloc), 1024);
     const uint32_t stg1 = (uint32_t)p2_round_up(a.caseA ? a.S * (int)a.stg_seg_stride : a.Ncta * (int)a.stg_pitch, 128);
-    // K chunk: 32 channels (16 when shared memory is short); rings as deep as the room allows
+    // Rings: the operand ring only decouples the relayout warps from the MMA issuer (2 stages); the RAW ring is what keeps
+    // global memory busy -- bytes in flight per SM = raw stages x stage bytes -- so it gets all the remaining room.  Pick the
+    // K chunk (32 or 16 channels) and the number of staging buffers that maximise the bytes in flight.
+    int best_bytes = -1;
     for (int kc = 32; kc >= 16; kc -= 16) {
         const uint32_t raw_b = (uint32_t)p2_round_up(a.S * kc * a.L * 2, 128);
         const uint32_t op_b = (uint32_t)a.atoms * (uint32_t)(kc >> 3) * 1024u;
         for (int bufs = 2; bufs >= 1; --bufs) {
-            const int64_t room = (int64_t)kP2Smem - fixed - (int64_t)bufs * stg1;
-            if (room < (int64_t)2 * (raw_b + op_b)) continue;
-            int stages = (int)(room / (raw_b + op_b));
+            const int64_t room = (int64_t)kP2Smem - fixed - (int64_t)bufs * stg1 - 2 * (int64_t)op_b;
+            if (room < (int64_t)2 * raw_b) continue;
+            int stages = (int)(room / raw_b);
             if (stages > kP2MaxRing) stages = kP2MaxRing;
+            int inflight = stages * (int)raw_b;
+            if (bufs == 2) inflight += inflight / 16;  // mild preference for the second staging buffer at equal depth
+            if (inflight <= best_bytes) continue;
+            best_bytes = inflight;
             a.kc = kc; a.G = kc >> 3;
             a.k_stages = cdiv(a.Kpad, kc);
-            a.raw_stages = a.op_stages = stages;
+            a.raw_stages = stages;
+            a.op_stages = 2;
             a.stg_bufs = bufs;
             a.raw_stage_bytes = raw_b; a.op_stage_bytes = op_b; a.stg_buf_bytes = stg1;
             a.off_op = fixed;                                    // 1 KiB aligned (SWIZZLE_128B atoms)
-            a.off_raw = a.off_op + (uint32_t)stages * op_b;
+            a.off_raw = a.off_op + 2u * op_b;
             a.off_stg = a.off_raw + (uint32_t)stages * raw_b;
             *smem_bytes = (size_t)a.off_stg + (size_t)bufs * stg1;
-            int gx = sm_count() / a.gy;
-            if (gx < 1) gx = 1;
-            if (gx > a.total_tiles) gx = a.total_tiles;
-            *grid = dim3((unsigned)gx, (unsigned)a.gy, 1);
-            return true;
         }
     }
-    return false;
+    if (best_bytes < 0) return false;
+    int gx = sm_count() / a.gy;
+    if (gx < 1) gx = 1;
+    if (gx > a.total_tiles) gx = a.total_tiles;
+    *grid = dim3((unsigned)gx, (unsigned)a.gy, 1);
+    return true;
 }
 
-template <int V, bool BN> int p2_launch(const P2Args &a, dim3 grid, size_t smem_bytes, cudaStream_t s) {
+template <int MODE, bool BN> int p2_launch(const P2Args &a, dim3 grid, size_t smem_bytes, cudaStream_t s) {
     static thread_local int configured_dev = -1;
     int dev = 0;
     cudaGetDevice(&dev);
     if (configured_dev != dev) {
-        cudaError_t e = cudaFuncSetAttribute(k_pw2<V, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kP2Smem);
+        cudaError_t e = cudaFuncSetAttribute(k_pw2<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kP2Smem);
         if (e != cudaSuccess) return fail(RB_ERR_CUDA, "cudaFuncSetAttribute(k_pw2): %s", cudaGetErrorString(e));
         configured_dev = dev;
     }
-    k_pw2<V, BN><<<grid, kP2Threads, smem_bytes, s>>>(a);
+    k_pw2<MODE, BN><<<grid, kP2Threads, smem_bytes, s>>>(a);
     return launched("k_pw2");
 }
 
 template <bool BN> int p2_launch_v(const P2Args &a, dim3 grid, size_t smem_bytes, cudaStream_t s) {
-    switch (a.V) {
-        case 8: return p2_launch<8, BN>(a, grid, smem_bytes, s);
-        case 4: return p2_launch<4, BN>(a, grid, smem_bytes, s);
-        case 2: return p2_launch<2, BN>(a, grid, smem_bytes, s);
-        default: return p2_launch<1, BN>(a, grid, smem_bytes, s);
-    }
+    if (a.V == 8) return p2_launch<16, BN>(a, grid, smem_bytes, s);
+    if (a.V == 4) return p2_launch<8, BN>(a, grid, smem_bytes, s);
+    return p2_launch<4, BN>(a, grid, smem_bytes, s);
 }
 
 // one thread per 16-byte unit (slice, k-group, row): 8 consecutive k of weight row n0 + n (zero beyond the matrix)
@@ -606,6 +689,10 @@ __global__ void k_pw2_pack(const float *__restrict__ w, unsigned char *__restric
 
 }  // namespace
 
+#ifdef RB_DEBUG_TRACE
+unsigned long long *pw_conv_get_trace();
+#endif
+
 // bytes of the packed image of a [rows x contraction] weight matrix (all slices)
 size_t pw2_weight_image_bytes(int rows, int contraction) {
     if (rows <= 0 || contraction <= 0) return 0;
@@ -629,13 +716,17 @@ int pw2_weight_pack(const float *w, int N, int K, int trans, void *image, cudaSt
     return launched("k_pw2_pack");
 }
 
-bool pw2_supported(int NI, int K, int N, int HW, int has_bn) {
+// 0: no image path; 1: supported; 2: supported and the faster schedule for this geometry (whole-image tiles: the raw ring
+// is fed by few large bulk copies.  Row-piece tiles of larger maps need one small copy per channel row, which the TMA unit
+// serialises -- measured slower than the first-generation kernel, profiles/r02b_bench_pw.log)
+int pw2_supported(int NI, int K, int N, int HW, int has_bn) {
     P2Args a{};
     a.NI = NI; a.K = K; a.N = N; a.HW = HW;
     a.a_sb = has_bn ? reinterpret_cast<const float *>(uintptr_t(16)) : nullptr;
     dim3 grid;
     size_t smem = 0;
-    return p2_plan(a, &grid, &smem);
+    if (!p2_plan(a, &grid, &smem)) return 0;
+    return a.caseA ? 2 : 1;
 }
 
 int pw2_forward(const void *x, const void *wimg, const void *residual, void *out, int NI, int K, int N, int HW,
@@ -651,6 +742,9 @@ int pw2_forward(const void *x, const void *wimg, const void *residual, void *out
     const uintptr_t al = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(residual) |
                          reinterpret_cast<uintptr_t>(wimg);
     if (al & 15) return fail(RB_ERR_INVALID_ARGUMENT, "pw_conv (image weights): pointers must be 16-byte aligned");
+#ifdef RB_DEBUG_TRACE
+    a.trace = pw_conv_get_trace();
+#endif
     return a_sb ? p2_launch_v<true>(a, grid, smem, s) : p2_launch_v<false>(a, grid, smem, s);
 }
 

@@ -124,7 +124,10 @@ def _pack_weight(weight, ni, hw):
     """bf16 operands of a fp32 conv weight [N,K,1,1] for the forward and the input-gradient GEMM: packed images for the
     TMA kernel when both geometries have an image path, else the plain [N,K] / [K,N] copies."""
     n, k = weight.shape[0], weight.shape[1]
-    if USE_IMAGE_KERNEL and ops.pw_image_supported(ni, k, n, hw, True) and ops.pw_image_supported(ni, n, k, hw, False):
+    # the optional single-launch shift+conv3 / epilogue-statistics schedules exist on the first-generation kernel only
+    if (USE_IMAGE_KERNEL and not FUSE_SHIFT_CONV3 and not EPILOGUE_BN_STATS
+            and ops.pw_image_supported(ni, k, n, hw, True, preferred=True)
+            and ops.pw_image_supported(ni, n, k, hw, False, preferred=True)):
         return ops.pw_weight_images(weight)
     return ops.pw_weight_pack(weight)
 

@@ -113,9 +113,11 @@ class WeightImage:
         self.image, self.rows, self.contraction = image, rows, contraction
 
 
-def pw_image_supported(ni, k, n, hw, has_bn=False):
-    """True when rb_pw_conv_forward has an image path for [ni, k, hw] -> [ni, n, hw]."""
-    return bool(_lib.lib().rb_pw_conv_image_supported(int(ni), int(k), int(n), int(hw), int(bool(has_bn))))
+def pw_image_supported(ni, k, n, hw, has_bn=False, preferred=False):
+    """True when rb_pw_conv_forward has an image path for [ni, k, hw] -> [ni, n, hw] (preferred=True: ... and it is the
+    faster schedule for this geometry)."""
+    level = _lib.lib().rb_pw_conv_image_supported(int(ni), int(k), int(n), int(hw), int(bool(has_bn)))
+    return level >= (2 if preferred else 1)
 
 
 def pw_weight_images(weight):

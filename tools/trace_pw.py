@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--mode", default="fwd")
     ap.add_argument("--wbf16", action="store_true", help="bf16 weights packed by rb_pw_weight_pack")
+    ap.add_argument("--v2", action="store_true", help="second-generation kernel (packed weight images, csrc/pw_conv2.cu)")
     a = ap.parse_args()
     # the stamps only exist in the debug library (python -m rubiksnet_b200.build --trace); point the loader at it
     _lib.LIB_PATH = _lib.LIB_PATH.replace(".so", "_trace.so")
@@ -32,6 +33,35 @@ def main():
     if a.wbf16:
         w, w_kn = ops.pw_weight_pack(w)
     sb = torch.stack([torch.rand(a.C, device="cuda") + 0.5, torch.randn(a.C, device="cuda")], dim=1).contiguous()
+    if a.v2:
+        img_f, img_b = ops.pw_weight_images(w)
+        res = torch.randn_like(x)
+        fn = {"fwd": lambda: ops.pw_conv(x, img_f), "bn": lambda: ops.pw_conv(x, img_f, in_scale_bias=sb),
+              "res": lambda: ops.pw_conv(x, img_f, residual=res), "dgrad": lambda: ops.pw_conv(x, img_b)}[a.mode]
+        for _ in range(3):
+            fn()
+        trace = torch.zeros(148 * 128, dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+        L.rb_debug_pw_trace(ctypes.c_void_p(trace.data_ptr()))
+        fn()
+        torch.cuda.synchronize()
+        L.rb_debug_pw_trace(None)
+        t = trace.view(-1, 128).cpu()
+        t = t[t[:, 0] > 0]
+        t0 = int(t[:, 0].min())
+        us = lambda v: (int(v) - t0) / 1e3 if int(v) else float("nan")  # noqa: E731
+        print("v2 %s C=%d H=%d: CTAs traced %d, kernel span %.1f us" % (a.mode, a.C, a.H, t.shape[0], (int(t[:, 3].max()) - t0) / 1e3))
+        names = ["mma-start", "stage0-full", "last-full", "epi-start", "staged", "stored", "tma-first", "tma-last", "rel-first-raw",
+                 "rel-last-done", "res-ready"]
+        for cta in (0, t.shape[0] // 2, t.shape[0] - 1):
+            r = t[cta]
+            print("CTA %d: start %.1f mma-ready %.1f weights %.1f end %.1f" % (cta, us(r[0]), us(r[1]), us(r[2]), us(r[3])))
+            for it in range(8):
+                b = 8 + it * 12
+                if int(r[b]) == 0:
+                    break
+                print("   tile %d: " % it + "  ".join("%s %.1f" % (n, us(r[b + i])) for i, n in enumerate(names)))
+        return
     fn = {"fwd": lambda: ops.pw_conv(x, w), "bn": lambda: ops.pw_conv(x, w, in_scale_bias=sb),
           "dgrad": (lambda: ops.pw_conv(x, w_kn)) if a.wbf16 else (lambda: ops.pw_conv(x, w, transposed=True))}[a.mode]
     for _ in range(3):
