@@ -247,6 +247,16 @@ int rb_shift3d_pw_conv_wgrad(const void *out_grad, const void *x, const void *sh
 size_t rb_pw_weight_image_bytes(int rows, int contraction);
 int rb_pw_weight_image_pack(const float *weight, int N, int K, int transposed, void *image, void *stream);
 int rb_pw_conv_image_supported(int NI, int K, int N, int HW, int has_in_scale_bias);
+/* Both images of MANY conv weights in one launch (once per training step, after the optimizer update): `items_device` is
+ * an array in DEVICE memory; image_fwd / image_bwd are 16-byte aligned buffers of rb_pw_weight_image_bytes(N, K) /
+ * rb_pw_weight_image_bytes(K, N) bytes. */
+typedef struct rb_pw_pack_item {
+    const float *weight; /* fp32 [N, K] */
+    void *image_fwd;     /* image of W   (rows = N, contraction = K) */
+    void *image_bwd;     /* image of W^T (rows = K, contraction = N) */
+    int N, K;
+} rb_pw_pack_item_t;
+int rb_pw_weight_image_pack_multi(const rb_pw_pack_item_t *items_device, int count, void *stream);
 
 /* Tiling override for rb_pw_conv_forward (process-global, like rb_set_impl): lower bound on the number of
  * output-channel splits (grid.y); more splits = a smaller resident weight block and a deeper activation ring per CTA

@@ -60,6 +60,7 @@ void pw_conv_set_tuning(int min_n_splits);
 size_t pw2_weight_image_bytes(int rows, int contraction);
 int pw2_weight_pack(const float *w, int N, int K, int trans, void *image, cudaStream_t s);
 int pw2_supported(int NI, int K, int N, int HW, int has_bn);
+int pw2_weight_pack_multi(const void *items_device, int count, cudaStream_t s);
 int pw2_forward(const void *x, const void *wimg, const void *residual, void *out, int NI, int K, int N, int HW,
                 const float *a_sb, cudaStream_t s);
 #ifdef RB_DEBUG_TRACE
@@ -299,6 +300,13 @@ int rb_pw_weight_image_pack(const float *weight, int N, int K, int transposed, v
     if (!weight || !image) return fail(RB_ERR_INVALID_ARGUMENT, "null pointer");
     if (reinterpret_cast<uintptr_t>(image) & 15) return fail(RB_ERR_INVALID_ARGUMENT, "weight image must be 16-byte aligned");
     return pw2_weight_pack(weight, N, K, transposed != 0, image, (cudaStream_t)stream);
+}
+
+int rb_pw_weight_image_pack_multi(const rb_pw_pack_item_t *items_device, int count, void *stream) {
+    if (count < 0 || count > 65535) return fail(RB_ERR_INVALID_ARGUMENT, "bad item count %d", count);
+    if (count == 0) return RB_OK;
+    if (!items_device) return fail(RB_ERR_INVALID_ARGUMENT, "null pointer");
+    return pw2_weight_pack_multi(items_device, count, (cudaStream_t)stream);
 }
 
 int rb_pw_conv_image_supported(int NI, int K, int N, int HW, int has_in_scale_bias) {

@@ -30,10 +30,13 @@ using namespace tc;
 
 namespace {
 
-constexpr int kP2Warps = 14;
-constexpr int kP2Threads = kP2Warps * 32;  // 448
-constexpr int kP2RelWarp0 = 2, kP2NumRel = 4;
-constexpr int kP2EpiWarp0 = 6, kP2NumEpi = 8;
+// warp roles: 0 MMA issuer (+ TMEM allocation), 1 TMA loads, 2 TMA stores, 3 idle (keeps the epilogue warps aligned with the
+// TMEM lane quarters: warp % 4), 4-11 relayout, 12-19 epilogue
+constexpr int kP2Warps = 20;
+constexpr int kP2Threads = kP2Warps * 32;  // 640
+constexpr int kP2MmaWarp = 0, kP2TmaWarp = 1, kP2StoreWarp = 2;
+constexpr int kP2RelWarp0 = 4, kP2NumRel = 8;
+constexpr int kP2EpiWarp0 = 12, kP2NumEpi = 8;
 constexpr int kP2MaxRing = 8;
 constexpr int kP2Smem = 227 * 1024;
 constexpr int kP2Hdr = 512;
@@ -71,7 +74,7 @@ __device__ __forceinline__ unsigned long long p2_gtime() {
 
 struct P2Hdr {
     uint64_t raw_full[kP2MaxRing], raw_empty[kP2MaxRing], op_full[kP2MaxRing], op_empty[kP2MaxRing];
-    uint64_t tmem_full[2], tmem_empty[2], res_full[2], stg_free, w_full;
+    uint64_t tmem_full[2], tmem_empty[2], res_full[2], stg_ready[2], stg_empty[2], w_full;
     uint32_t tmem_base;
 };
 static_assert(sizeof(P2Hdr) <= kP2Hdr, "header");
@@ -154,105 +157,132 @@ __device__ __forceinline__ void p2_tile(const P2Args &a, int tile, int &img0, in
     }
 }
 
-// byte offset of tile column c (first column of a piece) inside the operand row of channel kl = 8 g + r:
-//     (atom(c) * G + g) * 1024 + r * 128 + ((chunk(c) ^ r) << 4) + sub(c)
-// split into a part that only depends on the column (high bits: atom and sub-chunk offset, low 3 bits: chunk index) ...
-__device__ __forceinline__ uint32_t p2_col_part(uint32_t c, uint32_t G) { return ((((c >> 6) * G) << 10) + ((c & 7u) << 1)) | 0u; }
+// Operand layout: tile column c of channel kl = 8 g + r lives at
+//     (atom(c) * G + g) * 1024 + r * 128 + ((chunk(c) ^ r) << 4) + sub(c),   atom = c / 64, chunk = (c % 64) / 8, sub = 2 (c % 8)
+__device__ __forceinline__ uint32_t p2_col_part(uint32_t c, uint32_t G) { return (((c >> 6) * G) << 10) + ((c & 7u) << 1); }
 __device__ __forceinline__ uint32_t p2_col_chunk(uint32_t c) { return (c & 63u) >> 3; }
-// ... and the row part
-__device__ __forceinline__ uint32_t p2_dst(uint32_t op, uint32_t colpart, uint32_t chunk, uint32_t kl) {
-    const uint32_t r = kl & 7u;
-    return op + colpart + ((kl >> 3) << 10) + (r << 7) + ((chunk ^ r) << 4);
-}
 
-// Relayout of one raw stage: ONE WARP PER OPERAND ROW (segment s, channel kl), lanes along the row.  Column-dependent
-// address parts are lane constants per segment; rows are processed four at a time with all shared-memory loads issued
-// before the first store (the first version -- one flattened piece per thread and iteration, load -> store -- was bound
-// by the 29-cycle shared-memory latency: 4-13 us per tile instead of the 1-2 us of the MMAs).
+// Relayout of one raw stage into the UMMA operand.  A work unit is (segment, 8-channel group, 32 pieces along the row); the
+// relayout warps take units round-robin.  Inside a unit a lane owns ONE piece column and walks the 8 rows of the group with
+// compile-time row indices: 8 independent shared-memory loads, then 8 stores whose addresses differ by constants
+// (r * 128 and an XOR of the chunk index with r).  History (profiles/r02c_trace_l3.log): one piece per thread and iteration
+// with run-time row arithmetic made the relayout warps -- single warps issuing dependent ALU chains at ~0.17 instructions
+// per cycle -- the slowest stage of the pipeline (1.2 us per 32-channel stage against 0.1 us of MMA).
 //   MODE 16 / 8: pieces of 16 / 8 bytes (L % 8 == 0 / L % 4 == 0): source and destination pieces are equally aligned.
-//   MODE 4: any L (7x7 maps: rows of 49 elements start on odd elements): 4-byte destination words; the source pair of a
-//           word is either one aligned word or two 2-byte halves (uniform per row), row ends are written as 2-byte halves so
-//           that the neighbouring segment's columns in the same operand row are never touched.
+//   MODE 4: any L (7x7 maps: rows of 49 elements start on odd elements): 4-byte destination words, fetched as two aligned
+//           words + funnel shift whatever the source alignment; row ends are written as 2-byte halves so that the
+//           neighbouring segment's columns in the same operand row are never touched.
+// K % 8 == 0 (p2_plan), so an 8-channel group is either all real channels or all padding (zeros).
 template <int MODE, bool BN>
 __device__ __forceinline__ void p2_relayout_stage(const P2Args &a, uint32_t raw, uint32_t op, const float *sb, int kbase,
                                                   int rows_real, int rows_pad, int nseg, int rw, int lane) {
-    const uint32_t Lb = (uint32_t)a.L * 2u, G = (uint32_t)a.G;
-    constexpr int RU = 4;  // rows in flight per warp
+    const uint32_t L = (uint32_t)a.L, Lb = L * 2u, G = (uint32_t)a.G;
+    const int groups = rows_pad >> 3;
     if (MODE == 16 || MODE == 8) {
         constexpr uint32_t EPP = MODE / 2;  // elements per piece
-        const uint32_t ppr = (uint32_t)a.L / EPP;
-        for (int s = 0; s < nseg; ++s) {
-            for (uint32_t pc = (uint32_t)lane; pc < ppr; pc += 32) {
-                const uint32_t c = (uint32_t)s * (uint32_t)a.L + pc * EPP;
-                const uint32_t colpart = p2_col_part(c, G), chunk = p2_col_chunk(c);
-                const uint32_t src0 = raw + (uint32_t)s * (uint32_t)a.kc * Lb + pc * MODE;
-                for (int k0 = rw; k0 < rows_pad; k0 += kP2NumRel * RU) {
-                    uint4 v[RU];
+        const uint32_t ppr = L / EPP;
+        const int passes = (int)((ppr + 31u) >> 5);
+        const int units = nseg * groups * passes;
+        for (int u = rw; u < units; u += kP2NumRel) {
+            const int pass = u % passes, t = u / passes, g = t % groups, sg = t / groups;
+            const uint32_t pc = (uint32_t)(lane + 32 * pass);
+            if (pc >= ppr) continue;
+            const uint32_t c = (uint32_t)sg * L + pc * EPP;
+            const uint32_t chunk = p2_col_chunk(c);
+            const uint32_t dst = op + p2_col_part(c, G) + ((uint32_t)g << 10);
+            const uint32_t src = raw + ((uint32_t)sg * (uint32_t)a.kc + (uint32_t)g * 8u) * Lb + pc * MODE;
+            const bool real = g * 8 < rows_real;
+            uint4 v[8];
 #pragma unroll
-                    for (int u = 0; u < RU; ++u) {
-                        const int kl = k0 + u * kP2NumRel;
-                        v[u] = make_uint4(0u, 0u, 0u, 0u);
-                        if (kl < rows_real) {
-                            if (MODE == 16) v[u] = lds128(src0 + (uint32_t)kl * Lb);
-                            else { const uint2 t = lds64(src0 + (uint32_t)kl * Lb); v[u].x = t.x; v[u].y = t.y; }
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < RU; ++u) {
-                        const int kl = k0 + u * kP2NumRel;
-                        if (kl >= rows_pad) continue;
-                        if (BN && kl < rows_real) {
-                            const float sc = sb[kbase + kl], bi = sb[a.Kpad + kbase + kl];
-                            v[u].x = bnrelu2(v[u].x, sc, bi); v[u].y = bnrelu2(v[u].y, sc, bi);
-                            if (MODE == 16) { v[u].z = bnrelu2(v[u].z, sc, bi); v[u].w = bnrelu2(v[u].w, sc, bi); }
-                        }
-                        const uint32_t d = p2_dst(op, colpart, chunk, (uint32_t)kl);
-                        if (MODE == 16) sts128(d, v[u]); else sts64(d, make_uint2(v[u].x, v[u].y));
-                    }
+            for (int r = 0; r < 8; ++r) {
+                v[r] = make_uint4(0u, 0u, 0u, 0u);
+                if (real) {
+                    if (MODE == 16) v[r] = lds128(src + (uint32_t)r * Lb);
+                    else { const uint2 t2 = lds64(src + (uint32_t)r * Lb); v[r].x = t2.x; v[r].y = t2.y; }
                 }
+            }
+            if (BN && real) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const float sc = sb[kbase + g * 8 + r], bi = sb[a.Kpad + kbase + g * 8 + r];
+                    v[r].x = bnrelu2(v[r].x, sc, bi); v[r].y = bnrelu2(v[r].y, sc, bi);
+                    if (MODE == 16) { v[r].z = bnrelu2(v[r].z, sc, bi); v[r].w = bnrelu2(v[r].w, sc, bi); }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const uint32_t d = dst + ((uint32_t)r << 7) + ((chunk ^ (uint32_t)r) << 4);
+                if (MODE == 16) sts128(d, v[r]); else sts64(d, make_uint2(v[r].x, v[r].y));
             }
         }
     } else {
-        for (int s = 0; s < nseg; ++s) {
-            const uint32_t c0 = (uint32_t)s * (uint32_t)a.L, dpar = c0 & 1u, u0 = c0 >> 1;
-            const uint32_t nwords = ((c0 + (uint32_t)a.L - 1u) >> 1) - u0 + 1u;
-            for (uint32_t w = (uint32_t)lane; w < nwords; w += 32) {
-                const uint32_t c = 2u * (u0 + w);
-                const int p_lo = (int)c - (int)c0;  // -1 for the first word of a segment that starts on an odd column
-                const bool ok_lo = p_lo >= 0, ok_hi = p_lo + 1 < a.L;
-                const uint32_t colpart = p2_col_part(c, G), chunk = p2_col_chunk(c);
-                for (int k0 = rw; k0 < rows_pad; k0 += kP2NumRel * RU) {
-                    uint32_t lo[RU], hi[RU];
+        const int passes = (int)(((L >> 1) + 2u + 31u) >> 5);
+        const int units = nseg * groups * passes;
+        for (int u = rw; u < units; u += kP2NumRel) {
+            const int pass = u % passes, t = u / passes, g = t % groups, sg = t / groups;
+            const uint32_t c0 = (uint32_t)sg * L, u0 = c0 >> 1;
+            const uint32_t nwords = ((c0 + L - 1u) >> 1) - u0 + 1u;
+            const uint32_t w = (uint32_t)(lane + 32 * pass);
+            if (w >= nwords) continue;
+            const uint32_t c = 2u * (u0 + w);
+            const int p_lo = (int)c - (int)c0;  // -1 for the first word of a segment that starts on an odd column
+            const bool ok_lo = p_lo >= 0, ok_hi = p_lo + 1 < (int)L;
+            const uint32_t chunk = p2_col_chunk(c);
+            const uint32_t dst = op + p2_col_part(c, G) + ((uint32_t)g << 10);
+            // byte address of source column p_lo in row r = 0 of the group (row r: + r * Lb); may point 2 bytes in front of
+            // the stage (p_lo = -1 in its first row): still inside this CTA's shared memory, and the value is not stored
+            const uint32_t ad0 = raw + (uint32_t)((int)(((uint32_t)sg * (uint32_t)a.kc + (uint32_t)g * 8u) * L) + p_lo) * 2u;
+            const bool real = g * 8 < rows_real;
+            uint32_t v[8];
 #pragma unroll
-                    for (int u = 0; u < RU; ++u) {
-                        const int kl = k0 + u * kP2NumRel;
-                        lo[u] = hi[u] = 0u;
-                        if (kl < rows_real) {
-                            // element index of column p_lo in the raw stage; its parity is the same for every lane of the row
-                            const int e = (s * a.kc + kl) * a.L + p_lo;
-                            const uint32_t ad = raw + (uint32_t)(e * 2);
-                            if (((uint32_t)e & 1u) == 0u) {
-                                const uint32_t t = lds32(ad);
-                                lo[u] = t & 0xffffu; hi[u] = t >> 16;
-                            } else {
-                                lo[u] = lds16(ad); hi[u] = lds16(ad + 2u);
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < RU; ++u) {
-                        const int kl = k0 + u * kP2NumRel;
-                        if (kl >= rows_pad) continue;
-                        uint32_t v = lo[u] | (hi[u] << 16);
-                        if (BN && kl < rows_real) v = bnrelu2(v, sb[kbase + kl], sb[a.Kpad + kbase + kl]);
-                        const uint32_t d = p2_dst(op, colpart, chunk, (uint32_t)kl);
-                        if (ok_lo && ok_hi) sts32(d, v);
-                        else if (ok_lo) sts16(d, v & 0xffffu);
-                        else if (ok_hi) sts16(d + 2u, v >> 16);
-                    }
+            for (int r = 0; r < 8; ++r) {
+                v[r] = 0u;
+                if (real) {
+                    const uint32_t ad = ad0 + (uint32_t)r * Lb;
+                    const uint32_t w0 = lds32(ad & ~3u), w1 = lds32((ad & ~3u) + 4u);
+                    v[r] = __funnelshift_r(w0, w1, (ad & 2u) << 3);
                 }
             }
-            (void)dpar;
+            if (BN && real) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) v[r] = bnrelu2(v[r], sb[kbase + g * 8 + r], sb[a.Kpad + kbase + g * 8 + r]);
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const uint32_t d = dst + ((uint32_t)r << 7) + ((chunk ^ (uint32_t)r) << 4);
+                if (ok_lo && ok_hi) sts32(d, v[r]);
+                else if (ok_lo) sts16(d, v[r] & 0xffffu);
+                else if (ok_hi) sts16(d + 2u, v[r] >> 16);
+            }
+        }
+    }
+}
+
+// 2 x 16 accumulator columns of one output row -> bf16 -> (+ residual) -> staging row, in 8-byte pieces.  All residual
+// pieces are fetched before the first store (the shared-memory helpers are volatile asm: program order is issue order).
+__device__ __forceinline__ void p2_epi_round_fast(const uint32_t (&v0)[16], const uint32_t (&v1)[16], bool two, uint32_t rowaddr,
+                                                  int c0, int ncols, bool has_res) {
+    uint2 rr[8];
+    if (has_res) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = c0 + 4 * j;
+            rr[j] = make_uint2(0u, 0u);
+            if (c < ncols && (j < 4 || two)) rr[j] = lds64(rowaddr + (uint32_t)c * 2u);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = c0 + 4 * j;
+        if (c < ncols && (j < 4 || two)) {
+            const uint32_t *v = j < 4 ? &v0[4 * j] : &v1[4 * (j - 4)];
+            uint2 o = make_uint2(pack_bf16x2(__uint_as_float(v[0]), __uint_as_float(v[1])),
+                                 pack_bf16x2(__uint_as_float(v[2]), __uint_as_float(v[3])));
+            if (has_res) {
+                o.x = pack_bf16x2(bf16_lo(o.x) + bf16_lo(rr[j].x), bf16_hi(o.x) + bf16_hi(rr[j].x));
+                o.y = pack_bf16x2(bf16_lo(o.y) + bf16_lo(rr[j].y), bf16_hi(o.y) + bf16_hi(rr[j].y));
+            }
+            sts64(rowaddr + (uint32_t)c * 2u, o);
         }
     }
 }
@@ -282,8 +312,9 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
             mbar_init(&hdr->tmem_full[i], 1);
             mbar_init(&hdr->tmem_empty[i], kP2NumEpi);
             mbar_init(&hdr->res_full[i], 1);
+            mbar_init(&hdr->stg_ready[i], kP2NumEpi);
+            mbar_init(&hdr->stg_empty[i], 1);
         }
-        mbar_init(&hdr->stg_free, 1);
         mbar_init(&hdr->w_full, 1);
         mbar_fence_init();
     }
@@ -300,8 +331,9 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = hdr->tmem_base;
+    const uint32_t Lb = (uint32_t)a.L * 2u;
 
-    if (warp == 0) {
+    if (warp == kP2MmaWarp) {
         // ================================ MMA issuer: one thread ===================================================
         if (elect_one()) {
             const uint32_t idesc = instr_desc_bf16(128, a.Nmma, /*weights: K-major*/ 0, /*activations: MN-major*/ 1);
@@ -344,20 +376,21 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
             }
         }
         __syncwarp();
-    } else if (warp == 1) {
-        // ================================ TMA producer warp ========================================================
+    } else if (warp == kP2TmaWarp) {
+        // ================================ TMA load warp: weights, raw ring, residual blocks =========================
         if (lane == 0) {
             mbar_expect_tx(&hdr->w_full, a.w_bytes);
             bulk_g2s(s_w, a.wimg + (size_t)blockIdx.y * a.w_bytes, a.w_bytes, &hdr->w_full);
         }
-        const uint32_t Lb = (uint32_t)a.L * 2u;
         int n = 0, it = 0;
         for (int tile = tile0; tile < a.total_tiles; tile += tstride, ++it) {
             int img0, p0, nseg;
             p2_tile(a, tile, img0, p0, nseg);
             bool res_pending = has_res;
+            const int buf = it % a.stg_bufs;
+            // staging buffer `buf` is free once the store warp has seen the store of its previous use (j - 1) finish reading
+            const uint32_t empty_par = ((uint32_t)(it / a.stg_bufs) & 1u) ^ 1u;
             auto issue_residual = [&]() {
-                const int buf = it % a.stg_bufs;
                 const uint32_t dst0 = s_stg + (uint32_t)buf * a.stg_buf_bytes;
                 if (a.caseA) {
                     const uint32_t bytes = (uint32_t)nrows * Lb;
@@ -375,19 +408,10 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
                 }
                 res_pending = false;
             };
-            // the staging buffer of this tile is free once the store of tile it - stg_bufs has read it: the epilogue signals
-            // that at the end of tile it - 1 (arrival it - 1 on stg_free).  Every arrival is waited for, in order (also the
-            // ones a second staging buffer would let us skip), so that this warp is never two phases behind the barrier.
-            const bool need_free = it >= 1;
-            const uint32_t free_par = (uint32_t)(it - 1) & 1u;
             for (int st = 0; st < a.k_stages; ++st, ++n) {
                 P2_TRACE(lane == 0 && it < 8 && st == 0, 8 + it * 12 + 6);
                 P2_TRACE(lane == 0 && it < 8 && st == a.k_stages - 1, 8 + it * 12 + 7);
-                if (res_pending) {
-                    bool ok = !need_free;
-                    if (need_free) ok = __shfl_sync(0xffffffffu, (int)mbar_test(&hdr->stg_free, free_par), 0) != 0;
-                    if (ok) issue_residual();
-                }
+                if (res_pending && __shfl_sync(0xffffffffu, (int)mbar_test(&hdr->stg_empty[buf], empty_par), 0) != 0) issue_residual();
                 const int r = n % a.raw_stages;
                 mbar_wait(&hdr->raw_empty[r], ((uint32_t)(n / a.raw_stages) & 1u) ^ 1u);
                 const int k0 = st * a.kc;
@@ -409,11 +433,39 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
                 __syncwarp();
             }
             if (res_pending) {
-                if (need_free) mbar_wait(&hdr->stg_free, free_par);
+                mbar_wait(&hdr->stg_empty[buf], empty_par);
                 issue_residual();
             }
         }
-    } else if (warp < kP2EpiWarp0) {
+    } else if (warp == kP2StoreWarp) {
+        // ================================ TMA store warp ===========================================================
+        // waits until the 8 epilogue warps have filled a staging buffer, sends it to global memory with bulk copies, and hands
+        // the buffer back (stg_empty) once the copies have read it: to the load warp (next residual block) or, without a
+        // residual, straight to the epilogue warps
+        int it = 0;
+        for (int tile = tile0; tile < a.total_tiles; tile += tstride, ++it) {
+            int img0, p0, nseg;
+            p2_tile(a, tile, img0, p0, nseg);
+            const int buf = it % a.stg_bufs;
+            const uint32_t stg = s_stg + (uint32_t)buf * a.stg_buf_bytes;
+            mbar_wait(&hdr->stg_ready[buf], (uint32_t)(it / a.stg_bufs) & 1u);
+            P2_TRACE(lane == 0 && it < 8, 8 + it * 12 + 4);
+            if (a.caseA) {
+                if (lane < nseg)
+                    bulk_s2g(a.out + ((size_t)(img0 + lane) * a.N + n0) * a.HW, stg + (uint32_t)lane * a.stg_seg_stride,
+                             (uint32_t)nrows * Lb);
+            } else {
+                for (int mm = lane; mm < nrows; mm += 32)
+                    bulk_s2g(a.out + ((size_t)img0 * a.N + n0 + mm) * a.HW + p0, stg + (uint32_t)mm * a.stg_pitch, Lb);
+            }
+            bulk_commit();
+            bulk_wait_read<0>();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&hdr->stg_empty[buf]);
+            P2_TRACE(lane == 0 && it < 8, 8 + it * 12 + 5);
+        }
+        bulk_wait_all();  // global writes complete before the CTA exits
+    } else if (warp >= kP2RelWarp0 && warp < kP2EpiWarp0) {
         // ================================ relayout warps: raw stage -> UMMA operand =================================
         const int rw = warp - kP2RelWarp0;
         int n = 0;
@@ -439,7 +491,7 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
                 P2_TRACE(rw == 0 && lane == 0 && (tile - tile0) / tstride < 8 && st == a.k_stages - 1, 8 + ((tile - tile0) / tstride) * 12 + 9);
             }
         }
-    } else {
+    } else if (warp >= kP2EpiWarp0) {
         // ================================ epilogue warps ==========================================================
         const int e = warp - kP2EpiWarp0, q = warp & 3, half = e >> 2;
         const int m = q * 32 + lane;  // output channel row (TMEM lane) of this thread inside the CTA's slice
@@ -454,55 +506,48 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
             const int ncols = nseg * a.L;
             const int nch = (ncols + 15) >> 4, nch0 = (nch + 1) >> 1;
             const int ch_lo = half ? nch0 : 0, ch_hi = half ? nch : nch0;
-            // (1) the staging buffer is free (warp kP2EpiWarp0 waited for the store that last read it at the end of the
-            //     previous tile) -- barrier 3 publishes that to the other epilogue warps
-            asm volatile("bar.sync 3, %0;" ::"n"(kP2NumEpi * 32) : "memory");
             mbar_wait(&hdr->tmem_full[as], (uint32_t)(it >> 1) & 1u);
             tc_fence_after();
             P2_TRACE(e == 0 && lane == 0 && it < 8, 8 + it * 12 + 3);
+            // the staging buffer holds the residual block (which also means the previous store has released it), or is free
             if (has_res) mbar_wait(&hdr->res_full[buf], (uint32_t)(it / a.stg_bufs) & 1u);
+            else mbar_wait(&hdr->stg_empty[buf], ((uint32_t)(it / a.stg_bufs) & 1u) ^ 1u);
             P2_TRACE(e == 0 && lane == 0 && it < 8, 8 + it * 12 + 10);
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256u;
             const uint32_t rowaddr = stg + (uint32_t)m * a.stg_pitch;
-            for (int ch = ch_lo; ch < ch_hi; ++ch) {
+            // two 16-column chunks per round: both TMEM loads are in flight before the first conversion
+            for (int ch = ch_lo; ch < ch_hi; ch += 2) {
                 const int c0 = ch << 4;
-                uint32_t v[16];
+                const bool two = ch + 1 < ch_hi;
+                uint32_t v0[16], v1[16];
                 __syncwarp();
-                tmem_ld16(tbase + (uint32_t)c0, v);
+                tmem_ld16(tbase + (uint32_t)c0, v0);
+                if (two) tmem_ld16(tbase + (uint32_t)c0 + 16u, v1);
                 tmem_ld_wait();
-                if (ch == ch_hi - 1) {  // last TMEM read of this warp for the tile: hand the accumulator stage back
+                if (ch + 2 >= ch_hi) {  // last TMEM read of this warp for the tile: hand the accumulator stage back
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&hdr->tmem_empty[as]);
                 }
                 if (!rowok) continue;
                 if (fast) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int c = c0 + 4 * j;
-                        if (c < ncols) {
-                            uint2 o = make_uint2(pack_bf16x2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])),
-                                                 pack_bf16x2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
-                            const uint32_t ad = rowaddr + (uint32_t)c * 2u;
-                            if (has_res) {
-                                const uint2 rr = lds64(ad);
-                                o.x = pack_bf16x2(bf16_lo(o.x) + bf16_lo(rr.x), bf16_hi(o.x) + bf16_hi(rr.x));
-                                o.y = pack_bf16x2(bf16_lo(o.y) + bf16_lo(rr.y), bf16_hi(o.y) + bf16_hi(rr.y));
-                            }
-                            sts64(ad, o);
-                        }
-                    }
+                    p2_epi_round_fast(v0, v1, two, rowaddr, c0, ncols, has_res);
                 } else {
-                    int sg = c0 / a.L, p = c0 - sg * a.L;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        if (c0 + j < ncols) {
-                            const uint32_t ad = stg + (uint32_t)sg * a.stg_seg_stride + (uint32_t)m * a.stg_pitch + (uint32_t)p * 2u;
-                            float f = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[j])));
-                            if (has_res) f += __uint_as_float(lds16(ad) << 16);
-                            sts16(ad, (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(f)));
+                    for (int hh = 0; hh < 2; ++hh) {
+                        if (hh == 1 && !two) break;
+                        const int cb = c0 + 16 * hh;
+                        int sg = cb / a.L, p = cb - sg * a.L;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            if (cb + j < ncols) {
+                                const uint32_t ad = stg + (uint32_t)sg * a.stg_seg_stride + (uint32_t)m * a.stg_pitch + (uint32_t)p * 2u;
+                                float f = __bfloat162float(__float2bfloat16_rn(__uint_as_float(hh ? v1[j] : v0[j])));
+                                if (has_res) f += __uint_as_float(lds16(ad) << 16);
+                                sts16(ad, (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(f)));
+                            }
+                            if (++p == a.L) { p = 0; ++sg; }
                         }
-                        if (++p == a.L) { p = 0; ++sg; }
                     }
                 }
             }
@@ -511,29 +556,11 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&hdr->tmem_empty[as]);
             }
-            // (2) staging complete -> visible to the async proxy -> bulk stores by the first epilogue warp
+            // staging rows of this warp complete -> visible to the async proxy -> tell the store warp
             fence_proxy_async_smem();
-            asm volatile("bar.sync 2, %0;" ::"n"(kP2NumEpi * 32) : "memory");
-            P2_TRACE(e == 0 && lane == 0 && it < 8, 8 + it * 12 + 4);
-            if (e == 0) {
-                const uint32_t Lb = (uint32_t)a.L * 2u;
-                if (a.caseA) {
-                    if (lane < nseg)
-                        bulk_s2g(a.out + ((size_t)(img0 + lane) * a.N + n0) * a.HW, stg + (uint32_t)lane * a.stg_seg_stride,
-                                 (uint32_t)nrows * Lb);
-                } else {
-                    for (int mm = lane; mm < nrows; mm += 32)
-                        bulk_s2g(a.out + ((size_t)img0 * a.N + n0 + mm) * a.HW + p0, stg + (uint32_t)mm * a.stg_pitch, Lb);
-                }
-                bulk_commit();
-                // the buffer the NEXT tile writes (it + 1) was last read by the store of tile it + 1 - stg_bufs
-                if (a.stg_bufs == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
-                __syncwarp();
-                if (has_res && lane == 0) mbar_arrive(&hdr->stg_free);
-                P2_TRACE(lane == 0 && it < 8, 8 + it * 12 + 5);
-            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&hdr->stg_ready[buf]);
         }
-        if (e == 0) bulk_wait_all();  // global writes complete before the CTA exits
     }
 
     tc_fence_before();
@@ -546,14 +573,14 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
     }
 }
 
-int p2_round_up(int v, int m) { return (v + m - 1) / m * m; }
+__host__ __device__ inline int p2_round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 // output-channel slicing shared by the weight packer and the kernel: <= 128 rows per slice (one M tile), slices of <= 112 KiB
-void p2_slices(int rows, int contraction, int *gy, int *ncta, int *kpad, uint32_t *w_lbo, uint32_t *w_bytes) {
+__host__ __device__ inline void p2_slices(int rows, int contraction, int *gy, int *ncta, int *kpad, uint32_t *w_lbo, uint32_t *w_bytes) {
     const int Kpad = p2_round_up(contraction, 16);
-    int g = cdiv(rows, kP2MaxRows);
+    int g = (rows + kP2MaxRows - 1) / kP2MaxRows;
     for (;; ++g) {
-        const int nc = p2_round_up(cdiv(rows, g), 8);
+        const int nc = p2_round_up((rows + g - 1) / g, 8);
         const size_t bytes = (size_t)(Kpad >> 3) * (nc * 16 + 16);
         if (nc <= kP2MaxRows && (bytes <= 112 * 1024 || nc <= 8)) {
             *gy = g; *ncta = nc; *kpad = Kpad;
@@ -667,12 +694,9 @@ template <bool BN> int p2_launch_v(const P2Args &a, dim3 grid, size_t smem_bytes
     return p2_launch<4, BN>(a, grid, smem_bytes, s);
 }
 
-// one thread per 16-byte unit (slice, k-group, row): 8 consecutive k of weight row n0 + n (zero beyond the matrix)
-__global__ void k_pw2_pack(const float *__restrict__ w, unsigned char *__restrict__ img, int rows, int contraction, int trans,
-                           int gy, int ncta, int kgroups, uint32_t w_lbo, uint32_t w_bytes) {
-    const int64_t total = (int64_t)gy * kgroups * (ncta + 1);
-    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= total) return;
+// 16-byte unit u of the image of a [rows x contraction] matrix (trans: W^T of the [contraction x rows]... see pw2_weight_pack)
+__device__ __forceinline__ void p2_pack_unit(const float *__restrict__ w, unsigned char *__restrict__ img, int64_t u, int rows,
+                                             int contraction, int trans, int ncta, int kgroups, uint32_t w_lbo, uint32_t w_bytes) {
     const int n = (int)(u % (ncta + 1));
     const int kg = (int)((u / (ncta + 1)) % kgroups);
     const int sl = (int)(u / ((int64_t)(ncta + 1) * kgroups));
@@ -685,6 +709,34 @@ __global__ void k_pw2_pack(const float *__restrict__ w, unsigned char *__restric
     }
     *reinterpret_cast<uint4 *>(img + (size_t)sl * w_bytes + (size_t)kg * w_lbo + (size_t)n * 16) =
         make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+
+// all conv weights of a model in ONE launch (grid.y = weight): both orientations of every item
+struct P2PackItem {
+    const float *w;
+    unsigned char *img_fwd, *img_bwd;
+    int N, K;
+};
+__global__ void k_pw2_pack_multi(const P2PackItem *__restrict__ items) {
+    const P2PackItem it = items[blockIdx.y];
+    for (int trans = 0; trans < 2; ++trans) {
+        const int rows = trans ? it.K : it.N, contraction = trans ? it.N : it.K;
+        int gy, ncta, kpad;
+        uint32_t lbo, wb;
+        p2_slices(rows, contraction, &gy, &ncta, &kpad, &lbo, &wb);
+        const int64_t total = (int64_t)gy * (kpad >> 3) * (ncta + 1);
+        for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += (int64_t)gridDim.x * blockDim.x)
+            p2_pack_unit(it.w, trans ? it.img_bwd : it.img_fwd, u, rows, contraction, trans, ncta, kpad >> 3, lbo, wb);
+    }
+}
+
+// one thread per 16-byte unit (slice, k-group, row): 8 consecutive k of weight row n0 + n (zero beyond the matrix)
+__global__ void k_pw2_pack(const float *__restrict__ w, unsigned char *__restrict__ img, int rows, int contraction, int trans,
+                           int gy, int ncta, int kgroups, uint32_t w_lbo, uint32_t w_bytes) {
+    const int64_t total = (int64_t)gy * kgroups * (ncta + 1);
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= total) return;
+    p2_pack_unit(w, img, u, rows, contraction, trans, ncta, kgroups, w_lbo, w_bytes);
 }
 
 }  // namespace
@@ -719,6 +771,13 @@ int pw2_weight_pack(const float *w, int N, int K, int trans, void *image, cudaSt
 // 0: no image path; 1: supported; 2: supported and the faster schedule for this geometry (whole-image tiles: the raw ring
 // is fed by few large bulk copies.  Row-piece tiles of larger maps need one small copy per channel row, which the TMA unit
 // serialises -- measured slower than the first-generation kernel, profiles/r02b_bench_pw.log)
+// items: DEVICE array of `count` {const float *weight [N,K]; void *image_fwd; void *image_bwd; int N; int K} (rb_pw_pack_item_t)
+int pw2_weight_pack_multi(const void *items_device, int count, cudaStream_t s) {
+    static_assert(sizeof(P2PackItem) == 32, "rb_pw_pack_item_t layout");
+    k_pw2_pack_multi<<<dim3(48, (unsigned)count), 256, 0, s>>>((const P2PackItem *)items_device);
+    return launched("k_pw2_pack_multi");
+}
+
 int pw2_supported(int NI, int K, int N, int HW, int has_bn) {
     P2Args a{};
     a.NI = NI; a.K = K; a.N = N; a.HW = HW;
