@@ -145,8 +145,15 @@ class RubiksNetBackbone(nn.Module):
 
     def forward(self, x):
         x = self.conv1(x)
-        for i in range(5):
-            x = getattr(self, "layer%d" % i)(x)
+        packing = _use_fused(x) and x.dtype == torch.bfloat16
+        if packing:
+            fused.begin_step_pack(self)  # every conv-weight image of the network in one launch
+        try:
+            for i in range(5):
+                x = getattr(self, "layer%d" % i)(x)
+        finally:
+            if packing:
+                fused.end_step_pack(self)
         if _use_fused(x):
             x = self.avgpool(fused.bn_act(x, self.bn_last, relu=True))
         else:

@@ -61,6 +61,7 @@ size_t pw2_weight_image_bytes(int rows, int contraction);
 int pw2_weight_pack(const float *w, int N, int K, int trans, void *image, cudaStream_t s);
 int pw2_supported(int NI, int K, int N, int HW, int has_bn);
 int pw2_weight_pack_multi(const void *items_device, int count, cudaStream_t s);
+void pw2_set_tuning(int op_stages, int kc);
 int pw2_forward(const void *x, const void *wimg, const void *residual, void *out, int NI, int K, int N, int HW,
                 const float *a_sb, cudaStream_t s);
 #ifdef RB_DEBUG_TRACE
@@ -412,6 +413,7 @@ int rb_shift3d_pw_conv_wgrad(const void *out_grad, const void *x, const void *sh
 }
 
 void rb_pw_conv_set_tuning(int min_n_splits) { pw_conv_set_tuning(min_n_splits); }
+void rb_pw_conv_image_set_tuning(int operand_stages, int k_chunk) { pw2_set_tuning(operand_stages, k_chunk); }
 
 #ifdef RB_DEBUG_TRACE
 /* debug builds only: device buffer (128 x uint64 per CTA) receiving globaltimer stamps of k_pw_conv; NULL = off */

@@ -70,43 +70,27 @@ k_bn_reduce(const T *__restrict__ x, const T *__restrict__ dy, const float *__re
     const uint32_t total = (uint32_t)n_count * vpp.d;
     const int64_t img_stride = (int64_t)splits * C * HW;
     const int64_t base0 = ((int64_t)sp * C + c) * HW;
-    // U independent 128-bit loads per thread and operand are issued before any of them is consumed: with one load in
-    // flight per thread (round 1) the pass ran at 21 % of the HBM peak -- latency, not bandwidth
-    constexpr int U = 4;
-    for (uint32_t idx0 = threadIdx.x; idx0 < total; idx0 += kBT * U) {
-        Pack<T, V> xv[U], gv[U];
-        bool ok[U];
+    for (uint32_t idx = threadIdx.x; idx < total; idx += kBT) {
+        const uint32_t nl = fdiv(idx, vpp);
+        const uint32_t i = idx - nl * vpp.d;
+        const int64_t off = base0 + (int64_t)nl * img_stride + (int64_t)i * V;
+        const Pack<T, V> xv = *reinterpret_cast<const Pack<T, V> *>(x + off);
+        if (MODE == 0) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint32_t idx = idx0 + u * kBT;
-            ok[u] = idx < total;
-            if (ok[u]) {
-                const uint32_t nl = fdiv(idx, vpp);
-                const uint32_t i = idx - nl * vpp.d;
-                const int64_t off = base0 + (int64_t)nl * img_stride + (int64_t)i * V;
-                xv[u] = *reinterpret_cast<const Pack<T, V> *>(x + off);
-                if (MODE == 1) gv[u] = *reinterpret_cast<const Pack<T, V> *>(dy + off);
+            for (int k = 0; k < V; ++k) {
+                const float f = tof(xv.v[k]);
+                s0 += f;
+                s1 += f * f;
             }
-        }
+        } else {
+            const Pack<T, V> gv = *reinterpret_cast<const Pack<T, V> *>(dy + off);
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (!ok[u]) continue;
-            if (MODE == 0) {
-#pragma unroll
-                for (int k = 0; k < V; ++k) {
-                    const float f = tof(xv[u].v[k]);
-                    s0 += f;
-                    s1 += f * f;
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < V; ++k) {
-                    const float f = tof(xv[u].v[k]);
-                    float g = tof(gv[u].v[k]);
-                    if (relu && !(f * sc + bi > 0.f)) g = 0.f;
-                    s0 += g;
-                    s1 += g * ((f - mean) * invstd);
-                }
+            for (int k = 0; k < V; ++k) {
+                const float f = tof(xv.v[k]);
+                float g = tof(gv.v[k]);
+                if (relu && !(f * sc + bi > 0.f)) g = 0.f;
+                s0 += g;
+                s1 += g * ((f - mean) * invstd);
             }
         }
     }

@@ -355,13 +355,14 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)as * 256u;
                 uint32_t a_lo = a_lo0, acc = 0u;
-                P2_TRACE(it < 8, 8 + it * 12 + 0);
+                P2_TRACE(it < 6, 8 + it * 12 + 0);
                 for (int st = 0; st < a.k_stages; ++st, ++n) {
                     const int o = n % a.op_stages;
                     mbar_wait(&hdr->op_full[o], (uint32_t)(n / a.op_stages) & 1u);
                     tc_fence_after();
-                    P2_TRACE(it < 8 && st == 0, 8 + it * 12 + 1);
-                    P2_TRACE(it < 8 && st == a.k_stages - 1, 8 + it * 12 + 2);
+                    P2_TRACE(it < 6 && st == 0, 8 + it * 12 + 1);
+                    P2_TRACE(it < 6 && st == a.k_stages - 1, 8 + it * 12 + 2);
+                    P2_TRACE(it == 2 && st < 9, 80 + 2 * st);
                     const int ksteps = min(a.kc, a.Kpad - st * a.kc) >> 4;
                     uint32_t b_lo = b_lo0 + (uint32_t)o * op16;
                     for (int ks = 0; ks < ksteps; ++ks) {
@@ -371,6 +372,7 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
                         b_lo += 2048u >> 4;
                     }
                     mma_commit(&hdr->op_empty[o]);
+                    P2_TRACE(it == 2 && st < 9, 81 + 2 * st);
                 }
                 mma_commit(&hdr->tmem_full[as]);
             }
@@ -409,8 +411,8 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
                 res_pending = false;
             };
             for (int st = 0; st < a.k_stages; ++st, ++n) {
-                P2_TRACE(lane == 0 && it < 8 && st == 0, 8 + it * 12 + 6);
-                P2_TRACE(lane == 0 && it < 8 && st == a.k_stages - 1, 8 + it * 12 + 7);
+                P2_TRACE(lane == 0 && it < 6 && st == 0, 8 + it * 12 + 6);
+                P2_TRACE(lane == 0 && it < 6 && st == a.k_stages - 1, 8 + it * 12 + 7);
                 if (res_pending && __shfl_sync(0xffffffffu, (int)mbar_test(&hdr->stg_empty[buf], empty_par), 0) != 0) issue_residual();
                 const int r = n % a.raw_stages;
                 mbar_wait(&hdr->raw_empty[r], ((uint32_t)(n / a.raw_stages) & 1u) ^ 1u);
@@ -449,7 +451,7 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
             const int buf = it % a.stg_bufs;
             const uint32_t stg = s_stg + (uint32_t)buf * a.stg_buf_bytes;
             mbar_wait(&hdr->stg_ready[buf], (uint32_t)(it / a.stg_bufs) & 1u);
-            P2_TRACE(lane == 0 && it < 8, 8 + it * 12 + 4);
+            P2_TRACE(lane == 0 && it < 6, 8 + it * 12 + 4);
             if (a.caseA) {
                 if (lane < nseg)
                     bulk_s2g(a.out + ((size_t)(img0 + lane) * a.N + n0) * a.HW, stg + (uint32_t)lane * a.stg_seg_stride,
@@ -462,7 +464,7 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
             bulk_wait_read<0>();
             __syncwarp();
             if (lane == 0) mbar_arrive(&hdr->stg_empty[buf]);
-            P2_TRACE(lane == 0 && it < 8, 8 + it * 12 + 5);
+            P2_TRACE(lane == 0 && it < 6, 8 + it * 12 + 5);
         }
         bulk_wait_all();  // global writes complete before the CTA exits
     } else if (warp >= kP2RelWarp0 && warp < kP2EpiWarp0) {
@@ -478,17 +480,21 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
                 const int rows_real = min(a.kc, a.K - k0);
                 const int rows_pad = min(a.kc, a.Kpad - k0);  // 16 or 32
                 mbar_wait(&hdr->raw_full[r], (uint32_t)(n / a.raw_stages) & 1u);
-                P2_TRACE(rw == 0 && lane == 0 && (tile - tile0) / tstride < 8 && st == 0, 8 + ((tile - tile0) / tstride) * 12 + 8);
+                P2_TRACE(rw == 0 && lane == 0 && (tile - tile0) / tstride < 6 && st == 0, 8 + ((tile - tile0) / tstride) * 12 + 8);
+                P2_TRACE(rw == 0 && lane == 0 && tile == tile0 + 2 * tstride && st < 6, 104 + 4 * st);
                 mbar_wait(&hdr->op_empty[o], ((uint32_t)(n / a.op_stages) & 1u) ^ 1u);
+                P2_TRACE(rw == 0 && lane == 0 && tile == tile0 + 2 * tstride && st < 6, 105 + 4 * st);
                 p2_relayout_stage<MODE, BN>(a, s_raw + (uint32_t)r * a.raw_stage_bytes, s_op + (uint32_t)o * a.op_stage_bytes,
                                             smem_sb, k0, rows_real, rows_pad, nseg, rw, lane);
+                P2_TRACE(rw == 0 && lane == 0 && tile == tile0 + 2 * tstride && st < 6, 106 + 4 * st);
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
                     mbar_arrive(&hdr->op_full[o]);
                     mbar_arrive(&hdr->raw_empty[r]);
                 }
-                P2_TRACE(rw == 0 && lane == 0 && (tile - tile0) / tstride < 8 && st == a.k_stages - 1, 8 + ((tile - tile0) / tstride) * 12 + 9);
+                P2_TRACE(rw == 0 && lane == 0 && tile == tile0 + 2 * tstride && st < 6, 107 + 4 * st);
+                P2_TRACE(rw == 0 && lane == 0 && (tile - tile0) / tstride < 6 && st == a.k_stages - 1, 8 + ((tile - tile0) / tstride) * 12 + 9);
             }
         }
     } else if (warp >= kP2EpiWarp0) {
@@ -508,11 +514,11 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
             const int ch_lo = half ? nch0 : 0, ch_hi = half ? nch : nch0;
             mbar_wait(&hdr->tmem_full[as], (uint32_t)(it >> 1) & 1u);
             tc_fence_after();
-            P2_TRACE(e == 0 && lane == 0 && it < 8, 8 + it * 12 + 3);
+            P2_TRACE(e == 0 && lane == 0 && it < 6, 8 + it * 12 + 3);
             // the staging buffer holds the residual block (which also means the previous store has released it), or is free
             if (has_res) mbar_wait(&hdr->res_full[buf], (uint32_t)(it / a.stg_bufs) & 1u);
             else mbar_wait(&hdr->stg_empty[buf], ((uint32_t)(it / a.stg_bufs) & 1u) ^ 1u);
-            P2_TRACE(e == 0 && lane == 0 && it < 8, 8 + it * 12 + 10);
+            P2_TRACE(e == 0 && lane == 0 && it < 6, 8 + it * 12 + 10);
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256u;
             const uint32_t rowaddr = stg + (uint32_t)m * a.stg_pitch;
             // two 16-column chunks per round: both TMEM loads are in flight before the first conversion
@@ -591,6 +597,9 @@ __host__ __device__ inline void p2_slices(int rows, int contraction, int *gy, in
     }
 }
 
+// schedule overrides (rb_pw_conv_set_tuning2): operand-ring depth and K chunk of the image kernel; 0 = automatic
+int g_p2_op_stages = 0, g_p2_kc = 0;
+
 bool p2_plan(P2Args &a, dim3 *grid, size_t *smem_bytes) {
     if (a.NI <= 0 || a.K <= 0 || a.N <= 0 || a.HW <= 0) return false;
     if (a.K % 8 != 0 || a.N % 8 != 0) return false;
@@ -643,11 +652,13 @@ bool p2_plan(P2Args &a, dim3 *grid, size_t *smem_bytes) {
     // global memory busy -- bytes in flight per SM = raw stages x stage bytes -- so it gets all the remaining room.  Pick the
     // K chunk (32 or 16 channels) and the number of staging buffers that maximise the bytes in flight.
     int best_bytes = -1;
+    const int nop = g_p2_op_stages >= 2 && g_p2_op_stages <= kP2MaxRing ? g_p2_op_stages : 2;
     for (int kc = 32; kc >= 16; kc -= 16) {
+        if (g_p2_kc && kc != g_p2_kc) continue;
         const uint32_t raw_b = (uint32_t)p2_round_up(a.S * kc * a.L * 2, 128);
         const uint32_t op_b = (uint32_t)a.atoms * (uint32_t)(kc >> 3) * 1024u;
         for (int bufs = 2; bufs >= 1; --bufs) {
-            const int64_t room = (int64_t)kP2Smem - fixed - (int64_t)bufs * stg1 - 2 * (int64_t)op_b;
+            const int64_t room = (int64_t)kP2Smem - fixed - (int64_t)bufs * stg1 - nop * (int64_t)op_b;
             if (room < (int64_t)2 * raw_b) continue;
             int stages = (int)(room / raw_b);
             if (stages > kP2MaxRing) stages = kP2MaxRing;
@@ -658,11 +669,11 @@ bool p2_plan(P2Args &a, dim3 *grid, size_t *smem_bytes) {
             a.kc = kc; a.G = kc >> 3;
             a.k_stages = cdiv(a.Kpad, kc);
             a.raw_stages = stages;
-            a.op_stages = 2;
+            a.op_stages = nop;
             a.stg_bufs = bufs;
             a.raw_stage_bytes = raw_b; a.op_stage_bytes = op_b; a.stg_buf_bytes = stg1;
             a.off_op = fixed;                                    // 1 KiB aligned (SWIZZLE_128B atoms)
-            a.off_raw = a.off_op + 2u * op_b;
+            a.off_raw = a.off_op + (uint32_t)nop * op_b;
             a.off_stg = a.off_raw + (uint32_t)stages * raw_b;
             *smem_bytes = (size_t)a.off_stg + (size_t)bufs * stg1;
         }
@@ -744,6 +755,8 @@ __global__ void k_pw2_pack(const float *__restrict__ w, unsigned char *__restric
 #ifdef RB_DEBUG_TRACE
 unsigned long long *pw_conv_get_trace();
 #endif
+
+void pw2_set_tuning(int op_stages, int kc) { g_p2_op_stages = op_stages; g_p2_kc = (kc == 16 || kc == 32) ? kc : 0; }
 
 // bytes of the packed image of a [rows x contraction] weight matrix (all slices)
 size_t pw2_weight_image_bytes(int rows, int contraction) {

@@ -102,3 +102,43 @@ def test_image_kernel_on_a_side_stream_and_repeated_launches():
     s.synchronize()
     for o in outs:
         assert torch.equal(o, ref)  # deterministic: fixed schedule, no atomics
+
+
+def test_one_launch_weight_packing_matches_per_weight_packing():
+    """From the second forward pass on, RubiksNetBackbone packs all weight images in one launch (fused._StepPack); the step
+    must give the same loss and gradients as the first pass (per-weight packing) on identical parameters and inputs."""
+    import rubiksnet_b200 as rb
+    from rubiksnet_b200 import _lib, fused
+    torch.manual_seed(7)
+    net = rb.RubiksNet(tier="tiny", num_classes=5, num_frames=8).cuda().train()
+    clips = torch.randn(1, 8, 3, 224, 224, device="cuda")
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    results = []
+    for step in range(3):
+        net.load_state_dict(sd)
+        net.zero_grad(set_to_none=True)
+        _lib.timing.start()
+        with torch.autocast("cuda", dtype=BF):
+            loss = net(clips).float().square().mean()
+        loss.backward()
+        agg = _lib.timing.stop()
+        results.append((loss.item(), {n: p.grad.clone() for n, p in net.named_parameters()}, agg["pw_weight_pack"]["launches"]))
+    assert "_rb_pack_plan" in net.backbone.__dict__
+    assert results[0][2] > results[1][2] and results[1][2] == results[2][2]  # many launches, then 1 (+ plain packs)
+    for loss, grads, _ in results[1:]:
+        assert loss == results[0][0]
+        for n, g in grads.items():
+            assert torch.equal(g, results[0][1][n]), n
+    # a changed weight is picked up: the images are rebuilt from the parameters at every step
+    with torch.no_grad():
+        net.backbone.layer3[1].conv3.weight.mul_(0.5)
+    with torch.autocast("cuda", dtype=BF):
+        loss2 = net(clips).float().square().mean()
+    fused.USE_IMAGE_KERNEL = False
+    try:
+        with torch.autocast("cuda", dtype=BF):
+            loss3 = net(clips).float().square().mean()
+    finally:
+        fused.USE_IMAGE_KERNEL = True
+    assert loss2.item() != results[0][0]
+    assert abs(loss2.item() - loss3.item()) <= 1e-2 * max(1.0, abs(loss3.item()))

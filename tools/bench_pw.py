@@ -51,8 +51,11 @@ def main():
     ap.add_argument("--only", default=None)
     ap.add_argument("--modes", default="fwd,fwd2,res,res2,bn,bn2,dgrad,dgrad2,shift,wgrad,wgrad_shift,cublas")
     ap.add_argument("--splits", type=int, default=0, help="rb_pw_conv_set_tuning: minimum output-channel splits (0 = auto)")
+    ap.add_argument("--opstages", type=int, default=0, help="image kernel: operand ring depth (0 = auto)")
+    ap.add_argument("--kc", type=int, default=0, help="image kernel: channels per K chunk, 16 or 32 (0 = auto)")
     a = ap.parse_args()
     _lib.lib().rb_pw_conv_set_tuning(a.splits)
+    _lib.lib().rb_pw_conv_image_set_tuning(a.opstages, a.kc)
     modes = a.modes.split(",")
     T = 8
     print("device:", torch.cuda.get_device_name(0))

@@ -19,6 +19,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--mode", default="fwd")
     ap.add_argument("--wbf16", action="store_true", help="bf16 weights packed by rb_pw_weight_pack")
+    ap.add_argument("--opstages", type=int, default=0)
+    ap.add_argument("--kc", type=int, default=0)
     ap.add_argument("--v2", action="store_true", help="second-generation kernel (packed weight images, csrc/pw_conv2.cu)")
     a = ap.parse_args()
     # the stamps only exist in the debug library (python -m rubiksnet_b200.build --trace); point the loader at it
@@ -34,6 +36,8 @@ def main():
         w, w_kn = ops.pw_weight_pack(w)
     sb = torch.stack([torch.rand(a.C, device="cuda") + 0.5, torch.randn(a.C, device="cuda")], dim=1).contiguous()
     if a.v2:
+        L.rb_pw_conv_image_set_tuning.argtypes = [ctypes.c_int, ctypes.c_int]
+        L.rb_pw_conv_image_set_tuning(a.opstages, a.kc)
         img_f, img_b = ops.pw_weight_images(w)
         res = torch.randn_like(x)
         fn = {"fwd": lambda: ops.pw_conv(x, img_f), "bn": lambda: ops.pw_conv(x, img_f, in_scale_bias=sb),
@@ -56,11 +60,15 @@ def main():
         for cta in (0, t.shape[0] // 2, t.shape[0] - 1):
             r = t[cta]
             print("CTA %d: start %.1f mma-ready %.1f weights %.1f end %.1f" % (cta, us(r[0]), us(r[1]), us(r[2]), us(r[3])))
-            for it in range(8):
+            for it in range(6):
                 b = 8 + it * 12
                 if int(r[b]) == 0:
                     break
                 print("   tile %d: " % it + "  ".join("%s %.1f" % (n, us(r[b + i])) for i, n in enumerate(names)))
+            print("   tile 2 MMA per stage (op_full seen / issued+committed): " +
+                  "  ".join("%.2f/%.2f" % (us(r[80 + 2 * st]), us(r[81 + 2 * st])) for st in range(9) if int(r[80 + 2 * st])))
+            print("   tile 2 relayout warp 0 per stage (raw_full seen / op_empty seen / work done / fenced+arrived): " +
+                  "  ".join("%.2f/%.2f/%.2f/%.2f" % tuple(us(r[104 + 4 * st + i]) for i in range(4)) for st in range(6) if int(r[104 + 4 * st])))
         return
     fn = {"fwd": lambda: ops.pw_conv(x, w), "bn": lambda: ops.pw_conv(x, w, in_scale_bias=sb),
           "dgrad": (lambda: ops.pw_conv(x, w_kn)) if a.wbf16 else (lambda: ops.pw_conv(x, w, transposed=True))}[a.mode]
