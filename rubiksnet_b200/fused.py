@@ -272,10 +272,28 @@ class _Conv1x1TC(torch.autograd.Function):
         return gx, gw, gres
 
 
+class _conv_tf32:
+    """fp32 1x1 convolutions follow torch.backends.cudnn.allow_tf32 -- the switch that governs nn.Conv2d, which is what the
+    reference runs here (default True: TF32 tensor cores) -- although they are expressed as batched GEMMs."""
+
+    def __enter__(self):
+        self.prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = bool(torch.backends.cudnn.allow_tf32)
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32 = self.prev
+        return False
+
+
 class _Conv1x1(torch.autograd.Function):
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda")
     def forward(ctx, x, weight, residual):
+        with _conv_tf32():
+            return _Conv1x1._forward(ctx, x, weight, residual)
+
+    @staticmethod
+    def _forward(ctx, x, weight, residual):
         ni, cin = x.shape[0], x.shape[1]
         cout = weight.shape[0]
         hshape = x.shape[2:]
@@ -294,6 +312,11 @@ class _Conv1x1(torch.autograd.Function):
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, g):
+        with _conv_tf32():
+            return _Conv1x1._backward(ctx, g)
+
+    @staticmethod
+    def _backward(ctx, g):
         xb, wb = ctx.saved_tensors
         ni, cin, hw = xb.shape
         cout = wb.shape[0]
