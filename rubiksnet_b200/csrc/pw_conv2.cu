@@ -93,6 +93,14 @@ __device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Whole-warp wait with ONE polling lane: mbarrier.try_wait goes through the shared-memory pipeline like an atomic, and 32
+// lanes polling the same word are 32 serialised transactions -- with a dozen waiting warps that traffic alone slowed the
+// relayout warps' LDS/STS and the TMA unit's writes by an order of magnitude (profiles/r02e_trace_l3.log).  Lane 0 polls,
+// __syncwarp() releases the others and orders their subsequent reads after lane 0's acquire.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity, int lane) {
+    if (lane == 0) mbar_wait(bar, parity);
+    __syncwarp();
+}
 // global -> shared bulk copy (TMA, 1-D); completion is counted in bytes on `bar`
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -413,9 +421,13 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
             for (int st = 0; st < a.k_stages; ++st, ++n) {
                 P2_TRACE(lane == 0 && it < 6 && st == 0, 8 + it * 12 + 6);
                 P2_TRACE(lane == 0 && it < 6 && st == a.k_stages - 1, 8 + it * 12 + 7);
-                if (res_pending && __shfl_sync(0xffffffffu, (int)mbar_test(&hdr->stg_empty[buf], empty_par), 0) != 0) issue_residual();
+                if (res_pending) {
+                    int ok = 0;
+                    if (lane == 0) ok = (int)mbar_test(&hdr->stg_empty[buf], empty_par);
+                    if (__shfl_sync(0xffffffffu, ok, 0) != 0) issue_residual();
+                }
                 const int r = n % a.raw_stages;
-                mbar_wait(&hdr->raw_empty[r], ((uint32_t)(n / a.raw_stages) & 1u) ^ 1u);
+                mbar_wait_warp(&hdr->raw_empty[r], ((uint32_t)(n / a.raw_stages) & 1u) ^ 1u, lane);
                 const int k0 = st * a.kc;
                 const int rows = min(a.kc, a.K - k0);
                 const uint32_t dst0 = s_raw + (uint32_t)r * a.raw_stage_bytes;
@@ -435,7 +447,7 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
                 __syncwarp();
             }
             if (res_pending) {
-                mbar_wait(&hdr->stg_empty[buf], empty_par);
+                mbar_wait_warp(&hdr->stg_empty[buf], empty_par, lane);
                 issue_residual();
             }
         }
@@ -450,7 +462,7 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
             p2_tile(a, tile, img0, p0, nseg);
             const int buf = it % a.stg_bufs;
             const uint32_t stg = s_stg + (uint32_t)buf * a.stg_buf_bytes;
-            mbar_wait(&hdr->stg_ready[buf], (uint32_t)(it / a.stg_bufs) & 1u);
+            mbar_wait_warp(&hdr->stg_ready[buf], (uint32_t)(it / a.stg_bufs) & 1u, lane);
             P2_TRACE(lane == 0 && it < 6, 8 + it * 12 + 4);
             if (a.caseA) {
                 if (lane < nseg)
@@ -479,10 +491,10 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
                 const int k0 = st * a.kc;
                 const int rows_real = min(a.kc, a.K - k0);
                 const int rows_pad = min(a.kc, a.Kpad - k0);  // 16 or 32
-                mbar_wait(&hdr->raw_full[r], (uint32_t)(n / a.raw_stages) & 1u);
+                mbar_wait_warp(&hdr->raw_full[r], (uint32_t)(n / a.raw_stages) & 1u, lane);
                 P2_TRACE(rw == 0 && lane == 0 && (tile - tile0) / tstride < 6 && st == 0, 8 + ((tile - tile0) / tstride) * 12 + 8);
                 P2_TRACE(rw == 0 && lane == 0 && tile == tile0 + 2 * tstride && st < 6, 104 + 4 * st);
-                mbar_wait(&hdr->op_empty[o], ((uint32_t)(n / a.op_stages) & 1u) ^ 1u);
+                mbar_wait_warp(&hdr->op_empty[o], ((uint32_t)(n / a.op_stages) & 1u) ^ 1u, lane);
                 P2_TRACE(rw == 0 && lane == 0 && tile == tile0 + 2 * tstride && st < 6, 105 + 4 * st);
                 p2_relayout_stage<MODE, BN>(a, s_raw + (uint32_t)r * a.raw_stage_bytes, s_op + (uint32_t)o * a.op_stage_bytes,
                                             smem_sb, k0, rows_real, rows_pad, nseg, rw, lane);
@@ -512,12 +524,12 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
             const int ncols = nseg * a.L;
             const int nch = (ncols + 15) >> 4, nch0 = (nch + 1) >> 1;
             const int ch_lo = half ? nch0 : 0, ch_hi = half ? nch : nch0;
-            mbar_wait(&hdr->tmem_full[as], (uint32_t)(it >> 1) & 1u);
+            mbar_wait_warp(&hdr->tmem_full[as], (uint32_t)(it >> 1) & 1u, lane);
             tc_fence_after();
             P2_TRACE(e == 0 && lane == 0 && it < 6, 8 + it * 12 + 3);
             // the staging buffer holds the residual block (which also means the previous store has released it), or is free
-            if (has_res) mbar_wait(&hdr->res_full[buf], (uint32_t)(it / a.stg_bufs) & 1u);
-            else mbar_wait(&hdr->stg_empty[buf], ((uint32_t)(it / a.stg_bufs) & 1u) ^ 1u);
+            if (has_res) mbar_wait_warp(&hdr->res_full[buf], (uint32_t)(it / a.stg_bufs) & 1u, lane);
+            else mbar_wait_warp(&hdr->stg_empty[buf], ((uint32_t)(it / a.stg_bufs) & 1u) ^ 1u, lane);
             P2_TRACE(e == 0 && lane == 0 && it < 6, 8 + it * 12 + 10);
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256u;
             const uint32_t rowaddr = stg + (uint32_t)m * a.stg_pitch;
