@@ -271,6 +271,7 @@ void rb_pw_conv_image_set_tuning(int operand_stages, int k_chunk);
  * writes globaltimer stamps of its pipeline events (128 x uint64 per CTA) into this device buffer.  The product
  * library does not export this symbol and contains no tracing or work-skipping code. */
 void rb_debug_pw_trace(void *device_buffer);
+void rb_debug_pw_flags(int flags); /* image kernel: skip relayout (1) / MMA (2) / epilogue (4) / stores (8) / raw loads (16) */
 #endif
 
 #ifdef __cplusplus

@@ -416,6 +416,9 @@ void rb_pw_conv_set_tuning(int min_n_splits) { pw_conv_set_tuning(min_n_splits);
 void rb_pw_conv_image_set_tuning(int operand_stages, int k_chunk) { pw2_set_tuning(operand_stages, k_chunk); }
 
 #ifdef RB_DEBUG_TRACE
+namespace rb { void pw2_set_debug(int flags); }
+/* debug builds only: work-skipping switches of the image kernel (critical-path experiments, tools/trace_pw.py --dbg) */
+void rb_debug_pw_flags(int flags) { rb::pw2_set_debug(flags); }
 /* debug builds only: device buffer (128 x uint64 per CTA) receiving globaltimer stamps of k_pw_conv; NULL = off */
 void rb_debug_pw_trace(void *device_buffer) { pw_conv_set_trace(device_buffer); }
 #endif

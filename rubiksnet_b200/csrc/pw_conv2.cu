@@ -58,6 +58,7 @@ struct P2Args {
     uint32_t raw_stage_bytes, op_stage_bytes, stg_buf_bytes, stg_pitch, stg_seg_stride;
 #ifdef RB_DEBUG_TRACE
     unsigned long long *trace;  // debug builds only: 128 globaltimer stamps per CTA (tools/trace_pw.py --v2)
+    int dbg;                    // debug builds only: skip work to find the critical path (1 relayout, 2 MMA, 4 epilogue, 8 stores, 16 raw loads)
 #endif
 };
 
@@ -68,8 +69,10 @@ __device__ __forceinline__ unsigned long long p2_gtime() {
     return t;
 }
 #define P2_TRACE(cond, slot) do { if (a.trace && (cond)) a.trace[(blockIdx.y * gridDim.x + blockIdx.x) * 128 + (slot)] = p2_gtime(); } while (0)
+#define P2_DBG(bit) ((a.dbg & (bit)) != 0)
 #else
 #define P2_TRACE(cond, slot) do { } while (0)
+#define P2_DBG(bit) false
 #endif
 
 struct P2Hdr {
@@ -190,9 +193,13 @@ __device__ __forceinline__ void p2_relayout_stage(const P2Args &a, uint32_t raw,
         constexpr uint32_t EPP = MODE / 2;  // elements per piece
         const uint32_t ppr = L / EPP;
         const int passes = (int)((ppr + 31u) >> 5);
-        const int units = nseg * groups * passes;
-        for (int u = rw; u < units; u += kP2NumRel) {
-            const int pass = u % passes, t = u / passes, g = t % groups, sg = t / groups;
+        // units (segment, group, pass) are dealt round-robin to the relayout warps; plain nested loops with a running
+        // counter -- decoding a unit index with run-time divisions cost more than the unit itself
+        int ucount = 0;
+        for (int sg = 0; sg < nseg; ++sg)
+        for (int g = 0; g < groups; ++g)
+        for (int pass = 0; pass < passes; ++pass) {
+            if ((ucount++ & (kP2NumRel - 1)) != rw) continue;
             const uint32_t pc = (uint32_t)(lane + 32 * pass);
             if (pc >= ppr) continue;
             const uint32_t c = (uint32_t)sg * L + pc * EPP;
@@ -225,9 +232,11 @@ __device__ __forceinline__ void p2_relayout_stage(const P2Args &a, uint32_t raw,
         }
     } else {
         const int passes = (int)(((L >> 1) + 2u + 31u) >> 5);
-        const int units = nseg * groups * passes;
-        for (int u = rw; u < units; u += kP2NumRel) {
-            const int pass = u % passes, t = u / passes, g = t % groups, sg = t / groups;
+        int ucount = 0;
+        for (int sg = 0; sg < nseg; ++sg)
+        for (int g = 0; g < groups; ++g)
+        for (int pass = 0; pass < passes; ++pass) {
+            if ((ucount++ & (kP2NumRel - 1)) != rw) continue;
             const uint32_t c0 = (uint32_t)sg * L, u0 = c0 >> 1;
             const uint32_t nwords = ((c0 + L - 1u) >> 1) - u0 + 1u;
             const uint32_t w = (uint32_t)(lane + 32 * pass);
@@ -374,7 +383,7 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
                     const int ksteps = min(a.kc, a.Kpad - st * a.kc) >> 4;
                     uint32_t b_lo = b_lo0 + (uint32_t)o * op16;
                     for (int ks = 0; ks < ksteps; ++ks) {
-                        mma_bf16_lohi(tacc, a_lo, a_hi, b_lo, b_hi, idesc, acc);
+                        if (!P2_DBG(2)) mma_bf16_lohi(tacc, a_lo, a_hi, b_lo, b_hi, idesc, acc);
                         acc = 1u;
                         a_lo += a_kstep;
                         b_lo += 2048u >> 4;
@@ -431,7 +440,9 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
                 const int k0 = st * a.kc;
                 const int rows = min(a.kc, a.K - k0);
                 const uint32_t dst0 = s_raw + (uint32_t)r * a.raw_stage_bytes;
-                if (a.caseA) {
+                if (P2_DBG(16)) {
+                    if (lane == 0) mbar_arrive(&hdr->raw_full[r]);
+                } else if (a.caseA) {
                     const uint32_t bytes = (uint32_t)rows * Lb;
                     if (lane == 0) mbar_expect_tx(&hdr->raw_full[r], bytes * (uint32_t)nseg);
                     __syncwarp();
@@ -464,7 +475,8 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
             const uint32_t stg = s_stg + (uint32_t)buf * a.stg_buf_bytes;
             mbar_wait_warp(&hdr->stg_ready[buf], (uint32_t)(it / a.stg_bufs) & 1u, lane);
             P2_TRACE(lane == 0 && it < 6, 8 + it * 12 + 4);
-            if (a.caseA) {
+            if (P2_DBG(8)) {
+            } else if (a.caseA) {
                 if (lane < nseg)
                     bulk_s2g(a.out + ((size_t)(img0 + lane) * a.N + n0) * a.HW, stg + (uint32_t)lane * a.stg_seg_stride,
                              (uint32_t)nrows * Lb);
@@ -496,8 +508,9 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
                 P2_TRACE(rw == 0 && lane == 0 && tile == tile0 + 2 * tstride && st < 6, 104 + 4 * st);
                 mbar_wait_warp(&hdr->op_empty[o], ((uint32_t)(n / a.op_stages) & 1u) ^ 1u, lane);
                 P2_TRACE(rw == 0 && lane == 0 && tile == tile0 + 2 * tstride && st < 6, 105 + 4 * st);
-                p2_relayout_stage<MODE, BN>(a, s_raw + (uint32_t)r * a.raw_stage_bytes, s_op + (uint32_t)o * a.op_stage_bytes,
-                                            smem_sb, k0, rows_real, rows_pad, nseg, rw, lane);
+                if (!P2_DBG(1))
+                    p2_relayout_stage<MODE, BN>(a, s_raw + (uint32_t)r * a.raw_stage_bytes, s_op + (uint32_t)o * a.op_stage_bytes,
+                                                smem_sb, k0, rows_real, rows_pad, nseg, rw, lane);
                 P2_TRACE(rw == 0 && lane == 0 && tile == tile0 + 2 * tstride && st < 6, 106 + 4 * st);
                 fence_proxy_async_smem();
                 __syncwarp();
@@ -534,7 +547,7 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256u;
             const uint32_t rowaddr = stg + (uint32_t)m * a.stg_pitch;
             // two 16-column chunks per round: both TMEM loads are in flight before the first conversion
-            for (int ch = ch_lo; ch < ch_hi; ch += 2) {
+            for (int ch = ch_lo; ch < (P2_DBG(4) ? ch_lo : ch_hi); ch += 2) {
                 const int c0 = ch << 4;
                 const bool two = ch + 1 < ch_hi;
                 uint32_t v0[16], v1[16];
@@ -569,7 +582,7 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
                     }
                 }
             }
-            if (ch_lo >= ch_hi) {  // no column chunk for this warp (tiny tile): still release the accumulator
+            if (ch_lo >= ch_hi || P2_DBG(4)) {  // no column chunk for this warp (tiny tile): still release the accumulator
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&hdr->tmem_empty[as]);
@@ -766,6 +779,8 @@ __global__ void k_pw2_pack(const float *__restrict__ w, unsigned char *__restric
 
 #ifdef RB_DEBUG_TRACE
 unsigned long long *pw_conv_get_trace();
+static int g_p2_dbg = 0;
+void pw2_set_debug(int flags) { g_p2_dbg = flags; }
 #endif
 
 void pw2_set_tuning(int op_stages, int kc) { g_p2_op_stages = op_stages; g_p2_kc = (kc == 16 || kc == 32) ? kc : 0; }
@@ -828,6 +843,7 @@ int pw2_forward(const void *x, const void *wimg, const void *residual, void *out
     if (al & 15) return fail(RB_ERR_INVALID_ARGUMENT, "pw_conv (image weights): pointers must be 16-byte aligned");
 #ifdef RB_DEBUG_TRACE
     a.trace = pw_conv_get_trace();
+    a.dbg = g_p2_dbg;
 #endif
     return a_sb ? p2_launch_v<true>(a, grid, smem, s) : p2_launch_v<false>(a, grid, smem, s);
 }

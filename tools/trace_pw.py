@@ -19,6 +19,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--mode", default="fwd")
     ap.add_argument("--wbf16", action="store_true", help="bf16 weights packed by rb_pw_weight_pack")
+    ap.add_argument("--dbg", type=int, default=0, help="debug library: work-skipping flags of the image kernel")
+    ap.add_argument("--reps", type=int, default=0, help="also time `reps` launches with CUDA events (L2 flushed in between)")
     ap.add_argument("--opstages", type=int, default=0)
     ap.add_argument("--kc", type=int, default=0)
     ap.add_argument("--v2", action="store_true", help="second-generation kernel (packed weight images, csrc/pw_conv2.cu)")
@@ -38,12 +40,28 @@ def main():
     if a.v2:
         L.rb_pw_conv_image_set_tuning.argtypes = [ctypes.c_int, ctypes.c_int]
         L.rb_pw_conv_image_set_tuning(a.opstages, a.kc)
+        L.rb_debug_pw_flags.argtypes = [ctypes.c_int]
+        L.rb_debug_pw_flags.restype = None
+        L.rb_debug_pw_flags(a.dbg)
         img_f, img_b = ops.pw_weight_images(w)
         res = torch.randn_like(x)
         fn = {"fwd": lambda: ops.pw_conv(x, img_f), "bn": lambda: ops.pw_conv(x, img_f, in_scale_bias=sb),
               "res": lambda: ops.pw_conv(x, img_f, residual=res), "dgrad": lambda: ops.pw_conv(x, img_b)}[a.mode]
         for _ in range(3):
             fn()
+        if a.reps:
+            flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+            ts = []
+            for _ in range(a.reps):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                e1.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            ts.sort()
+            print("dbg=%d %s C=%d H=%d: median %.1f us" % (a.dbg, a.mode, a.C, a.H, ts[len(ts) // 2] * 1e3))
         trace = torch.zeros(148 * 128, dtype=torch.int64, device="cuda")
         torch.cuda.synchronize()
         L.rb_debug_pw_trace(ctypes.c_void_p(trace.data_ptr()))
