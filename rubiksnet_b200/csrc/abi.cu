@@ -62,6 +62,9 @@ int pw2_weight_pack(const float *w, int N, int K, int trans, void *image, cudaSt
 int pw2_supported(int NI, int K, int N, int HW, int has_bn);
 int pw2_weight_pack_multi(const void *items_device, int count, cudaStream_t s);
 void pw2_set_tuning(int op_stages, int kc);
+#ifdef RB_DEBUG_TRACE
+void pw2_set_debug(int flags);
+#endif
 int pw2_forward(const void *x, const void *wimg, const void *residual, void *out, int NI, int K, int N, int HW,
                 const float *a_sb, cudaStream_t s);
 #ifdef RB_DEBUG_TRACE
@@ -416,9 +419,8 @@ void rb_pw_conv_set_tuning(int min_n_splits) { pw_conv_set_tuning(min_n_splits);
 void rb_pw_conv_image_set_tuning(int operand_stages, int k_chunk) { pw2_set_tuning(operand_stages, k_chunk); }
 
 #ifdef RB_DEBUG_TRACE
-namespace rb { void pw2_set_debug(int flags); }
 /* debug builds only: work-skipping switches of the image kernel (critical-path experiments, tools/trace_pw.py --dbg) */
-void rb_debug_pw_flags(int flags) { rb::pw2_set_debug(flags); }
+void rb_debug_pw_flags(int flags) { pw2_set_debug(flags); }
 /* debug builds only: device buffer (128 x uint64 per CTA) receiving globaltimer stamps of k_pw_conv; NULL = off */
 void rb_debug_pw_trace(void *device_buffer) { pw_conv_set_trace(device_buffer); }
 #endif
