@@ -184,22 +184,41 @@ __device__ __forceinline__ uint32_t p2_col_chunk(uint32_t c) { return (c & 63u) 
 //           words + funnel shift whatever the source alignment; row ends are written as 2-byte halves so that the
 //           neighbouring segment's columns in the same operand row are never touched.
 // K % 8 == 0 (p2_plan), so an 8-channel group is either all real channels or all padding (zeros).
+// units of a FULL stage (S segments x G groups x passes) owned by one relayout warp, decoded once per kernel: byte 0 =
+// segment, byte 1 = group, byte 2 = pass.  Partial stages / tiles skip the units they do not have.
+constexpr int kP2MaxUnits = 4;
+struct P2Units {
+    int n;
+    uint32_t u[kP2MaxUnits];
+};
+__device__ __forceinline__ int p2_passes(const P2Args &a, int mode) {
+    if (mode == 16 || mode == 8) return (int)(((uint32_t)a.L / (uint32_t)(mode / 2) + 31u) >> 5);
+    return (int)((((uint32_t)a.L >> 1) + 2u + 31u) >> 5);
+}
+__device__ __forceinline__ P2Units p2_make_units(const P2Args &a, int mode, int rw) {
+    P2Units pu;
+    pu.n = 0;
+    const int passes = p2_passes(a, mode), total = a.S * a.G * passes;
+    for (int u = rw; u < total && pu.n < kP2MaxUnits; u += kP2NumRel) {
+        const int pass = u % passes, t = u / passes, g = t % a.G, sg = t / a.G;
+        pu.u[pu.n++] = (uint32_t)sg | ((uint32_t)g << 8) | ((uint32_t)pass << 16);
+    }
+    return pu;
+}
+
 template <int MODE, bool BN>
 __device__ __forceinline__ void p2_relayout_stage(const P2Args &a, uint32_t raw, uint32_t op, const float *sb, int kbase,
-                                                  int rows_real, int rows_pad, int nseg, int rw, int lane) {
+                                                  int rows_real, int rows_pad, int nseg, const P2Units &pu, int lane) {
     const uint32_t L = (uint32_t)a.L, Lb = L * 2u, G = (uint32_t)a.G;
     const int groups = rows_pad >> 3;
     if (MODE == 16 || MODE == 8) {
         constexpr uint32_t EPP = MODE / 2;  // elements per piece
         const uint32_t ppr = L / EPP;
-        const int passes = (int)((ppr + 31u) >> 5);
-        // units (segment, group, pass) are dealt round-robin to the relayout warps; plain nested loops with a running
-        // counter -- decoding a unit index with run-time divisions cost more than the unit itself
-        int ucount = 0;
-        for (int sg = 0; sg < nseg; ++sg)
-        for (int g = 0; g < groups; ++g)
-        for (int pass = 0; pass < passes; ++pass) {
-            if ((ucount++ & (kP2NumRel - 1)) != rw) continue;
+#pragma unroll
+        for (int iu = 0; iu < kP2MaxUnits; ++iu) {
+            if (iu >= pu.n) break;
+            const int sg = (int)(pu.u[iu] & 0xffu), g = (int)((pu.u[iu] >> 8) & 0xffu), pass = (int)(pu.u[iu] >> 16);
+            if (sg >= nseg || g >= groups) continue;
             const uint32_t pc = (uint32_t)(lane + 32 * pass);
             if (pc >= ppr) continue;
             const uint32_t c = (uint32_t)sg * L + pc * EPP;
@@ -231,12 +250,11 @@ __device__ __forceinline__ void p2_relayout_stage(const P2Args &a, uint32_t raw,
             }
         }
     } else {
-        const int passes = (int)(((L >> 1) + 2u + 31u) >> 5);
-        int ucount = 0;
-        for (int sg = 0; sg < nseg; ++sg)
-        for (int g = 0; g < groups; ++g)
-        for (int pass = 0; pass < passes; ++pass) {
-            if ((ucount++ & (kP2NumRel - 1)) != rw) continue;
+#pragma unroll
+        for (int iu = 0; iu < kP2MaxUnits; ++iu) {
+            if (iu >= pu.n) break;
+            const int sg = (int)(pu.u[iu] & 0xffu), g = (int)((pu.u[iu] >> 8) & 0xffu), pass = (int)(pu.u[iu] >> 16);
+            if (sg >= nseg || g >= groups) continue;
             const uint32_t c0 = (uint32_t)sg * L, u0 = c0 >> 1;
             const uint32_t nwords = ((c0 + L - 1u) >> 1) - u0 + 1u;
             const uint32_t w = (uint32_t)(lane + 32 * pass);
@@ -372,13 +390,13 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)as * 256u;
                 uint32_t a_lo = a_lo0, acc = 0u;
-                P2_TRACE(it < 6, 8 + it * 12 + 0);
+                P2_TRACE(it < 4, 8 + it * 12 + 0);
                 for (int st = 0; st < a.k_stages; ++st, ++n) {
                     const int o = n % a.op_stages;
                     mbar_wait(&hdr->op_full[o], (uint32_t)(n / a.op_stages) & 1u);
                     tc_fence_after();
-                    P2_TRACE(it < 6 && st == 0, 8 + it * 12 + 1);
-                    P2_TRACE(it < 6 && st == a.k_stages - 1, 8 + it * 12 + 2);
+                    P2_TRACE(it < 4 && st == 0, 8 + it * 12 + 1);
+                    P2_TRACE(it < 4 && st == a.k_stages - 1, 8 + it * 12 + 2);
                     P2_TRACE(it == 2 && st < 9, 80 + 2 * st);
                     const int ksteps = min(a.kc, a.Kpad - st * a.kc) >> 4;
                     uint32_t b_lo = b_lo0 + (uint32_t)o * op16;
@@ -428,8 +446,8 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
                 res_pending = false;
             };
             for (int st = 0; st < a.k_stages; ++st, ++n) {
-                P2_TRACE(lane == 0 && it < 6 && st == 0, 8 + it * 12 + 6);
-                P2_TRACE(lane == 0 && it < 6 && st == a.k_stages - 1, 8 + it * 12 + 7);
+                P2_TRACE(lane == 0 && it < 4 && st == 0, 8 + it * 12 + 6);
+                P2_TRACE(lane == 0 && it < 4 && st == a.k_stages - 1, 8 + it * 12 + 7);
                 if (res_pending) {
                     int ok = 0;
                     if (lane == 0) ok = (int)mbar_test(&hdr->stg_empty[buf], empty_par);
@@ -456,6 +474,7 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
                         bulk_g2s(dst0 + (uint32_t)lane * Lb, a.x + ((size_t)img0 * a.K + k0 + lane) * a.HW + p0, Lb, &hdr->raw_full[r]);
                 }
                 __syncwarp();
+                P2_TRACE(lane == 0 && it == 2 && st < 9, 56 + st);
             }
             if (res_pending) {
                 mbar_wait_warp(&hdr->stg_empty[buf], empty_par, lane);
@@ -474,7 +493,7 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
             const int buf = it % a.stg_bufs;
             const uint32_t stg = s_stg + (uint32_t)buf * a.stg_buf_bytes;
             mbar_wait_warp(&hdr->stg_ready[buf], (uint32_t)(it / a.stg_bufs) & 1u, lane);
-            P2_TRACE(lane == 0 && it < 6, 8 + it * 12 + 4);
+            P2_TRACE(lane == 0 && it < 4, 8 + it * 12 + 4);
             if (P2_DBG(8)) {
             } else if (a.caseA) {
                 if (lane < nseg)
@@ -488,12 +507,24 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
             bulk_wait_read<0>();
             __syncwarp();
             if (lane == 0) mbar_arrive(&hdr->stg_empty[buf]);
-            P2_TRACE(lane == 0 && it < 6, 8 + it * 12 + 5);
+            P2_TRACE(lane == 0 && it < 4, 8 + it * 12 + 5);
         }
         bulk_wait_all();  // global writes complete before the CTA exits
+#ifdef RB_DEBUG_TRACE
+    } else if (warp == 3) {
+        // probe (debug builds): when does the data of each raw stage of tile 2 land?
+        if (lane == 0 && a.trace && tile0 + 2 * tstride < a.total_tiles) {
+            for (int st = 0; st < a.k_stages && st < 9; ++st) {
+                const int n = 2 * a.k_stages + st;
+                mbar_wait(&hdr->raw_full[n % a.raw_stages], (uint32_t)(n / a.raw_stages) & 1u);
+                P2_TRACE(true, 65 + st);
+            }
+        }
+#endif
     } else if (warp >= kP2RelWarp0 && warp < kP2EpiWarp0) {
         // ================================ relayout warps: raw stage -> UMMA operand =================================
         const int rw = warp - kP2RelWarp0;
+        const P2Units pu = p2_make_units(a, MODE, rw);
         int n = 0;
         for (int tile = tile0; tile < a.total_tiles; tile += tstride) {
             int img0, p0, nseg;
@@ -504,13 +535,13 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
                 const int rows_real = min(a.kc, a.K - k0);
                 const int rows_pad = min(a.kc, a.Kpad - k0);  // 16 or 32
                 mbar_wait_warp(&hdr->raw_full[r], (uint32_t)(n / a.raw_stages) & 1u, lane);
-                P2_TRACE(rw == 0 && lane == 0 && (tile - tile0) / tstride < 6 && st == 0, 8 + ((tile - tile0) / tstride) * 12 + 8);
+                P2_TRACE(rw == 0 && lane == 0 && (tile - tile0) / tstride < 4 && st == 0, 8 + ((tile - tile0) / tstride) * 12 + 8);
                 P2_TRACE(rw == 0 && lane == 0 && tile == tile0 + 2 * tstride && st < 6, 104 + 4 * st);
                 mbar_wait_warp(&hdr->op_empty[o], ((uint32_t)(n / a.op_stages) & 1u) ^ 1u, lane);
                 P2_TRACE(rw == 0 && lane == 0 && tile == tile0 + 2 * tstride && st < 6, 105 + 4 * st);
                 if (!P2_DBG(1))
                     p2_relayout_stage<MODE, BN>(a, s_raw + (uint32_t)r * a.raw_stage_bytes, s_op + (uint32_t)o * a.op_stage_bytes,
-                                                smem_sb, k0, rows_real, rows_pad, nseg, rw, lane);
+                                                smem_sb, k0, rows_real, rows_pad, nseg, pu, lane);
                 P2_TRACE(rw == 0 && lane == 0 && tile == tile0 + 2 * tstride && st < 6, 106 + 4 * st);
                 fence_proxy_async_smem();
                 __syncwarp();
@@ -519,7 +550,7 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
                     mbar_arrive(&hdr->raw_empty[r]);
                 }
                 P2_TRACE(rw == 0 && lane == 0 && tile == tile0 + 2 * tstride && st < 6, 107 + 4 * st);
-                P2_TRACE(rw == 0 && lane == 0 && (tile - tile0) / tstride < 6 && st == a.k_stages - 1, 8 + ((tile - tile0) / tstride) * 12 + 9);
+                P2_TRACE(rw == 0 && lane == 0 && (tile - tile0) / tstride < 4 && st == a.k_stages - 1, 8 + ((tile - tile0) / tstride) * 12 + 9);
             }
         }
     } else if (warp >= kP2EpiWarp0) {
@@ -539,11 +570,11 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
             const int ch_lo = half ? nch0 : 0, ch_hi = half ? nch : nch0;
             mbar_wait_warp(&hdr->tmem_full[as], (uint32_t)(it >> 1) & 1u, lane);
             tc_fence_after();
-            P2_TRACE(e == 0 && lane == 0 && it < 6, 8 + it * 12 + 3);
+            P2_TRACE(e == 0 && lane == 0 && it < 4, 8 + it * 12 + 3);
             // the staging buffer holds the residual block (which also means the previous store has released it), or is free
             if (has_res) mbar_wait_warp(&hdr->res_full[buf], (uint32_t)(it / a.stg_bufs) & 1u, lane);
             else mbar_wait_warp(&hdr->stg_empty[buf], ((uint32_t)(it / a.stg_bufs) & 1u) ^ 1u, lane);
-            P2_TRACE(e == 0 && lane == 0 && it < 6, 8 + it * 12 + 10);
+            P2_TRACE(e == 0 && lane == 0 && it < 4, 8 + it * 12 + 10);
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256u;
             const uint32_t rowaddr = stg + (uint32_t)m * a.stg_pitch;
             // two 16-column chunks per round: both TMEM loads are in flight before the first conversion
@@ -704,6 +735,11 @@ bool p2_plan(P2Args &a, dim3 *grid, size_t *smem_bytes) {
         }
     }
     if (best_bytes < 0) return false;
+    {   // every relayout warp owns at most kP2MaxUnits (segment, group, 32-piece pass) units of a stage
+        const int mode = a.V == 8 ? 16 : (a.V == 4 ? 8 : 4);
+        const int passes = (mode == 4) ? ((a.L >> 1) + 2 + 31) >> 5 : (a.L / (mode / 2) + 31) >> 5;
+        if (a.S * a.G * passes > kP2NumRel * kP2MaxUnits) return false;
+    }
     int gx = sm_count() / a.gy;
     if (gx < 1) gx = 1;
     if (gx > a.total_tiles) gx = a.total_tiles;

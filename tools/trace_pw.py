@@ -78,11 +78,13 @@ def main():
         for cta in (0, t.shape[0] // 2, t.shape[0] - 1):
             r = t[cta]
             print("CTA %d: start %.1f mma-ready %.1f weights %.1f end %.1f" % (cta, us(r[0]), us(r[1]), us(r[2]), us(r[3])))
-            for it in range(6):
+            for it in range(4):
                 b = 8 + it * 12
                 if int(r[b]) == 0:
                     break
                 print("   tile %d: " % it + "  ".join("%s %.1f" % (n, us(r[b + i])) for i, n in enumerate(names)))
+            print("   tile 2 raw loads per stage (issued / landed): " +
+                  "  ".join("%.2f/%.2f" % (us(r[56 + st]), us(r[65 + st])) for st in range(9) if int(r[56 + st])))
             print("   tile 2 MMA per stage (op_full seen / issued+committed): " +
                   "  ".join("%.2f/%.2f" % (us(r[80 + 2 * st]), us(r[81 + 2 * st])) for st in range(9) if int(r[80 + 2 * st])))
             print("   tile 2 relayout warp 0 per stage (raw_full seen / op_empty seen / work done / fenced+arrived): " +
