@@ -100,8 +100,24 @@ __device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
 // lanes polling the same word are 32 serialised transactions -- with a dozen waiting warps that traffic alone slowed the
 // relayout warps' LDS/STS and the TMA unit's writes by an order of magnitude (profiles/r02e_trace_l3.log).  Lane 0 polls,
 // __syncwarp() releases the others and orders their subsequent reads after lane 0's acquire.
+// Pure polling wait (mbarrier.test_wait never suspends the thread).  mbarrier.try_wait may put the thread to sleep for a
+// hardware-chosen quantum when the phase is not complete at the time of the call; in a ring of producers and consumers that
+// all wait on each other those quanta add up to ~0.7 us per pipeline stage with NO work at all (profiles/r02i_dbg_l3.log).
+__device__ __forceinline__ void p2_spin(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
 __device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity, int lane) {
-    if (lane == 0) mbar_wait(bar, parity);
+    if (lane == 0) p2_spin(bar, parity);
     __syncwarp();
 }
 // global -> shared bulk copy (TMA, 1-D); completion is counted in bytes on `bar`
@@ -380,20 +396,20 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
             const uint32_t a_lo0 = (uint32_t)adesc0, b_lo0 = (uint32_t)bdesc0;
             const uint32_t a_kstep = (2 * a.w_lbo) >> 4, op16 = a.op_stage_bytes >> 4;
             P2_TRACE(true, 1);
-            mbar_wait(&hdr->w_full, 0);
+            p2_spin(&hdr->w_full, 0);
             tc_fence_after();
             P2_TRACE(true, 2);
             int n = 0, it = 0;
             for (int tile = tile0; tile < a.total_tiles; tile += tstride, ++it) {
                 const int as = it & 1;
-                mbar_wait(&hdr->tmem_empty[as], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+                p2_spin(&hdr->tmem_empty[as], ((uint32_t)(it >> 1) & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)as * 256u;
                 uint32_t a_lo = a_lo0, acc = 0u;
                 P2_TRACE(it < 4, 8 + it * 12 + 0);
                 for (int st = 0; st < a.k_stages; ++st, ++n) {
                     const int o = n % a.op_stages;
-                    mbar_wait(&hdr->op_full[o], (uint32_t)(n / a.op_stages) & 1u);
+                    p2_spin(&hdr->op_full[o], (uint32_t)(n / a.op_stages) & 1u);
                     tc_fence_after();
                     P2_TRACE(it < 4 && st == 0, 8 + it * 12 + 1);
                     P2_TRACE(it < 4 && st == a.k_stages - 1, 8 + it * 12 + 2);
