@@ -263,8 +263,9 @@ int rb_pw_weight_image_pack_multi(const rb_pw_pack_item_t *items_device, int cou
  * at the price of reading the activations once per split (from L2).  0 = automatic (default).  Changes the schedule
  * only, never the arithmetic. */
 void rb_pw_conv_set_tuning(int min_n_splits);
-/* Same for the image kernel: depth of the operand ring (2..8) and channels per K chunk (16 / 32); 0 = automatic. */
-void rb_pw_conv_image_set_tuning(int operand_stages, int k_chunk);
+/* Same for the image kernel: depth of the operand ring (2..8), channels per K chunk (16 / 32) and the suspend-time hint
+ * (ns) of its mbarrier waits; 0 = automatic / hardware default. */
+void rb_pw_conv_image_set_tuning(int operand_stages, int k_chunk, int wait_hint_ns);
 
 #ifdef RB_DEBUG_TRACE
 /* Debug builds only (python -m rubiksnet_b200.build --trace; tools/trace_pw.py): when non-NULL, every k_pw_conv CTA

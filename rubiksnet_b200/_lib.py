@@ -87,7 +87,7 @@ def _declare(lib):
     lib.rb_pw_weight_image_pack_multi.restype = i
     lib.rb_pw_conv_image_supported.argtypes = [i, i, i, i, i]
     lib.rb_pw_conv_image_supported.restype = i
-    lib.rb_pw_conv_image_set_tuning.argtypes = [i, i]
+    lib.rb_pw_conv_image_set_tuning.argtypes = [i, i, i]
     lib.rb_pw_conv_image_set_tuning.restype = None
     lib.rb_pw_conv_set_tuning.argtypes = [i]
     lib.rb_pw_conv_set_tuning.restype = None

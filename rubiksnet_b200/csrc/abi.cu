@@ -61,7 +61,7 @@ size_t pw2_weight_image_bytes(int rows, int contraction);
 int pw2_weight_pack(const float *w, int N, int K, int trans, void *image, cudaStream_t s);
 int pw2_supported(int NI, int K, int N, int HW, int has_bn);
 int pw2_weight_pack_multi(const void *items_device, int count, cudaStream_t s);
-void pw2_set_tuning(int op_stages, int kc);
+void pw2_set_tuning(int op_stages, int kc, int wait_ns);
 #ifdef RB_DEBUG_TRACE
 void pw2_set_debug(int flags);
 #endif
@@ -416,7 +416,9 @@ int rb_shift3d_pw_conv_wgrad(const void *out_grad, const void *x, const void *sh
 }
 
 void rb_pw_conv_set_tuning(int min_n_splits) { pw_conv_set_tuning(min_n_splits); }
-void rb_pw_conv_image_set_tuning(int operand_stages, int k_chunk) { pw2_set_tuning(operand_stages, k_chunk); }
+void rb_pw_conv_image_set_tuning(int operand_stages, int k_chunk, int wait_hint_ns) {
+    pw2_set_tuning(operand_stages, k_chunk, wait_hint_ns);
+}
 
 #ifdef RB_DEBUG_TRACE
 /* debug builds only: work-skipping switches of the image kernel (critical-path experiments, tools/trace_pw.py --dbg) */

@@ -53,6 +53,7 @@ struct P2Args {
     int L, S, tpi, caseA;        // segment length, segments per tile, tiles per image (case B), whole-image segments?
     int Nmma, atoms, kc, G, k_stages, raw_stages, op_stages, stg_bufs, total_tiles;
     int V;                       // elements per relayout piece (8 / 4 / 2 / 1)
+    uint32_t wait_ns;            // suspend-time hint of the mbarrier waits (0 = hardware default)
     uint32_t ppr, ppr_mul, ppr_shr;  // pieces per row and its exact-division constants
     uint32_t w_lbo, w_bytes, off_sb, off_w, off_raw, off_op, off_stg;
     uint32_t raw_stage_bytes, op_stage_bytes, stg_buf_bytes, stg_pitch, stg_seg_stride;
@@ -100,24 +101,29 @@ __device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
 // lanes polling the same word are 32 serialised transactions -- with a dozen waiting warps that traffic alone slowed the
 // relayout warps' LDS/STS and the TMA unit's writes by an order of magnitude (profiles/r02e_trace_l3.log).  Lane 0 polls,
 // __syncwarp() releases the others and orders their subsequent reads after lane 0's acquire.
-// Pure polling wait (mbarrier.test_wait never suspends the thread).  mbarrier.try_wait may put the thread to sleep for a
-// hardware-chosen quantum when the phase is not complete at the time of the call; in a ring of producers and consumers that
-// all wait on each other those quanta add up to ~0.7 us per pipeline stage with NO work at all (profiles/r02i_dbg_l3.log).
-__device__ __forceinline__ void p2_spin(uint64_t *bar, uint32_t parity) {
+// mbarrier.try_wait with an explicit suspend-time hint (ns).  Measured (profiles/r02i_dbg_l3.log): pure polling
+// (test_wait) floods the shared-memory pipeline -- every fence and LDS/STS of the working warps gets several times slower --
+// while try_wait without a hint lets a blocked thread sleep for a hardware-chosen quantum, which in a ring of actors that
+// wait on each other costs ~0.7 us per pipeline stage with no work at all.
+__device__ __forceinline__ void p2_spin(uint64_t *bar, uint32_t parity, uint32_t hint_ns = 0) {
     const uint32_t addr = smem_u32(bar);
     uint32_t ok;
+    if (hint_ns == 0) {
+        mbar_wait(bar, parity);
+        return;
+    }
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok)
-            : "r"(addr), "r"(parity)
+            : "r"(addr), "r"(parity), "r"(hint_ns)
             : "memory");
     } while (!ok);
 }
-__device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity, int lane) {
-    if (lane == 0) p2_spin(bar, parity);
+__device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity, int lane, uint32_t hint_ns = 0) {
+    if (lane == 0) p2_spin(bar, parity, hint_ns);
     __syncwarp();
 }
 // global -> shared bulk copy (TMA, 1-D); completion is counted in bytes on `bar`
@@ -396,20 +402,20 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
             const uint32_t a_lo0 = (uint32_t)adesc0, b_lo0 = (uint32_t)bdesc0;
             const uint32_t a_kstep = (2 * a.w_lbo) >> 4, op16 = a.op_stage_bytes >> 4;
             P2_TRACE(true, 1);
-            p2_spin(&hdr->w_full, 0);
+            p2_spin(&hdr->w_full, 0, a.wait_ns);
             tc_fence_after();
             P2_TRACE(true, 2);
             int n = 0, it = 0;
             for (int tile = tile0; tile < a.total_tiles; tile += tstride, ++it) {
                 const int as = it & 1;
-                p2_spin(&hdr->tmem_empty[as], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+                p2_spin(&hdr->tmem_empty[as], ((uint32_t)(it >> 1) & 1u) ^ 1u, a.wait_ns);
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)as * 256u;
                 uint32_t a_lo = a_lo0, acc = 0u;
                 P2_TRACE(it < 4, 8 + it * 12 + 0);
                 for (int st = 0; st < a.k_stages; ++st, ++n) {
                     const int o = n % a.op_stages;
-                    p2_spin(&hdr->op_full[o], (uint32_t)(n / a.op_stages) & 1u);
+                    p2_spin(&hdr->op_full[o], (uint32_t)(n / a.op_stages) & 1u, a.wait_ns);
                     tc_fence_after();
                     P2_TRACE(it < 4 && st == 0, 8 + it * 12 + 1);
                     P2_TRACE(it < 4 && st == a.k_stages - 1, 8 + it * 12 + 2);
@@ -470,7 +476,7 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
                     if (__shfl_sync(0xffffffffu, ok, 0) != 0) issue_residual();
                 }
                 const int r = n % a.raw_stages;
-                mbar_wait_warp(&hdr->raw_empty[r], ((uint32_t)(n / a.raw_stages) & 1u) ^ 1u, lane);
+                mbar_wait_warp(&hdr->raw_empty[r], ((uint32_t)(n / a.raw_stages) & 1u) ^ 1u, lane, a.wait_ns);
                 const int k0 = st * a.kc;
                 const int rows = min(a.kc, a.K - k0);
                 const uint32_t dst0 = s_raw + (uint32_t)r * a.raw_stage_bytes;
@@ -493,7 +499,7 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
                 P2_TRACE(lane == 0 && it == 2 && st < 9, 56 + st);
             }
             if (res_pending) {
-                mbar_wait_warp(&hdr->stg_empty[buf], empty_par, lane);
+                mbar_wait_warp(&hdr->stg_empty[buf], empty_par, lane, a.wait_ns);
                 issue_residual();
             }
         }
@@ -508,7 +514,7 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
             p2_tile(a, tile, img0, p0, nseg);
             const int buf = it % a.stg_bufs;
             const uint32_t stg = s_stg + (uint32_t)buf * a.stg_buf_bytes;
-            mbar_wait_warp(&hdr->stg_ready[buf], (uint32_t)(it / a.stg_bufs) & 1u, lane);
+            mbar_wait_warp(&hdr->stg_ready[buf], (uint32_t)(it / a.stg_bufs) & 1u, lane, a.wait_ns);
             P2_TRACE(lane == 0 && it < 4, 8 + it * 12 + 4);
             if (P2_DBG(8)) {
             } else if (a.caseA) {
@@ -550,10 +556,10 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
                 const int k0 = st * a.kc;
                 const int rows_real = min(a.kc, a.K - k0);
                 const int rows_pad = min(a.kc, a.Kpad - k0);  // 16 or 32
-                mbar_wait_warp(&hdr->raw_full[r], (uint32_t)(n / a.raw_stages) & 1u, lane);
+                mbar_wait_warp(&hdr->raw_full[r], (uint32_t)(n / a.raw_stages) & 1u, lane, a.wait_ns);
                 P2_TRACE(rw == 0 && lane == 0 && (tile - tile0) / tstride < 4 && st == 0, 8 + ((tile - tile0) / tstride) * 12 + 8);
                 P2_TRACE(rw == 0 && lane == 0 && tile == tile0 + 2 * tstride && st < 6, 104 + 4 * st);
-                mbar_wait_warp(&hdr->op_empty[o], ((uint32_t)(n / a.op_stages) & 1u) ^ 1u, lane);
+                mbar_wait_warp(&hdr->op_empty[o], ((uint32_t)(n / a.op_stages) & 1u) ^ 1u, lane, a.wait_ns);
                 P2_TRACE(rw == 0 && lane == 0 && tile == tile0 + 2 * tstride && st < 6, 105 + 4 * st);
                 if (!P2_DBG(1))
                     p2_relayout_stage<MODE, BN>(a, s_raw + (uint32_t)r * a.raw_stage_bytes, s_op + (uint32_t)o * a.op_stage_bytes,
@@ -584,12 +590,12 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
             const int ncols = nseg * a.L;
             const int nch = (ncols + 15) >> 4, nch0 = (nch + 1) >> 1;
             const int ch_lo = half ? nch0 : 0, ch_hi = half ? nch : nch0;
-            mbar_wait_warp(&hdr->tmem_full[as], (uint32_t)(it >> 1) & 1u, lane);
+            mbar_wait_warp(&hdr->tmem_full[as], (uint32_t)(it >> 1) & 1u, lane, a.wait_ns);
             tc_fence_after();
             P2_TRACE(e == 0 && lane == 0 && it < 4, 8 + it * 12 + 3);
             // the staging buffer holds the residual block (which also means the previous store has released it), or is free
-            if (has_res) mbar_wait_warp(&hdr->res_full[buf], (uint32_t)(it / a.stg_bufs) & 1u, lane);
-            else mbar_wait_warp(&hdr->stg_empty[buf], ((uint32_t)(it / a.stg_bufs) & 1u) ^ 1u, lane);
+            if (has_res) mbar_wait_warp(&hdr->res_full[buf], (uint32_t)(it / a.stg_bufs) & 1u, lane, a.wait_ns);
+            else mbar_wait_warp(&hdr->stg_empty[buf], ((uint32_t)(it / a.stg_bufs) & 1u) ^ 1u, lane, a.wait_ns);
             P2_TRACE(e == 0 && lane == 0 && it < 4, 8 + it * 12 + 10);
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256u;
             const uint32_t rowaddr = stg + (uint32_t)m * a.stg_pitch;
@@ -670,11 +676,12 @@ __host__ __device__ inline void p2_slices(int rows, int contraction, int *gy, in
 }
 
 // schedule overrides (rb_pw_conv_set_tuning2): operand-ring depth and K chunk of the image kernel; 0 = automatic
-int g_p2_op_stages = 0, g_p2_kc = 0;
+int g_p2_op_stages = 0, g_p2_kc = 0, g_p2_wait_ns = 0;
 
 bool p2_plan(P2Args &a, dim3 *grid, size_t *smem_bytes) {
     if (a.NI <= 0 || a.K <= 0 || a.N <= 0 || a.HW <= 0) return false;
     if (a.K % 8 != 0 || a.N % 8 != 0) return false;
+    a.wait_ns = (uint32_t)g_p2_wait_ns;
     if ((int64_t)a.NI * a.HW * (a.K > a.N ? a.K : a.N) >= (int64_t(1) << 31)) return false;
     p2_slices(a.N, a.K, &a.gy, &a.Ncta, &a.Kpad, &a.w_lbo, &a.w_bytes);
     if (a.gy > 148) return false;
@@ -835,7 +842,11 @@ static int g_p2_dbg = 0;
 void pw2_set_debug(int flags) { g_p2_dbg = flags; }
 #endif
 
-void pw2_set_tuning(int op_stages, int kc) { g_p2_op_stages = op_stages; g_p2_kc = (kc == 16 || kc == 32) ? kc : 0; }
+void pw2_set_tuning(int op_stages, int kc, int wait_ns) {
+    g_p2_op_stages = op_stages;
+    g_p2_kc = (kc == 16 || kc == 32) ? kc : 0;
+    g_p2_wait_ns = wait_ns < 0 ? 0 : wait_ns;
+}
 
 // bytes of the packed image of a [rows x contraction] weight matrix (all slices)
 size_t pw2_weight_image_bytes(int rows, int contraction) {

@@ -53,9 +53,10 @@ def main():
     ap.add_argument("--splits", type=int, default=0, help="rb_pw_conv_set_tuning: minimum output-channel splits (0 = auto)")
     ap.add_argument("--opstages", type=int, default=0, help="image kernel: operand ring depth (0 = auto)")
     ap.add_argument("--kc", type=int, default=0, help="image kernel: channels per K chunk, 16 or 32 (0 = auto)")
+    ap.add_argument("--waitns", type=int, default=0, help="image kernel: mbarrier suspend-time hint in ns (0 = default)")
     a = ap.parse_args()
     _lib.lib().rb_pw_conv_set_tuning(a.splits)
-    _lib.lib().rb_pw_conv_image_set_tuning(a.opstages, a.kc)
+    _lib.lib().rb_pw_conv_image_set_tuning(a.opstages, a.kc, a.waitns)
     modes = a.modes.split(",")
     T = 8
     print("device:", torch.cuda.get_device_name(0))

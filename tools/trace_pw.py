@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--reps", type=int, default=0, help="also time `reps` launches with CUDA events (L2 flushed in between)")
     ap.add_argument("--opstages", type=int, default=0)
     ap.add_argument("--kc", type=int, default=0)
+    ap.add_argument("--waitns", type=int, default=0)
     ap.add_argument("--v2", action="store_true", help="second-generation kernel (packed weight images, csrc/pw_conv2.cu)")
     a = ap.parse_args()
     # the stamps only exist in the debug library (python -m rubiksnet_b200.build --trace); point the loader at it
@@ -38,8 +39,8 @@ def main():
         w, w_kn = ops.pw_weight_pack(w)
     sb = torch.stack([torch.rand(a.C, device="cuda") + 0.5, torch.randn(a.C, device="cuda")], dim=1).contiguous()
     if a.v2:
-        L.rb_pw_conv_image_set_tuning.argtypes = [ctypes.c_int, ctypes.c_int]
-        L.rb_pw_conv_image_set_tuning(a.opstages, a.kc)
+        L.rb_pw_conv_image_set_tuning.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        L.rb_pw_conv_image_set_tuning(a.opstages, a.kc, a.waitns)
         L.rb_debug_pw_flags.argtypes = [ctypes.c_int]
         L.rb_debug_pw_flags.restype = None
         L.rb_debug_pw_flags(a.dbg)
