@@ -565,7 +565,7 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
                     p2_relayout_stage<MODE, BN>(a, s_raw + (uint32_t)r * a.raw_stage_bytes, s_op + (uint32_t)o * a.op_stage_bytes,
                                                 smem_sb, k0, rows_real, rows_pad, nseg, pu, lane);
                 P2_TRACE(rw == 0 && lane == 0 && tile == tile0 + 2 * tstride && st < 6, 106 + 4 * st);
-                fence_proxy_async_smem();
+                if (!P2_DBG(32)) fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
                     mbar_arrive(&hdr->op_full[o]);
@@ -641,7 +641,7 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
                 if (lane == 0) mbar_arrive(&hdr->tmem_empty[as]);
             }
             // staging rows of this warp complete -> visible to the async proxy -> tell the store warp
-            fence_proxy_async_smem();
+            if (!P2_DBG(64)) fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&hdr->stg_ready[buf]);
         }
