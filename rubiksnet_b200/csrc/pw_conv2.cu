@@ -476,7 +476,9 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
                     if (__shfl_sync(0xffffffffu, ok, 0) != 0) issue_residual();
                 }
                 const int r = n % a.raw_stages;
+                P2_TRACE(lane == 0 && it == 2 && st < 9, 56 + 2 * st);
                 mbar_wait_warp(&hdr->raw_empty[r], ((uint32_t)(n / a.raw_stages) & 1u) ^ 1u, lane, a.wait_ns);
+                P2_TRACE(lane == 0 && it == 2 && st < 9, 57 + 2 * st);
                 const int k0 = st * a.kc;
                 const int rows = min(a.kc, a.K - k0);
                 const uint32_t dst0 = s_raw + (uint32_t)r * a.raw_stage_bytes;
@@ -496,7 +498,6 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
                         bulk_g2s(dst0 + (uint32_t)lane * Lb, a.x + ((size_t)img0 * a.K + k0 + lane) * a.HW + p0, Lb, &hdr->raw_full[r]);
                 }
                 __syncwarp();
-                P2_TRACE(lane == 0 && it == 2 && st < 9, 56 + st);
             }
             if (res_pending) {
                 mbar_wait_warp(&hdr->stg_empty[buf], empty_par, lane, a.wait_ns);
@@ -532,17 +533,6 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
             P2_TRACE(lane == 0 && it < 4, 8 + it * 12 + 5);
         }
         bulk_wait_all();  // global writes complete before the CTA exits
-#ifdef RB_DEBUG_TRACE
-    } else if (warp == 3) {
-        // probe (debug builds): when does the data of each raw stage of tile 2 land?
-        if (lane == 0 && a.trace && tile0 + 2 * tstride < a.total_tiles) {
-            for (int st = 0; st < a.k_stages && st < 9; ++st) {
-                const int n = 2 * a.k_stages + st;
-                mbar_wait(&hdr->raw_full[n % a.raw_stages], (uint32_t)(n / a.raw_stages) & 1u);
-                P2_TRACE(true, 65 + st);
-            }
-        }
-#endif
     } else if (warp >= kP2RelWarp0 && warp < kP2EpiWarp0) {
         // ================================ relayout warps: raw stage -> UMMA operand =================================
         const int rw = warp - kP2RelWarp0;
@@ -572,6 +562,7 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
                     mbar_arrive(&hdr->raw_empty[r]);
                 }
                 P2_TRACE(rw == 0 && lane == 0 && tile == tile0 + 2 * tstride && st < 6, 107 + 4 * st);
+                P2_TRACE(lane == 0 && tile == tile0 + 2 * tstride && st == 3, (rw < 6 ? 74 + rw : 98 + rw - 6));
                 P2_TRACE(rw == 0 && lane == 0 && (tile - tile0) / tstride < 4 && st == a.k_stages - 1, 8 + ((tile - tile0) / tstride) * 12 + 9);
             }
         }

@@ -84,8 +84,10 @@ def main():
                 if int(r[b]) == 0:
                     break
                 print("   tile %d: " % it + "  ".join("%s %.1f" % (n, us(r[b + i])) for i, n in enumerate(names)))
-            print("   tile 2 raw loads per stage (issued / landed): " +
-                  "  ".join("%.2f/%.2f" % (us(r[56 + st]), us(r[65 + st])) for st in range(9) if int(r[56 + st])))
+            print("   tile 2 TMA warp per stage (before / after its raw_empty wait): " +
+                  "  ".join("%.2f/%.2f" % (us(r[56 + 2 * st]), us(r[57 + 2 * st])) for st in range(9) if int(r[56 + 2 * st])))
+            print("   tile 2 stage 3: arrival of the 8 relayout warps: " +
+                  "  ".join("%.2f" % us(r[74 + w] if w < 6 else r[98 + w - 6]) for w in range(8)))
             print("   tile 2 MMA per stage (op_full seen / issued+committed): " +
                   "  ".join("%.2f/%.2f" % (us(r[80 + 2 * st]), us(r[81 + 2 * st])) for st in range(9) if int(r[80 + 2 * st])))
             print("   tile 2 relayout warp 0 per stage (raw_full seen / op_empty seen / work done / fenced+arrived): " +
