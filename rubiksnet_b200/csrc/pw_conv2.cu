@@ -35,7 +35,7 @@ namespace {
 constexpr int kP2Warps = 20;
 constexpr int kP2Threads = kP2Warps * 32;  // 640
 constexpr int kP2MmaWarp = 0, kP2TmaWarp = 1, kP2StoreWarp = 2;
-constexpr int kP2RelWarp0 = 4, kP2NumRel = 8;
+constexpr int kP2RelWarp0 = 4, kP2NumRel = 8, kP2RelGroups = 2, kP2RelPerGroup = kP2NumRel / kP2RelGroups;
 constexpr int kP2EpiWarp0 = 12, kP2NumEpi = 8;
 constexpr int kP2MaxRing = 8;
 constexpr int kP2Smem = 227 * 1024;
@@ -208,7 +208,7 @@ __device__ __forceinline__ uint32_t p2_col_chunk(uint32_t c) { return (c & 63u) 
 // K % 8 == 0 (p2_plan), so an 8-channel group is either all real channels or all padding (zeros).
 // units of a FULL stage (S segments x G groups x passes) owned by one relayout warp, decoded once per kernel: byte 0 =
 // segment, byte 1 = group, byte 2 = pass.  Partial stages / tiles skip the units they do not have.
-constexpr int kP2MaxUnits = 4;
+constexpr int kP2MaxUnits = 8;
 struct P2Units {
     int n;
     uint32_t u[kP2MaxUnits];
@@ -221,7 +221,7 @@ __device__ __forceinline__ P2Units p2_make_units(const P2Args &a, int mode, int 
     P2Units pu;
     pu.n = 0;
     const int passes = p2_passes(a, mode), total = a.S * a.G * passes;
-    for (int u = rw; u < total && pu.n < kP2MaxUnits; u += kP2NumRel) {
+    for (int u = rw; u < total && pu.n < kP2MaxUnits; u += kP2RelPerGroup) {
         const int pass = u % passes, t = u / passes, g = t % a.G, sg = t / a.G;
         pu.u[pu.n++] = (uint32_t)sg | ((uint32_t)g << 8) | ((uint32_t)pass << 16);
     }
@@ -361,8 +361,8 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
     if (tid == 0) {
         for (int i = 0; i < kP2MaxRing; ++i) {
             mbar_init(&hdr->raw_full[i], 1);
-            mbar_init(&hdr->raw_empty[i], kP2NumRel);
-            mbar_init(&hdr->op_full[i], kP2NumRel);
+            mbar_init(&hdr->raw_empty[i], kP2RelPerGroup);
+            mbar_init(&hdr->op_full[i], kP2RelPerGroup);
             mbar_init(&hdr->op_empty[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
@@ -405,7 +405,11 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
             p2_spin(&hdr->w_full, 0, a.wait_ns);
             tc_fence_after();
             P2_TRACE(true, 2);
-            int n = 0, it = 0;
+            // ring positions advance incrementally everywhere in this kernel: a run-time `%` is ~40 dependent instructions,
+            // and the control code of a stage -- not its work -- is what sets the pace of these single-warp roles
+            int it = 0, o = 0;
+            uint32_t oph = 0;
+            const int ksteps_full = a.kc >> 4, ksteps_last = (a.Kpad - (a.k_stages - 1) * a.kc) >> 4;
             for (int tile = tile0; tile < a.total_tiles; tile += tstride, ++it) {
                 const int as = it & 1;
                 p2_spin(&hdr->tmem_empty[as], ((uint32_t)(it >> 1) & 1u) ^ 1u, a.wait_ns);
@@ -413,14 +417,13 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
                 const uint32_t tacc = tmem_base + (uint32_t)as * 256u;
                 uint32_t a_lo = a_lo0, acc = 0u;
                 P2_TRACE(it < 4, 8 + it * 12 + 0);
-                for (int st = 0; st < a.k_stages; ++st, ++n) {
-                    const int o = n % a.op_stages;
-                    p2_spin(&hdr->op_full[o], (uint32_t)(n / a.op_stages) & 1u, a.wait_ns);
+                for (int st = 0; st < a.k_stages; ++st) {
+                    p2_spin(&hdr->op_full[o], oph, a.wait_ns);
                     tc_fence_after();
                     P2_TRACE(it < 4 && st == 0, 8 + it * 12 + 1);
                     P2_TRACE(it < 4 && st == a.k_stages - 1, 8 + it * 12 + 2);
                     P2_TRACE(it == 2 && st < 9, 80 + 2 * st);
-                    const int ksteps = min(a.kc, a.Kpad - st * a.kc) >> 4;
+                    const int ksteps = st == a.k_stages - 1 ? ksteps_last : ksteps_full;
                     uint32_t b_lo = b_lo0 + (uint32_t)o * op16;
                     for (int ks = 0; ks < ksteps; ++ks) {
                         if (!P2_DBG(2)) mma_bf16_lohi(tacc, a_lo, a_hi, b_lo, b_hi, idesc, acc);
@@ -430,6 +433,7 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
                     }
                     mma_commit(&hdr->op_empty[o]);
                     P2_TRACE(it == 2 && st < 9, 81 + 2 * st);
+                    if (++o == a.op_stages) { o = 0; oph ^= 1u; }
                 }
                 mma_commit(&hdr->tmem_full[as]);
             }
@@ -441,14 +445,16 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
             mbar_expect_tx(&hdr->w_full, a.w_bytes);
             bulk_g2s(s_w, a.wimg + (size_t)blockIdx.y * a.w_bytes, a.w_bytes, &hdr->w_full);
         }
-        int n = 0, it = 0;
+        int it = 0, r = 0, buf = 0;
+        uint32_t rph = 0, bph = 0;  // raw-ring phase, staging-buffer phase
+        const uint32_t rows_last = (uint32_t)(a.K - (a.k_stages - 1) * a.kc);
+        const size_t stage_elems = (size_t)a.kc * a.HW;  // source advance per K chunk
         for (int tile = tile0; tile < a.total_tiles; tile += tstride, ++it) {
             int img0, p0, nseg;
             p2_tile(a, tile, img0, p0, nseg);
             bool res_pending = has_res;
-            const int buf = it % a.stg_bufs;
-            // staging buffer `buf` is free once the store warp has seen the store of its previous use (j - 1) finish reading
-            const uint32_t empty_par = ((uint32_t)(it / a.stg_bufs) & 1u) ^ 1u;
+            // staging buffer `buf` is free once the store warp has seen the store of its previous use finish reading
+            const uint32_t empty_par = bph ^ 1u;
             auto issue_residual = [&]() {
                 const uint32_t dst0 = s_stg + (uint32_t)buf * a.stg_buf_bytes;
                 if (a.caseA) {
@@ -467,7 +473,11 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
                 }
                 res_pending = false;
             };
-            for (int st = 0; st < a.k_stages; ++st, ++n) {
+            // this lane's source of stage 0: case A lane = segment (image img0 + lane), case B lane = channel row
+            const __nv_bfloat16 *src = a.caseA ? a.x + (size_t)(img0 + (lane < nseg ? lane : 0)) * a.K * a.HW
+                                               : a.x + ((size_t)img0 * a.K + lane) * a.HW + p0;
+            const uint32_t dlane = a.caseA ? (uint32_t)lane * (uint32_t)a.kc * Lb : (uint32_t)lane * Lb;
+            for (int st = 0; st < a.k_stages; ++st) {
                 P2_TRACE(lane == 0 && it < 4 && st == 0, 8 + it * 12 + 6);
                 P2_TRACE(lane == 0 && it < 4 && st == a.k_stages - 1, 8 + it * 12 + 7);
                 if (res_pending) {
@@ -475,47 +485,46 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
                     if (lane == 0) ok = (int)mbar_test(&hdr->stg_empty[buf], empty_par);
                     if (__shfl_sync(0xffffffffu, ok, 0) != 0) issue_residual();
                 }
-                const int r = n % a.raw_stages;
                 P2_TRACE(lane == 0 && it == 2 && st < 9, 56 + 2 * st);
-                mbar_wait_warp(&hdr->raw_empty[r], ((uint32_t)(n / a.raw_stages) & 1u) ^ 1u, lane, a.wait_ns);
+                mbar_wait_warp(&hdr->raw_empty[r], rph ^ 1u, lane, a.wait_ns);
                 P2_TRACE(lane == 0 && it == 2 && st < 9, 57 + 2 * st);
-                const int k0 = st * a.kc;
-                const int rows = min(a.kc, a.K - k0);
+                const uint32_t rows = st == a.k_stages - 1 ? rows_last : (uint32_t)a.kc;
                 const uint32_t dst0 = s_raw + (uint32_t)r * a.raw_stage_bytes;
                 if (P2_DBG(16)) {
                     if (lane == 0) mbar_arrive(&hdr->raw_full[r]);
                 } else if (a.caseA) {
-                    const uint32_t bytes = (uint32_t)rows * Lb;
+                    const uint32_t bytes = rows * Lb;
                     if (lane == 0) mbar_expect_tx(&hdr->raw_full[r], bytes * (uint32_t)nseg);
                     __syncwarp();
-                    if (lane < nseg)
-                        bulk_g2s(dst0 + (uint32_t)lane * (uint32_t)a.kc * Lb, a.x + ((size_t)(img0 + lane) * a.K + k0) * a.HW, bytes,
-                                 &hdr->raw_full[r]);
+                    if (lane < nseg) bulk_g2s(dst0 + dlane, src, bytes, &hdr->raw_full[r]);
                 } else {
-                    if (lane == 0) mbar_expect_tx(&hdr->raw_full[r], (uint32_t)rows * Lb);
+                    if (lane == 0) mbar_expect_tx(&hdr->raw_full[r], rows * Lb);
                     __syncwarp();
-                    if (lane < rows)
-                        bulk_g2s(dst0 + (uint32_t)lane * Lb, a.x + ((size_t)img0 * a.K + k0 + lane) * a.HW + p0, Lb, &hdr->raw_full[r]);
+                    for (uint32_t row = (uint32_t)lane; row < rows; row += 32)
+                        bulk_g2s(dst0 + row * Lb, src + (size_t)(row - (uint32_t)lane) * a.HW, Lb, &hdr->raw_full[r]);
                 }
                 __syncwarp();
+                src += stage_elems;
+                if (++r == a.raw_stages) { r = 0; rph ^= 1u; }
             }
             if (res_pending) {
                 mbar_wait_warp(&hdr->stg_empty[buf], empty_par, lane, a.wait_ns);
                 issue_residual();
             }
+            if (++buf == a.stg_bufs) { buf = 0; bph ^= 1u; }
         }
     } else if (warp == kP2StoreWarp) {
         // ================================ TMA store warp ===========================================================
         // waits until the 8 epilogue warps have filled a staging buffer, sends it to global memory with bulk copies, and hands
         // the buffer back (stg_empty) once the copies have read it: to the load warp (next residual block) or, without a
         // residual, straight to the epilogue warps
-        int it = 0;
+        int it = 0, buf = 0;
+        uint32_t bph = 0;
         for (int tile = tile0; tile < a.total_tiles; tile += tstride, ++it) {
             int img0, p0, nseg;
             p2_tile(a, tile, img0, p0, nseg);
-            const int buf = it % a.stg_bufs;
             const uint32_t stg = s_stg + (uint32_t)buf * a.stg_buf_bytes;
-            mbar_wait_warp(&hdr->stg_ready[buf], (uint32_t)(it / a.stg_bufs) & 1u, lane, a.wait_ns);
+            mbar_wait_warp(&hdr->stg_ready[buf], bph, lane, a.wait_ns);
             P2_TRACE(lane == 0 && it < 4, 8 + it * 12 + 4);
             if (P2_DBG(8)) {
             } else if (a.caseA) {
@@ -531,40 +540,47 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
             __syncwarp();
             if (lane == 0) mbar_arrive(&hdr->stg_empty[buf]);
             P2_TRACE(lane == 0 && it < 4, 8 + it * 12 + 5);
+            if (++buf == a.stg_bufs) { buf = 0; bph ^= 1u; }
         }
         bulk_wait_all();  // global writes complete before the CTA exits
     } else if (warp >= kP2RelWarp0 && warp < kP2EpiWarp0) {
         // ================================ relayout warps: raw stage -> UMMA operand =================================
-        const int rw = warp - kP2RelWarp0;
-        const P2Units pu = p2_make_units(a, MODE, rw);
-        int n = 0;
-        for (int tile = tile0; tile < a.total_tiles; tile += tstride) {
+        // The 8 relayout warps form kP2RelGroups groups that take alternate stages: the fixed cost of a stage for a warp (two
+        // barrier waits, fence, arrivals: ~0.3 us of serial latency) is then paid every other stage period.
+        const int rw = warp - kP2RelWarp0, grp = rw % kP2RelGroups, wg = rw / kP2RelGroups;
+        const P2Units pu = p2_make_units(a, MODE, wg);
+        int tile = tile0, st = grp, r = grp, o = grp;
+        uint32_t rph = 0, oph = 0;
+        while (st >= a.k_stages) { st -= a.k_stages; tile += tstride; }
+        while (r >= a.raw_stages) { r -= a.raw_stages; rph ^= 1u; }
+        while (o >= a.op_stages) { o -= a.op_stages; oph ^= 1u; }
+        const int rows_real_last = a.K - (a.k_stages - 1) * a.kc, rows_pad_last = a.Kpad - (a.k_stages - 1) * a.kc;
+        while (tile < a.total_tiles) {
             int img0, p0, nseg;
             p2_tile(a, tile, img0, p0, nseg);
-            for (int st = 0; st < a.k_stages; ++st, ++n) {
-                const int r = n % a.raw_stages, o = n % a.op_stages;
-                const int k0 = st * a.kc;
-                const int rows_real = min(a.kc, a.K - k0);
-                const int rows_pad = min(a.kc, a.Kpad - k0);  // 16 or 32
-                mbar_wait_warp(&hdr->raw_full[r], (uint32_t)(n / a.raw_stages) & 1u, lane, a.wait_ns);
-                P2_TRACE(rw == 0 && lane == 0 && (tile - tile0) / tstride < 4 && st == 0, 8 + ((tile - tile0) / tstride) * 12 + 8);
-                P2_TRACE(rw == 0 && lane == 0 && tile == tile0 + 2 * tstride && st < 6, 104 + 4 * st);
-                mbar_wait_warp(&hdr->op_empty[o], ((uint32_t)(n / a.op_stages) & 1u) ^ 1u, lane, a.wait_ns);
-                P2_TRACE(rw == 0 && lane == 0 && tile == tile0 + 2 * tstride && st < 6, 105 + 4 * st);
-                if (!P2_DBG(1))
-                    p2_relayout_stage<MODE, BN>(a, s_raw + (uint32_t)r * a.raw_stage_bytes, s_op + (uint32_t)o * a.op_stage_bytes,
-                                                smem_sb, k0, rows_real, rows_pad, nseg, pu, lane);
-                P2_TRACE(rw == 0 && lane == 0 && tile == tile0 + 2 * tstride && st < 6, 106 + 4 * st);
-                if (!P2_DBG(32)) fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(&hdr->op_full[o]);
-                    mbar_arrive(&hdr->raw_empty[r]);
-                }
-                P2_TRACE(rw == 0 && lane == 0 && tile == tile0 + 2 * tstride && st < 6, 107 + 4 * st);
-                P2_TRACE(lane == 0 && tile == tile0 + 2 * tstride && st == 3, (rw < 6 ? 74 + rw : 98 + rw - 6));
-                P2_TRACE(rw == 0 && lane == 0 && (tile - tile0) / tstride < 4 && st == a.k_stages - 1, 8 + ((tile - tile0) / tstride) * 12 + 9);
+            const bool last = st == a.k_stages - 1;
+            const int rows_real = last ? rows_real_last : a.kc, rows_pad = last ? rows_pad_last : a.kc;
+            mbar_wait_warp(&hdr->raw_full[r], rph, lane, a.wait_ns);
+            P2_TRACE(rw == 0 && lane == 0 && (tile - tile0) / tstride < 4 && st == 0, 8 + ((tile - tile0) / tstride) * 12 + 8);
+            P2_TRACE(rw == 0 && lane == 0 && tile == tile0 + 2 * tstride && st < 12, 104 + 2 * st);
+            mbar_wait_warp(&hdr->op_empty[o], oph ^ 1u, lane, a.wait_ns);
+            if (!P2_DBG(1))
+                p2_relayout_stage<MODE, BN>(a, s_raw + (uint32_t)r * a.raw_stage_bytes, s_op + (uint32_t)o * a.op_stage_bytes, smem_sb,
+                                            st * a.kc, rows_real, rows_pad, nseg, pu, lane);
+            if (!P2_DBG(32)) fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&hdr->op_full[o]);
+                mbar_arrive(&hdr->raw_empty[r]);
             }
+            P2_TRACE(rw == 0 && lane == 0 && tile == tile0 + 2 * tstride && st < 12, 105 + 2 * st);
+            P2_TRACE(rw == 0 && lane == 0 && (tile - tile0) / tstride < 4 && last, 8 + ((tile - tile0) / tstride) * 12 + 9);
+            st += kP2RelGroups;
+            while (st >= a.k_stages) { st -= a.k_stages; tile += tstride; }
+            r += kP2RelGroups;
+            while (r >= a.raw_stages) { r -= a.raw_stages; rph ^= 1u; }
+            o += kP2RelGroups;
+            while (o >= a.op_stages) { o -= a.op_stages; oph ^= 1u; }
         }
     } else if (warp >= kP2EpiWarp0) {
         // ================================ epilogue warps ==========================================================
@@ -572,11 +588,12 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
         const int m = q * 32 + lane;  // output channel row (TMEM lane) of this thread inside the CTA's slice
         const bool rowok = m < nrows;
         const bool fast = (a.S == 1) && (a.L % 4 == 0);
-        int it = 0;
+        int it = 0, buf = 0;
+        uint32_t bph = 0;
         for (int tile = tile0; tile < a.total_tiles; tile += tstride, ++it) {
             int img0, p0, nseg;
             p2_tile(a, tile, img0, p0, nseg);
-            const int as = it & 1, buf = it % a.stg_bufs;
+            const int as = it & 1;
             const uint32_t stg = s_stg + (uint32_t)buf * a.stg_buf_bytes;
             const int ncols = nseg * a.L;
             const int nch = (ncols + 15) >> 4, nch0 = (nch + 1) >> 1;
@@ -585,8 +602,8 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
             tc_fence_after();
             P2_TRACE(e == 0 && lane == 0 && it < 4, 8 + it * 12 + 3);
             // the staging buffer holds the residual block (which also means the previous store has released it), or is free
-            if (has_res) mbar_wait_warp(&hdr->res_full[buf], (uint32_t)(it / a.stg_bufs) & 1u, lane, a.wait_ns);
-            else mbar_wait_warp(&hdr->stg_empty[buf], ((uint32_t)(it / a.stg_bufs) & 1u) ^ 1u, lane, a.wait_ns);
+            if (has_res) mbar_wait_warp(&hdr->res_full[buf], bph, lane, a.wait_ns);
+            else mbar_wait_warp(&hdr->stg_empty[buf], bph ^ 1u, lane, a.wait_ns);
             P2_TRACE(e == 0 && lane == 0 && it < 4, 8 + it * 12 + 10);
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256u;
             const uint32_t rowaddr = stg + (uint32_t)m * a.stg_pitch;
@@ -635,6 +652,7 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
             if (!P2_DBG(64)) fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&hdr->stg_ready[buf]);
+            if (++buf == a.stg_bufs) { buf = 0; bph ^= 1u; }
         }
     }
 
@@ -722,7 +740,7 @@ bool p2_plan(P2Args &a, dim3 *grid, size_t *smem_bytes) {
     // global memory busy -- bytes in flight per SM = raw stages x stage bytes -- so it gets all the remaining room.  Pick the
     // K chunk (32 or 16 channels) and the number of staging buffers that maximise the bytes in flight.
     int best_bytes = -1;
-    const int nop = g_p2_op_stages >= 2 && g_p2_op_stages <= kP2MaxRing ? g_p2_op_stages : 2;
+    const int nop = g_p2_op_stages >= 2 && g_p2_op_stages <= kP2MaxRing ? g_p2_op_stages : 3;
     for (int kc = 32; kc >= 16; kc -= 16) {
         if (g_p2_kc && kc != g_p2_kc) continue;
         const uint32_t raw_b = (uint32_t)p2_round_up(a.S * kc * a.L * 2, 128);
@@ -752,7 +770,7 @@ bool p2_plan(P2Args &a, dim3 *grid, size_t *smem_bytes) {
     {   // every relayout warp owns at most kP2MaxUnits (segment, group, 32-piece pass) units of a stage
         const int mode = a.V == 8 ? 16 : (a.V == 4 ? 8 : 4);
         const int passes = (mode == 4) ? ((a.L >> 1) + 2 + 31) >> 5 : (a.L / (mode / 2) + 31) >> 5;
-        if (a.S * a.G * passes > kP2NumRel * kP2MaxUnits) return false;
+        if (a.S * a.G * passes > kP2RelPerGroup * kP2MaxUnits) return false;
     }
     int gx = sm_count() / a.gy;
     if (gx < 1) gx = 1;

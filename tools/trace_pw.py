@@ -90,8 +90,8 @@ def main():
                   "  ".join("%.2f" % us(r[74 + w] if w < 6 else r[98 + w - 6]) for w in range(8)))
             print("   tile 2 MMA per stage (op_full seen / issued+committed): " +
                   "  ".join("%.2f/%.2f" % (us(r[80 + 2 * st]), us(r[81 + 2 * st])) for st in range(9) if int(r[80 + 2 * st])))
-            print("   tile 2 relayout warp 0 per stage (raw_full seen / op_empty seen / work done / fenced+arrived): " +
-                  "  ".join("%.2f/%.2f/%.2f/%.2f" % tuple(us(r[104 + 4 * st + i]) for i in range(4)) for st in range(6) if int(r[104 + 4 * st])))
+            print("   tile 2 relayout warp 0, its stages (raw_full seen / arrived): " +
+                  "  ".join("st%d %.2f/%.2f" % (st, us(r[104 + 2 * st]), us(r[105 + 2 * st])) for st in range(12) if int(r[104 + 2 * st])))
         return
     fn = {"fwd": lambda: ops.pw_conv(x, w), "bn": lambda: ops.pw_conv(x, w, in_scale_bias=sb),
           "dgrad": (lambda: ops.pw_conv(x, w_kn)) if a.wbf16 else (lambda: ops.pw_conv(x, w, transposed=True))}[a.mode]
