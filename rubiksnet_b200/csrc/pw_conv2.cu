@@ -422,7 +422,6 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
                     tc_fence_after();
                     P2_TRACE(it < 4 && st == 0, 8 + it * 12 + 1);
                     P2_TRACE(it < 4 && st == a.k_stages - 1, 8 + it * 12 + 2);
-                    P2_TRACE(it == 2 && st < 9, 80 + 2 * st);
                     const int ksteps = st == a.k_stages - 1 ? ksteps_last : ksteps_full;
                     uint32_t b_lo = b_lo0 + (uint32_t)o * op16;
                     for (int ks = 0; ks < ksteps; ++ks) {
@@ -432,7 +431,6 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
                         b_lo += 2048u >> 4;
                     }
                     mma_commit(&hdr->op_empty[o]);
-                    P2_TRACE(it == 2 && st < 9, 81 + 2 * st);
                     if (++o == a.op_stages) { o = 0; oph ^= 1u; }
                 }
                 mma_commit(&hdr->tmem_full[as]);
@@ -560,10 +558,13 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
             p2_tile(a, tile, img0, p0, nseg);
             const bool last = st == a.k_stages - 1;
             const int rows_real = last ? rows_real_last : a.kc, rows_pad = last ? rows_pad_last : a.kc;
+            if (P2_DBG(128)) mbar_wait_warp(&hdr->op_empty[o], oph ^ 1u, lane, a.wait_ns);
+            P2_TRACE(rw == 0 && lane == 0 && tile == tile0 + 2 * tstride && st < 12 && P2_DBG(128), 80 + 2 * st);
             mbar_wait_warp(&hdr->raw_full[r], rph, lane, a.wait_ns);
             P2_TRACE(rw == 0 && lane == 0 && (tile - tile0) / tstride < 4 && st == 0, 8 + ((tile - tile0) / tstride) * 12 + 8);
             P2_TRACE(rw == 0 && lane == 0 && tile == tile0 + 2 * tstride && st < 12, 104 + 2 * st);
-            mbar_wait_warp(&hdr->op_empty[o], oph ^ 1u, lane, a.wait_ns);
+            if (!P2_DBG(128)) mbar_wait_warp(&hdr->op_empty[o], oph ^ 1u, lane, a.wait_ns);
+            P2_TRACE(rw == 0 && lane == 0 && tile == tile0 + 2 * tstride && st < 12 && !P2_DBG(128), 80 + 2 * st);
             if (!P2_DBG(1))
                 p2_relayout_stage<MODE, BN>(a, s_raw + (uint32_t)r * a.raw_stage_bytes, s_op + (uint32_t)o * a.op_stage_bytes, smem_sb,
                                             st * a.kc, rows_real, rows_pad, nseg, pu, lane);

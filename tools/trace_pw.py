@@ -88,8 +88,8 @@ def main():
                   "  ".join("%.2f/%.2f" % (us(r[56 + 2 * st]), us(r[57 + 2 * st])) for st in range(9) if int(r[56 + 2 * st])))
             print("   tile 2 stage 3: arrival of the 8 relayout warps: " +
                   "  ".join("%.2f" % us(r[74 + w] if w < 6 else r[98 + w - 6]) for w in range(8)))
-            print("   tile 2 MMA per stage (op_full seen / issued+committed): " +
-                  "  ".join("%.2f/%.2f" % (us(r[80 + 2 * st]), us(r[81 + 2 * st])) for st in range(9) if int(r[80 + 2 * st])))
+            print("   tile 2 relayout warp 0: the other wait seen at: " +
+                  "  ".join("st%d %.2f" % (st, us(r[80 + 2 * st])) for st in range(12) if int(r[80 + 2 * st])))
             print("   tile 2 relayout warp 0, its stages (raw_full seen / arrived): " +
                   "  ".join("st%d %.2f/%.2f" % (st, us(r[104 + 2 * st]), us(r[105 + 2 * st])) for st in range(12) if int(r[104 + 2 * st])))
         return
