@@ -558,12 +558,12 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
             p2_tile(a, tile, img0, p0, nseg);
             const bool last = st == a.k_stages - 1;
             const int rows_real = last ? rows_real_last : a.kc, rows_pad = last ? rows_pad_last : a.kc;
-            if (P2_DBG(128)) mbar_wait_warp(&hdr->op_empty[o], oph ^ 1u, lane, a.wait_ns);
+            if (P2_DBG(128) && !P2_DBG(512)) mbar_wait_warp(&hdr->op_empty[o], oph ^ 1u, lane, a.wait_ns);
             P2_TRACE(rw == 0 && lane == 0 && tile == tile0 + 2 * tstride && st < 12 && P2_DBG(128), 80 + 2 * st);
-            mbar_wait_warp(&hdr->raw_full[r], rph, lane, a.wait_ns);
+            if (!P2_DBG(256)) mbar_wait_warp(&hdr->raw_full[r], rph, lane, a.wait_ns);
             P2_TRACE(rw == 0 && lane == 0 && (tile - tile0) / tstride < 4 && st == 0, 8 + ((tile - tile0) / tstride) * 12 + 8);
             P2_TRACE(rw == 0 && lane == 0 && tile == tile0 + 2 * tstride && st < 12, 104 + 2 * st);
-            if (!P2_DBG(128)) mbar_wait_warp(&hdr->op_empty[o], oph ^ 1u, lane, a.wait_ns);
+            if (!P2_DBG(128) && !P2_DBG(512)) mbar_wait_warp(&hdr->op_empty[o], oph ^ 1u, lane, a.wait_ns);
             P2_TRACE(rw == 0 && lane == 0 && tile == tile0 + 2 * tstride && st < 12 && !P2_DBG(128), 80 + 2 * st);
             if (!P2_DBG(1))
                 p2_relayout_stage<MODE, BN>(a, s_raw + (uint32_t)r * a.raw_stage_bytes, s_op + (uint32_t)o * a.op_stage_bytes, smem_sb,
