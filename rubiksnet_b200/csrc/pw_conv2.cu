@@ -742,8 +742,8 @@ bool p2_plan(P2Args &a, dim3 *grid, size_t *smem_bytes) {
     // K chunk (32 or 16 channels) and the number of staging buffers that maximise the bytes in flight.
     int best_bytes = -1;
     const int nop = g_p2_op_stages >= 2 && g_p2_op_stages <= kP2MaxRing ? g_p2_op_stages : 3;
-    for (int kc = 32; kc >= 16; kc -= 16) {
-        if (g_p2_kc && kc != g_p2_kc) continue;
+    for (int kc = 64; kc >= 16; kc -= 16) {
+        if (kc == 48 || (g_p2_kc ? kc != g_p2_kc : kc == 64)) continue;  // 64-channel chunks only on request (tuning)
         const uint32_t raw_b = (uint32_t)p2_round_up(a.S * kc * a.L * 2, 128);
         const uint32_t op_b = (uint32_t)a.atoms * (uint32_t)(kc >> 3) * 1024u;
         for (int bufs = 2; bufs >= 1; --bufs) {
@@ -854,7 +854,7 @@ void pw2_set_debug(int flags) { g_p2_dbg = flags; }
 
 void pw2_set_tuning(int op_stages, int kc, int wait_ns) {
     g_p2_op_stages = op_stages;
-    g_p2_kc = (kc == 16 || kc == 32) ? kc : 0;
+    g_p2_kc = (kc == 16 || kc == 32 || kc == 64) ? kc : 0;
     g_p2_wait_ns = wait_ns < 0 ? 0 : wait_ns;
 }
 
