@@ -239,9 +239,9 @@ int rb_shift3d_pw_conv_wgrad(const void *out_grad, const void *x, const void *sh
  *        transposed == 1: image of W^T (rows = K, contraction = N)  -> its input-gradient GEMM;
  *   rb_pw_conv_forward(x, image, RB_W_IMAGE, 0, ...)  runs it: K = contraction, N = rows of the packed matrix;
  *   rb_pw_conv_image_supported(NI, K, N, HW, has_in_scale_bias): 0 = this geometry has no image path (call
- *        rb_pw_conv_forward with a plain fp32 / bf16 weight), 1 = supported, 2 = supported and the faster of the two
- *        schedules (whole-image tiles: HW <= 224).  Needs K % 8 == 0, N % 8 == 0 and HW <= 224, or HW % 8 == 0 with a
- *        divisor in [64, 256] that is a multiple of 8.
+ *        rb_pw_conv_forward with a plain fp32 / bf16 weight), 1 = supported, 2 = supported and measured faster than the
+ *        plain path (several whole images per tile: maps of <= 112 pixels, e.g. 7x7).  Needs K % 8 == 0, N % 8 == 0 and
+ *        HW <= 224, or HW % 8 == 0 with a divisor in [64, 256] that is a multiple of 8.
  * Same arithmetic as the plain path (bf16 operands, fp32 accumulation, bf16 result, `+= residual` on the rounded value). */
 #define RB_W_IMAGE 16
 size_t rb_pw_weight_image_bytes(int rows, int contraction);

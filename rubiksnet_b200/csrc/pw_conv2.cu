@@ -881,16 +881,11 @@ int pw2_weight_pack(const float *w, int N, int K, int trans, void *image, cudaSt
     return launched("k_pw2_pack");
 }
 
-// 0: no image path; 1: supported; 2: supported and the faster schedule for this geometry (whole-image tiles: the raw ring
-// is fed by few large bulk copies.  Row-piece tiles of larger maps need one small copy per channel row, which the TMA unit
-// serialises -- measured slower than the first-generation kernel, profiles/r02b_bench_pw.log)
-// items: DEVICE array of `count` {const float *weight [N,K]; void *image_fwd; void *image_bwd; int N; int K} (rb_pw_pack_item_t)
-int pw2_weight_pack_multi(const void *items_device, int count, cudaStream_t s) {
-    static_assert(sizeof(P2PackItem) == 32, "rb_pw_pack_item_t layout");
-    k_pw2_pack_multi<<<dim3(48, (unsigned)count), 256, 0, s>>>((const P2PackItem *)items_device);
-    return launched("k_pw2_pack_multi");
-}
-
+// 0: no image path; 1: supported; 2: supported and measured faster than the first-generation kernel for this geometry.
+// Measured on B200 at 32 clips (profiles/r02l_bench_pw.log, us per launch, first generation -> image kernel):
+//   7x7 maps (4 images per tile): plain 161 -> 116, +residual 165 -> 116, bn+relu producer 269 -> 132   => level 2
+//   14x14 maps (1 image per tile): plain 41 -> 43, +residual 57 -> 51, bn+relu 51 -> 57                  => level 1 (a wash)
+//   28x28 .. 112x112 (row pieces, one small bulk copy per channel row: ~300 ns of issue each)  1.5-4x slower => level 1
 int pw2_supported(int NI, int K, int N, int HW, int has_bn) {
     P2Args a{};
     a.NI = NI; a.K = K; a.N = N; a.HW = HW;
@@ -898,7 +893,7 @@ int pw2_supported(int NI, int K, int N, int HW, int has_bn) {
     dim3 grid;
     size_t smem = 0;
     if (!p2_plan(a, &grid, &smem)) return 0;
-    return a.caseA ? 2 : 1;
+    return (a.caseA && a.S > 1) ? 2 : 1;
 }
 
 int pw2_forward(const void *x, const void *wimg, const void *residual, void *out, int NI, int K, int N, int HW,
