@@ -881,6 +881,13 @@ int pw2_weight_pack(const float *w, int N, int K, int trans, void *image, cudaSt
     return launched("k_pw2_pack");
 }
 
+// items: DEVICE array of `count` {const float *weight [N,K]; void *image_fwd; void *image_bwd; int N; int K} (rb_pw_pack_item_t)
+int pw2_weight_pack_multi(const void *items_device, int count, cudaStream_t s) {
+    static_assert(sizeof(P2PackItem) == 32, "rb_pw_pack_item_t layout");
+    k_pw2_pack_multi<<<dim3(48, (unsigned)count), 256, 0, s>>>((const P2PackItem *)items_device);
+    return launched("k_pw2_pack_multi");
+}
+
 // 0: no image path; 1: supported; 2: supported and measured faster than the first-generation kernel for this geometry.
 // Measured on B200 at 32 clips (profiles/r02l_bench_pw.log, us per launch, first generation -> image kernel):
 //   7x7 maps (4 images per tile): plain 161 -> 116, +residual 165 -> 116, bn+relu producer 269 -> 132   => level 2
