@@ -257,6 +257,9 @@ typedef struct rb_pw_pack_item {
     int N, K;
 } rb_pw_pack_item_t;
 int rb_pw_weight_image_pack_multi(const rb_pw_pack_item_t *items_device, int count, void *stream);
+/* The plain copies of rb_pw_weight_pack for many weights in one launch: image_fwd = weight_nk [N,K] bf16,
+ * image_bwd = weight_kn [K,N] bf16. */
+int rb_pw_weight_pack_multi(const rb_pw_pack_item_t *items_device, int count, void *stream);
 
 /* Tiling override for rb_pw_conv_forward (process-global, like rb_set_impl): lower bound on the number of
  * output-channel splits (grid.y); more splits = a smaller resident weight block and a deeper activation ring per CTA

@@ -83,6 +83,8 @@ def _declare(lib):
     lib.rb_pw_weight_image_bytes.restype = sz
     lib.rb_pw_weight_image_pack.argtypes = [vp, i, i, i, vp, vp]
     lib.rb_pw_weight_image_pack.restype = i
+    lib.rb_pw_weight_pack_multi.argtypes = [vp, i, vp]
+    lib.rb_pw_weight_pack_multi.restype = i
     lib.rb_pw_weight_image_pack_multi.argtypes = [vp, i, vp]
     lib.rb_pw_weight_image_pack_multi.restype = i
     lib.rb_pw_conv_image_supported.argtypes = [i, i, i, i, i]

@@ -25,7 +25,7 @@ class _AttentionMix(torch.autograd.Function):
         nt, c, h, w = x.shape
         assert nt % n_segment == 0, "batch (N*T) must be a multiple of n_segment"
         out = torch.empty_like(x)
-        with _on_device(x.device):
+        with _on_device(x.device), _lib.timed("attention_shift_forward", _lib.nbytes(x, out)):
             _lib.check(_lib.lib().rb_attention_shift_forward(
                 _lib.ptr(x), _lib.ptr(taps), _lib.ptr(out), _lib.dtype_code(x), nt // n_segment, n_segment,
                 c, h * w, _lib.stream_handle(x.device)))
@@ -49,9 +49,10 @@ class _AttentionMix(torch.autograd.Function):
             L = _lib.lib()
             nbytes = L.rb_attention_shift_backward_workspace_bytes(n, ctx.n_segment, c, h * w) if need_t else 0
             ws = _lib.workspace(nbytes, x.device)
-            _lib.check(L.rb_attention_shift_backward(
-                _lib.ptr(x), _lib.ptr(taps), _lib.ptr(grad_out), _lib.ptr(gx), _lib.ptr(gt), _lib.dtype_code(x),
-                n, ctx.n_segment, c, h * w, _lib.ptr(ws), nbytes, _lib.stream_handle(x.device)))
+            with _lib.timed("attention_shift_backward", _lib.nbytes(x, grad_out, gx)):
+                _lib.check(L.rb_attention_shift_backward(
+                    _lib.ptr(x), _lib.ptr(taps), _lib.ptr(grad_out), _lib.ptr(gx), _lib.ptr(gt), _lib.dtype_code(x),
+                    n, ctx.n_segment, c, h * w, _lib.ptr(ws), nbytes, _lib.stream_handle(x.device)))
         return gx, gt, None
 
 

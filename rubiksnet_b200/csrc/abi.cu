@@ -71,6 +71,7 @@ int pw2_forward(const void *x, const void *wimg, const void *residual, void *out
 void pw_conv_set_trace(void *p);
 #endif
 int pw_weight_pack(const float *w, void *w_nk, void *w_kn, int N, int K, cudaStream_t s);
+int pw_weight_pack_multi(const void *items_device, int count, cudaStream_t s);
 int pw_conv_wgrad(const void *g, const void *x, float *dw, int NI, int M, int N, int HW, const float *x_sb,
                   const void *shift, int shift_dt, int T, int H, int W, void *workspace, cudaStream_t s);
 
@@ -304,6 +305,13 @@ int rb_pw_weight_image_pack(const float *weight, int N, int K, int transposed, v
     if (!weight || !image) return fail(RB_ERR_INVALID_ARGUMENT, "null pointer");
     if (reinterpret_cast<uintptr_t>(image) & 15) return fail(RB_ERR_INVALID_ARGUMENT, "weight image must be 16-byte aligned");
     return pw2_weight_pack(weight, N, K, transposed != 0, image, (cudaStream_t)stream);
+}
+
+int rb_pw_weight_pack_multi(const rb_pw_pack_item_t *items_device, int count, void *stream) {
+    if (count < 0 || count > 65535) return fail(RB_ERR_INVALID_ARGUMENT, "bad item count %d", count);
+    if (count == 0) return RB_OK;
+    if (!items_device) return fail(RB_ERR_INVALID_ARGUMENT, "null pointer");
+    return pw_weight_pack_multi(items_device, count, (cudaStream_t)stream);
 }
 
 int rb_pw_weight_image_pack_multi(const rb_pw_pack_item_t *items_device, int count, void *stream) {

@@ -1401,6 +1401,39 @@ __global__ void k_pw_weight_pack(const float *__restrict__ w, __nv_bfloat16 *__r
     }
 }
 
+// the same for MANY weights in one launch (grid.y = weight, blocks stride over its 32x32 tiles); items as rb_pw_pack_item_t
+struct PackItem {
+    const float *w;
+    __nv_bfloat16 *w_nk, *w_kn;
+    int N, K;
+};
+__global__ void k_pw_weight_pack_multi(const PackItem *__restrict__ items) {
+    __shared__ float tile[32][33];
+    const PackItem it = items[blockIdx.y];
+    const int tk = (it.K + 31) / 32, tn = (it.N + 31) / 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int t = blockIdx.x; t < tk * tn; t += gridDim.x) {
+        const int k0 = (t % tk) * 32, n0 = (t / tk) * 32;
+        __syncthreads();
+        for (int r = ty; r < 32; r += 8) {
+            const int n = n0 + r, k = k0 + tx;
+            const float v = (n < it.N && k < it.K) ? it.w[(int64_t)n * it.K + k] : 0.f;
+            tile[r][tx] = v;
+            if (n < it.N && k < it.K) it.w_nk[(int64_t)n * it.K + k] = __float2bfloat16_rn(v);
+        }
+        __syncthreads();
+        for (int r = ty; r < 32; r += 8) {
+            const int k = k0 + r, n = n0 + tx;
+            if (n < it.N && k < it.K) it.w_kn[(int64_t)k * it.N + n] = __float2bfloat16_rn(tile[tx][r]);
+        }
+    }
+}
+
+int pw_weight_pack_multi(const void *items_device, int count, cudaStream_t s) {
+    static_assert(sizeof(PackItem) == 32, "rb_pw_pack_item_t layout");
+    k_pw_weight_pack_multi<<<dim3(24, (unsigned)count), 256, 0, s>>>((const PackItem *)items_device);
+    return launched("k_pw_weight_pack_multi");
+}
+
 int pw_weight_pack(const float *w, void *w_nk, void *w_kn, int N, int K, cudaStream_t s) {
     dim3 grid((unsigned)cdiv(K, 32), (unsigned)cdiv(N, 32));
     k_pw_weight_pack<<<grid, 256, 0, s>>>(w, (__nv_bfloat16 *)w_nk, (__nv_bfloat16 *)w_kn, N, K);

@@ -35,11 +35,12 @@ class _BNAct(torch.autograd.Function):
             L = _lib.lib()
             nbytes = L.rb_bn_workspace_bytes(ni, c)
             ws = _lib.workspace(nbytes, x.device)
-            _lib.check(L.rb_bn_act_forward(
-                _lib.ptr(x), _lib.ptr(weight), _lib.ptr(bias), _lib.ptr(running_mean), _lib.ptr(running_var),
-                _lib.ptr(y), _lib.ptr(mean_invstd), _lib.ptr(scale_bias), _lib.dtype_code(x), ni, c, hw,
-                int(training), float(momentum), float(eps), int(relu), _lib.ptr(ws), nbytes,
-                _lib.stream_handle(x.device)))
+            with _lib.timed("bn_forward<stats+apply>" if training else "bn_forward<eval>", _lib.nbytes(x) * (2 if training else 1) + _lib.nbytes(y)):
+                _lib.check(L.rb_bn_act_forward(
+                    _lib.ptr(x), _lib.ptr(weight), _lib.ptr(bias), _lib.ptr(running_mean), _lib.ptr(running_var),
+                    _lib.ptr(y), _lib.ptr(mean_invstd), _lib.ptr(scale_bias), _lib.dtype_code(x), ni, c, hw,
+                    int(training), float(momentum), float(eps), int(relu), _lib.ptr(ws), nbytes,
+                    _lib.stream_handle(x.device)))
         ctx.save_for_backward(x, weight, mean_invstd, scale_bias)
         ctx.cfg = (ni, c, hw, bool(training), bool(relu))
         return y
@@ -59,10 +60,11 @@ class _BNAct(torch.autograd.Function):
             L = _lib.lib()
             nbytes = L.rb_bn_workspace_bytes(ni, c)
             ws = _lib.workspace(nbytes, x.device)
-            _lib.check(L.rb_bn_act_backward(
-                _lib.ptr(x), _lib.ptr(dy), None, _lib.ptr(weight), _lib.ptr(mean_invstd), _lib.ptr(scale_bias),
-                _lib.ptr(dx), _lib.ptr(dgamma), _lib.ptr(dbeta), _lib.dtype_code(x), ni, c, hw, int(training),
-                int(relu), _lib.ptr(ws), nbytes, _lib.stream_handle(x.device)))
+            with _lib.timed("bn_backward", 2 * _lib.nbytes(x, dy) + _lib.nbytes(dx)):
+                _lib.check(L.rb_bn_act_backward(
+                    _lib.ptr(x), _lib.ptr(dy), None, _lib.ptr(weight), _lib.ptr(mean_invstd), _lib.ptr(scale_bias),
+                    _lib.ptr(dx), _lib.ptr(dgamma), _lib.ptr(dbeta), _lib.dtype_code(x), ni, c, hw, int(training),
+                    int(relu), _lib.ptr(ws), nbytes, _lib.stream_handle(x.device)))
         return dx, dgamma, dbeta, None, None, None, None, None, None
 
 
@@ -122,41 +124,42 @@ USE_IMAGE_KERNEL = True
 
 def _pack_weight(weight, ni, hw):
     """bf16 operands of a fp32 conv weight [N,K,1,1] for the forward and the input-gradient GEMM: packed images for the
-    TMA kernel when both geometries have an image path, else the plain [N,K] / [K,N] copies."""
+    TMA kernel where that is the faster schedule, else the plain [N,K] / [K,N] copies.  Inside a forward pass of a module
+    that called begin_step_pack() both kinds come out of ONE launch per step."""
     n, k = weight.shape[0], weight.shape[1]
     # the optional single-launch shift+conv3 / epilogue-statistics schedules exist on the first-generation kernel only
-    if (USE_IMAGE_KERNEL and not FUSE_SHIFT_CONV3 and not EPILOGUE_BN_STATS
-            and ops.pw_image_supported(ni, k, n, hw, True, preferred=True)
-            and ops.pw_image_supported(ni, n, k, hw, False, preferred=True)):
-        pre = _STEP_PACK.lookup(weight)
-        if pre is not None:
-            return pre
-        _STEP_PACK.note(weight)
-        return ops.pw_weight_images(weight)
-    return ops.pw_weight_pack(weight)
+    image = (USE_IMAGE_KERNEL and not FUSE_SHIFT_CONV3 and not EPILOGUE_BN_STATS
+             and ops.pw_image_supported(ni, k, n, hw, True, preferred=True)
+             and ops.pw_image_supported(ni, n, k, hw, False, preferred=True))
+    pre = _STEP_PACK.lookup(weight, image)
+    if pre is not None:
+        return pre
+    _STEP_PACK.note(weight, image)
+    return ops.pw_weight_images(weight) if image else ops.pw_weight_pack(weight)
 
 
 class _StepPack:
-    """All weight images of a model in ONE launch per step (rb_pw_weight_image_pack_multi) instead of two small launches
-    per conv and step (106 `pw_weight_pack` launches, 2.4 ms of an eager RubiksNet-Large step in round 1).
+    """All packed weight operands of a model in ONE launch per kind and step (rb_pw_weight_pack_multi /
+    rb_pw_weight_image_pack_multi) instead of one or two small launches per conv and step (106 `pw_weight_pack` launches,
+    2.4 ms of an eager RubiksNet-Large step in round 1).
 
-    The first forward pass of an `owner` module packs every weight on its own and records which weights asked for images;
-    from the second pass on `begin(owner)` fills all their images with one kernel into a persistent buffer and
-    `_pack_weight` hands out views of it.  The images of step i are overwritten by `begin` of step i+1, i.e. after the
+    The first forward pass of an `owner` module packs every weight on its own and records which weights asked for which
+    kind; from the second pass on `begin(owner)` fills all of them with one kernel per kind into a persistent buffer and
+    `_pack_weight` hands out views of it.  The operands of step i are overwritten by `begin` of step i+1, i.e. after the
     backward pass of step i has been enqueued on the same stream."""
 
     def __init__(self):
-        self.current = None      # {id(weight): (fwd WeightImage, bwd WeightImage)} of the running forward pass
-        self.collecting = None   # list of weights seen in a recording pass
+        self.current = None      # {(id(weight), image?): (fwd operand, bwd operand)} of the running forward pass
+        self.collecting = None   # [(weight, image?)] seen in a recording pass
 
-    def lookup(self, weight):
+    def lookup(self, weight, image):
         if self.current is None:
             return None
-        return self.current.get(id(weight))
+        return self.current.get((id(weight), image))
 
-    def note(self, weight):
-        if self.collecting is not None and all(w is not weight for w in self.collecting):
-            self.collecting.append(weight)
+    def note(self, weight, image):
+        if self.collecting is not None and all(not (w is weight and im == image) for w, im in self.collecting):
+            self.collecting.append((weight, image))
 
     def begin(self, owner):
         plan = owner.__dict__.get("_rb_pack_plan")
@@ -168,7 +171,7 @@ class _StepPack:
             self.collecting = []
             return
         plan.launch()
-        self.current = plan.images
+        self.current = plan.operands
 
     def end(self, owner):
         if self.collecting:
@@ -177,41 +180,46 @@ class _StepPack:
 
 
 class _PackPlan:
-    def __init__(self, weights):
+    def __init__(self, entries):
         import struct
-        self.weights = list(weights)
-        self.ptrs = [w.data_ptr() for w in self.weights]
-        dev = self.weights[0].device
+        self.entries = list(entries)
+        self.ptrs = [w.data_ptr() for w, _ in self.entries]
+        dev = self.entries[0][0].device
         L = _lib.lib()
         sizes = []
-        for w in self.weights:
+        for w, image in self.entries:
             n, k = w.shape[0], w.shape[1]
-            sizes.append((L.rb_pw_weight_image_bytes(n, k), L.rb_pw_weight_image_bytes(k, n)))
-        total = sum((a + 255) // 256 * 256 + (b + 255) // 256 * 256 for a, b in sizes)
-        self.buffer = torch.empty(total, dtype=torch.uint8, device=dev)
-        self.images = {}
-        table = b""
+            sizes.append((L.rb_pw_weight_image_bytes(n, k), L.rb_pw_weight_image_bytes(k, n)) if image else (2 * n * k, 2 * n * k))
+        al = lambda v: (v + 255) // 256 * 256  # noqa: E731
+        self.buffer = torch.empty(sum(al(a) + al(b) for a, b in sizes), dtype=torch.uint8, device=dev)
+        self.operands = {}
+        tables = {True: b"", False: b""}
         off = 0
-        for w, (a, b) in zip(self.weights, sizes):
+        for (w, image), (a, b) in zip(self.entries, sizes):
             n, k = w.shape[0], w.shape[1]
             fwd = self.buffer[off:off + a]
-            off += (a + 255) // 256 * 256
+            off += al(a)
             bwd = self.buffer[off:off + b]
-            off += (b + 255) // 256 * 256
-            self.images[id(w)] = (ops.WeightImage(fwd, n, k), ops.WeightImage(bwd, k, n))
-            table += struct.pack("<QQQii", w.data_ptr(), fwd.data_ptr(), bwd.data_ptr(), n, k)  # rb_pw_pack_item_t
-        self.table = torch.frombuffer(bytearray(table), dtype=torch.uint8).to(dev)
+            off += al(b)
+            if image:
+                self.operands[(id(w), True)] = (ops.WeightImage(fwd, n, k), ops.WeightImage(bwd, k, n))
+            else:
+                self.operands[(id(w), False)] = (fwd.view(torch.bfloat16).view(n, k), bwd.view(torch.bfloat16).view(k, n))
+            tables[image] += struct.pack("<QQQii", w.data_ptr(), fwd.data_ptr(), bwd.data_ptr(), n, k)  # rb_pw_pack_item_t
+        self.tables = {im: (torch.frombuffer(bytearray(t), dtype=torch.uint8).to(dev), len(t) // 32) for im, t in tables.items() if t}
         self.device = dev
 
     def valid(self):
         return all(w.data_ptr() == p and w.dtype == torch.float32 and w.is_contiguous() and w.device == self.device
-                   for w, p in zip(self.weights, self.ptrs))
+                   for (w, _), p in zip(self.entries, self.ptrs))
 
     def launch(self):
+        L = _lib.lib()
         with _on_device(self.device):
             with _lib.timed("pw_weight_pack", 0):
-                _lib.check(_lib.lib().rb_pw_weight_image_pack_multi(_lib.ptr(self.table), len(self.weights),
-                                                                   _lib.stream_handle(self.device)))
+                for image, (table, count) in self.tables.items():
+                    fn = L.rb_pw_weight_image_pack_multi if image else L.rb_pw_weight_pack_multi
+                    _lib.check(fn(_lib.ptr(table), count, _lib.stream_handle(self.device)))
 
 
 _STEP_PACK = _StepPack()

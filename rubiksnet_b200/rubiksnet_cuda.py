@@ -65,7 +65,7 @@ def rubiks2d_forward(input, shift, strides, paddings, quantize, output):
     if tuple(shift.shape) != (2, C):
         raise RuntimeError("ShapeException: rubiks shift expected shape = [2, %d]; actual shape = %s"
                            % (C, list(shift.shape)))
-    with _on_device(input.device):
+    with _on_device(input.device), _lib.timed("shift2d_forward", _lib.nbytes(input, output)):
         _lib.check(_lib.lib().rb_shift2d_forward(
             _lib.ptr(input), _lib.ptr(shift), _lib.ptr(output), _lib.dtype_code(input), _lib.dtype_code(shift),
             N, C, H, W, int(strides[0]), int(strides[1]), int(paddings[0]), int(paddings[1]),
@@ -86,11 +86,12 @@ def rubiks2d_backward(upstream_grad, input, shift, strides, paddings, normalize_
         L = _lib.lib()
         nbytes = L.rb_shift2d_backward_workspace_bytes(dt, N, C, H, W, sH, sW, pH, pW) if enable_shift_grad else 0
         ws = _lib.workspace(nbytes, input.device)
-        _lib.check(L.rb_shift2d_backward(
-            _lib.ptr(input), _lib.ptr(shift), _lib.ptr(upstream_grad), _lib.ptr(input_grad), _lib.ptr(shift_grad),
-            dt, _lib.dtype_code(shift), N, C, H, W, sH, sW, pH, pW, int(bool(normalize_grad)),
-            int(bool(enable_shift_grad)), int(bool(quantize)), _lib.ptr(ws), nbytes,
-            _lib.stream_handle(input.device)))
+        with _lib.timed("shift2d_backward", _lib.nbytes(input, upstream_grad, input_grad)):
+            _lib.check(L.rb_shift2d_backward(
+                _lib.ptr(input), _lib.ptr(shift), _lib.ptr(upstream_grad), _lib.ptr(input_grad), _lib.ptr(shift_grad),
+                dt, _lib.dtype_code(shift), N, C, H, W, sH, sW, pH, pW, int(bool(normalize_grad)),
+                int(bool(enable_shift_grad)), int(bool(quantize)), _lib.ptr(ws), nbytes,
+                _lib.stream_handle(input.device)))
     return 0
 
 
