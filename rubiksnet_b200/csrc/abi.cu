@@ -39,6 +39,12 @@ int shift3d_forward_strip(const void *, const void *, void *, int, int, const Ge
 size_t shift3d_backward_strip_workspace(int dt, const Geom3 &g);
 int shift3d_backward_strip(const void *, const void *, const void *, void *, void *, int, int, const Geom3 &, int,
                            double, void *, cudaStream_t);
+// shift3d_strip.cu: the 2D shift through the strip kernels (one-frame clips)
+bool shift2d_strip_supported(int dt, const Geom2 &g, int quantize);
+int shift2d_forward_strip(const void *x, const void *shift, void *out, int dt, int sdt, const Geom2 &g, cudaStream_t s);
+size_t shift2d_backward_strip_workspace(int dt, const Geom2 &g);
+int shift2d_backward_strip(const void *x, const void *shift, const void *og, void *gin, void *gshift, int dt, int sdt,
+                           const Geom2 &g, int normalize, void *workspace, cudaStream_t s);
 // shift2d_generic.cu
 int shift2d_bwd_chunks(const Geom2 &g);
 int shift2d_forward_generic(const void *, const void *, void *, int, int, const Geom2 &, int, cudaStream_t);
@@ -220,6 +226,15 @@ static int make_geom2(Geom2 &g, int N, int C, int H, int W, int sH, int sW, int 
     return RB_OK;
 }
 
+// stride-1 / pad-0 / non-quantized 2D shifts (what RubiksNet's attention-quantized variant uses outside its 4 down-sampling
+// blocks) run on the TMA-staged strip kernels; rb_set_impl(RB_IMPL_GENERIC) forces the generic gather
+static bool use_strip2d(int dtype, int shift_dtype, const Geom2 &g, int quantize) {
+    const int forced = g_forced_impl.load(std::memory_order_relaxed);
+    if (forced == RB_IMPL_GENERIC || forced == RB_IMPL_TILED) return false;
+    if (shift_dtype == RB_F64) return false;
+    return shift2d_strip_supported(dtype, g, quantize);
+}
+
 int rb_shift2d_forward(const void *x, const void *shift, void *out, int dtype, int shift_dtype, int N,
                        int C, int H, int W, int sH, int sW, int pH, int pW, int quantize, void *stream) {
     Geom2 g;
@@ -228,17 +243,22 @@ int rb_shift2d_forward(const void *x, const void *shift, void *out, int dtype, i
     if ((rc = check_dtypes(dtype, shift_dtype))) return rc;
     if ((int64_t)N * C * g.Ho * g.Wo == 0) return RB_OK;
     if (!x || !shift || !out) return fail(RB_ERR_INVALID_ARGUMENT, "null pointer");
+    if (use_strip2d(dtype, shift_dtype, g, quantize)) {
+        g_last_impl = RB_IMPL_STRIP;
+        return shift2d_forward_strip(x, shift, out, dtype, shift_dtype, g, (cudaStream_t)stream);
+    }
     g_last_impl = RB_IMPL_GENERIC;
     return shift2d_forward_generic(x, shift, out, dtype, shift_dtype, g, quantize, (cudaStream_t)stream);
 }
 
 size_t rb_shift2d_backward_workspace_bytes(int dtype, int N, int C, int H, int W, int sH, int sW, int pH,
                                            int pW) {
-    (void)dtype;
     Geom2 g;
     if (make_geom2(g, N, C, H, W, sH, sW, pH, pW)) return 0;
     if ((int64_t)N * C * g.Ho * g.Wo == 0) return 0;
     size_t need = (size_t)C * shift2d_bwd_chunks(g) * 2 * sizeof(double);
+    const size_t strip = shift2d_strip_supported(dtype, g, 0) ? shift2d_backward_strip_workspace(dtype, g) : 0;
+    if (strip > need) need = strip;
     return (need + 255) & ~(size_t)255;
 }
 
@@ -264,6 +284,10 @@ int rb_shift2d_backward(const void *x, const void *shift, const void *out_grad, 
     if (shift_grad && (!workspace || workspace_bytes < need))
         return fail(RB_ERR_WORKSPACE, "shift2d backward needs %zu workspace bytes, got %zu", need,
                     workspace_bytes);
+    if (use_strip2d(dtype, shift_dtype, g, quantize)) {  // input gradient + shift gradient in one launch (+ finalize)
+        g_last_impl = RB_IMPL_STRIP;
+        return shift2d_backward_strip(x, shift, out_grad, x_grad, shift_grad, dtype, shift_dtype, g, normalize_grad, workspace, s);
+    }
     g_last_impl = RB_IMPL_GENERIC;
     if (shift_grad) {
         rc = shift2d_bwd_shift_generic(x, shift, out_grad, shift_grad, dtype, shift_dtype, g, normalize_grad,

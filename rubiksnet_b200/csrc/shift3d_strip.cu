@@ -46,6 +46,7 @@ struct StripArgs {
     double *partial;  // BWD: [C][N*row_tiles][3]
     int sdt;
     int N, Tn, C, H, W;
+    int mode2d;       // 2D shift (cuda_src/rubiks2d_kernels.cu): shift is [2, C] (H, W), every "clip" is one image (Tn = 1)
     StripCfg cfg;
 };
 
@@ -155,12 +156,28 @@ __global__ void __launch_bounds__(kSNT) k_shift3d_strip(const StripArgs a) {
     const int c = c0 + cl;
     const int ncols = min(CW, W - wd0);
 
-    float sT = ld_param<float>(a.shift, a.sdt, c), sH = ld_param<float>(a.shift, a.sdt, a.C + c),
-          sW = ld_param<float>(a.shift, a.sdt, 2 * a.C + c);
+    float sT, sH, sW;
+    if (a.mode2d) {
+        sT = 0.f;
+        sH = ld_param<float>(a.shift, a.sdt, c);
+        sW = ld_param<float>(a.shift, a.sdt, a.C + c);
+        if (MODE == SMODE_BWD) {
+            // the 2D shift gradient treats |r| < 1e-7 as an exact integer shift (rubiks2d_kernels.cu:189): snap the shift
+            // itself, which moves the input gradient by at most 1e-7 of a tap
+            const float fh = floorf(sH), fw = floorf(sW);
+            if (fabsf(sH - fh) < 1e-7f) sH = fh;
+            if (fabsf(sW - fw) < 1e-7f) sW = fw;
+        }
+    } else {
+        sT = ld_param<float>(a.shift, a.sdt, c);
+        sH = ld_param<float>(a.shift, a.sdt, a.C + c);
+        sW = ld_param<float>(a.shift, a.sdt, 2 * a.C + c);
+    }
     if (MODE == SMODE_BWD) { sT = -sT; sH = -sH; sW = -sW; }
     const int fT = floor3d(sT), fH = floor3d(sH), fW = floor3d(sW);
     const float rT = sT - fT, rH = sH - fH, rW = sW - fW;
-    const bool intT = rT == 0.f, intH = rH == 0.f, intW = rW == 0.f;
+    // 2D: there is no temporal component (sT = 0 selects frame t with weight 1 and must not trigger the integer rule)
+    const bool intT = !a.mode2d && rT == 0.f, intH = rH == 0.f, intW = rW == 0.f;
     const bool slow = (MODE == SMODE_BWD) && (intT || intH || intW);
 
     // ---- staged source rows (CTA-uniform: CG == 1 implies every thread reads channel c0's shift) ----
@@ -357,7 +374,30 @@ __global__ void __launch_bounds__(kSNT) k_shift3d_strip(const StripArgs a) {
                         }
                         dst[di] = cvt<T, float>(v);
                     }
-                    if (want_grad) {
+                    if (want_grad && a.mode2d) {
+                        // 2D rule (rubiks2d_kernels.cu:189-253) in adjoint form: regular axis = difference of the two
+                        // taps; exact-integer axis = 0.5 * central difference (taps -1 and +1); the other axis always
+                        // interpolates with (1 - r, r) -- an integer shift there does not move the taps (unlike 3D)
+                        float gH = 0.f, gW = 0.f;
+#pragma unroll 1
+                        for (int dy = -1; dy <= 1; ++dy) {
+                            const float bh = sc_a(dy, rH);
+                            const float sh = intH ? (dy == -1 ? 0.5f : (dy == 1 ? -0.5f : 0.f)) : (dy == 0 ? 1.f : (dy == 1 ? -1.f : 0.f));
+#pragma unroll 1
+                            for (int dx = -1; dx <= 1; ++dx) {
+                                const float bw = sc_a(dx, rW);
+                                const float sw = intW ? (dx == -1 ? 0.5f : (dx == 1 ? -0.5f : 0.f)) : (dx == 0 ? 1.f : (dx == 1 ? -1.f : 0.f));
+                                const float cH = sh * bw, cW2 = bh * sw;
+                                if (cH == 0.f && cW2 == 0.f) continue;
+                                const float qq = tap(t0, h0 + dy, w0 + dx);
+                                gH += cH * qq;
+                                gW += cW2 * qq;
+                            }
+                        }
+                        const float xv = s_tof(xin[di]);
+                        accH += xv * gH;
+                        accW += xv * gW;
+                    } else if (want_grad) {
                         float gT = 0.f, gH = 0.f, gW = 0.f;
 #pragma unroll 1
                         for (int dt = -1; dt <= 1; ++dt) {
@@ -510,6 +550,73 @@ int shift3d_backward_strip(const void *x, const void *shift, const void *og, voi
     int rc = strip_dtype<SMODE_BWD>(dt, a, s);
     if (rc || !gshift) return rc;
     return shift3d_finalize((const double *)workspace, g.N * a.cfg.row_tiles, gshift, dt, sdt, g.C, normalize, factor, s);
+}
+
+// ---- 2D shift on [N, C, H, W] through the same kernels: every image is a one-frame clip, the shift has no T row ---------
+__global__ void k_shift2d_strip_finalize(const double *__restrict__ partial, int parts, void *shift_grad, int sdt, int C,
+                                         int normalize) {
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= C) return;
+    const int lane = threadIdx.x & 31;
+    double s0 = 0, s1 = 0;
+    const double *p = partial + (int64_t)c * parts * 3;
+    for (int i = lane; i < parts; i += 32) {
+        s0 += p[i * 3 + 1];
+        s1 += p[i * 3 + 2];
+    }
+    s0 = warp_sum(s0);
+    s1 = warp_sum(s1);
+    if (lane != 0) return;
+    float gh = (float)s0, gw = (float)s1;
+    if (normalize) {  // rubiks2d_kernels.cu:386-396
+        const float mag = sqrtf(gh * gh + gw * gw);
+        if (mag > 0) {
+            gh = gh / mag;
+            gw = gw / mag;
+        }
+    }
+    st_param<float>(shift_grad, sdt, c, gh);
+    st_param<float>(shift_grad, sdt, C + c, gw);
+}
+
+bool shift2d_strip_supported(int dt, const Geom2 &g, int quantize) {
+    if (quantize) return false;
+    if (dt != RB_F32 && dt != RB_F16 && dt != RB_BF16) return false;
+    if (g.sH != 1 || g.sW != 1 || g.pH != 0 || g.pW != 0) return false;
+    StripCfg c;
+    if (!pick_strip_cfg((int)dtype_size(dt), 1, g.C, g.H, g.W, &c)) return false;
+    return (int64_t)g.N * c.groups * c.row_tiles <= 0x7fffffffLL;
+}
+
+int shift2d_forward_strip(const void *x, const void *shift, void *out, int dt, int sdt, const Geom2 &g, cudaStream_t s) {
+    StripArgs a{};
+    a.src = x; a.dst = out; a.xin = nullptr; a.shift = shift; a.partial = nullptr; a.sdt = sdt;
+    a.N = g.N; a.Tn = 1; a.C = g.C; a.H = g.H; a.W = g.W; a.mode2d = 1;
+    if (!pick_strip_cfg((int)dtype_size(dt), 1, g.C, g.H, g.W, &a.cfg))
+        return fail(RB_ERR_UNSUPPORTED, "2D strip forward: no configuration");
+    return strip_dtype<SMODE_FWD>(dt, a, s);
+}
+
+size_t shift2d_backward_strip_workspace(int dt, const Geom2 &g) {
+    StripCfg c;
+    if (!pick_strip_cfg((int)dtype_size(dt), 1, g.C, g.H, g.W, &c)) return 0;
+    return (size_t)g.C * g.N * c.row_tiles * 3 * sizeof(double);
+}
+
+int shift2d_backward_strip(const void *x, const void *shift, const void *og, void *gin, void *gshift, int dt, int sdt,
+                           const Geom2 &g, int normalize, void *workspace, cudaStream_t s) {
+    StripArgs a{};
+    a.src = og; a.dst = gin; a.xin = gshift ? x : nullptr; a.shift = shift;
+    a.partial = gshift ? (double *)workspace : nullptr; a.sdt = sdt;
+    a.N = g.N; a.Tn = 1; a.C = g.C; a.H = g.H; a.W = g.W; a.mode2d = 1;
+    if (!pick_strip_cfg((int)dtype_size(dt), 1, g.C, g.H, g.W, &a.cfg))
+        return fail(RB_ERR_UNSUPPORTED, "2D strip backward: no configuration");
+    int rc = strip_dtype<SMODE_BWD>(dt, a, s);
+    if (rc || !gshift) return rc;
+    const int warps = 4;
+    k_shift2d_strip_finalize<<<cdiv(g.C, warps), warps * 32, 0, s>>>((const double *)workspace, g.N * a.cfg.row_tiles, gshift, sdt,
+                                                                    g.C, normalize);
+    return launched("k_shift2d_strip_finalize");
 }
 
 }  // namespace rb
