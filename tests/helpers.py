@@ -34,14 +34,30 @@ def make_shift(rng, kind, dims, C, dtype=np.float32):
 
 
 def assert_close(actual, expected, tol, what=""):
+    """|actual - expected| <= tol * max(1, |expected|) ELEMENT BY ELEMENT (absolute `tol` for values below 1, relative above:
+    the meaning of north_star's "within 1e-4 fp32 / 1e-2 bf16").
+
+    Reductions over many terms -- the shift gradients, recognised by "shift_grad" / "gshift" / "gweight" / "taps grad" in
+    `what` -- are compared with `tol` relative to the LARGEST expected entry instead: an fp32 sum of 10^4..10^6 products has a
+    rounding error proportional to the sum of the |terms|, not to the (possibly cancelling) result of one channel, and the
+    reference itself adds them with atomics in arbitrary order."""
     actual = np.asarray(actual, dtype=np.float64)
     expected = np.asarray(expected, dtype=np.float64)
     assert actual.shape == expected.shape, (what, actual.shape, expected.shape)
     if actual.size == 0:
         return
-    scale = max(1.0, float(np.abs(expected).max()))
-    err = float(np.abs(actual - expected).max())
-    assert err <= tol * scale, "%s: max abs err %.3e > %.1e * %.3g" % (what, err, tol, scale)
+    err = np.abs(actual - expected)
+    reduction = any(k in what for k in ("shift_grad", "gshift", "gweight", "taps grad", "gs"))
+    if reduction:
+        scale = max(1.0, float(np.abs(expected).max()))
+        assert float(err.max()) <= tol * scale, "%s: max abs err %.3e > %.1e * %.3g" % (what, float(err.max()), tol, scale)
+        return
+    bound = tol * np.maximum(1.0, np.abs(expected))
+    bad = err > bound
+    if bad.any():
+        i = int(np.argmax(err - bound))
+        raise AssertionError("%s: %d of %d elements off; worst |%.6g - %.6g| = %.3e > %.1e * max(1, |expected|)" % (
+            what, int(bad.sum()), err.size, actual.flat[i], expected.flat[i], float(err.flat[i]), tol))
 
 
 def load_golden(name):
