@@ -156,6 +156,17 @@ int rb_bn_act_backward(const void *x, const void *dy, const void *residual, cons
                        float *dbeta, int dtype, int NI, int C, int HW, int training, int relu,
                        void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---------------------------------------------------------------- squeeze-and-excitation ------- */
+
+/* The two passes over the activation tensor of SELayer (rubiksnet/backbone.py:56-71; tier "small") and their gradients:
+ *   rb_plane_reduce: out[plane] = scale * sum_p a[plane, p] * (b ? b[plane, p] : 1)   fp32 out, plane = (image, channel)
+ *                    (avg pool: b = NULL, scale = 1/HW; gate gradient: a = dL/dy, b = x, scale = 1)
+ *   rb_plane_scale:  out[plane, p] = a[plane, p] * s[plane] + (t ? t[plane] : 0)
+ *                    (y = x * gate;  dL/dx = dL/dy * gate + dpool / HW)
+ * a / b / out are [planes, HW] contiguous in fp32 / fp16 / bf16; s, t and the reduction result are fp32. */
+int rb_plane_reduce(const void *a, const void *b, float *out, int dtype, int planes, int HW, float scale, void *stream);
+int rb_plane_scale(const void *a, const float *s, const float *t, void *out, int dtype, int planes, int HW, void *stream);
+
 /* ---------------------------------------------------------------- pointwise (1x1) convolutions -- */
 
 /* Conv1x1 of RubiksShiftBlock (rubiksnet/backbone.py:45-47: nn.Conv2d(k=1, bias=False); conv2 / conv3 /

@@ -61,6 +61,10 @@ def _declare(lib):
     lib.rb_bn_act_forward.restype = i
     lib.rb_bn_act_backward.argtypes = [vp] * 9 + [i, i, i, i, i, i, vp, sz, vp]
     lib.rb_bn_act_backward.restype = i
+    lib.rb_plane_reduce.argtypes = [vp, vp, vp, i, i, i, fl, vp]
+    lib.rb_plane_reduce.restype = i
+    lib.rb_plane_scale.argtypes = [vp, vp, vp, vp, i, i, i, vp]
+    lib.rb_plane_scale.restype = i
     lib.rb_pw_conv_forward.argtypes = [vp, vp, i, i, vp, vp, i, i, i, i, i, vp, vp]
     lib.rb_pw_conv_forward.restype = i
     lib.rb_pw_conv_forward_stats.argtypes = [vp, vp, i, i, vp, vp, i, i, i, i, i, vp, vp, sz, ctypes.POINTER(ctypes.c_int), vp]

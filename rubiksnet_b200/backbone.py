@@ -107,7 +107,7 @@ class RubiksShiftBlock(nn.Module):
         out = fused.bn_act(out, self.bn2, relu=True)
         out = self.as3(out)
         if self.se is not None:
-            out = self.se(out)
+            out = fused.se_gate(out, self.se)
         return fused.conv1x1(out, self.conv3.weight, residual=shortcut)
 
 

@@ -18,7 +18,7 @@ import torch
 from . import _lib, ops
 from .rubiksnet_cuda import _on_device
 
-__all__ = ["bn_act", "conv1x1", "rubiks_block", "rubiks_block_supported"]
+__all__ = ["bn_act", "conv1x1", "se_gate", "rubiks_block", "rubiks_block_supported"]
 
 
 class _BNAct(torch.autograd.Function):
@@ -347,6 +347,67 @@ def conv1x1(x, weight, residual=None, stride=1):
     if x.dtype == torch.bfloat16 and weight.dtype in (torch.float32, torch.bfloat16):
         return _Conv1x1TC.apply(x, weight, residual)
     return _Conv1x1.apply(x, weight, residual)
+
+
+# ------------------------------------------------------------------------------------- squeeze-and-excitation
+
+def _plane_reduce(a, b, scale):
+    ni, c = a.shape[0], a.shape[1]
+    hw = a.numel() // max(ni * c, 1)
+    out = torch.empty(ni, c, dtype=torch.float32, device=a.device)
+    with _on_device(a.device), _lib.timed("se_plane_reduce", _lib.nbytes(a, b)):
+        _lib.check(_lib.lib().rb_plane_reduce(_lib.ptr(a), _lib.ptr(b), _lib.ptr(out), _lib.dtype_code(a), ni * c, hw, float(scale),
+                                              _lib.stream_handle(a.device)))
+    return out
+
+
+def _plane_scale(a, s, t):
+    ni, c = a.shape[0], a.shape[1]
+    hw = a.numel() // max(ni * c, 1)
+    out = torch.empty_like(a)
+    with _on_device(a.device), _lib.timed("se_plane_scale", _lib.nbytes(a, out)):
+        _lib.check(_lib.lib().rb_plane_scale(_lib.ptr(a), _lib.ptr(s), _lib.ptr(t), _lib.ptr(out), _lib.dtype_code(a), ni * c, hw,
+                                             _lib.stream_handle(a.device)))
+    return out
+
+
+class _SEGate(torch.autograd.Function):
+    """y = x * sigmoid(W2 relu(W1 avgpool(x)))  (SELayer, rubiksnet/backbone.py:56-71).  The two passes over x (pool,
+    rescale) and the two passes of the backward (sum of g*x per plane, dx = g*gate + dpool/HW) are librubiks_b200 kernels;
+    the gate MLP and its gradients act on [NI, C] / [NI, C/r] matrices."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, x, w1, w2):
+        x = x.contiguous()
+        hw = x.shape[2] * x.shape[3]
+        pooled = _plane_reduce(x, None, 1.0 / hw)                      # [NI, C] fp32
+        w1f, w2f = w1.float(), w2.float()
+        hidden = torch.relu(pooled @ w1f.t())                          # [NI, C/r]
+        gate = torch.sigmoid(hidden @ w2f.t()).contiguous()            # [NI, C]
+        ctx.save_for_backward(x, pooled, hidden, gate, w1f, w2f)
+        ctx.wdtypes = (w1.dtype, w2.dtype)
+        return _plane_scale(x, gate, None)
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, g):
+        x, pooled, hidden, gate, w1f, w2f = ctx.saved_tensors
+        g = g.contiguous()
+        hw = x.shape[2] * x.shape[3]
+        dgate = _plane_reduce(g, x, 1.0)                               # sum_p g * x
+        dz2 = dgate * gate * (1.0 - gate)
+        dw2 = dz2.t() @ hidden
+        dz1 = (dz2 @ w2f) * (hidden > 0).to(dz2.dtype)
+        dw1 = dz1.t() @ pooled
+        dpool = ((dz1 @ w1f) * (1.0 / hw)).contiguous()
+        dx = _plane_scale(g, gate, dpool) if ctx.needs_input_grad[0] else None
+        return dx, dw1.to(ctx.wdtypes[0]), dw2.to(ctx.wdtypes[1])
+
+
+def se_gate(x, se):
+    """SELayer forward on a CUDA NCHW tensor in fp32 / fp16 / bf16 (se.fc = Linear, ReLU, Linear, Sigmoid; no biases)."""
+    return _SEGate.apply(x, se.fc[0].weight, se.fc[2].weight)
 
 
 # ------------------------------------------------------------------------------------- whole block
