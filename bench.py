@@ -52,6 +52,9 @@ def parse():
     ap.add_argument("--ref-autocast", action="store_true",
                     help="--impl reference only: run the reference model under bf16 autocast with .float() casts around its "
                          "(fp32-only) shift ops -- the like-for-like precision arm of SURVEY 8d(1)")
+    ap.add_argument("--graph-multi", default="whole", choices=["whole", "fwdbwd"],
+                    help="N > 1: capture the whole step including the NCCL all-reduce and the SGD update (whole), or only "
+                         "forward + backward with the exchange and the update eager (fwdbwd, round-1 behaviour)")
     ap.add_argument("--graph", default="on", choices=["on", "off"],
                     help="replay the whole step from a CUDA graph (rubiksnet_b200.graph.GraphedStep); off = eager launches")
     return ap.parse_args()
@@ -213,7 +216,7 @@ class Trainer:
         if self.kind != "ours" or self.args.graph != "on":
             return self.step
         from rubiksnet_b200.graph import GraphedStep
-        if self.world == 1 or self.args.infer or os.environ.get("RB_GRAPH_MULTI"):
+        if self.world == 1 or self.args.infer or self.args.graph_multi == "whole":
             if self.graphed is None:
                 self.graphed = GraphedStep(self.step, clips, labels, warmup=2)
             return self.graphed
@@ -231,6 +234,17 @@ class Trainer:
             self.opt.step()
             return loss
         return run
+
+    def close(self):
+        """Releases the captured graph BEFORE the process group goes away: a CUDA graph that holds NCCL kernels keeps the
+        communicator busy, and destroying the communicator first hung the process at exit in round 1 (gpurun_out/s31)."""
+        torch = self.torch
+        torch.cuda.synchronize()
+        if self.graphed is not None:
+            g, self.graphed = self.graphed, None
+            g.graph.reset()
+            del g
+        torch.cuda.synchronize()
 
     def infer(self, clips, labels):
         torch = self.torch
@@ -459,7 +473,7 @@ def main():
               "clips_per_gpu": args.batch, "frames": FRAMES, "num_classes": NUM_CLASSES,
               "parallelism": "dp%d (batch sharded, NCCL grad all-reduce)" % args.gpus,
               "launch": ("eager" if args.graph != "on" or args.impl != "ours" else
-                         "whole step replayed from one CUDA graph" if args.gpus == 1 else
+                         "whole step replayed from one CUDA graph" if args.gpus == 1 or args.graph_multi == "whole" else
                          "forward + backward replayed from one CUDA graph, NCCL all-reduce + SGD eager"),
               "l2": "working set per step (>10 GB of activations) far exceeds the 126 MB L2; no flush needed"}
 
@@ -547,8 +561,10 @@ def main():
             line["cpu_baseline"] = {"value": None, "error": repr(e)}
     if rank == 0:
         print(json.dumps(line))
+    tr.close()
     if world > 1:
         import torch.distributed as dist
+        dist.barrier()
         dist.destroy_process_group()
 
 
