@@ -57,6 +57,8 @@ def parse():
                          "forward + backward with the exchange and the update eager (fwdbwd, round-1 behaviour)")
     ap.add_argument("--graph", default="on", choices=["on", "off"],
                     help="replay the whole step from a CUDA graph (rubiksnet_b200.graph.GraphedStep); off = eager launches")
+    ap.add_argument("--pdl", default="on", choices=["on", "off"],
+                    help="programmatic dependent launch of the library's kernels (rb_set_dependent_launch); off = A/B arm")
     return ap.parse_args()
 
 
@@ -497,6 +499,10 @@ def main():
     world, rank, local = dist_setup(args)
     assert have_cuda, "bench.py needs a CUDA device (there is no CPU fallback for the product path)"
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node %d" % args.gpus
+    if args.impl == "ours":
+        from rubiksnet_b200 import _lib as _rb_lib
+        _rb_lib.set_dependent_launch(args.pdl == "on")
+        config["dependent_launch"] = args.pdl
     tr = Trainer("ours" if args.impl == "ours" else "reference", args, world)
     clips, labels = synthetic_batch(args.batch, 100 + rank)
     dclips, dlabels = clips.cuda(), labels.cuda()

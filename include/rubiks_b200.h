@@ -255,6 +255,14 @@ int rb_shift3d_pw_conv_wgrad(const void *out_grad, const void *x, const void *sh
  *        HW <= 224, or HW % 8 == 0 with a divisor in [64, 256] that is a multiple of 8.
  * Same arithmetic as the plain path (bf16 operands, fp32 accumulation, bf16 result, `+= residual` on the rounded value). */
 #define RB_W_IMAGE 16
+/* OR-ed into weight_dtype (RB_F32 / RB_BF16): the weight buffer was written by rb_pw_weight_pack* (which fence
+ * themselves) or at least two launches before this call on `stream`.  Every kernel of the library is launched with
+ * programmatic stream serialization: it sets up barriers / tensor memory while its predecessor in the stream drains and
+ * waits for that predecessor (griddepcontrol.wait) before touching its results; a resident weight block is staged
+ * before that wait as well.  Packed images (RB_W_IMAGE) are always resident.  Without the flag nothing is read early. */
+#define RB_W_RESIDENT 256
+/* Programmatic dependent launch on (default, 1) / off (0): process-global switch for A/B measurements. */
+void rb_set_dependent_launch(int enabled);
 size_t rb_pw_weight_image_bytes(int rows, int contraction);
 int rb_pw_weight_image_pack(const float *weight, int N, int K, int transposed, void *image, void *stream);
 int rb_pw_conv_image_supported(int NI, int K, int N, int HW, int has_in_scale_bias);

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "librubiks_b200.so")
 
 RB_F32, RB_F64, RB_F16, RB_BF16 = 0, 1, 2, 3
 RB_W_IMAGE = 16  # weight argument of rb_pw_conv_forward is a packed image (rb_pw_weight_image_pack)
+RB_W_RESIDENT = 256  # OR-ed into weight_dtype: the buffer came from rb_pw_weight_pack* (may be staged before the PDL wait)
 RB_IMPL_AUTO, RB_IMPL_GENERIC, RB_IMPL_TILED, RB_IMPL_STRIP = 0, 1, 2, 3
 _DTYPES = {torch.float32: RB_F32, torch.float64: RB_F64, torch.float16: RB_F16, torch.bfloat16: RB_BF16}
 
@@ -33,6 +34,8 @@ def _declare(lib):
     lib.rb_launch_count_reset.restype = None
     lib.rb_set_impl.argtypes = [i]
     lib.rb_set_impl.restype = None
+    lib.rb_set_dependent_launch.argtypes = [i]
+    lib.rb_set_dependent_launch.restype = None
     lib.rb_last_impl.restype = i
     lib.rb_out_len.argtypes = [i, i, i]
     lib.rb_out_len.restype = i
@@ -217,6 +220,11 @@ def reset_launch_count():
 
 def set_impl(impl):
     lib().rb_set_impl(int(impl))
+
+
+def set_dependent_launch(enabled):
+    """Programmatic dependent launch of every library kernel on (default) / off -- for A/B measurements."""
+    lib().rb_set_dependent_launch(int(bool(enabled)))
 
 
 def last_impl():

@@ -9,6 +9,16 @@ thread_local char g_err[512] = {0};
 thread_local int g_last_impl = RB_IMPL_AUTO;
 std::atomic<uint64_t> g_launches{0};
 std::atomic<int> g_forced_impl{RB_IMPL_AUTO};
+std::atomic<int> g_pdl{1};
+
+// Plain (not programmatically serialized) empty kernel: it starts only after everything before it in the stream has
+// completed, and a programmatically launched successor starts only after it -- whatever was written before the fence is
+// "two launches old" for every later kernel (common.cuh).
+__global__ void k_launch_fence() {}
+int launch_fence(cudaStream_t s) {
+    k_launch_fence<<<1, 32, 0, s>>>();
+    return launched("k_launch_fence");
+}
 
 int sm_count() {
     static thread_local int cached_dev = -1, cached = 0;
@@ -137,6 +147,7 @@ const char *rb_last_error(void) { return g_err; }
 uint64_t rb_launch_count(void) { return g_launches.load(); }
 void rb_launch_count_reset(void) { g_launches.store(0); }
 void rb_set_impl(int impl) { g_forced_impl.store(impl); }
+void rb_set_dependent_launch(int enabled) { g_pdl.store(enabled ? 1 : 0); }
 int rb_last_impl(void) { return g_last_impl; }
 
 int rb_out_len(int in_len, int stride, int pad) { return (in_len + 2 * pad - 1) / stride + 1; }
@@ -299,6 +310,7 @@ int rb_shift2d_backward(const void *x, const void *shift, const void *out_grad, 
 }
 
 static int check_weight_dtype(int wdt) {
+    wdt &= ~RB_W_RESIDENT;
     if (wdt != RB_F32 && wdt != RB_BF16) return fail(RB_ERR_INVALID_ARGUMENT, "weight dtype must be RB_F32 or RB_BF16, got %d", wdt);
     return RB_OK;
 }
@@ -306,6 +318,7 @@ static int check_weight_dtype(int wdt) {
 int rb_pw_conv_forward(const void *x, const void *weight, int weight_dtype, int weight_transposed, const void *residual,
                        void *out, int dtype, int NI, int K, int N, int HW, const float *in_scale_bias, void *stream) {
     if (dtype != RB_BF16) return fail(RB_ERR_UNSUPPORTED, "rb_pw_conv_forward: bf16 activations only (got dtype %d)", dtype);
+    if ((weight_dtype & ~RB_W_RESIDENT) == RB_W_IMAGE) weight_dtype = RB_W_IMAGE;
     int rc = weight_dtype == RB_W_IMAGE ? RB_OK : check_weight_dtype(weight_dtype);
     if (rc) return rc;
     if (NI < 0 || K <= 0 || N <= 0 || HW < 0) return fail(RB_ERR_INVALID_ARGUMENT, "bad extent [%d,%d,%d,%d]", NI, K, N, HW);

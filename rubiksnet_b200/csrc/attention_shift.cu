@@ -13,6 +13,7 @@ template <typename T>
 __global__ void __launch_bounds__(kAThreads)
 k_attn_fwd(const T *__restrict__ x, const float *__restrict__ taps, T *__restrict__ out, int Tn, int C,
            int HW) {
+    pdl_sync();
     const int p = blockIdx.x * kAThreads + threadIdx.x;
     const int c = blockIdx.y, n = blockIdx.z;
     if (p >= HW) return;
@@ -35,6 +36,7 @@ __global__ void __launch_bounds__(kAThreads)
 k_attn_bwd(const T *__restrict__ x, const float *__restrict__ taps, const T *__restrict__ og,
            T *__restrict__ gx, float *__restrict__ partial, int Tn, int C, int HW, int want_gx,
            int want_gt) {
+    pdl_sync();
     const int p = blockIdx.x * kAThreads + threadIdx.x;
     const int c = blockIdx.y, n = blockIdx.z;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
@@ -85,6 +87,7 @@ k_attn_bwd(const T *__restrict__ x, const float *__restrict__ taps, const T *__r
 }
 
 __global__ void k_attn_finalize(const float *__restrict__ partial, int parts, float *gtaps, int C) {
+    pdl_sync();
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= C) return;
     const int lane = threadIdx.x & 31;
@@ -119,7 +122,7 @@ extern "C" int rb_attention_shift_forward(const void *x, const float *taps, void
     if (C > 65535 || N > 65535) return fail(RB_ERR_UNSUPPORTED, "attention shift: C or N > 65535");
     dim3 grid(cdiv(HW, kAThreads), C, N);
     cudaStream_t s = (cudaStream_t)stream;
-    RB_DISPATCH_DTYPE(dtype, (k_attn_fwd<T><<<grid, kAThreads, 0, s>>>((const T *)x, taps, (T *)out,
+    RB_DISPATCH_DTYPE(dtype, (launch_kernel(k_attn_fwd<T>, dim3(grid), dim3(kAThreads), 0, s, (const T *)x, taps, (T *)out,
                                                                       Tn, C, HW)));
     return launched("k_attn_fwd");
 }
@@ -149,14 +152,14 @@ extern "C" int rb_attention_shift_backward(const void *x, const float *taps, con
         return fail(RB_ERR_WORKSPACE, "attention shift backward needs %zu workspace bytes, got %zu",
                     need, workspace_bytes);
     dim3 grid(cdiv(HW, kAThreads), C, N);
-    RB_DISPATCH_DTYPE(dtype, (k_attn_bwd<T><<<grid, kAThreads, 0, s>>>(
+    RB_DISPATCH_DTYPE(dtype, (launch_kernel(k_attn_bwd<T>, dim3(grid), dim3(kAThreads), 0, s, 
                                  (const T *)x, taps, (const T *)out_grad, (T *)x_grad,
                                  (float *)workspace, Tn, C, HW, x_grad != nullptr,
                                  taps_grad != nullptr)));
     int rc = launched("k_attn_bwd");
     if (rc || !taps_grad) return rc;
     const int warps = 4;
-    k_attn_finalize<<<cdiv(C, warps), warps * 32, 0, s>>>((const float *)workspace,
+    launch_kernel(k_attn_finalize, dim3(cdiv(C, warps)), dim3(warps * 32), 0, s, (const float *)workspace,
                                                           (int)(grid.x * grid.z), taps_grad, C);
     return launched("k_attn_finalize");
 }

@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(kBT)
 k_bn_reduce(const T *__restrict__ x, const T *__restrict__ dy, const float *__restrict__ mean_invstd,
             const float *__restrict__ scale_bias, double *__restrict__ partial, int NI, int C, int HW, FastDiv vpp,
             int relu) {
+    pdl_sync();
     const int sp = blockIdx.x, c = blockIdx.y, splits = gridDim.x;
     float s0 = 0.f, s1 = 0.f;
     float mean = 0.f, invstd = 1.f, sc = 1.f, bi = 0.f;
@@ -120,7 +121,7 @@ static void launch_bn_reduce(const T *x, const T *dy, const float *mean_invstd, 
     while (V > 1 && HW % V != 0) V >>= 1;
     const FastDiv vpp = make_fastdiv((uint32_t)(HW / V));
 #define RB_BN_REDUCE(VV)                                                                                          \
-    k_bn_reduce<T, MODE, (VV <= VMAX ? VV : 1)><<<grid, kBT, 0, s>>>(x, dy, mean_invstd, scale_bias, partial, NI, C, HW, \
+    launch_kernel(k_bn_reduce<T, MODE, (VV <= VMAX ? VV : 1)>, dim3(grid), dim3(kBT), 0, s, x, dy, mean_invstd, scale_bias, partial, NI, C, HW, \
                                                                     vpp, relu)
     switch (V) {
         case 8: RB_BN_REDUCE(8); break;
@@ -136,6 +137,7 @@ __global__ void k_bn_stats_finalize(const double *__restrict__ partial, int spli
                                     const float *__restrict__ gamma, const float *__restrict__ beta,
                                     float *running_mean, float *running_var, float momentum, float eps,
                                     float *__restrict__ mean_invstd, float *__restrict__ scale_bias) {
+    pdl_sync();
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= C) return;
     const int lane = threadIdx.x & 31;
@@ -167,6 +169,7 @@ __global__ void k_bn_stats_finalize(const double *__restrict__ partial, int spli
 __global__ void k_bn_eval_coeffs(const float *__restrict__ gamma, const float *__restrict__ beta,
                                  const float *__restrict__ running_mean, const float *__restrict__ running_var,
                                  float eps, int C, float *__restrict__ mean_invstd, float *__restrict__ scale_bias) {
+    pdl_sync();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const float invstd = rsqrtf(running_var[c] + eps);
@@ -182,6 +185,7 @@ __global__ void k_bn_bwd_finalize(const double *__restrict__ partial, int splits
                                   const float *__restrict__ gamma, const float *__restrict__ mean_invstd,
                                   int training, float *__restrict__ dgamma, float *__restrict__ dbeta,
                                   float *__restrict__ coef) {
+    pdl_sync();
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= C) return;
     const int lane = threadIdx.x & 31;
@@ -217,6 +221,7 @@ __global__ void __launch_bounds__(kBT)
 k_bn_apply(const T *__restrict__ x, const T *__restrict__ dy, const T *__restrict__ residual,
            const float *__restrict__ scale_bias, const float *__restrict__ coef, T *__restrict__ out,
            int64_t total, int C, FastDiv hw, int relu) {
+    pdl_sync();
     constexpr int V = Vec<T>::N;
     const int64_t nvec = total / V;
     const Pack<T, V> *xp = reinterpret_cast<const Pack<T, V> *>(x);
@@ -309,7 +314,7 @@ using namespace rb;
 int rb::bn_stats_finalize(const double *partial, int splits, int C, double count, const float *gamma, const float *beta,
                           float *running_mean, float *running_var, float momentum, float eps, float *mean_invstd,
                           float *scale_bias, cudaStream_t s) {
-    k_bn_stats_finalize<<<cdiv(C, 4), 128, 0, s>>>(partial, splits, C, count, gamma, beta, running_mean, running_var, momentum,
+    launch_kernel(k_bn_stats_finalize, dim3(cdiv(C, 4)), dim3(128), 0, s, partial, splits, C, count, gamma, beta, running_mean, running_var, momentum,
                                                    eps, mean_invstd, scale_bias);
     return launched("k_bn_stats_finalize");
 }
@@ -328,7 +333,7 @@ int rb::bn_apply_forward(const void *x, const float *scale_bias, void *y, int dt
         const int cap = sm_count() * 16;
         if (blocks > cap) blocks = cap;
         if (blocks < 1) blocks = 1;
-        k_bn_apply<T, 0><<<blocks, kBT, 0, s>>>((const T *)x, nullptr, nullptr, scale_bias, nullptr, (T *)y, total, C, hw, relu);
+        launch_kernel(k_bn_apply<T, 0>, dim3(blocks), dim3(kBT), 0, s, (const T *)x, nullptr, nullptr, scale_bias, nullptr, (T *)y, total, C, hw, relu);
     });
     return launched("k_bn_apply<fwd>");
 }
@@ -361,11 +366,11 @@ extern "C" int rb_bn_act_forward(const void *x, const float *gamma, const float 
         RB_DISPATCH_DTYPE(dtype, (launch_bn_reduce<T, 0>((const T *)x, (const T *)x, nullptr, nullptr, (double *)workspace,
                                                          NI, C, HW, 0, splits, s)));
         if ((rc = launched("k_bn_reduce<stats>"))) return rc;
-        k_bn_stats_finalize<<<cdiv(C, 4), 128, 0, s>>>((const double *)workspace, splits, C, (double)NI * HW, gamma, beta,
+        launch_kernel(k_bn_stats_finalize, dim3(cdiv(C, 4)), dim3(128), 0, s, (const double *)workspace, splits, C, (double)NI * HW, gamma, beta,
                                                        running_mean, running_var, momentum, eps, mean_invstd, scale_bias);
         if ((rc = launched("k_bn_stats_finalize"))) return rc;
     } else {
-        k_bn_eval_coeffs<<<cdiv(C, 128), 128, 0, s>>>(gamma, beta, running_mean, running_var, eps, C, mean_invstd,
+        launch_kernel(k_bn_eval_coeffs, dim3(cdiv(C, 128)), dim3(128), 0, s, gamma, beta, running_mean, running_var, eps, C, mean_invstd,
                                                       scale_bias);
         if ((rc = launched("k_bn_eval_coeffs"))) return rc;
     }
@@ -377,7 +382,7 @@ extern "C" int rb_bn_act_forward(const void *x, const float *gamma, const float 
         const int cap = sm_count() * 16;
         if (blocks > cap) blocks = cap;
         if (blocks < 1) blocks = 1;
-        k_bn_apply<T, 0><<<blocks, kBT, 0, s>>>((const T *)x, nullptr, nullptr, scale_bias, nullptr, (T *)y, total, C, hw,
+        launch_kernel(k_bn_apply<T, 0>, dim3(blocks), dim3(kBT), 0, s, (const T *)x, nullptr, nullptr, scale_bias, nullptr, (T *)y, total, C, hw,
                                                relu);
     });
     return launched("k_bn_apply<fwd>");
@@ -410,7 +415,7 @@ extern "C" int rb_bn_act_backward(const void *x, const void *dy, const void *res
     RB_DISPATCH_DTYPE(dtype, (launch_bn_reduce<T, 1>((const T *)x, (const T *)dy, mean_invstd, scale_bias, partial, NI, C,
                                                      HW, relu, splits, s)));
     if ((rc = launched("k_bn_reduce<bwd>"))) return rc;
-    k_bn_bwd_finalize<<<cdiv(C, 4), 128, 0, s>>>(partial, splits, C, (double)NI * HW, gamma, mean_invstd, training, dgamma,
+    launch_kernel(k_bn_bwd_finalize, dim3(cdiv(C, 4)), dim3(128), 0, s, partial, splits, C, (double)NI * HW, gamma, mean_invstd, training, dgamma,
                                                  dbeta, coef);
     if ((rc = launched("k_bn_bwd_finalize"))) return rc;
     if (!dx) return RB_OK;
@@ -421,7 +426,7 @@ extern "C" int rb_bn_act_backward(const void *x, const void *dy, const void *res
         const int cap = sm_count() * 16;
         if (blocks > cap) blocks = cap;
         if (blocks < 1) blocks = 1;
-        k_bn_apply<T, 1><<<blocks, kBT, 0, s>>>((const T *)x, (const T *)dy, (const T *)residual, scale_bias, coef,
+        launch_kernel(k_bn_apply<T, 1>, dim3(blocks), dim3(kBT), 0, s, (const T *)x, (const T *)dy, (const T *)residual, scale_bias, coef,
                                                (T *)dx, total, C, hw, relu);
     });
     return launched("k_bn_apply<bwd>");

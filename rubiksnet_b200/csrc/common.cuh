@@ -8,6 +8,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <utility>
 
 #include "../../include/rubiks_b200.h"
 
@@ -18,6 +19,7 @@ extern thread_local char g_err[512];
 extern thread_local int g_last_impl;
 extern std::atomic<uint64_t> g_launches;
 extern std::atomic<int> g_forced_impl;
+extern std::atomic<int> g_pdl;  // programmatic dependent launch on (default) / off: rb_set_dependent_launch()
 
 inline int fail(int code, const char *fmt, ...) {
     va_list ap;
@@ -50,6 +52,40 @@ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 int sm_count();
+int launch_fence(cudaStream_t s);  // abi.cu
+
+// ---- programmatic dependent launch ---------------------------------------------------------------
+// A training step is ~1 400 launches of 10-60 us each, so the launch gap, the drain of the previous grid and every
+// kernel's own prologue (barrier init, TMEM allocation, the weight block of the 1x1 convs) are a measurable share of it.
+// Every kernel of the library is launched with the programmatic-stream-serialization attribute and follows ONE rule:
+//     prologue that touches no global memory written by an earlier launch  ->  pdl_wait()  ->  pdl_trigger()  ->  body
+// pdl_wait() (griddepcontrol.wait) returns once the previous kernel in the stream has completed and its writes are
+// visible; triggering only AFTER the wait bounds the overlap to one kernel: when a grid passes its wait, everything
+// older than its predecessor is complete, so a prologue may read data produced two or more launches earlier (the packed
+// weights of a step: rb_pw_weight_pack* launch a fence kernel behind the pack) and never anything newer.  No global
+// writes happen before the wait, so there are no write-after-read hazards against the predecessor either.  Kernels of
+// other libraries (cuDNN conv1, the optimizer) are launched without the attribute and serialize as usual.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() {
+    pdl_wait();
+    pdl_trigger();
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = g_pdl.load(std::memory_order_relaxed) ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // ---- element conversion ----------------------------------------------------------------------
 template <typename T> struct Acc { using type = float; };

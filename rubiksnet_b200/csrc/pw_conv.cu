@@ -272,6 +272,7 @@ struct PwArgs {
     const __nv_bfloat16 *x;    // [NI, K, HW]
     const void *w;             // [N, K] (w_trans: [K, N]), bf16 or fp32 (w_dt)
     int w_dt, w_trans;
+    int w_resident;            // RB_W_RESIDENT: the weight buffer may be read before griddepcontrol.wait
     const __nv_bfloat16 *res;  // [NI, N, HW] or null
     __nv_bfloat16 *out;        // [NI, N, HW]
     const float *a_sb;         // PROD_BNRELU: per input channel (scale, bias) pairs [K, 2]
@@ -530,6 +531,11 @@ __global__ void __launch_bounds__(PROD == PROD_SHIFT3D ? kThreads : kRowThreads,
         __syncwarp();
         tmem_alloc(&hdr->tmem_base, (uint32_t)a.tmem_cols);
     }
+    // Everything up to here touches no global memory.  A weight buffer flagged RB_W_RESIDENT was written at least two
+    // launches ago (common.cuh: programmatic dependent launch), so the weight block is staged while the previous kernel of
+    // the stream is still draining; activations, residual and BN coefficients come from that kernel and wait for it.
+    if (a.w_resident && warp < kProdWarp0) stage_weights(a, smem_w, n0, nrows, tid, kProdWarp0 * 32);
+    pdl_sync();
     if (PROD == PROD_BNRELU)
         for (int k = tid; k < a.Kpad; k += (int)blockDim.x) {
             smem_sb[k] = k < a.K ? a.a_sb[2 * k] : 0.f;
@@ -543,7 +549,7 @@ __global__ void __launch_bounds__(PROD == PROD_SHIFT3D ? kThreads : kRowThreads,
     tc_fence_after();
     const uint32_t tmem_base = hdr->tmem_base;
     if (warp < kProdWarp0) {
-        stage_weights(a, smem_w, n0, nrows, tid, kProdWarp0 * 32);
+        if (!a.w_resident) stage_weights(a, smem_w, n0, nrows, tid, kProdWarp0 * 32);
         fence_proxy_async_smem();
         asm volatile("bar.sync 1, %0;" ::"n"(kProdWarp0 * 32) : "memory");
     }
@@ -1013,7 +1019,7 @@ template <int PROD, int VEC> int launch(const PwArgs &a, dim3 grid, size_t smem_
         if (e != cudaSuccess) return fail(RB_ERR_CUDA, "cudaFuncSetAttribute(k_pw_conv): %s", cudaGetErrorString(e));
         configured_dev = dev;
     }
-    k_pw_conv<PROD, VEC><<<grid, PROD == PROD_SHIFT3D ? kThreads : kRowThreads, smem_bytes, s>>>(a);
+    launch_kernel(k_pw_conv<PROD, VEC>, dim3(grid), dim3(PROD == PROD_SHIFT3D ? kThreads : kRowThreads), smem_bytes, s, a);
     return launched("k_pw_conv");
 }
 
@@ -1100,6 +1106,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_pw_wgrad(const WgArgs a) {
         __syncwarp();
         tmem_alloc(&hdr->tmem_base, (uint32_t)a.tmem_cols);
     }
+    pdl_sync();  // barriers and tensor memory are set up while the previous kernel drains
     if (PROD == PROD_BNRELU)
         for (int k = tid; k < a.N; k += kWgThreads) {
             smem_sb[k] = a.x_sb[2 * k];
@@ -1305,6 +1312,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_pw_wgrad(const WgArgs a) {
 // partial: [splits][N][M] (M contiguous); out: [M][N].  Thread -> (n, m) with m fastest, so the slice reads are coalesced;
 // the transposed write of the small result is not, and does not matter.
 __global__ void k_wg_reduce(const float *__restrict__ partial, float *__restrict__ out, int splits, int M, int N) {
+    pdl_sync();
     const int64_t count = (int64_t)M * N;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
@@ -1368,7 +1376,7 @@ template <int PROD, int VEC> int wg_launch(const WgArgs &a, dim3 grid, size_t sm
         if (e != cudaSuccess) return fail(RB_ERR_CUDA, "cudaFuncSetAttribute(k_pw_wgrad): %s", cudaGetErrorString(e));
         configured_dev = dev;
     }
-    k_pw_wgrad<PROD, VEC><<<grid, kWgThreads, smem_bytes, s>>>(a);
+    launch_kernel(k_pw_wgrad<PROD, VEC>, dim3(grid), dim3(kWgThreads), smem_bytes, s, a);
     return launched("k_pw_wgrad");
 }
 
@@ -1386,6 +1394,7 @@ template <int PROD> int wg_launch_vec(const WgArgs &a, dim3 grid, size_t smem_by
 // weight matrix of the input-gradient GEMM).  32x32 tiles through shared memory: reads and both writes are coalesced.
 __global__ void k_pw_weight_pack(const float *__restrict__ w, __nv_bfloat16 *__restrict__ w_nk, __nv_bfloat16 *__restrict__ w_kn,
                                  int N, int K) {
+    pdl_sync();
     __shared__ float tile[32][33];
     const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8 threads
     for (int r = ty; r < 32; r += 8) {
@@ -1408,6 +1417,7 @@ struct PackItem {
     int N, K;
 };
 __global__ void k_pw_weight_pack_multi(const PackItem *__restrict__ items) {
+    pdl_sync();
     __shared__ float tile[32][33];
     const PackItem it = items[blockIdx.y];
     const int tk = (it.K + 31) / 32, tn = (it.N + 31) / 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -1430,14 +1440,16 @@ __global__ void k_pw_weight_pack_multi(const PackItem *__restrict__ items) {
 
 int pw_weight_pack_multi(const void *items_device, int count, cudaStream_t s) {
     static_assert(sizeof(PackItem) == 32, "rb_pw_pack_item_t layout");
-    k_pw_weight_pack_multi<<<dim3(24, (unsigned)count), 256, 0, s>>>((const PackItem *)items_device);
-    return launched("k_pw_weight_pack_multi");
+    launch_kernel(k_pw_weight_pack_multi, dim3(dim3(24, (unsigned)count)), dim3(256), 0, s, (const PackItem *)items_device);
+    if (int rc = launched("k_pw_weight_pack_multi")) return rc;
+    return launch_fence(s);  // the packed operands are RB_W_RESIDENT for every later launch
 }
 
 int pw_weight_pack(const float *w, void *w_nk, void *w_kn, int N, int K, cudaStream_t s) {
     dim3 grid((unsigned)cdiv(K, 32), (unsigned)cdiv(N, 32));
-    k_pw_weight_pack<<<grid, 256, 0, s>>>(w, (__nv_bfloat16 *)w_nk, (__nv_bfloat16 *)w_kn, N, K);
-    return launched("k_pw_weight_pack");
+    launch_kernel(k_pw_weight_pack, dim3(grid), dim3(256), 0, s, w, (__nv_bfloat16 *)w_nk, (__nv_bfloat16 *)w_kn, N, K);
+    if (int rc = launched("k_pw_weight_pack")) return rc;
+    return launch_fence(s);  // the packed operands are RB_W_RESIDENT for every later launch
 }
 
 #ifdef RB_DEBUG_TRACE
@@ -1452,7 +1464,7 @@ int pw_conv_forward(const void *x, const void *w, int w_dt, int w_trans, const v
                     int N, int HW, const float *a_sb, const void *shift, int shift_dt, int T, int H, int W, cudaStream_t s,
                     double *stats, size_t stats_bytes, int *stats_splits) {
     PwArgs a{};
-    a.x = (const __nv_bfloat16 *)x; a.w = w; a.w_dt = w_dt; a.w_trans = w_trans; a.res = (const __nv_bfloat16 *)residual;
+    a.x = (const __nv_bfloat16 *)x; a.w = w; a.w_dt = w_dt & ~RB_W_RESIDENT; a.w_resident = (w_dt & RB_W_RESIDENT) != 0; a.w_trans = w_trans; a.res = (const __nv_bfloat16 *)residual;
     a.out = (__nv_bfloat16 *)out; a.a_sb = a_sb; a.shift = shift; a.shift_dt = shift_dt;
     a.T = T; a.H = H; a.W = W; a.NI = NI; a.K = K; a.N = N; a.HW = HW;
 #ifdef RB_DEBUG_TRACE
@@ -1504,7 +1516,7 @@ int pw_conv_wgrad(const void *g, const void *x, float *dw, int NI, int M, int N,
     else rc = wg_launch_vec<PROD_PLAIN>(a, grid, smem_bytes, s);
     if (rc) return rc;
     const int64_t count = (int64_t)M * N;
-    k_wg_reduce<<<(unsigned)cdiv64(count, 256), 256, 0, s>>>(a.partial, dw, (int)grid.x, M, N);
+    launch_kernel(k_wg_reduce, dim3((unsigned)cdiv64(count, 256)), dim3(256), 0, s, a.partial, dw, (int)grid.x, M, N);
     return launched("k_wg_reduce");
 }
 

@@ -374,11 +374,16 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
         }
         mbar_init(&hdr->w_full, 1);
         mbar_fence_init();
+        // the weight image was packed (and fenced) at least two launches ago: fetch it while the previous kernel of the
+        // stream drains (common.cuh: programmatic dependent launch); everything else waits for that kernel below
+        mbar_expect_tx(&hdr->w_full, a.w_bytes);
+        bulk_g2s(s_w, a.wimg + (size_t)blockIdx.y * a.w_bytes, a.w_bytes, &hdr->w_full);
     }
     if (warp == 0) {
         __syncwarp();
         tmem_alloc(&hdr->tmem_base, 512u);
     }
+    pdl_sync();
     if (BN)
         for (int k = tid; k < a.Kpad; k += kP2Threads) {
             smem_sb[k] = k < a.K ? a.a_sb[2 * k] : 0.f;
@@ -439,10 +444,6 @@ template <int MODE, bool BN> __global__ void __launch_bounds__(kP2Threads, 1) k_
         __syncwarp();
     } else if (warp == kP2TmaWarp) {
         // ================================ TMA load warp: weights, raw ring, residual blocks =========================
-        if (lane == 0) {
-            mbar_expect_tx(&hdr->w_full, a.w_bytes);
-            bulk_g2s(s_w, a.wimg + (size_t)blockIdx.y * a.w_bytes, a.w_bytes, &hdr->w_full);
-        }
         int it = 0, r = 0, buf = 0;
         uint32_t rph = 0, bph = 0;  // raw-ring phase, staging-buffer phase
         const uint32_t rows_last = (uint32_t)(a.K - (a.k_stages - 1) * a.kc);
@@ -789,7 +790,7 @@ template <int MODE, bool BN> int p2_launch(const P2Args &a, dim3 grid, size_t sm
         if (e != cudaSuccess) return fail(RB_ERR_CUDA, "cudaFuncSetAttribute(k_pw2): %s", cudaGetErrorString(e));
         configured_dev = dev;
     }
-    k_pw2<MODE, BN><<<grid, kP2Threads, smem_bytes, s>>>(a);
+    launch_kernel(k_pw2<MODE, BN>, dim3(grid), dim3(kP2Threads), smem_bytes, s, a);
     return launched("k_pw2");
 }
 
@@ -823,6 +824,7 @@ struct P2PackItem {
     int N, K;
 };
 __global__ void k_pw2_pack_multi(const P2PackItem *__restrict__ items) {
+    pdl_sync();
     const P2PackItem it = items[blockIdx.y];
     for (int trans = 0; trans < 2; ++trans) {
         const int rows = trans ? it.K : it.N, contraction = trans ? it.N : it.K;
@@ -838,6 +840,7 @@ __global__ void k_pw2_pack_multi(const P2PackItem *__restrict__ items) {
 // one thread per 16-byte unit (slice, k-group, row): 8 consecutive k of weight row n0 + n (zero beyond the matrix)
 __global__ void k_pw2_pack(const float *__restrict__ w, unsigned char *__restrict__ img, int rows, int contraction, int trans,
                            int gy, int ncta, int kgroups, uint32_t w_lbo, uint32_t w_bytes) {
+    pdl_sync();
     const int64_t total = (int64_t)gy * kgroups * (ncta + 1);
     const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= total) return;
@@ -876,16 +879,18 @@ int pw2_weight_pack(const float *w, int N, int K, int trans, void *image, cudaSt
     p2_slices(rows, contraction, &gy, &ncta, &kpad, &lbo, &wb);
     const int64_t total = (int64_t)gy * (kpad >> 3) * (ncta + 1);
     // `w` is indexed [N, K] in both cases: W^T[row = k, col = n] = w[n * K + k] = w[col * rows + row]
-    k_pw2_pack<<<(unsigned)cdiv64(total, 256), 256, 0, s>>>(w, (unsigned char *)image, rows, contraction, trans, gy, ncta, kpad >> 3,
+    launch_kernel(k_pw2_pack, dim3((unsigned)cdiv64(total, 256)), dim3(256), 0, s, w, (unsigned char *)image, rows, contraction, trans, gy, ncta, kpad >> 3,
                                                           lbo, wb);
-    return launched("k_pw2_pack");
+    if (int rc = launched("k_pw2_pack")) return rc;
+    return launch_fence(s);  // the packed operands are RB_W_RESIDENT for every later launch
 }
 
 // items: DEVICE array of `count` {const float *weight [N,K]; void *image_fwd; void *image_bwd; int N; int K} (rb_pw_pack_item_t)
 int pw2_weight_pack_multi(const void *items_device, int count, cudaStream_t s) {
     static_assert(sizeof(P2PackItem) == 32, "rb_pw_pack_item_t layout");
-    k_pw2_pack_multi<<<dim3(48, (unsigned)count), 256, 0, s>>>((const P2PackItem *)items_device);
-    return launched("k_pw2_pack_multi");
+    launch_kernel(k_pw2_pack_multi, dim3(dim3(48, (unsigned)count)), dim3(256), 0, s, (const P2PackItem *)items_device);
+    if (int rc = launched("k_pw2_pack_multi")) return rc;
+    return launch_fence(s);  // the packed operands are RB_W_RESIDENT for every later launch
 }
 
 // 0: no image path; 1: supported; 2: supported and measured faster than the first-generation kernel for this geometry.

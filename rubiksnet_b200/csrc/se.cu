@@ -19,6 +19,7 @@ template <typename T, int V> struct alignas(sizeof(T) * V) SePack { T v[V]; };
 template <typename T, int V>
 __global__ void __launch_bounds__(256) k_plane_reduce(const T *__restrict__ a, const T *__restrict__ b, float *__restrict__ out,
                                                       int planes, int HW, float scale) {
+    pdl_sync();
     const int plane = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (plane >= planes) return;
     const T *pa = a + (int64_t)plane * HW, *pb = b ? b + (int64_t)plane * HW : nullptr;
@@ -41,6 +42,7 @@ __global__ void __launch_bounds__(256) k_plane_reduce(const T *__restrict__ a, c
 template <typename T, int V>
 __global__ void __launch_bounds__(256) k_plane_scale(const T *__restrict__ a, const float *__restrict__ s, const float *__restrict__ t,
                                                      T *__restrict__ out, int64_t nvec, int vec_per_plane) {
+    pdl_sync();
     for (int64_t v = (int64_t)blockIdx.x * 256 + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * 256) {
         const int plane = (int)(v / vec_per_plane);
         const float sc = __ldg(s + plane), tt = t ? __ldg(t + plane) : 0.f;
@@ -74,7 +76,7 @@ extern "C" int rb_plane_reduce(const void *a, const void *b, float *out, int dty
     const unsigned blocks = (unsigned)cdiv(planes, 8);
     const int v = pick_v(HW, dtype_size(dtype), a, b, nullptr);
 #define RB_SE_RED(VV)                                                                                                    \
-    RB_DISPATCH_DTYPE(dtype, (k_plane_reduce<T, (VV * sizeof(T) <= 16 ? VV : 1)><<<blocks, 256, 0, s>>>((const T *)a, (const T *)b, \
+    RB_DISPATCH_DTYPE(dtype, (launch_kernel(k_plane_reduce<T, (VV * sizeof(T) <= 16 ? VV : 1)>, dim3(blocks), dim3(256), 0, s, (const T *)a, (const T *)b, \
                                                                                                        out, planes, HW, scale)))
     switch (v) {
         case 8: RB_SE_RED(8); break;
@@ -99,7 +101,7 @@ extern "C" int rb_plane_scale(const void *a, const float *s_, const float *t, vo
     const int cap = sm_count() * 16;
     if (blocks > cap) blocks = cap;
 #define RB_SE_SC(VV)                                                                                                   \
-    RB_DISPATCH_DTYPE(dtype, (k_plane_scale<T, (VV * sizeof(T) <= 16 ? VV : 1)><<<blocks, 256, 0, s>>>((const T *)a, s_, t, (T *)out, \
+    RB_DISPATCH_DTYPE(dtype, (launch_kernel(k_plane_scale<T, (VV * sizeof(T) <= 16 ? VV : 1)>, dim3(blocks), dim3(256), 0, s, (const T *)a, s_, t, (T *)out, \
                                                                                                       nvec, HW / v)))
     switch (v) {
         case 8: RB_SE_SC(8); break;

@@ -23,6 +23,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_shift2d_fwd(const T *__restrict__ x, const void *__restrict__ shift, int sdt, T *__restrict__ out,
               Geom2 g, int bpp, int quantize) {
+    pdl_sync();
     using A = typename Acc<T>::type;
     const int plane = blockIdx.x / bpp, chunk = blockIdx.x % bpp;
     const int c = plane % g.C;
@@ -64,6 +65,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_shift2d_bwd_input(const void *__restrict__ shift, int sdt, const T *__restrict__ og,
                     T *__restrict__ gin, Geom2 g, int bpp, int quantize) {
+    pdl_sync();
     using A = typename Acc<T>::type;
     const int plane = blockIdx.x / bpp, chunk = blockIdx.x % bpp;
     const int c = plane % g.C;
@@ -100,6 +102,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_shift2d_bwd_shift(const T *__restrict__ x, const void *__restrict__ shift, int sdt,
                     const T *__restrict__ og, double *__restrict__ partial, Geom2 g, int chunks) {
+    pdl_sync();
     using A = typename Acc<T>::type;
     const int chunk = blockIdx.x, c = blockIdx.y;
     const A offh = ld_param<A>(shift, sdt, c), offw = ld_param<A>(shift, sdt, g.C + c);
@@ -153,6 +156,7 @@ k_shift2d_bwd_shift(const T *__restrict__ x, const void *__restrict__ shift, int
 template <typename A>
 __global__ void k_shift2d_finalize(const double *__restrict__ partial, int parts, void *shift_grad,
                                    int sdt, int C, int normalize) {
+    pdl_sync();
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= C) return;
     const int lane = threadIdx.x & 31;
@@ -188,7 +192,7 @@ int shift2d_forward_generic(const void *x, const void *shift, void *out, int dt,
     const int64_t blocks = (int64_t)g.N * g.C * bpp;
     if (blocks == 0) return RB_OK;
     if (blocks > 0x7fffffffLL) return fail(RB_ERR_UNSUPPORTED, "shift2d forward: tensor too large");
-    RB_DISPATCH_DTYPE(dt, (k_shift2d_fwd<T><<<(unsigned)blocks, kThreads, 0, s>>>(
+    RB_DISPATCH_DTYPE(dt, (launch_kernel(k_shift2d_fwd<T>, dim3((unsigned)blocks), dim3(kThreads), 0, s, 
                               (const T *)x, shift, sdt, (T *)out, g, bpp, quantize)));
     return launched("k_shift2d_fwd");
 }
@@ -199,7 +203,7 @@ int shift2d_bwd_input_generic(const void *shift, const void *og, void *gin, int 
     const int64_t blocks = (int64_t)g.N * g.C * bpp;
     if (blocks == 0) return RB_OK;
     if (blocks > 0x7fffffffLL) return fail(RB_ERR_UNSUPPORTED, "shift2d backward: tensor too large");
-    RB_DISPATCH_DTYPE(dt, (k_shift2d_bwd_input<T><<<(unsigned)blocks, kThreads, 0, s>>>(
+    RB_DISPATCH_DTYPE(dt, (launch_kernel(k_shift2d_bwd_input<T>, dim3((unsigned)blocks), dim3(kThreads), 0, s, 
                               shift, sdt, (const T *)og, (T *)gin, g, bpp, quantize)));
     return launched("k_shift2d_bwd_input");
 }
@@ -210,16 +214,16 @@ int shift2d_bwd_shift_generic(const void *x, const void *shift, const void *og, 
     const int chunks = shift2d_bwd_chunks(g);
     if (g.C > 65535) return fail(RB_ERR_UNSUPPORTED, "shift2d backward: C > 65535");
     dim3 grid(chunks, g.C);
-    RB_DISPATCH_DTYPE(dt, (k_shift2d_bwd_shift<T><<<grid, kThreads, 0, s>>>(
+    RB_DISPATCH_DTYPE(dt, (launch_kernel(k_shift2d_bwd_shift<T>, dim3(grid), dim3(kThreads), 0, s, 
                               (const T *)x, shift, sdt, (const T *)og, partial, g, chunks)));
     int rc = launched("k_shift2d_bwd_shift");
     if (rc) return rc;
     const int warps = 4;
     if (dt == RB_F64)
-        k_shift2d_finalize<double><<<cdiv(g.C, warps), warps * 32, 0, s>>>(partial, chunks, shift_grad,
+        launch_kernel(k_shift2d_finalize<double>, dim3(cdiv(g.C, warps)), dim3(warps * 32), 0, s, partial, chunks, shift_grad,
                                                                           sdt, g.C, normalize);
     else
-        k_shift2d_finalize<float><<<cdiv(g.C, warps), warps * 32, 0, s>>>(partial, chunks, shift_grad,
+        launch_kernel(k_shift2d_finalize<float>, dim3(cdiv(g.C, warps)), dim3(warps * 32), 0, s, partial, chunks, shift_grad,
                                                                          sdt, g.C, normalize);
     return launched("k_shift2d_finalize");
 }

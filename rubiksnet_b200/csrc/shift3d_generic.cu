@@ -27,6 +27,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_shift3d_fwd_generic(const T *__restrict__ x, const void *__restrict__ shift, int sdt,
                       T *__restrict__ out, Geom3 g, int bpp, int quantize) {
+    pdl_sync();
     using A = typename Acc<T>::type;
     const int plane = blockIdx.x / bpp, chunk = blockIdx.x % bpp;
     const int c = plane % g.C, nt = plane / g.C, to = nt % g.To, n = nt / g.To;
@@ -90,6 +91,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_shift3d_bwd_input_generic(const void *__restrict__ shift, int sdt, const T *__restrict__ og,
                             T *__restrict__ gin, Geom3 g, int bpp, int quantize) {
+    pdl_sync();
     using A = typename Acc<T>::type;
     const int plane = blockIdx.x / bpp, chunk = blockIdx.x % bpp;
     const int c = plane % g.C, nt = plane / g.C, t = nt % g.T, n = nt / g.T;
@@ -153,6 +155,7 @@ __global__ void __launch_bounds__(kThreads)
 k_shift3d_bwd_shift_generic(const T *__restrict__ x, const void *__restrict__ shift, int sdt,
                             const T *__restrict__ og, double *__restrict__ partial, Geom3 g,
                             int chunks) {
+    pdl_sync();
     using A = typename Acc<T>::type;
     const int chunk = blockIdx.x, c = blockIdx.y;
     const A st = ld_param<A>(shift, sdt, c), sh = ld_param<A>(shift, sdt, g.C + c),
@@ -218,6 +221,7 @@ k_shift3d_bwd_shift_generic(const T *__restrict__ x, const void *__restrict__ sh
 template <typename A>
 __global__ void k_shift3d_finalize(const double *__restrict__ partial, int parts, void *shift_grad,
                                    int sdt, int C, int normalize, A factor) {
+    pdl_sync();
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= C) return;
     const int lane = threadIdx.x & 31;
@@ -271,7 +275,7 @@ int shift3d_forward_generic(const void *x, const void *shift, void *out, int dt,
     const int64_t blocks = (int64_t)g.N * g.To * g.C * bpp;
     if (blocks == 0) return RB_OK;
     if (blocks > 0x7fffffffLL) return fail(RB_ERR_UNSUPPORTED, "shift3d forward: tensor too large");
-    RB_DISPATCH_DTYPE(dt, (k_shift3d_fwd_generic<T><<<(unsigned)blocks, kThreads, 0, s>>>(
+    RB_DISPATCH_DTYPE(dt, (launch_kernel(k_shift3d_fwd_generic<T>, dim3((unsigned)blocks), dim3(kThreads), 0, s, 
                               (const T *)x, shift, sdt, (T *)out, g, bpp, quantize)));
     return launched("k_shift3d_fwd_generic");
 }
@@ -283,7 +287,7 @@ int shift3d_bwd_input_generic(const void *shift, const void *og, void *gin, int 
     const int64_t blocks = (int64_t)g.N * g.T * g.C * bpp;
     if (blocks == 0) return RB_OK;
     if (blocks > 0x7fffffffLL) return fail(RB_ERR_UNSUPPORTED, "shift3d backward: tensor too large");
-    RB_DISPATCH_DTYPE(dt, (k_shift3d_bwd_input_generic<T><<<(unsigned)blocks, kThreads, 0, s>>>(
+    RB_DISPATCH_DTYPE(dt, (launch_kernel(k_shift3d_bwd_input_generic<T>, dim3((unsigned)blocks), dim3(kThreads), 0, s, 
                               shift, sdt, (const T *)og, (T *)gin, g, bpp, quantize)));
     return launched("k_shift3d_bwd_input_generic");
 }
@@ -292,10 +296,10 @@ int shift3d_finalize(const double *partial, int parts, void *shift_grad, int dt,
                      int normalize, double factor, cudaStream_t s) {
     const int warps = 4;
     if (dt == RB_F64)
-        k_shift3d_finalize<double><<<cdiv(C, warps), warps * 32, 0, s>>>(partial, parts, shift_grad,
+        launch_kernel(k_shift3d_finalize<double>, dim3(cdiv(C, warps)), dim3(warps * 32), 0, s, partial, parts, shift_grad,
                                                                          sdt, C, normalize, factor);
     else
-        k_shift3d_finalize<float><<<cdiv(C, warps), warps * 32, 0, s>>>(
+        launch_kernel(k_shift3d_finalize<float>, dim3(cdiv(C, warps)), dim3(warps * 32), 0, s, 
             partial, parts, shift_grad, sdt, C, normalize, (float)factor);
     return launched("k_shift3d_finalize");
 }
@@ -306,7 +310,7 @@ int shift3d_bwd_shift_generic(const void *x, const void *shift, const void *og, 
     const int chunks = generic_bwd_chunks(g);
     if (g.C > 65535) return fail(RB_ERR_UNSUPPORTED, "shift3d backward: C > 65535");
     dim3 grid(chunks, g.C);
-    RB_DISPATCH_DTYPE(dt, (k_shift3d_bwd_shift_generic<T><<<grid, kThreads, 0, s>>>(
+    RB_DISPATCH_DTYPE(dt, (launch_kernel(k_shift3d_bwd_shift_generic<T>, dim3(grid), dim3(kThreads), 0, s, 
                               (const T *)x, shift, sdt, (const T *)og, partial, g, chunks)));
     int rc = launched("k_shift3d_bwd_shift_generic");
     if (rc) return rc;

@@ -123,6 +123,7 @@ __device__ __forceinline__ float sc_sg(int d, bool integer) {
 
 template <typename T, int MODE, int R, bool VEC>
 __global__ void __launch_bounds__(kSNT) k_shift3d_strip(const StripArgs a) {
+    pdl_sync();
     constexpr int ES = (int)sizeof(T);
     constexpr int CW = StripTraits<T>::CW;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -505,7 +506,7 @@ template <typename T, int MODE, int R, bool VEC> static int strip_launch(const S
         configured_dev = dev;
     }
     const unsigned blocks = (unsigned)((int64_t)a.N * a.cfg.groups * a.cfg.row_tiles);
-    k_shift3d_strip<T, MODE, R, VEC><<<blocks, kSNT, a.cfg.smem_bytes, s>>>(a);
+    launch_kernel(k_shift3d_strip<T, MODE, R, VEC>, dim3(blocks), dim3(kSNT), a.cfg.smem_bytes, s, a);
     return launched(MODE == SMODE_FWD ? "k_shift3d_strip<fwd>" : "k_shift3d_strip<bwd>");
 }
 
@@ -555,6 +556,7 @@ int shift3d_backward_strip(const void *x, const void *shift, const void *og, voi
 // ---- 2D shift on [N, C, H, W] through the same kernels: every image is a one-frame clip, the shift has no T row ---------
 __global__ void k_shift2d_strip_finalize(const double *__restrict__ partial, int parts, void *shift_grad, int sdt, int C,
                                          int normalize) {
+    pdl_sync();
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= C) return;
     const int lane = threadIdx.x & 31;
@@ -614,7 +616,7 @@ int shift2d_backward_strip(const void *x, const void *shift, const void *og, voi
     int rc = strip_dtype<SMODE_BWD>(dt, a, s);
     if (rc || !gshift) return rc;
     const int warps = 4;
-    k_shift2d_strip_finalize<<<cdiv(g.C, warps), warps * 32, 0, s>>>((const double *)workspace, g.N * a.cfg.row_tiles, gshift, sdt,
+    launch_kernel(k_shift2d_strip_finalize, dim3(cdiv(g.C, warps)), dim3(warps * 32), 0, s, (const double *)workspace, g.N * a.cfg.row_tiles, gshift, sdt,
                                                                     g.C, normalize);
     return launched("k_shift2d_strip_finalize");
 }

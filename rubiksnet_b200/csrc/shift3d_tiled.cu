@@ -122,6 +122,7 @@ __device__ __forceinline__ float coef_sg(int d, bool integer) {
 
 template <typename T, int MODE, int K>
 __global__ void __launch_bounds__(kNW * 32) k_shift3d_tiled(const TiledArgs a) {
+    pdl_sync();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);           // [kMaxFrames]
     double *red = reinterpret_cast<double *>(smem_raw + 128);          // [kNW][3]
@@ -499,7 +500,7 @@ template <typename T, int MODE, int K> static int launch_k(const TiledArgs &a, c
         configured_dev = dev;
     }
     const unsigned blocks = (unsigned)((int64_t)a.N * a.cfg.groups * a.cfg.row_tiles);
-    k_shift3d_tiled<T, MODE, K><<<blocks, kNW * 32, a.cfg.smem_bytes, s>>>(a);
+    launch_kernel(k_shift3d_tiled<T, MODE, K>, dim3(blocks), dim3(kNW * 32), a.cfg.smem_bytes, s, a);
     return launched(MODE == MODE_FWD ? "k_shift3d_tiled<fwd>" : "k_shift3d_tiled<bwd>");
 }
 

@@ -261,7 +261,7 @@ class _Conv1x1TC(torch.autograd.Function):
             w_nk, w_kn = weight, None
         w_kn_t, ctx.wmeta = _wsave(w_kn)
         ctx.save_for_backward(x, weight, w_kn_t)
-        return ops.pw_conv(x, w_nk, residual=residual)
+        return ops.pw_conv(x, w_nk, residual=residual, resident=w_kn is not None)
 
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
@@ -271,7 +271,7 @@ class _Conv1x1TC(torch.autograd.Function):
         g = g.contiguous()
         gx = None
         if ctx.needs_input_grad[0]:
-            gx = (ops.pw_conv(g, w_kn, name="pw_conv<dgrad>") if w_kn is not None
+            gx = (ops.pw_conv(g, w_kn, name="pw_conv<dgrad>", resident=True) if w_kn is not None
                   else ops.pw_conv(g, weight, transposed=True, name="pw_conv<dgrad>"))
         gw = None
         if ctx.needs_input_grad[1]:
@@ -463,11 +463,11 @@ class _RubiksBlockFn(torch.autograd.Function):
         else:
             _, mi1, sb1 = ops.bn_forward(x, g1, b1, rm1, rv1, tr1, mom1, eps1, relu=True, apply=False)
         if tr2 and EPILOGUE_BN_STATS and not isinstance(w2_nk, ops.WeightImage):
-            y2, st2 = ops.pw_conv(x, w2_nk, in_scale_bias=sb1, name="pw_conv<bn+relu>", stats=True)
+            y2, st2 = ops.pw_conv(x, w2_nk, in_scale_bias=sb1, name="pw_conv<bn+relu>", stats=True, resident=True)
             mi2, sb2 = ops.bn_finalize(st2, count, g2, b2, rm2, rv2, mom2, eps2)
             a2 = ops.bn_apply(y2, sb2, relu=True)
         else:
-            y2 = ops.pw_conv(x, w2_nk, in_scale_bias=sb1, name="pw_conv<bn+relu>")
+            y2 = ops.pw_conv(x, w2_nk, in_scale_bias=sb1, name="pw_conv<bn+relu>", resident=True)
             a2, mi2, sb2 = ops.bn_forward(y2, g2, b2, rm2, rv2, tr2, mom2, eps2, relu=True, apply=True)
         out_stats = None
         if FUSE_SHIFT_CONV3 and not isinstance(w3_nk, ops.WeightImage):
@@ -476,9 +476,9 @@ class _RubiksBlockFn(torch.autograd.Function):
         else:
             s3 = _shift3d_forward(a2, shift, frames)
             if EPILOGUE_BN_STATS and not isinstance(w3_nk, ops.WeightImage):
-                out, out_stats = ops.pw_conv(s3, w3_nk, residual=x, name="pw_conv<+residual>", stats=True)
+                out, out_stats = ops.pw_conv(s3, w3_nk, residual=x, name="pw_conv<+residual>", stats=True, resident=True)
             else:
-                out = ops.pw_conv(s3, w3_nk, residual=x, name="pw_conv<+residual>")
+                out = ops.pw_conv(s3, w3_nk, residual=x, name="pw_conv<+residual>", resident=True)
         w2_kn_t, m2 = _wsave(w2_kn)
         w3_kn_t, m3 = _wsave(w3_kn)
         ctx.save_for_backward(x, y2, a2, s3, mi1, sb1, mi2, sb2, g1, g2, w2, w3, shift, w2_kn_t, w3_kn_t)
@@ -497,7 +497,7 @@ class _RubiksBlockFn(torch.autograd.Function):
         w2_kn, w3_kn = _wload(w2_kn, ctx.wmeta[0]), _wload(w3_kn, ctx.wmeta[1])
         g = g.contiguous()
         need = ctx.needs_input_grad
-        gs = ops.pw_conv(g, w3_kn, name="pw_conv<dgrad>")
+        gs = ops.pw_conv(g, w3_kn, name="pw_conv<dgrad>", resident=True)
         gw3 = None
         if need[7]:
             gw3 = (ops.shift3d_pw_conv_wgrad(g, a2, shift, frames) if s3 is None else ops.pw_conv_wgrad(g, s3)).view(w3.shape)
@@ -506,7 +506,7 @@ class _RubiksBlockFn(torch.autograd.Function):
         del gs
         gy2, dg2, db2 = ops.bn_backward(y2, ga2, None, g2, mi2, sb2, tr2, relu=True)
         del ga2
-        go = ops.pw_conv(gy2, w2_kn, name="pw_conv<dgrad>")
+        go = ops.pw_conv(gy2, w2_kn, name="pw_conv<dgrad>", resident=True)
         gw2 = ops.pw_conv_wgrad(gy2, x, in_scale_bias=sb1, name="pw_conv_wgrad<bn+relu>").view(w2.shape) if need[3] else None
         del gy2
         gx, dg1, db1 = ops.bn_backward(x, go, g, g1, mi1, sb1, tr1, relu=True, need_dx=need[0])

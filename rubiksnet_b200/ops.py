@@ -135,11 +135,13 @@ def pw_weight_images(weight):
     return WeightImage(fwd, n, k), WeightImage(bwd, k, n)
 
 
-def pw_conv(x, weight, residual=None, in_scale_bias=None, transposed=False, name="pw_conv", stats=False):
+def pw_conv(x, weight, residual=None, in_scale_bias=None, transposed=False, name="pw_conv", stats=False, resident=False):
     """out[i,n,p] = sum_k W[n,k] A[i,k,p] (+ residual).  weight: Conv2d parameter [N,K,1,1] / [N,K] (fp32 or bf16), or a
     WeightImage (second-generation TMA kernel); transposed=True reads a plain weight as [K,N] (input gradient of that
-    conv).  A = relu(x*scale+bias) with in_scale_bias."""
+    conv).  A = relu(x*scale+bias) with in_scale_bias.  resident=True: `weight` came out of pw_weight_pack (RB_W_RESIDENT: the
+    kernel stages it while the previous kernel of the stream is still draining)."""
     assert x.dtype == BF16 and x.is_contiguous()
+    rflag = _lib.RB_W_RESIDENT if resident else 0
     if isinstance(weight, WeightImage):
         assert not transposed and not stats
         ni, k, n = x.shape[0], x.shape[1], weight.rows
@@ -170,12 +172,12 @@ def pw_conv(x, weight, residual=None, in_scale_bias=None, transposed=False, name
                 partial = torch.empty(n * _MAX_STAT_SPLITS * 2, dtype=torch.float64, device=x.device)
                 splits = ctypes.c_int(0)
                 _lib.check(_lib.lib().rb_pw_conv_forward_stats(
-                    _lib.ptr(x), _lib.ptr(weight), _wdt(weight), int(transposed), _lib.ptr(residual), _lib.ptr(out),
+                    _lib.ptr(x), _lib.ptr(weight), _wdt(weight) | rflag, int(transposed), _lib.ptr(residual), _lib.ptr(out),
                     _lib.RB_BF16, ni, k, n, hw, _lib.ptr(in_scale_bias), _lib.ptr(partial), partial.numel() * 8,
                     ctypes.byref(splits), _lib.stream_handle(x.device)))
                 return out, (partial, splits.value)
             _lib.check(_lib.lib().rb_pw_conv_forward(
-                _lib.ptr(x), _lib.ptr(weight), _wdt(weight), int(transposed), _lib.ptr(residual), _lib.ptr(out), _lib.RB_BF16,
+                _lib.ptr(x), _lib.ptr(weight), _wdt(weight) | rflag, int(transposed), _lib.ptr(residual), _lib.ptr(out), _lib.RB_BF16,
                 ni, k, n, hw, _lib.ptr(in_scale_bias), _lib.stream_handle(x.device)))
     return out
 
