@@ -364,6 +364,8 @@ def summarize_roofline(agg):
     tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
     # the dominant KERNEL: the timed call names split k_pw_conv / k_pw_wgrad by role (dgrad, +residual, bn+relu producer)
     def family(name):
+        if name.startswith("pw_conv_tf32"):
+            return "pw_conv_tf32"
         return "pw_conv_wgrad" if name.startswith("pw_conv_wgrad") else "pw_conv" if name.startswith("pw_conv") else name
     fam = {}
     for name, d in agg.items():
@@ -371,8 +373,9 @@ def summarize_roofline(agg):
         for key in f:
             f[key] += d[key]
     top_family = max(fam, key=lambda k: fam[k]["ms"])
-    if top_family in ("pw_conv", "pw_conv_wgrad"):
-        label = {"pw_conv": "k_pw_conv (all roles: " , "pw_conv_wgrad": "k_pw_wgrad (all roles: "}[top_family]
+    if top_family in ("pw_conv", "pw_conv_wgrad", "pw_conv_tf32"):
+        label = {"pw_conv": "k_pw_conv (all roles: ", "pw_conv_wgrad": "k_pw_wgrad (all roles: ",
+                 "pw_conv_tf32": "k_pw_tf32 (all roles: "}[top_family]
         label += ", ".join(sorted(n for n in agg if family(n) == top_family)) + ")"
         agg = dict(agg)
         agg[label] = fam[top_family]
@@ -387,7 +390,8 @@ def summarize_roofline(agg):
              "algorithmic_bytes_per_step": d["bytes"], "kernel_ms_per_step": round(d["ms"], 3)}
         if d["flops"]:
             e["tensor_tflops"] = round(d["flops"] / d["ms"] / 1e9, 1)
-            e["tensor_frac"] = round(d["flops"] / d["ms"] / 1e9 / tf_peak, 4)
+            # TF32 runs at half the bf16 rate: the measured bf16 peak / 2 is the denominator for the tf32 kernel
+            e["tensor_frac"] = round(d["flops"] / d["ms"] / 1e9 / (tf_peak / 2 if "tf32" in name else tf_peak), 4)
         return e
 
     out = {"bound": "hbm", "peak": peak, "unit": "GB/s", "traffic": None, "peak_source": peak_src}

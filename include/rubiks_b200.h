@@ -194,6 +194,17 @@ int rb_pw_conv_forward_stats(const void *x, const void *weight, int weight_dtype
                              const float *in_scale_bias, double *stats_partial, size_t stats_bytes, int *stats_splits,
                              void *stream);
 
+/* 1x1 convolution on fp32 activations as a tcgen05 kind::tf32 GEMM (csrc/pw_conv_tf32.cu): the fp32 inference path of
+ * RubiksShiftBlock (rubiksnet/backbone.py:123-135; the reference runs cuDNN TF32 convolutions between separate BatchNorm /
+ * ReLU passes).  x [NI, K, HW], weight [N, K] fp32 (the Conv2d parameter), residual / out [NI, N, HW] fp32:
+ *     out = [relu]( conv(A) * out_scale[n] + out_bias[n] ) + residual,   A = x  or  relu(x * in_scale[k] + in_bias[k])
+ * in_scale_bias [K, 2] / out_scale_bias [N, 2] are eval-mode BatchNorm coefficients as produced by rb_bn_act_forward
+ * (training = 0); each may be NULL, as may residual (which may alias out).  Operands are rounded to TF32 (10-bit
+ * mantissa), accumulation and everything after it is fp32.  flags: RB_W_RESIDENT or 0. */
+int rb_pw_conv_forward_f32(const float *x, const float *weight, const float *residual, float *out, int NI, int K, int N,
+                           int HW, const float *in_scale_bias, const float *out_scale_bias, int out_relu, int flags,
+                           void *stream);
+
 /* Batch statistics -> (mean, invstd), (scale, bias) and the running-statistics update of nn.BatchNorm2d in training
  * mode, from partial sums [C][splits][2] over `count` elements per channel (what rb_bn_act_forward does after its own
  * reduction pass).  running_mean / running_var may be NULL. */

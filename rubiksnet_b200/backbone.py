@@ -93,6 +93,8 @@ class RubiksShiftBlock(nn.Module):
     def _forward_fused(self, x):
         """Same arithmetic with librubiks_b200's BN+ReLU passes and GEMM 1x1 convolutions; the residual add is the
         epilogue of the conv3 GEMM.  Identity-shortcut 3D blocks in bf16 run as one fused autograd Function."""
+        if FUSED_WHOLE_BLOCK and fused.eval_block_supported(self, x):
+            return fused.eval_block(self, x)
         if FUSED_WHOLE_BLOCK and fused.rubiks_block_supported(self, x):
             return fused.rubiks_block(self, x)
         out = fused.bn_act(x, self.bn1, relu=True)

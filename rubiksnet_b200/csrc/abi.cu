@@ -81,6 +81,8 @@ void pw2_set_tuning(int op_stages, int kc, int wait_ns);
 #ifdef RB_DEBUG_TRACE
 void pw2_set_debug(int flags);
 #endif
+int pw_tf32_forward(const float *x, const float *w, const float *res, float *out, int NI, int K, int N, int HW,
+                    const float *in_sb, const float *out_sb, int relu, int resident, cudaStream_t s);
 int pw2_forward(const void *x, const void *wimg, const void *residual, void *out, int NI, int K, int N, int HW,
                 const float *a_sb, cudaStream_t s);
 #ifdef RB_DEBUG_TRACE
@@ -333,6 +335,20 @@ int rb_pw_conv_forward(const void *x, const void *weight, int weight_dtype, int 
     }
     return pw_conv_forward(x, weight, weight_dtype, weight_transposed != 0, residual, out, NI, K, N, HW, in_scale_bias,
                            nullptr, 0, 0, 0, 0, (cudaStream_t)stream);
+}
+
+int rb_pw_conv_forward_f32(const float *x, const float *weight, const float *residual, float *out, int NI, int K, int N, int HW,
+                           const float *in_scale_bias, const float *out_scale_bias, int out_relu, int flags, void *stream) {
+    if (NI < 0 || K <= 0 || N <= 0 || HW < 0) return fail(RB_ERR_INVALID_ARGUMENT, "bad extent [%d,%d,%d,%d]", NI, K, N, HW);
+    if ((int64_t)NI * K * HW > 0x7fffffffLL || (int64_t)NI * N * HW > 0x7fffffffLL)
+        return fail(RB_ERR_UNSUPPORTED, "tensors with more than 2^31-1 elements are not supported");
+    if ((int64_t)NI * HW == 0) return RB_OK;
+    if (!x || !weight || !out) return fail(RB_ERR_INVALID_ARGUMENT, "null pointer");
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(weight) | reinterpret_cast<uintptr_t>(out) |
+         reinterpret_cast<uintptr_t>(residual)) & 3)
+        return fail(RB_ERR_INVALID_ARGUMENT, "rb_pw_conv_forward_f32: pointers must be 4-byte aligned");
+    return pw_tf32_forward(x, weight, residual, out, NI, K, N, HW, in_scale_bias, out_scale_bias, out_relu != 0,
+                           (flags & RB_W_RESIDENT) != 0, (cudaStream_t)stream);
 }
 
 size_t rb_pw_weight_image_bytes(int rows, int contraction) { return pw2_weight_image_bytes(rows, contraction); }

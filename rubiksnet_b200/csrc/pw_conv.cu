@@ -1316,8 +1316,18 @@ __global__ void k_wg_reduce(const float *__restrict__ partial, float *__restrict
     const int64_t count = (int64_t)M * N;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
+    // fixed summation order (deterministic); the loads of 8 slices are issued together
     float s = 0.f;
-    for (int k = 0; k < splits; ++k) s += partial[(int64_t)k * count + i];
+    const float *p = partial + i;
+    int k = 0;
+    for (; k + 8 <= splits; k += 8) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __ldg(p + (int64_t)(k + j) * count);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[j];
+    }
+    for (; k < splits; ++k) s += __ldg(p + (int64_t)k * count);
     const int n = (int)(i / M), m = (int)(i - (int64_t)n * M);
     out[(int64_t)m * N + n] = s;
 }

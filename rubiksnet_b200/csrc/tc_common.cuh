@@ -95,7 +95,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- descriptors (cute/arch/mma_sm100_desc.hpp bit layout) -------------------------------------------------
-enum { LAYOUT_NONE = 0, LAYOUT_SW128 = 2 };
+enum { LAYOUT_NONE = 0, LAYOUT_SW128_BASE32B = 1, LAYOUT_SW128 = 2 };
 
 // shared-memory matrix descriptor: start address, leading / stride byte offsets (all >> 4), version 1, swizzle mode
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {

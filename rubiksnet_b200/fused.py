@@ -14,6 +14,7 @@
 All are autograd Functions over [N*T, C, H, W] activations; parameters stay fp32 (activations may be bf16).
 """
 import torch
+import torch.nn as nn
 
 from . import _lib, ops
 from .rubiksnet_cuda import _on_device
@@ -362,6 +363,7 @@ def _plane_reduce(a, b, scale):
 
 
 def _plane_scale(a, s, t):
+    assert s.dtype == torch.float32 and s.is_contiguous() and (t is None or (t.dtype == torch.float32 and t.is_contiguous()))
     ni, c = a.shape[0], a.shape[1]
     hw = a.numel() // max(ni * c, 1)
     out = torch.empty_like(a)
@@ -381,10 +383,11 @@ class _SEGate(torch.autograd.Function):
     def forward(ctx, x, w1, w2):
         x = x.contiguous()
         hw = x.shape[2] * x.shape[3]
-        pooled = _plane_reduce(x, None, 1.0 / hw)                      # [NI, C] fp32
-        w1f, w2f = w1.float(), w2.float()
-        hidden = torch.relu(pooled @ w1f.t())                          # [NI, C/r]
-        gate = torch.sigmoid(hidden @ w2f.t()).contiguous()            # [NI, C]
+        with torch.autocast(device_type="cuda", enabled=False):  # the gate MLP stays in fp32 (the kernels read float gates)
+            pooled = _plane_reduce(x, None, 1.0 / hw)                      # [NI, C] fp32
+            w1f, w2f = w1.float(), w2.float()
+            hidden = torch.relu(pooled @ w1f.t())                          # [NI, C/r]
+            gate = torch.sigmoid(hidden @ w2f.t()).contiguous()            # [NI, C]
         ctx.save_for_backward(x, pooled, hidden, gate, w1f, w2f)
         ctx.wdtypes = (w1.dtype, w2.dtype)
         return _plane_scale(x, gate, None)
@@ -395,12 +398,13 @@ class _SEGate(torch.autograd.Function):
         x, pooled, hidden, gate, w1f, w2f = ctx.saved_tensors
         g = g.contiguous()
         hw = x.shape[2] * x.shape[3]
-        dgate = _plane_reduce(g, x, 1.0)                               # sum_p g * x
-        dz2 = dgate * gate * (1.0 - gate)
-        dw2 = dz2.t() @ hidden
-        dz1 = (dz2 @ w2f) * (hidden > 0).to(dz2.dtype)
-        dw1 = dz1.t() @ pooled
-        dpool = ((dz1 @ w1f) * (1.0 / hw)).contiguous()
+        with torch.autocast(device_type="cuda", enabled=False):
+            dgate = _plane_reduce(g, x, 1.0)                               # sum_p g * x
+            dz2 = dgate * gate * (1.0 - gate)
+            dw2 = dz2.t() @ hidden
+            dz1 = (dz2 @ w2f) * (hidden > 0).to(dz2.dtype)
+            dw1 = dz1.t() @ pooled
+            dpool = ((dz1 @ w1f) * (1.0 / hw)).contiguous()
         dx = _plane_scale(g, gate, dpool) if ctx.needs_input_grad[0] else None
         return dx, dw1.to(ctx.wdtypes[0]), dw2.to(ctx.wdtypes[1])
 
@@ -408,6 +412,67 @@ class _SEGate(torch.autograd.Function):
 def se_gate(x, se):
     """SELayer forward on a CUDA NCHW tensor in fp32 / fp16 / bf16 (se.fc = Linear, ReLU, Linear, Sigmoid; no biases)."""
     return _SEGate.apply(x, se.fc[0].weight, se.fc[2].weight)
+
+
+# ------------------------------------------------------------------------------------- eval-mode block (fp32)
+
+def _eval_bn_ok(bn):
+    return (not bn.training and bn.running_mean is not None and bn.running_mean.dtype == torch.float32
+            and bn.running_var.dtype == torch.float32 and bn.weight is not None and bn.weight.dtype == torch.float32)
+
+
+def eval_block_supported(block, x):
+    """fp32 inference (no autograd, BatchNorms in eval mode) with TF32 convolutions allowed -- the switch nn.Conv2d follows
+    in the reference, default True: the block runs on the tcgen05 kind::tf32 kernel with both BatchNorm+ReLU pairs folded
+    into the two GEMMs.  torch.backends.cudnn.allow_tf32 = False keeps full-fp32 GEMMs (cuBLAS)."""
+    if not (x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled() and torch.backends.cudnn.allow_tf32):
+        return False
+    conv2 = block.conv2[1] if isinstance(block.conv2, nn.Sequential) else block.conv2
+    convs = [conv2, block.conv3] + ([] if isinstance(block.shortcut, nn.Identity) else [block.shortcut])
+    return (_eval_bn_ok(block.bn1) and _eval_bn_ok(block.bn2)
+            and all(c.weight.dtype == torch.float32 and c.weight.is_contiguous() for c in convs))
+
+
+def _eval_coeffs(bn):
+    """(scale, bias) [C, 2] of an eval-mode BatchNorm (rb_bn_act_forward, training = 0, no apply pass: one tiny launch).
+    Cached on the module and keyed by the version counters of its parameters / buffers, so steady-state inference launches
+    nothing; while a CUDA graph is being captured the kernel is always recorded, so that replays follow the buffers."""
+    tensors = (bn.weight, bn.bias, bn.running_mean, bn.running_var)
+    key = tuple((t.data_ptr(), t._version) for t in tensors) + (bn.eps,)
+    capturing = torch.cuda.is_current_stream_capturing()
+    hit = bn.__dict__.get("_rb_eval_sb")
+    if hit is not None and hit[0] == key and not capturing:
+        return hit[1]
+    like = torch.empty(1, bn.num_features, 1, 4, dtype=torch.float32, device=bn.weight.device)  # shape carrier, never read
+    _, _, sb = ops.bn_forward(like, bn.weight, bn.bias, bn.running_mean, bn.running_var, False, 0.0, bn.eps, relu=True, apply=False)
+    if not capturing:
+        bn.__dict__["_rb_eval_sb"] = (key, sb)
+    return sb
+
+
+def eval_block(block, x):
+    """RubiksShiftBlock.forward (rubiksnet/backbone.py:109-135) in eval mode as three launches for an identity-shortcut
+    block: conv2 [bn1+relu in the operand producer, bn2+relu in the epilogue] -> shift -> conv3 [+ shortcut in the epilogue]."""
+    x = _aligned(x)
+    sb1, sb2 = _eval_coeffs(block.bn1), _eval_coeffs(block.bn2)
+    aq = isinstance(block.conv2, nn.Sequential)
+    identity = isinstance(block.shortcut, nn.Identity)
+    w2 = (block.conv2[1] if aq else block.conv2).weight
+    if identity and not aq:
+        shortcut = x
+        a2 = ops.pw_conv_f32(x, w2, in_scale_bias=sb1, out_scale_bias=sb2, relu=True, resident=True)
+    else:
+        o = ops.bn_apply(x, sb1, relu=True)
+        if identity:
+            shortcut = x
+        else:
+            st = block.shortcut.stride[0]
+            shortcut = ops.pw_conv_f32(o if st == 1 else o[:, :, ::st, ::st].contiguous(), block.shortcut.weight, resident=True)
+        a2 = ops.pw_conv_f32(block.conv2[0](o).contiguous() if aq else o, w2, out_scale_bias=sb2, relu=True, resident=True)
+    s3 = block.as3(a2)
+    if block.se is not None:
+        s3 = se_gate(s3, block.se)
+    return ops.pw_conv_f32(s3.contiguous(), block.conv3.weight, residual=shortcut, resident=True)
 
 
 # ------------------------------------------------------------------------------------- whole block

@@ -182,6 +182,28 @@ def pw_conv(x, weight, residual=None, in_scale_bias=None, transposed=False, name
     return out
 
 
+def pw_conv_f32(x, weight, residual=None, in_scale_bias=None, out_scale_bias=None, relu=False, resident=False,
+                name="pw_conv_tf32"):
+    """fp32 1x1 convolution on the tcgen05 kind::tf32 kernel (inference path):
+    out = [relu](conv(A) * out_scale + out_bias) + residual,  A = x or relu(x * in_scale + in_bias).
+    x [NI,K,H,W] fp32, weight [N,K(,1,1)] fp32; the coefficient tensors are fp32 [C,2] as returned by bn_forward."""
+    assert x.dtype == torch.float32 and x.is_contiguous() and weight.dtype == torch.float32 and weight.is_contiguous()
+    ni, k, n = x.shape[0], x.shape[1], weight.shape[0]
+    assert weight.shape[1] == k, "channel mismatch"
+    hw = x.numel() // max(ni * k, 1)
+    out = torch.empty((ni, n) + tuple(x.shape[2:]), dtype=torch.float32, device=x.device)
+    if residual is not None:
+        assert residual.dtype == torch.float32 and residual.is_contiguous() and residual.shape == out.shape
+    for sb, c in ((in_scale_bias, k), (out_scale_bias, n)):
+        assert sb is None or (sb.dtype == torch.float32 and sb.is_contiguous() and sb.numel() == 2 * c)
+    with _on_device(x.device):
+        with _timed(name, _nbytes(x, residual, out), 2 * ni * hw * k * n):
+            _lib.check(_lib.lib().rb_pw_conv_forward_f32(
+                _lib.ptr(x), _lib.ptr(weight), _lib.ptr(residual), _lib.ptr(out), ni, k, n, hw, _lib.ptr(in_scale_bias),
+                _lib.ptr(out_scale_bias), int(bool(relu)), _lib.RB_W_RESIDENT if resident else 0, _lib.stream_handle(x.device)))
+    return out
+
+
 def pw_weight_pack(weight):
     """bf16 copies of a fp32 conv weight [N,K(,1,1)] in both orientations: (w_nk [N,K], w_kn [K,N]); one launch.
     pw_conv(x, w_nk) is the forward, pw_conv(g, w_kn) the input gradient (no transposing weight staging)."""

@@ -191,6 +191,25 @@ def test_se_gate_matches_module(shape, dtype, tol):
         assert _rel(p.grad, r) <= max(tol, 1e-4)
 
 
+def test_se_gate_under_autocast():
+    """Inside a bf16 autocast region the gate MLP must stay fp32: the rescale kernel reads float gates."""
+    torch.manual_seed(10)
+    se = backbone.SELayer(72, reduction=12).cuda()
+    x = torch.randn(16, 72, 14, 14, device="cuda").bfloat16()
+    g = torch.randn_like(x)
+    xr = x.float().clone().requires_grad_()
+    se(xr).backward(g.float())
+    ref_w = [p.grad.clone() for p in se.parameters()]
+    se.zero_grad(set_to_none=True)
+    xn = x.clone().requires_grad_()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        yn = fused.se_gate(xn, se)
+    yn.backward(g)
+    assert _rel(yn, se(x.float())) <= 1e-2 and _rel(xn.grad, xr.grad) <= 1e-2
+    for p, r in zip(se.parameters(), ref_w):
+        assert _rel(p.grad, r) <= 1e-2
+
+
 def test_small_tier_uses_se_kernels():
     from rubiksnet_b200 import _lib
     torch.manual_seed(9)
