@@ -59,6 +59,9 @@ struct TfArgs {
     int Kpad, k_stages, stages, NP, total_tiles;
     uint32_t off_sb, off_stg, off_w, off_a;
     uint32_t hw_mul, hw_shr;
+    uint32_t kp_mul, kp_shr;  // exact division by Kpad for indices < 2^31
+    uint32_t kq_mul, kq_shr;  // ... by Kpad / 4
+    int w_vec4;               // weight rows may be read with 16-byte loads
 };
 
 struct TfHdr {
@@ -95,15 +98,52 @@ __device__ __forceinline__ void mma_tf32_lohi(uint32_t tmem_d, uint32_t a_lo, ui
 }
 
 // Resident weight block: W[n0 + n, k] (n < nrows, k < K) -> (k/4)*kTfWLbo + (n/8)*128 + (n%8)*16 + (k%4)*4, i.e. K-major
-// 8-row x 16-byte core matrices; rows >= nrows and columns >= K are zero.  A warp walks one weight row at a time (coalesced
-// 128-byte reads); kTfWLbo / 4 = 516 = 4 (mod 32), so the 8 core-matrix columns a warp writes fall into different banks.
-__device__ __forceinline__ void tf_stage_weights(const TfArgs &a, unsigned char *smem_w, int n0, int nrows, int wl, int nw, int lane) {
-    for (int n = wl; n < kTfRows; n += nw) {
-        const float *row = a.w + (int64_t)(n0 + n) * a.w_row_stride;
-        unsigned char *dst = smem_w + (n >> 3) * 128 + (n & 7) * 16;
-        for (int k = lane; k < a.Kpad; k += 32) {
-            const float v = (n < nrows && k < a.K) ? __ldg(row + k) : 0.f;
-            *reinterpret_cast<uint32_t *>(dst + (k >> 2) * kTfWLbo + (k & 3) * 4) = to_tf32(v);
+// 8-row x 16-byte core matrices; rows >= nrows and columns >= K are zero.  The 128 x Kpad elements are walked as one flat
+// index (consecutive threads = consecutive k of a row: coalesced 4-byte reads, and kTfWLbo / 4 = 516 = 4 (mod 32) keeps the
+// scattered 4-byte stores of a warp in different banks); a thread keeps 16 loads in flight, so the whole block costs a few
+// memory latencies instead of one per element.
+__device__ __forceinline__ void tf_stage_weights(const TfArgs &a, unsigned char *smem_w, int n0, int nrows, int t, int nthreads) {
+    if (a.w_vec4) {
+        // rows are 16-byte aligned and K % 4 == 0: one 16-byte load = one core-matrix row (4 consecutive k of a weight row)
+        constexpr int UB = 8;
+        const int kq = a.Kpad >> 2, total = kTfRows * kq;
+        for (int u0 = t; u0 < total; u0 += UB * nthreads) {
+            float4 v[UB];
+#pragma unroll
+            for (int b = 0; b < UB; ++b) {
+                const int u = u0 + b * nthreads;
+                const int n = (int)(__umulhi((uint32_t)u, a.kq_mul) >> a.kq_shr), q = u - n * kq;
+                v[b] = (u < total && n < nrows && 4 * q < a.K)
+                           ? __ldg(reinterpret_cast<const float4 *>(a.w + (int64_t)(n0 + n) * a.w_row_stride) + q)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int b = 0; b < UB; ++b) {
+                const int u = u0 + b * nthreads;
+                if (u >= total) continue;
+                const int n = (int)(__umulhi((uint32_t)u, a.kq_mul) >> a.kq_shr), q = u - n * kq;
+                *reinterpret_cast<uint4 *>(smem_w + q * kTfWLbo + (n >> 3) * 128 + (n & 7) * 16) =
+                    make_uint4(to_tf32(v[b].x), to_tf32(v[b].y), to_tf32(v[b].z), to_tf32(v[b].w));
+            }
+        }
+        return;
+    }
+    constexpr int UB = 16;
+    const int total = kTfRows * a.Kpad;
+    for (int e0 = t; e0 < total; e0 += UB * nthreads) {
+        float v[UB];
+#pragma unroll
+        for (int b = 0; b < UB; ++b) {
+            const int e = e0 + b * nthreads;
+            const int n = (int)(__umulhi((uint32_t)e, a.kp_mul) >> a.kp_shr), k = e - n * a.Kpad;
+            v[b] = (e < total && n < nrows && k < a.K) ? __ldg(a.w + (int64_t)(n0 + n) * a.w_row_stride + k) : 0.f;
+        }
+#pragma unroll
+        for (int b = 0; b < UB; ++b) {
+            const int e = e0 + b * nthreads;
+            if (e >= total) continue;
+            const int n = (int)(__umulhi((uint32_t)e, a.kp_mul) >> a.kp_shr), k = e - n * a.Kpad;
+            *reinterpret_cast<uint32_t *>(smem_w + (k >> 2) * kTfWLbo + (n >> 3) * 128 + (n & 7) * 16 + (k & 3) * 4) = to_tf32(v[b]);
         }
     }
 }
@@ -137,7 +177,10 @@ __global__ void __launch_bounds__(kTfThreads, 1) k_pw_tf32(const TfArgs a) {
     }
     // nothing above touches global memory; a resident weight block (RB_W_RESIDENT: parameters of an eval-mode network) is
     // staged while the previous kernel of the stream drains (common.cuh: programmatic dependent launch)
-    if (a.w_resident && warp < kTfProdWarp0) tf_stage_weights(a, smem_w, n0, nrows, warp, kTfProdWarp0, lane);
+    if (a.w_resident) {  // every warp: nobody has anything else to do yet
+        tf_stage_weights(a, smem_w, n0, nrows, tid, kTfThreads);
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core after the CTA sync below
+    }
     pdl_sync();
     if (BN)
         for (int k = tid; k < a.Kpad; k += kTfThreads) {
@@ -148,8 +191,9 @@ __global__ void __launch_bounds__(kTfThreads, 1) k_pw_tf32(const TfArgs a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = hdr->tmem_base;
-    if (warp < kTfProdWarp0) {
-        if (!a.w_resident) tf_stage_weights(a, smem_w, n0, nrows, warp, kTfProdWarp0, lane);
+    if (!a.w_resident && warp < kTfProdWarp0) {
+        // the producer warps already load activations while the MMA + epilogue warps stage the weight block
+        tf_stage_weights(a, smem_w, n0, nrows, tid, kTfProdWarp0 * 32);
         fence_proxy_async_smem();
         asm volatile("bar.sync 1, %0;" ::"n"(kTfProdWarp0 * 32) : "memory");
     }
@@ -252,38 +296,49 @@ __global__ void __launch_bounds__(kTfThreads, 1) k_pw_tf32(const TfArgs a) {
                     *reinterpret_cast<float4 *>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) = o;
                 }
                 __syncwarp();
+                // read-back: lane = (row rsub + 4 i, 16-byte chunk).  `pre` / `res` of all 8 rows are fetched first (all loads
+                // in flight together; `pre` may alias `out`, so the compiler would not move them above the stores itself)
+                float4 pv[8], rv[8];
+                bool live[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int grow = q * 32 + rsub + 4 * i;
+                    const int o = off[0] + grow * a.HW;
+                    live[i] = grow < nrows && (VEC == 4 ? ok[0] : true);
+                    pv[i] = rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (!live[i]) continue;
+                    if (VEC == 4) {
+                        if (a.pre != nullptr) pv[i] = *reinterpret_cast<const float4 *>(a.pre + o);
+                        if (a.res != nullptr) rv[i] = __ldg(reinterpret_cast<const float4 *>(a.res + o));
+                    } else {
+                        const int roff = grow * a.HW;
+                        float *pp = reinterpret_cast<float *>(&pv[i]), *rp = reinterpret_cast<float *>(&rv[i]);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            if (!ok[VEC == 4 ? 0 : e]) continue;
+                            const int oe = off[VEC == 4 ? 0 : e] + roff;
+                            if (a.pre != nullptr) pp[e] = a.pre[oe];
+                            if (a.res != nullptr) rp[e] = a.res[oe];
+                        }
+                    }
+                }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int rrow = rsub + 4 * i;
                     const int grow = q * 32 + rrow;
                     float4 t = *reinterpret_cast<const float4 *>(stg + rrow * 128 + ((chunk ^ (rrow & 7)) << 4));
-                    if (grow >= nrows) continue;
+                    if (!live[i]) continue;
+                    t.x += pv[i].x; t.y += pv[i].y; t.z += pv[i].z; t.w += pv[i].w;
+                    if (a.relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
+                    t.x += rv[i].x; t.y += rv[i].y; t.z += rv[i].z; t.w += rv[i].w;
                     const int roff = grow * a.HW;
                     if (VEC == 4) {
-                        if (!ok[0]) continue;
-                        const int o = off[0] + roff;
-                        if (a.pre != nullptr) {
-                            const float4 p = *reinterpret_cast<const float4 *>(a.pre + o);
-                            t.x += p.x; t.y += p.y; t.z += p.z; t.w += p.w;
-                        }
-                        if (a.relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
-                        if (a.res != nullptr) {
-                            const float4 p = *reinterpret_cast<const float4 *>(a.res + o);
-                            t.x += p.x; t.y += p.y; t.z += p.z; t.w += p.w;
-                        }
-                        *reinterpret_cast<float4 *>(a.out + o) = t;
+                        *reinterpret_cast<float4 *>(a.out + off[0] + roff) = t;
                     } else {
-                        float tv[4] = {t.x, t.y, t.z, t.w};
+                        const float tv[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            if (!ok[VEC == 4 ? 0 : e]) continue;
-                            const int o = off[VEC == 4 ? 0 : e] + roff;
-                            float u = tv[e];
-                            if (a.pre != nullptr) u += a.pre[o];
-                            if (a.relu) u = fmaxf(u, 0.f);
-                            if (a.res != nullptr) u += a.res[o];
-                            a.out[o] = u;
-                        }
+                        for (int e = 0; e < 4; ++e)
+                            if (ok[VEC == 4 ? 0 : e]) a.out[off[VEC == 4 ? 0 : e] + roff] = tv[e];
                     }
                 }
             }
@@ -435,6 +490,18 @@ int pw_tf32_forward(const float *x, const float *w, const float *res, float *out
             while ((1u << l) < (uint32_t)HW) ++l;
             a.hw_mul = (uint32_t)(((uint64_t(1) << (31 + l)) + (uint32_t)HW - 1) / (uint32_t)HW);
             a.hw_shr = l - 1;
+        }
+        {
+            uint32_t l = 0;
+            while ((1u << l) < (uint32_t)a.Kpad) ++l;  // Kpad >= 8
+            a.kp_mul = (uint32_t)(((uint64_t(1) << (31 + l)) + (uint32_t)a.Kpad - 1) / (uint32_t)a.Kpad);
+            a.kp_shr = l - 1;
+            const uint32_t kq = (uint32_t)a.Kpad >> 2;  // >= 2
+            l = 0;
+            while ((1u << l) < kq) ++l;
+            a.kq_mul = (uint32_t)(((uint64_t(1) << (31 + l)) + kq - 1) / kq);
+            a.kq_shr = l - 1;
+            a.w_vec4 = (a.K % 4 == 0 && K % 4 == 0 && (reinterpret_cast<uintptr_t>(a.w) & 15) == 0) ? 1 : 0;
         }
         const int gy = cdiv(N, kTfRows);
         int gx = sm_count() / gy;

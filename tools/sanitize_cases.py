@@ -70,6 +70,16 @@ def misc_cases():
         y, mi, sb = ops.bn_forward(xd, bn_g, bn_b, rm, rv, True, 0.1, 1e-5, relu=True, apply=True)
         ops.bn_backward(xd, torch.randn_like(xd), xd, bn_g, mi, sb, True, relu=True)
         torch.cuda.synchronize()
+    # tcgen05 kind::tf32 kernel: vector and scalar paths, producer / epilogue folds, split contraction; SE kernels; pack fence
+    for ni, k, n, h in ((4, 54, 54, 14), (2, 216, 432, 7), (2, 432, 72, 7), (3, 20, 12, 5)):
+        x = torch.randn(ni, k, h, h, device="cuda")
+        w = torch.randn(n, k, device="cuda") / k ** 0.5
+        res = torch.randn(ni, n, h, h, device="cuda")
+        isb = torch.stack([torch.rand(k, device="cuda") + 0.5, torch.randn(k, device="cuda")], dim=1).contiguous()
+        osb = torch.stack([torch.rand(n, device="cuda") + 0.5, torch.randn(n, device="cuda")], dim=1).contiguous()
+        ops.pw_conv_f32(x, w)
+        ops.pw_conv_f32(x, w, residual=res, in_scale_bias=isb, out_scale_bias=osb, relu=True, resident=True)
+        torch.cuda.synchronize()
     print("misc ok", flush=True)
 
 
