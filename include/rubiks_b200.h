@@ -205,6 +205,14 @@ int rb_pw_conv_forward_f32(const float *x, const float *weight, const float *res
                            int HW, const float *in_scale_bias, const float *out_scale_bias, int out_relu, int flags,
                            void *stream);
 
+/* Patch matrix of the 3x3 / stride-S / padding-1 first convolution (rubiksnet/backbone.py:148-149): cols [NI, Tpad, Ho, Wo],
+ * cols[i, (ci*3 + kh)*3 + kw, ho, wo] = x[i, ci, ho*S - 1 + kh, wo*S - 1 + kw] (0 outside the image), rows >= 9*Cin zero.
+ * conv1(x) = rb_pw_conv_forward / rb_pw_conv_forward_f32 (cols, weight viewed [Cout, 9*Cin] and zero-padded to Tpad);
+ * its weight gradient = rb_pw_conv_wgrad(out_grad, cols).  x [NI, Cin, H, W] in in_dtype (RB_F32 / RB_BF16), cols in
+ * out_dtype (RB_BF16, or RB_F32 from RB_F32); Wo must be a multiple of 8; cols 16-byte aligned. */
+int rb_im2col3x3(const void *x, void *cols, int in_dtype, int out_dtype, int NI, int Cin, int H, int W, int stride, int Tpad,
+                 void *stream);
+
 /* Batch statistics -> (mean, invstd), (scale, bias) and the running-statistics update of nn.BatchNorm2d in training
  * mode, from partial sums [C][splits][2] over `count` elements per channel (what rb_bn_act_forward does after its own
  * reduction pass).  running_mean / running_var may be NULL. */

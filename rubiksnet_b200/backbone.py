@@ -146,7 +146,7 @@ class RubiksNetBackbone(nn.Module):
         return nn.Sequential(*blocks)
 
     def forward(self, x):
-        x = self.conv1(x)
+        x = fused.stem_conv(self.conv1, x) if FUSED_BLOCK else self.conv1(x)
         packing = _use_fused(x) and x.dtype == torch.bfloat16
         if packing:
             fused.begin_step_pack(self)  # every conv-weight image of the network in one launch

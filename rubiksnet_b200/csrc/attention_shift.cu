@@ -8,81 +8,149 @@ namespace rb {
 
 static constexpr int kAThreads = 128;
 
+template <typename T, int V> struct alignas(sizeof(T) * V) APack { T v[V]; };
+
+// Thread layout shared by both kernels: a thread owns V consecutive pixels of one channel plane (one 2V- / 4V-byte vector
+// per frame) and streams the T frames of its clip through registers.  Planes with fewer than 128 vectors (14x14, 7x7) share a
+// CTA: CG = 128 / (vectors per plane) channels per block.  grid = (blocks per plane, channel groups, clips).
+struct ASlot {
+    int c, p, cl;   // channel, first pixel, channel index inside the CTA
+    bool active;
+};
+template <int V> __device__ __forceinline__ ASlot a_slot(int C, int HW, int vpc, int CG) {
+    ASlot s;
+    if (CG > 1) {
+        s.cl = threadIdx.x / vpc;
+        s.p = (threadIdx.x - s.cl * vpc) * V;
+        s.c = blockIdx.y * CG + s.cl;
+        s.active = s.cl < CG && s.c < C;
+    } else {
+        s.cl = 0;
+        s.p = (blockIdx.x * kAThreads + threadIdx.x) * V;
+        s.c = blockIdx.y;
+        s.active = s.p < HW;
+    }
+    return s;
+}
+
 // x/out: [N, T, C, HW]; taps fp32 [C,3]
-template <typename T>
+template <typename T, int V>
 __global__ void __launch_bounds__(kAThreads)
-k_attn_fwd(const T *__restrict__ x, const float *__restrict__ taps, T *__restrict__ out, int Tn, int C,
-           int HW) {
+k_attn_fwd(const T *__restrict__ x, const float *__restrict__ taps, T *__restrict__ out, int Tn, int C, int HW, int vpc, int CG) {
     pdl_sync();
-    const int p = blockIdx.x * kAThreads + threadIdx.x;
-    const int c = blockIdx.y, n = blockIdx.z;
-    if (p >= HW) return;
+    const ASlot sl = a_slot<V>(C, HW, vpc, CG);
+    if (!sl.active) return;
+    const int c = sl.c, n = blockIdx.z;
     const float a0 = taps[c * 3 + 0], a1 = taps[c * 3 + 1], a2 = taps[c * 3 + 2];
     const int64_t fs = (int64_t)C * HW;
-    const T *xp = x + ((int64_t)n * Tn * C + c) * HW + p;
-    T *op = out + ((int64_t)n * Tn * C + c) * HW + p;
-    float prev = 0.f, cur = ld<float, T>(xp);
+    const int64_t base = ((int64_t)n * Tn * C + c) * HW + sl.p;
+    using P = APack<T, V>;
+    float prev[V], cur[V];
+    {
+        const P v0 = *reinterpret_cast<const P *>(x + base);
+#pragma unroll
+        for (int i = 0; i < V; ++i) { prev[i] = 0.f; cur[i] = ld<float, T>(&v0.v[i]); }
+    }
     for (int t = 0; t < Tn; ++t) {
-        const float nxt = (t + 1 < Tn) ? ld<float, T>(xp + (t + 1) * fs) : 0.f;
-        op[t * fs] = cvt<T, float>(a0 * prev + a1 * cur + a2 * nxt);
-        prev = cur;
-        cur = nxt;
+        float nxt[V];
+        if (t + 1 < Tn) {
+            const P vn = *reinterpret_cast<const P *>(x + base + (t + 1) * fs);
+#pragma unroll
+            for (int i = 0; i < V; ++i) nxt[i] = ld<float, T>(&vn.v[i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < V; ++i) nxt[i] = 0.f;
+        }
+        P o;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            o.v[i] = cvt<T, float>(a0 * prev[i] + a1 * cur[i] + a2 * nxt[i]);
+            prev[i] = cur[i];
+            cur[i] = nxt[i];
+        }
+        *reinterpret_cast<P *>(out + base + t * fs) = o;
     }
 }
 
 // gx[t] = a0 g[t+1] + a1 g[t] + a2 g[t-1];  gtaps[c,k] = sum g[t] x[t+k-1]
-template <typename T>
+template <typename T, int V>
 __global__ void __launch_bounds__(kAThreads)
-k_attn_bwd(const T *__restrict__ x, const float *__restrict__ taps, const T *__restrict__ og,
-           T *__restrict__ gx, float *__restrict__ partial, int Tn, int C, int HW, int want_gx,
-           int want_gt) {
+k_attn_bwd(const T *__restrict__ x, const float *__restrict__ taps, const T *__restrict__ og, T *__restrict__ gx,
+           float *__restrict__ partial, int Tn, int C, int HW, int vpc, int CG, int want_gx, int want_gt) {
     pdl_sync();
-    const int p = blockIdx.x * kAThreads + threadIdx.x;
-    const int c = blockIdx.y, n = blockIdx.z;
+    const ASlot sl = a_slot<V>(C, HW, vpc, CG);
+    const int n = blockIdx.z;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-    if (p < HW) {
+    using P = APack<T, V>;
+    if (sl.active) {
+        const int c = sl.c;
         const float a0 = taps[c * 3 + 0], a1 = taps[c * 3 + 1], a2 = taps[c * 3 + 2];
         const int64_t fs = (int64_t)C * HW;
-        const int64_t base = ((int64_t)n * Tn * C + c) * HW + p;
-        const T *xp = x + base;
-        const T *gp = og + base;
-        float gprev = 0.f, gcur = ld<float, T>(gp);
-        float xprev = 0.f, xcur = want_gt ? ld<float, T>(xp) : 0.f;
+        const int64_t base = ((int64_t)n * Tn * C + c) * HW + sl.p;
+        float gprev[V], gcur[V], xprev[V], xcur[V];
+        {
+            const P g0 = *reinterpret_cast<const P *>(og + base);
+#pragma unroll
+            for (int i = 0; i < V; ++i) { gprev[i] = 0.f; gcur[i] = ld<float, T>(&g0.v[i]); xprev[i] = 0.f; xcur[i] = 0.f; }
+            if (want_gt) {
+                const P x0 = *reinterpret_cast<const P *>(x + base);
+#pragma unroll
+                for (int i = 0; i < V; ++i) xcur[i] = ld<float, T>(&x0.v[i]);
+            }
+        }
         for (int t = 0; t < Tn; ++t) {
             const bool more = t + 1 < Tn;
-            const float gnxt = more ? ld<float, T>(gp + (t + 1) * fs) : 0.f;
-            if (want_gx) gx[base + t * fs] = cvt<T, float>(a0 * gnxt + a1 * gcur + a2 * gprev);
-            if (want_gt) {
-                const float xnxt = more ? ld<float, T>(xp + (t + 1) * fs) : 0.f;
-                s0 += gcur * xprev;
-                s1 += gcur * xcur;
-                s2 += gcur * xnxt;
-                xprev = xcur;
-                xcur = xnxt;
+            float gnxt[V], xnxt[V];
+#pragma unroll
+            for (int i = 0; i < V; ++i) { gnxt[i] = 0.f; xnxt[i] = 0.f; }
+            if (more) {
+                const P gn = *reinterpret_cast<const P *>(og + base + (t + 1) * fs);
+#pragma unroll
+                for (int i = 0; i < V; ++i) gnxt[i] = ld<float, T>(&gn.v[i]);
+                if (want_gt) {
+                    const P xn = *reinterpret_cast<const P *>(x + base + (t + 1) * fs);
+#pragma unroll
+                    for (int i = 0; i < V; ++i) xnxt[i] = ld<float, T>(&xn.v[i]);
+                }
             }
-            gprev = gcur;
-            gcur = gnxt;
+            if (want_gx) {
+                P o;
+#pragma unroll
+                for (int i = 0; i < V; ++i) o.v[i] = cvt<T, float>(a0 * gnxt[i] + a1 * gcur[i] + a2 * gprev[i]);
+                *reinterpret_cast<P *>(gx + base + t * fs) = o;
+            }
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                if (want_gt) {
+                    s0 += gcur[i] * xprev[i];
+                    s1 += gcur[i] * xcur[i];
+                    s2 += gcur[i] * xnxt[i];
+                    xprev[i] = xcur[i];
+                    xcur[i] = xnxt[i];
+                }
+                gprev[i] = gcur[i];
+                gcur[i] = gnxt[i];
+            }
         }
     }
     if (!want_gt) return;
-    __shared__ float red[3][kAThreads / 32];
-    s0 = warp_sum(s0);
-    s1 = warp_sum(s1);
-    s2 = warp_sum(s2);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) {
-        red[0][warp] = s0;
-        red[1][warp] = s1;
-        red[2][warp] = s2;
-    }
+    // deterministic per-channel sums: every thread parks its three sums, thread (channel, axis) adds its channel's slots in order
+    __shared__ float red[kAThreads][3];
+    red[threadIdx.x][0] = s0;
+    red[threadIdx.x][1] = s1;
+    red[threadIdx.x][2] = s2;
     __syncthreads();
-    if (threadIdx.x < 3) {
-        float s = 0.f;
-#pragma unroll
-        for (int w = 0; w < kAThreads / 32; ++w) s += red[threadIdx.x][w];
-        const int parts = gridDim.x * gridDim.z;
-        const int part = blockIdx.z * gridDim.x + blockIdx.x;
-        partial[((int64_t)c * parts + part) * 3 + threadIdx.x] = s;
+    if (threadIdx.x < CG * 3) {
+        const int l = threadIdx.x / 3, ax = threadIdx.x - l * 3;
+        const int c = CG > 1 ? blockIdx.y * CG + l : blockIdx.y;
+        if (c < C) {
+            const int lo = CG > 1 ? l * vpc : 0, hi = CG > 1 ? lo + vpc : kAThreads;
+            float s = 0.f;
+            for (int i = lo; i < hi; ++i) s += red[i][ax];
+            const int parts = gridDim.x * gridDim.z;
+            const int part = blockIdx.z * gridDim.x + blockIdx.x;
+            partial[((int64_t)c * parts + part) * 3 + ax] = s;
+        }
     }
 }
 
@@ -112,6 +180,37 @@ __global__ void k_attn_finalize(const float *__restrict__ partial, int parts, fl
 
 using namespace rb;
 
+namespace {
+
+struct APlan {
+    int V, vpc, CG;
+    dim3 grid;
+};
+
+// widest vector (elements) that divides the plane and that every base pointer is aligned for
+APlan a_plan(int dtype, int N, int C, int HW, const void *p0, const void *p1, const void *p2) {
+    const size_t es = dtype_size(dtype);
+    const uintptr_t al = reinterpret_cast<uintptr_t>(p0) | reinterpret_cast<uintptr_t>(p1) | reinterpret_cast<uintptr_t>(p2);
+    APlan p;
+    p.V = (int)(16 / es);
+    if (p.V > 8) p.V = 8;
+    while (p.V > 1 && (HW % p.V != 0 || (al & (uintptr_t)(p.V * es - 1)) != 0)) p.V >>= 1;
+    p.vpc = HW / p.V;
+    p.CG = p.vpc >= kAThreads ? 1 : kAThreads / p.vpc;
+    p.grid = p.CG > 1 ? dim3(1, (unsigned)cdiv(C, p.CG), (unsigned)N) : dim3((unsigned)cdiv(p.vpc, kAThreads), (unsigned)C, (unsigned)N);
+    return p;
+}
+
+}  // namespace
+
+#define RB_ATTN_V(V_, ...)                 \
+    switch (V_) {                          \
+        case 8: { constexpr int VV = 8; __VA_ARGS__; } break; \
+        case 4: { constexpr int VV = 4; __VA_ARGS__; } break; \
+        case 2: { constexpr int VV = 2; __VA_ARGS__; } break; \
+        default: { constexpr int VV = 1; __VA_ARGS__; } break; \
+    }
+
 // NB: the frame count is called Tn below because RB_DISPATCH_DTYPE binds the element type to `T`.
 extern "C" int rb_attention_shift_forward(const void *x, const float *taps, void *out, int dtype,
                                           int N, int Tn, int C, int HW, void *stream) {
@@ -120,17 +219,17 @@ extern "C" int rb_attention_shift_forward(const void *x, const float *taps, void
     if ((int64_t)N * Tn * C * HW == 0) return RB_OK;
     if (!x || !taps || !out) return fail(RB_ERR_INVALID_ARGUMENT, "null pointer");
     if (C > 65535 || N > 65535) return fail(RB_ERR_UNSUPPORTED, "attention shift: C or N > 65535");
-    dim3 grid(cdiv(HW, kAThreads), C, N);
+    const APlan p = a_plan(dtype, N, C, HW, x, out, nullptr);
     cudaStream_t s = (cudaStream_t)stream;
-    RB_DISPATCH_DTYPE(dtype, (launch_kernel(k_attn_fwd<T>, dim3(grid), dim3(kAThreads), 0, s, (const T *)x, taps, (T *)out,
-                                                                      Tn, C, HW)));
+    RB_DISPATCH_DTYPE(dtype, RB_ATTN_V(p.V, (launch_kernel(k_attn_fwd<T, (VV * sizeof(T) <= 16 ? VV : 1)>, p.grid, dim3(kAThreads), 0, s,
+                                                           (const T *)x, taps, (T *)out, Tn, C, HW, p.vpc, p.CG))));
     return launched("k_attn_fwd");
 }
 
 extern "C" size_t rb_attention_shift_backward_workspace_bytes(int N, int Tn, int C, int HW) {
     (void)Tn;
     if (N <= 0 || C <= 0 || HW <= 0) return 0;
-    return (size_t)C * N * cdiv(HW, kAThreads) * 3 * sizeof(float);
+    return (size_t)C * N * cdiv(HW, kAThreads) * 3 * sizeof(float);  // upper bound over every vector width
 }
 
 extern "C" int rb_attention_shift_backward(const void *x, const float *taps, const void *out_grad,
@@ -151,15 +250,14 @@ extern "C" int rb_attention_shift_backward(const void *x, const float *taps, con
     if (taps_grad && (!workspace || workspace_bytes < need))
         return fail(RB_ERR_WORKSPACE, "attention shift backward needs %zu workspace bytes, got %zu",
                     need, workspace_bytes);
-    dim3 grid(cdiv(HW, kAThreads), C, N);
-    RB_DISPATCH_DTYPE(dtype, (launch_kernel(k_attn_bwd<T>, dim3(grid), dim3(kAThreads), 0, s, 
-                                 (const T *)x, taps, (const T *)out_grad, (T *)x_grad,
-                                 (float *)workspace, Tn, C, HW, x_grad != nullptr,
-                                 taps_grad != nullptr)));
+    const APlan p = a_plan(dtype, N, C, HW, x, out_grad, x_grad);
+    RB_DISPATCH_DTYPE(dtype, RB_ATTN_V(p.V, (launch_kernel(k_attn_bwd<T, (VV * sizeof(T) <= 16 ? VV : 1)>, p.grid, dim3(kAThreads), 0, s,
+                                                           (const T *)x, taps, (const T *)out_grad, (T *)x_grad, (float *)workspace, Tn,
+                                                           C, HW, p.vpc, p.CG, x_grad != nullptr, taps_grad != nullptr))));
     int rc = launched("k_attn_bwd");
     if (rc || !taps_grad) return rc;
     const int warps = 4;
     launch_kernel(k_attn_finalize, dim3(cdiv(C, warps)), dim3(warps * 32), 0, s, (const float *)workspace,
-                                                          (int)(grid.x * grid.z), taps_grad, C);
+                  (int)(p.grid.x * p.grid.z), taps_grad, C);
     return launched("k_attn_finalize");
 }

@@ -46,7 +46,7 @@ struct StripArgs {
     double *partial;  // BWD: [C][N*row_tiles][3]
     int sdt;
     int N, Tn, C, H, W;
-    int mode2d;       // 2D shift (cuda_src/rubiks2d_kernels.cu): shift is [2, C] (H, W), every "clip" is one image (Tn = 1)
+    int mode2d;       // 2D shift (cuda_src/rubiks2d_kernels.cu): shift is [2, C] (H, W); the Tn "frames" of a CTA are independent images
     StripCfg cfg;
 };
 
@@ -290,13 +290,13 @@ __global__ void __launch_bounds__(kSNT) k_shift3d_strip(const StripArgs a) {
                 if (step >= 1 && want_dst && active && k < nrows) {
                     float v[CW];
 #pragma unroll
-                    for (int i = 0; i < CW; ++i) v[i] = wT0 * pB[k][i] + wT1 * Bk[i];
+                    for (int i = 0; i < CW; ++i) v[i] = a.mode2d ? pB[k][i] : wT0 * pB[k][i] + wT1 * Bk[i];  // 2D: frames are independent images
                     s_store<T, VEC>(dst + dbase + (step - 1) * dst_fs + k * W, v, ncols);
                 }
 #pragma unroll
                 for (int i = 0; i < CW; ++i) {
                     if (MODE == SMODE_BWD) {
-                        const float xm = wT0 * xn[k][i] + wT1 * xp[k][i];
+                        const float xm = a.mode2d ? xn[k][i] : wT0 * xn[k][i] + wT1 * xp[k][i];
                         const float xd = xn[k][i] - xp[k][i];
                         accT += Bk[i] * xd;
                         accH += DHk[i] * xm;
@@ -370,8 +370,8 @@ __global__ void __launch_bounds__(kSNT) k_shift3d_strip(const StripArgs a) {
                             const float q121 = tap(t0, h0 + 1, w0), q122 = tap(t0, h0 + 1, w0 + 1);
                             const float q211 = tap(t0 + 1, h0, w0), q212 = tap(t0 + 1, h0, w0 + 1);
                             const float q221 = tap(t0 + 1, h0 + 1, w0), q222 = tap(t0 + 1, h0 + 1, w0 + 1);
-                            v = wT0 * (wH0 * (q111 * wW0 + q112 * wW1) + wH1 * (q121 * wW0 + q122 * wW1)) +
-                                wT1 * (wH0 * (q211 * wW0 + q212 * wW1) + wH1 * (q221 * wW0 + q222 * wW1));
+                            v = wH0 * (q111 * wW0 + q112 * wW1) + wH1 * (q121 * wW0 + q122 * wW1);
+                            if (!a.mode2d) v = wT0 * v + wT1 * (wH0 * (q211 * wW0 + q212 * wW1) + wH1 * (q221 * wW0 + q222 * wW1));
                         }
                         dst[di] = cvt<T, float>(v);
                     }
@@ -581,28 +581,39 @@ __global__ void k_shift2d_strip_finalize(const double *__restrict__ partial, int
     st_param<float>(shift_grad, sdt, C + c, gw);
 }
 
+// 2D images are processed in groups of Tn "frames" per CTA (independent images: no temporal taps), which gives a CTA the
+// same amount of work per staging round trip as a 3D clip; Tn = the largest of 8, 4, 2, 1 that divides the batch
+static int strip2d_frames(int dt, const Geom2 &g, StripCfg *c) {
+    for (int tn = 8; tn >= 1; tn >>= 1)
+        if (g.N % tn == 0 && pick_strip_cfg((int)dtype_size(dt), tn, g.C, g.H, g.W, c)) return tn;
+    return 0;
+}
+
 bool shift2d_strip_supported(int dt, const Geom2 &g, int quantize) {
     if (quantize) return false;
     if (dt != RB_F32 && dt != RB_F16 && dt != RB_BF16) return false;
     if (g.sH != 1 || g.sW != 1 || g.pH != 0 || g.pW != 0) return false;
     StripCfg c;
-    if (!pick_strip_cfg((int)dtype_size(dt), 1, g.C, g.H, g.W, &c)) return false;
-    return (int64_t)g.N * c.groups * c.row_tiles <= 0x7fffffffLL;
+    const int tn = strip2d_frames(dt, g, &c);
+    if (!tn) return false;
+    return (int64_t)(g.N / tn) * c.groups * c.row_tiles <= 0x7fffffffLL;
 }
 
 int shift2d_forward_strip(const void *x, const void *shift, void *out, int dt, int sdt, const Geom2 &g, cudaStream_t s) {
     StripArgs a{};
     a.src = x; a.dst = out; a.xin = nullptr; a.shift = shift; a.partial = nullptr; a.sdt = sdt;
-    a.N = g.N; a.Tn = 1; a.C = g.C; a.H = g.H; a.W = g.W; a.mode2d = 1;
-    if (!pick_strip_cfg((int)dtype_size(dt), 1, g.C, g.H, g.W, &a.cfg))
-        return fail(RB_ERR_UNSUPPORTED, "2D strip forward: no configuration");
+    a.C = g.C; a.H = g.H; a.W = g.W; a.mode2d = 1;
+    a.Tn = strip2d_frames(dt, g, &a.cfg);
+    if (!a.Tn) return fail(RB_ERR_UNSUPPORTED, "2D strip forward: no configuration");
+    a.N = g.N / a.Tn;
     return strip_dtype<SMODE_FWD>(dt, a, s);
 }
 
 size_t shift2d_backward_strip_workspace(int dt, const Geom2 &g) {
     StripCfg c;
-    if (!pick_strip_cfg((int)dtype_size(dt), 1, g.C, g.H, g.W, &c)) return 0;
-    return (size_t)g.C * g.N * c.row_tiles * 3 * sizeof(double);
+    const int tn = strip2d_frames(dt, g, &c);
+    if (!tn) return 0;
+    return (size_t)g.C * (g.N / tn) * c.row_tiles * 3 * sizeof(double);
 }
 
 int shift2d_backward_strip(const void *x, const void *shift, const void *og, void *gin, void *gshift, int dt, int sdt,
@@ -610,14 +621,15 @@ int shift2d_backward_strip(const void *x, const void *shift, const void *og, voi
     StripArgs a{};
     a.src = og; a.dst = gin; a.xin = gshift ? x : nullptr; a.shift = shift;
     a.partial = gshift ? (double *)workspace : nullptr; a.sdt = sdt;
-    a.N = g.N; a.Tn = 1; a.C = g.C; a.H = g.H; a.W = g.W; a.mode2d = 1;
-    if (!pick_strip_cfg((int)dtype_size(dt), 1, g.C, g.H, g.W, &a.cfg))
-        return fail(RB_ERR_UNSUPPORTED, "2D strip backward: no configuration");
+    a.C = g.C; a.H = g.H; a.W = g.W; a.mode2d = 1;
+    a.Tn = strip2d_frames(dt, g, &a.cfg);
+    if (!a.Tn) return fail(RB_ERR_UNSUPPORTED, "2D strip backward: no configuration");
+    a.N = g.N / a.Tn;
     int rc = strip_dtype<SMODE_BWD>(dt, a, s);
     if (rc || !gshift) return rc;
     const int warps = 4;
-    launch_kernel(k_shift2d_strip_finalize, dim3(cdiv(g.C, warps)), dim3(warps * 32), 0, s, (const double *)workspace, g.N * a.cfg.row_tiles, gshift, sdt,
-                                                                    g.C, normalize);
+    launch_kernel(k_shift2d_strip_finalize, dim3(cdiv(g.C, warps)), dim3(warps * 32), 0, s, (const double *)workspace, a.N * a.cfg.row_tiles, gshift, sdt,
+                  g.C, normalize);
     return launched("k_shift2d_strip_finalize");
 }
 

@@ -19,7 +19,7 @@ import torch.nn as nn
 from . import _lib, ops
 from .rubiksnet_cuda import _on_device
 
-__all__ = ["bn_act", "conv1x1", "se_gate", "rubiks_block", "rubiks_block_supported"]
+__all__ = ["bn_act", "conv1x1", "se_gate", "stem_conv", "rubiks_block", "rubiks_block_supported"]
 
 
 class _BNAct(torch.autograd.Function):
@@ -348,6 +348,59 @@ def conv1x1(x, weight, residual=None, stride=1):
     if x.dtype == torch.bfloat16 and weight.dtype in (torch.float32, torch.bfloat16):
         return _Conv1x1TC.apply(x, weight, residual)
     return _Conv1x1.apply(x, weight, residual)
+
+
+# ------------------------------------------------------------------------------------- first layer (conv1)
+
+class _StemConv(torch.autograd.Function):
+    """conv1 (3x3, stride 2, padding 1, no bias; rubiksnet/backbone.py:148-149) on the library's own kernels: one im2col
+    launch builds the bf16 patch matrix [NI, 32, Ho, Wo] (27 taps + 5 zero rows) straight from the fp32 clips, the
+    convolution is the tcgen05 1x1 GEMM on it and the weight gradient the tcgen05 weight-gradient kernel on the saved
+    patches -- instead of a cast, cuDNN's implicit GEMM and two NCHW<->NHWC transposes per direction (2.5 ms of a
+    RubiksNet-Large step at 32 clips).  The input gets no gradient (clips are data)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, stride):
+        cout, cin = weight.shape[0], weight.shape[1]
+        t = 9 * cin
+        tpad = (t + 15) // 16 * 16
+        cols = ops.im2col3x3(x.contiguous(), stride, tpad, torch.bfloat16)
+        w = torch.nn.functional.pad(weight.detach().reshape(cout, t).float(), (0, tpad - t)).contiguous()
+        ctx.save_for_backward(cols)
+        ctx.wshape, ctx.wdtype, ctx.t = weight.shape, weight.dtype, t
+        return ops.pw_conv(cols, w, name="pw_conv<conv1>")
+
+    @staticmethod
+    def backward(ctx, g):
+        (cols,) = ctx.saved_tensors
+        gw = None
+        if ctx.needs_input_grad[1]:
+            gw = ops.pw_conv_wgrad(g.contiguous(), cols, name="pw_conv_wgrad<conv1>")[:, :ctx.t].reshape(ctx.wshape).to(ctx.wdtype)
+        return None, gw, None
+
+
+def _stem_geometry_ok(conv, x):
+    return (isinstance(conv, nn.Conv2d) and conv.kernel_size == (3, 3) and conv.padding == (1, 1) and conv.dilation == (1, 1)
+            and conv.stride[0] == conv.stride[1] and conv.stride[0] in (1, 2) and conv.groups == 1 and conv.bias is None and conv.padding_mode == "zeros"
+            and x.is_cuda and x.dim() == 4 and not x.requires_grad and ((x.shape[3] - 1) // conv.stride[0] + 1) % 8 == 0)
+
+
+def stem_conv(conv, x):
+    """conv(x) for the network's first layer.  bf16 autocast (training or inference): im2col + tcgen05 GEMM (+ tcgen05
+    weight gradient); fp32 inference with TF32 convolutions allowed: im2col + the kind::tf32 GEMM; anything else (fp64,
+    fp32 training, an input that needs a gradient, odd geometries): the nn.Conv2d itself."""
+    if not _stem_geometry_ok(conv, x):
+        return conv(x)
+    if (torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.bfloat16
+            and x.dtype in (torch.float32, torch.bfloat16) and conv.weight.dtype == torch.float32):
+        with torch.autocast(device_type="cuda", enabled=False):
+            return _StemConv.apply(x, conv.weight, conv.stride[0])
+    if (x.dtype == torch.float32 and conv.weight.dtype == torch.float32 and not torch.is_grad_enabled()
+            and not torch.is_autocast_enabled("cuda") and torch.backends.cudnn.allow_tf32):
+        t = 9 * conv.weight.shape[1]
+        cols = ops.im2col3x3(x.contiguous(), conv.stride[0], t, torch.float32)
+        return ops.pw_conv_f32(cols, conv.weight.reshape(conv.weight.shape[0], t), resident=True, name="pw_conv_tf32<conv1>")
+    return conv(x)
 
 
 # ------------------------------------------------------------------------------------- squeeze-and-excitation

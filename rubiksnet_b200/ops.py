@@ -204,6 +204,19 @@ def pw_conv_f32(x, weight, residual=None, in_scale_bias=None, out_scale_bias=Non
     return out
 
 
+def im2col3x3(x, stride, tpad, out_dtype):
+    """Patch matrix [NI, tpad, Ho, Wo] of a 3x3 / padding-1 convolution of x [NI, Cin, H, W] (rows >= 9*Cin are zero)."""
+    assert x.is_contiguous() and x.dim() == 4
+    ni, cin, h, w = x.shape
+    ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
+    cols = torch.empty(ni, tpad, ho, wo, dtype=out_dtype, device=x.device)
+    with _on_device(x.device):
+        with _timed("im2col3x3", _nbytes(x, cols)):
+            _lib.check(_lib.lib().rb_im2col3x3(_lib.ptr(x), _lib.ptr(cols), _lib.dtype_code(x), _lib.dtype_code(cols), ni, cin, h, w,
+                                               int(stride), int(tpad), _lib.stream_handle(x.device)))
+    return cols
+
+
 def pw_weight_pack(weight):
     """bf16 copies of a fp32 conv weight [N,K(,1,1)] in both orientations: (w_nk [N,K], w_kn [K,N]); one launch.
     pw_conv(x, w_nk) is the forward, pw_conv(g, w_kn) the input gradient (no transposing weight staging)."""

@@ -222,3 +222,43 @@ def test_small_tier_uses_se_kernels():
     agg = _lib.timing.stop()
     assert agg["se_plane_scale"]["launches"] == 2 * 17 and agg["se_plane_reduce"]["launches"] == 2 * 17
     assert torch.isfinite(loss).item() and all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
+
+
+@pytest.mark.parametrize("cout,hw,stride", [(72, 224, 2), (54, 64, 2), (24, 32, 1)])
+def test_stem_conv_bf16_autocast_matches_conv2d(cout, hw, stride):
+    """conv1 as im2col + tcgen05 GEMM (+ tcgen05 weight gradient) vs nn.Conv2d in fp32 on the same clips."""
+    torch.manual_seed(11)
+    conv = nn.Conv2d(3, cout, 3, stride=stride, padding=1, bias=False).cuda()
+    x = torch.randn(6, 3, hw, hw, device="cuda")
+    want = conv(x)
+    g = torch.randn_like(want)
+    want.backward(g)
+    gw_ref = conv.weight.grad.clone()
+    conv.weight.grad = None
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        got = fused.stem_conv(conv, x)
+    assert got.dtype == torch.bfloat16 and got.shape == want.shape
+    got.backward(g.bfloat16())
+    assert _rel(got, want) <= 1e-2
+    assert _rel(conv.weight.grad, gw_ref) <= 1e-2
+
+
+def test_stem_conv_fp32_inference_and_fallbacks():
+    torch.manual_seed(12)
+    conv = nn.Conv2d(3, 54, 3, stride=2, padding=1, bias=False).cuda()
+    x = torch.randn(5, 3, 224, 224, device="cuda")
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    try:
+        with torch.no_grad():
+            got = fused.stem_conv(conv, x)  # kind::tf32 GEMM on the fp32 patch matrix
+            torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+            want = conv(x)
+            assert torch.equal(fused.stem_conv(conv, x), want)  # TF32 off: the module itself
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    assert got.dtype == torch.float32 and _rel(got, want) <= 2e-3
+    xg = x.clone().requires_grad_()  # an input that needs a gradient: the module itself
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = fused.stem_conv(conv, xg)
+    y.float().sum().backward()
+    assert xg.grad is not None
