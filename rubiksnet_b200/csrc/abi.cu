@@ -53,6 +53,11 @@ int shift3d_backward_strip(const void *, const void *, const void *, void *, voi
 bool shift2d_strip_supported(int dt, const Geom2 &g, int quantize);
 int shift2d_forward_strip(const void *x, const void *shift, void *out, int dt, int sdt, const Geom2 &g, cudaStream_t s);
 size_t shift2d_backward_strip_workspace(int dt, const Geom2 &g);
+bool shift2d_tiled_supported(int dt, const Geom2 &g, int quantize);
+int shift2d_forward_tiled(const void *x, const void *shift, void *out, int dt, int sdt, const Geom2 &g, cudaStream_t s);
+size_t shift2d_backward_tiled_workspace(int dt, const Geom2 &g);
+int shift2d_backward_tiled(const void *x, const void *shift, const void *og, void *gin, void *gshift, int dt, int sdt,
+                           const Geom2 &g, int normalize, void *workspace, cudaStream_t s);
 int shift2d_backward_strip(const void *x, const void *shift, const void *og, void *gin, void *gshift, int dt, int sdt,
                            const Geom2 &g, int normalize, void *workspace, cudaStream_t s);
 // shift2d_generic.cu
@@ -247,6 +252,13 @@ static bool use_strip2d(int dtype, int shift_dtype, const Geom2 &g, int quantize
     if (shift_dtype == RB_F64) return false;
     return shift2d_strip_supported(dtype, g, quantize);
 }
+// ... and the stride-2 ones of the down-sampling blocks (or any geometry under rb_set_impl(RB_IMPL_TILED)) on the tiled kernel
+static bool use_tiled2d(int dtype, int shift_dtype, const Geom2 &g, int quantize) {
+    const int forced = g_forced_impl.load(std::memory_order_relaxed);
+    if (forced == RB_IMPL_GENERIC || forced == RB_IMPL_STRIP) return false;
+    if (shift_dtype == RB_F64) return false;
+    return shift2d_tiled_supported(dtype, g, quantize);
+}
 
 int rb_shift2d_forward(const void *x, const void *shift, void *out, int dtype, int shift_dtype, int N,
                        int C, int H, int W, int sH, int sW, int pH, int pW, int quantize, void *stream) {
@@ -260,6 +272,10 @@ int rb_shift2d_forward(const void *x, const void *shift, void *out, int dtype, i
         g_last_impl = RB_IMPL_STRIP;
         return shift2d_forward_strip(x, shift, out, dtype, shift_dtype, g, (cudaStream_t)stream);
     }
+    if (use_tiled2d(dtype, shift_dtype, g, quantize)) {
+        g_last_impl = RB_IMPL_TILED;
+        return shift2d_forward_tiled(x, shift, out, dtype, shift_dtype, g, (cudaStream_t)stream);
+    }
     g_last_impl = RB_IMPL_GENERIC;
     return shift2d_forward_generic(x, shift, out, dtype, shift_dtype, g, quantize, (cudaStream_t)stream);
 }
@@ -272,6 +288,8 @@ size_t rb_shift2d_backward_workspace_bytes(int dtype, int N, int C, int H, int W
     size_t need = (size_t)C * shift2d_bwd_chunks(g) * 2 * sizeof(double);
     const size_t strip = shift2d_strip_supported(dtype, g, 0) ? shift2d_backward_strip_workspace(dtype, g) : 0;
     if (strip > need) need = strip;
+    const size_t tiled = shift2d_tiled_supported(dtype, g, 0) ? shift2d_backward_tiled_workspace(dtype, g) : 0;
+    if (tiled > need) need = tiled;
     return (need + 255) & ~(size_t)255;
 }
 
@@ -300,6 +318,10 @@ int rb_shift2d_backward(const void *x, const void *shift, const void *out_grad, 
     if (use_strip2d(dtype, shift_dtype, g, quantize)) {  // input gradient + shift gradient in one launch (+ finalize)
         g_last_impl = RB_IMPL_STRIP;
         return shift2d_backward_strip(x, shift, out_grad, x_grad, shift_grad, dtype, shift_dtype, g, normalize_grad, workspace, s);
+    }
+    if (use_tiled2d(dtype, shift_dtype, g, quantize)) {
+        g_last_impl = RB_IMPL_TILED;
+        return shift2d_backward_tiled(x, shift, out_grad, x_grad, shift_grad, dtype, shift_dtype, g, normalize_grad, workspace, s);
     }
     g_last_impl = RB_IMPL_GENERIC;
     if (shift_grad) {

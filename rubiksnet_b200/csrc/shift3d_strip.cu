@@ -122,7 +122,9 @@ __device__ __forceinline__ float sc_sg(int d, bool integer) {
 }
 
 template <typename T, int MODE, int R, bool VEC>
-__global__ void __launch_bounds__(kSNT) k_shift3d_strip(const StripArgs a) {
+// backward: 5 CTAs per SM (96 registers, 28 bytes of spills) instead of the 4 that its natural 125 registers allow -- the kernel is
+// issue/latency-bound at 21 % active warps (profiles/r02_ncu_shift_kernels.txt), so residency buys more than the spills cost
+__global__ void __launch_bounds__(kSNT, MODE == SMODE_BWD ? 5 : 1) k_shift3d_strip(const StripArgs a) {
     pdl_sync();
     constexpr int ES = (int)sizeof(T);
     constexpr int CW = StripTraits<T>::CW;
@@ -589,6 +591,8 @@ static int strip2d_frames(int dt, const Geom2 &g, StripCfg *c) {
     return 0;
 }
 
+int shift2d_strip_finalize(const double *partial, int parts, void *gshift, int sdt, int C, int normalize, cudaStream_t s);
+
 bool shift2d_strip_supported(int dt, const Geom2 &g, int quantize) {
     if (quantize) return false;
     if (dt != RB_F32 && dt != RB_F16 && dt != RB_BF16) return false;
@@ -627,9 +631,13 @@ int shift2d_backward_strip(const void *x, const void *shift, const void *og, voi
     a.N = g.N / a.Tn;
     int rc = strip_dtype<SMODE_BWD>(dt, a, s);
     if (rc || !gshift) return rc;
+    return shift2d_strip_finalize((const double *)workspace, a.N * a.cfg.row_tiles, gshift, sdt, g.C, normalize, s);
+}
+
+// partial [C][parts][3] (temporal slot unused) -> shift_grad [2, C] incl. the 2D normalisation; also used by the tiled kernel
+int shift2d_strip_finalize(const double *partial, int parts, void *gshift, int sdt, int C, int normalize, cudaStream_t s) {
     const int warps = 4;
-    launch_kernel(k_shift2d_strip_finalize, dim3(cdiv(g.C, warps)), dim3(warps * 32), 0, s, (const double *)workspace, a.N * a.cfg.row_tiles, gshift, sdt,
-                  g.C, normalize);
+    launch_kernel(k_shift2d_strip_finalize, dim3(cdiv(C, warps)), dim3(warps * 32), 0, s, partial, parts, gshift, sdt, C, normalize);
     return launched("k_shift2d_strip_finalize");
 }
 

@@ -59,6 +59,7 @@ struct TiledArgs {
     int N, Tn, C;
     int Hs, Ws, Hd, Wd; // source / destination plane extents
     int S;              // spatial stride (1 or 2)
+    int mode2d;         // 2D shift (cuda_src/rubiks2d_kernels.cu): shift is [2, C] (H, W); the Tn frames of a CTA are independent images
     TileCfg cfg;
 };
 
@@ -148,12 +149,27 @@ __global__ void __launch_bounds__(kNW * 32) k_shift3d_tiled(const TiledArgs a) {
     const int HWs = Hs * Ws, HWd = Hd * Wd;
 
     // ---- warp-uniform channel parameters --------------------------------------------------------
-    float sT = ld_param<float>(a.shift, a.sdt, cc), sH = ld_param<float>(a.shift, a.sdt, a.C + cc),
-          sW = ld_param<float>(a.shift, a.sdt, 2 * a.C + cc);
+    float sT, sH, sW;
+    if (a.mode2d) {
+        sT = 0.f;
+        sH = ld_param<float>(a.shift, a.sdt, cc);
+        sW = ld_param<float>(a.shift, a.sdt, a.C + cc);
+        if (MODE == MODE_BWD) {
+            // the 2D shift gradient treats |r| < 1e-7 as an exact integer shift (rubiks2d_kernels.cu:189): snap the shift
+            const float fh = floorf(sH), fw = floorf(sW);
+            if (fabsf(sH - fh) < 1e-7f) sH = fh;
+            if (fabsf(sW - fw) < 1e-7f) sW = fw;
+        }
+    } else {
+        sT = ld_param<float>(a.shift, a.sdt, cc);
+        sH = ld_param<float>(a.shift, a.sdt, a.C + cc);
+        sW = ld_param<float>(a.shift, a.sdt, 2 * a.C + cc);
+    }
     if (MODE == MODE_BWD) { sT = -sT; sH = -sH; sW = -sW; }  // adjoint gathers at the negated shift (:505-507)
     const int fT = floor3d(sT), fH = floor3d(sH), fW = floor3d(sW);
     const float rT = sT - fT, rH = sH - fH, rW = sW - fW;
-    const bool intT = (rT == 0.f), intH = (rH == 0.f), intW = (rW == 0.f);
+    // 2D: no temporal component (frame t reads frame t with weight 1; must not trigger the integer rule)
+    const bool intT = !a.mode2d && (rT == 0.f), intH = (rH == 0.f), intW = (rW == 0.f);
     const bool slow = (MODE == MODE_BWD) && (intT || intH || intW);
 
     // ---- rows of the source plane this CTA stages (CTA-uniform) ---------------------------------
@@ -312,12 +328,12 @@ __global__ void __launch_bounds__(kNW * 32) k_shift3d_tiled(const TiledArgs a) {
                 }
                 if (td >= 0) {
                     const int p = p0 + k * pstride;
-                    const float v = wT0 * pB[k] + wT1 * cB;
+                    const float v = a.mode2d ? pB[k] : wT0 * pB[k] + wT1 * cB;
                     if (want_dst && c_ok && p < P) dst[dst_chan + td * dst_fs + p] = cvt<T, float>(v);
                     if (MODE == MODE_BWD) {
                         accT += xv[k] * (pB[k] - cB);
-                        accH += xv[k] * (wT0 * pDH[k] + wT1 * cDH);
-                        accW += xv[k] * (wT0 * pDW[k] + wT1 * cDW);
+                        accH += xv[k] * (a.mode2d ? pDH[k] : wT0 * pDH[k] + wT1 * cDH);
+                        accW += xv[k] * (a.mode2d ? pDW[k] : wT0 * pDW[k] + wT1 * cDW);
                     }
                 }
                 pB[k] = cB;
@@ -352,12 +368,35 @@ __global__ void __launch_bounds__(kNW * 32) k_shift3d_tiled(const TiledArgs a) {
                         const float q121 = tap(t0, h0 + 1, w0), q122 = tap(t0, h0 + 1, w0 + 1);
                         const float q211 = tap(t0 + 1, h0, w0), q212 = tap(t0 + 1, h0, w0 + 1);
                         const float q221 = tap(t0 + 1, h0 + 1, w0), q222 = tap(t0 + 1, h0 + 1, w0 + 1);
-                        v = wT0 * (wH0 * (q111 * wW0 + q112 * wW1) + wH1 * (q121 * wW0 + q122 * wW1)) +
-                            wT1 * (wH0 * (q211 * wW0 + q212 * wW1) + wH1 * (q221 * wW0 + q222 * wW1));
+                        v = wH0 * (q111 * wW0 + q112 * wW1) + wH1 * (q121 * wW0 + q122 * wW1);
+                        if (!a.mode2d) v = wT0 * v + wT1 * (wH0 * (q211 * wW0 + q212 * wW1) + wH1 * (q221 * wW0 + q222 * wW1));
                     }
                     dst[dst_chan + td * dst_fs + p] = cvt<T, float>(v);
                 }
-                if (want_grad) {
+                if (want_grad && a.mode2d) {
+                    // 2D rule (rubiks2d_kernels.cu:189-253) in adjoint form: regular axis = difference of the two taps;
+                    // exact-integer axis = 0.5 * central difference (taps -1 and +1); the other axis always interpolates
+                    // with (1 - r, r)
+                    float gH = 0.f, gW = 0.f;
+#pragma unroll 1
+                    for (int dy = -1; dy <= 1; ++dy) {
+                        const float bh = coef_a(dy, rH);
+                        const float sh = intH ? (dy == -1 ? 0.5f : (dy == 1 ? -0.5f : 0.f)) : (dy == 0 ? 1.f : (dy == 1 ? -1.f : 0.f));
+#pragma unroll 1
+                        for (int dx = -1; dx <= 1; ++dx) {
+                            const float bw = coef_a(dx, rW);
+                            const float sw = intW ? (dx == -1 ? 0.5f : (dx == 1 ? -0.5f : 0.f)) : (dx == 0 ? 1.f : (dx == 1 ? -1.f : 0.f));
+                            const float cH = sh * bw, cW = bh * sw;
+                            if (cH == 0.f && cW == 0.f) continue;
+                            const float qq = tap(t0, h0 + dy, w0 + dx);
+                            gH += cH * qq;
+                            gW += cW * qq;
+                        }
+                    }
+                    const float xv = ld<float, T>(xin + dst_chan + td * dst_fs + p);
+                    accH += xv * gH;
+                    accW += xv * gW;
+                } else if (want_grad) {
                     float gT = 0.f, gH = 0.f, gW = 0.f;
 #pragma unroll 1
                     for (int dt = -1; dt <= 1; ++dt) {
@@ -552,6 +591,62 @@ int shift3d_backward_tiled(const void *x, const void *shift, const void *og, voi
     if (rc || !gshift) return rc;
     return shift3d_finalize((const double *)workspace, g.N * a.cfg.row_tiles, gshift, dt, sdt, g.C, normalize,
                             factor, s);
+}
+
+// ---- 2D shift (stride 1 or 2) on the same kernel: groups of Tn images per CTA, no temporal taps ---------------------
+int shift2d_strip_finalize(const double *partial, int parts, void *gshift, int sdt, int C, int normalize, cudaStream_t s);
+
+static int tiled2d_frames(int dt, const Geom2 &g, TileCfg *cf, TileCfg *cb) {
+    const int es = (int)dtype_size(dt);
+    for (int tn = 8; tn >= 1; tn >>= 1)
+        if (g.N % tn == 0 && pick_cfg(MODE_FWD, es, tn, g.C, g.H, g.W, g.Ho, g.Wo, g.sH, kKmaxFwd, cf) &&
+            pick_cfg(MODE_BWD, es, tn, g.C, g.Ho, g.Wo, g.H, g.W, g.sH, kKmaxBwd, cb))
+            return tn;
+    return 0;
+}
+
+bool shift2d_tiled_supported(int dt, const Geom2 &g, int quantize) {
+    if (quantize) return false;
+    if (dt != RB_F32 && dt != RB_F16 && dt != RB_BF16) return false;
+    if (g.pH != 0 || g.pW != 0 || g.sH != g.sW || (g.sH != 1 && g.sH != 2)) return false;
+    if (g.Ho <= 0 || g.Wo <= 0) return false;
+    TileCfg cf, cb;
+    const int tn = tiled2d_frames(dt, g, &cf, &cb);
+    if (!tn) return false;
+    return (int64_t)(g.N / tn) * cf.groups * cf.row_tiles <= 0x7fffffffLL && (int64_t)(g.N / tn) * cb.groups * cb.row_tiles <= 0x7fffffffLL;
+}
+
+int shift2d_forward_tiled(const void *x, const void *shift, void *out, int dt, int sdt, const Geom2 &g, cudaStream_t s) {
+    TiledArgs a{};
+    TileCfg cb;
+    a.src = x; a.dst = out; a.xin = nullptr; a.shift = shift; a.partial = nullptr; a.sdt = sdt;
+    a.C = g.C; a.Hs = g.H; a.Ws = g.W; a.Hd = g.Ho; a.Wd = g.Wo; a.S = g.sH; a.mode2d = 1;
+    a.Tn = tiled2d_frames(dt, g, &a.cfg, &cb);
+    if (!a.Tn) return fail(RB_ERR_UNSUPPORTED, "2D tiled forward: no tile configuration");
+    a.N = g.N / a.Tn;
+    return launch_dtype<MODE_FWD>(dt, a, s);
+}
+
+size_t shift2d_backward_tiled_workspace(int dt, const Geom2 &g) {
+    TileCfg cf, cb;
+    const int tn = tiled2d_frames(dt, g, &cf, &cb);
+    if (!tn) return 0;
+    return (size_t)g.C * (g.N / tn) * cb.row_tiles * 3 * sizeof(double);
+}
+
+int shift2d_backward_tiled(const void *x, const void *shift, const void *og, void *gin, void *gshift, int dt, int sdt,
+                           const Geom2 &g, int normalize, void *workspace, cudaStream_t s) {
+    TiledArgs a{};
+    TileCfg cf;
+    a.src = og; a.dst = gin; a.xin = gshift ? x : nullptr; a.shift = shift;
+    a.partial = gshift ? (double *)workspace : nullptr; a.sdt = sdt;
+    a.C = g.C; a.Hs = g.Ho; a.Ws = g.Wo; a.Hd = g.H; a.Wd = g.W; a.S = g.sH; a.mode2d = 1;
+    a.Tn = tiled2d_frames(dt, g, &cf, &a.cfg);
+    if (!a.Tn) return fail(RB_ERR_UNSUPPORTED, "2D tiled backward: no tile configuration");
+    a.N = g.N / a.Tn;
+    int rc = launch_dtype<MODE_BWD>(dt, a, s);
+    if (rc || !gshift) return rc;
+    return shift2d_strip_finalize((const double *)workspace, a.N * a.cfg.row_tiles, gshift, sdt, g.C, normalize, s);
 }
 
 }  // namespace rb

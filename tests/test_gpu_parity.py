@@ -193,6 +193,34 @@ def test_shift2d_vs_oracle(shape, stride, padding, kind, dtype):
     assert_close(gs.double().cpu().numpy(), gs_ref, 1e-4 if dtype != "float64" else 1e-10, "shift_grad")
 
 
+@pytest.mark.parametrize("dtype", ["float32", "bfloat16"])
+@pytest.mark.parametrize("kind", ["rand1", "rand3", "integer", "halves", "zero"])
+@pytest.mark.parametrize("shape,stride", [((16, 12, 28, 28), 2), ((8, 5, 56, 56), 2), ((6, 7, 14, 14), 1), ((3, 4, 30, 22), 2)])
+def test_shift2d_tiled_kernel_vs_oracle(shape, stride, kind, dtype):
+    """2D shift on the TMA-staged tiled kernel (stride 2: the down-sampling blocks of the attention-quantized variant;
+    groups of images share a CTA, 2D integer rule in the slow path) vs the oracle; the dispatcher must pick it."""
+    rng = np.random.default_rng(17)
+    td = TDT[dtype]
+    x = rng.standard_normal(shape).astype(np.float32)
+    s = make_shift(rng, kind, 2, shape[1])
+    og = rng.standard_normal(oracle.shift2d_forward(x, s, stride, 0).shape).astype(np.float32)
+    tx, tg, ts = _cuda(x, td), _cuda(og, td), _cuda(s)
+    try:
+        _lib.set_impl(_lib.RB_IMPL_TILED if stride == 1 else _lib.RB_IMPL_AUTO)
+        out = rubiks2d_forward(tx, ts, stride, 0)
+        assert _lib.last_impl() == _lib.RB_IMPL_TILED
+        gin, gs = rubiks2d_backward(tg, tx, ts, stride, 0, normalize_grad=False)
+        assert _lib.last_impl() == _lib.RB_IMPL_TILED
+    finally:
+        _lib.set_impl(_lib.RB_IMPL_AUTO)
+    rx, rg = tx.float().cpu().numpy(), tg.float().cpu().numpy()
+    o_ref = oracle.shift2d_forward(rx, s, stride, 0)
+    gin_ref, gs_ref = oracle.shift2d_backward(rx, s, rg, stride, 0, normalize_grad=False)
+    assert_close(out.float().cpu().numpy(), o_ref, TOL[dtype], "out")
+    assert_close(gin.float().cpu().numpy(), gin_ref, TOL[dtype], "x_grad")
+    assert_close(gs.float().cpu().numpy(), gs_ref, 1e-4, "shift_grad")
+
+
 @pytest.mark.skipif(GOLD is None, reason="tests/golden/shift_golden.npz not generated yet")
 @pytest.mark.parametrize("name", sorted(cases2d()))
 def test_shift2d_vs_reference_golden(name):
