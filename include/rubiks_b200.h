@@ -205,6 +205,14 @@ int rb_pw_conv_forward_f32(const float *x, const float *weight, const float *res
                            int HW, const float *in_scale_bias, const float *out_scale_bias, int out_relu, int flags,
                            void *stream);
 
+/* Input pipeline on the GPU (rubiksnet/transforms.py:66-79,329-363: Stack -> ToTorchFormatTensor -> GroupNormalize, which the
+ * reference runs on the CPU per sample): frames_u8 [N, H, W, channels] uint8 (channels = 3 * frames, RGB-minor, as `Stack`
+ * concatenates them) -> out [N, channels, H, W] (= [N * frames, 3, H, W], the model input) in out_dtype RB_F32 / RB_BF16,
+ *     out[n, c, h, w] = ((div255 ? x / 255 : x) - mean3[c % 3]) / std3[c % 3].
+ * mean3 / std3 are HOST arrays of 3 floats (RubiksNet.input_mean / input_std). */
+int rb_frames_to_clip(const void *frames_u8, void *out, int out_dtype, int N, int H, int W, int channels, const float *mean3,
+                      const float *std3, int div255, void *stream);
+
 /* Patch matrix of the 3x3 / stride-S / padding-1 first convolution (rubiksnet/backbone.py:148-149): cols [NI, Tpad, Ho, Wo],
  * cols[i, (ci*3 + kh)*3 + kw, ho, wo] = x[i, ci, ho*S - 1 + kh, wo*S - 1 + kw] (0 outside the image), rows >= 9*Cin zero.
  * conv1(x) = rb_pw_conv_forward / rb_pw_conv_forward_f32 (cols, weight viewed [Cout, 9*Cin] and zero-padded to Tpad);

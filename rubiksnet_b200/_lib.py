@@ -74,6 +74,8 @@ def _declare(lib):
     lib.rb_pw_conv_forward_f32.restype = i
     lib.rb_im2col3x3.argtypes = [vp, vp, i, i, i, i, i, i, i, i, vp]
     lib.rb_im2col3x3.restype = i
+    lib.rb_frames_to_clip.argtypes = [vp, vp, i, i, i, i, i, ctypes.POINTER(fl), ctypes.POINTER(fl), i, vp]
+    lib.rb_frames_to_clip.restype = i
     lib.rb_pw_conv_forward_stats.argtypes = [vp, vp, i, i, vp, vp, i, i, i, i, i, vp, vp, sz, ctypes.POINTER(ctypes.c_int), vp]
     lib.rb_pw_conv_forward_stats.restype = i
     lib.rb_bn_stats_finalize.argtypes = [vp, i, i, dbl, vp, vp, vp, vp, fl, fl, vp, vp, vp]

@@ -122,9 +122,10 @@ __device__ __forceinline__ float sc_sg(int d, bool integer) {
 }
 
 template <typename T, int MODE, int R, bool VEC>
-// backward: 5 CTAs per SM (96 registers, 28 bytes of spills) instead of the 4 that its natural 125 registers allow -- the kernel is
-// issue/latency-bound at 21 % active warps (profiles/r02_ncu_shift_kernels.txt), so residency buys more than the spills cost
-__global__ void __launch_bounds__(kSNT, MODE == SMODE_BWD ? 5 : 1) k_shift3d_strip(const StripArgs a) {
+// (forcing 5 CTAs/SM on the backward -- 96 registers, 28 bytes of spills instead of 125 registers -- was measured SLOWER on every
+// geometry, 0.631 -> 0.761 ms at 112x112 and 0.052 -> 0.058 ms at 14x14, gpurun_out/r02ae: the kernel is issue-bound, not
+// residency-bound)
+__global__ void __launch_bounds__(kSNT) k_shift3d_strip(const StripArgs a) {
     pdl_sync();
     constexpr int ES = (int)sizeof(T);
     constexpr int CW = StripTraits<T>::CW;

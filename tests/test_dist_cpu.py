@@ -59,3 +59,46 @@ def test_shard_batch():
     assert [shard_batch(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
     assert shard_batch(32, 0, 1) == (0, 32)
     assert [shard_batch(2, r, 4) for r in range(4)] == [(0, 1), (1, 2), (2, 2), (2, 2)]
+
+
+# ---------------------------------------------------------------- sharded evaluation loop (scripts/test_models.py:140-200)
+
+class _ClipNet(nn.Module):
+    """Stand-in for RubiksNet: [B, T, 3, H, W] clips -> [B, classes] logits."""
+
+    def __init__(self):
+        super().__init__()
+        torch.manual_seed(1)
+        self.fc = nn.Linear(3, 7)
+
+    def forward(self, clips):
+        return self.fc(clips.mean(dim=(1, 3, 4)))
+
+
+def _eval_batches():
+    g = torch.Generator().manual_seed(5)
+    return [(torch.randn(4, 2 * 8 * 3, 6, 6, generator=g), torch.randint(0, 7, (4,), generator=g)) for _ in range(5)]
+
+
+def _eval_worker(rank, world, port, out):
+    from rubiksnet_b200.evaluate import evaluate
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    res = evaluate(_ClipNet(), _eval_batches(), num_crops=2, frames=8)
+    if rank == 0:
+        torch.save(res, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_evaluation_matches_single_process(tmp_path):
+    from rubiksnet_b200.evaluate import evaluate, topk_hits
+    out = str(tmp_path / "e.pt")
+    mp.spawn(_eval_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = torch.load(out)
+    want = evaluate(_ClipNet(), _eval_batches(), num_crops=2, frames=8)
+    assert got["videos"] == want["videos"] == 20
+    assert got["prec1"] == want["prec1"] and got["prec5"] == want["prec5"]
+    # the counters follow the reference's accuracy(): label among the k largest averaged logits
+    logits = torch.tensor([[0.1, 0.9, 0.0], [0.8, 0.1, 0.1], [0.2, 0.3, 0.5]])
+    assert topk_hits(logits, torch.tensor([1, 2, 2]), (1, 2)) == [2, 2]
