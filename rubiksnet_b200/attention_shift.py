@@ -15,20 +15,43 @@ from .rubiksnet_cuda import _on_device
 __all__ = ["AttentionShift", "attention_shift_mix"]
 
 
+def attention_mix_forward(x, taps, n_segment):
+    """Plain (no autograd) forward of the 3-tap temporal mix: x [N*T, C, H, W] contiguous, taps fp32 [C, 3]."""
+    assert x.is_cuda, "attention shift only works on CUDA tensors"
+    nt, c, h, w = x.shape
+    assert nt % n_segment == 0, "batch (N*T) must be a multiple of n_segment"
+    out = torch.empty_like(x)
+    with _on_device(x.device), _lib.timed("attention_shift_forward", _lib.nbytes(x, out)):
+        _lib.check(_lib.lib().rb_attention_shift_forward(
+            _lib.ptr(x), _lib.ptr(taps), _lib.ptr(out), _lib.dtype_code(x), nt // n_segment, n_segment,
+            c, h * w, _lib.stream_handle(x.device)))
+    return out
+
+
+def attention_mix_backward(x, taps, grad_out, n_segment, need_x=True, need_t=True):
+    """(x_grad, taps_grad) of attention_mix_forward; either may be skipped."""
+    nt, c, h, w = x.shape
+    n = nt // n_segment
+    gx = torch.empty_like(x) if need_x else None
+    gt = torch.empty_like(taps) if need_t else None
+    with _on_device(x.device):
+        L = _lib.lib()
+        nbytes = L.rb_attention_shift_backward_workspace_bytes(n, n_segment, c, h * w) if need_t else 0
+        ws = _lib.workspace(nbytes, x.device)
+        with _lib.timed("attention_shift_backward", _lib.nbytes(x, grad_out, gx)):
+            _lib.check(L.rb_attention_shift_backward(
+                _lib.ptr(x), _lib.ptr(taps), _lib.ptr(grad_out), _lib.ptr(gx), _lib.ptr(gt), _lib.dtype_code(x),
+                n, n_segment, c, h * w, _lib.ptr(ws), nbytes, _lib.stream_handle(x.device)))
+    return gx, gt
+
+
 class _AttentionMix(torch.autograd.Function):
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda")
     def forward(ctx, x, taps, n_segment):
-        assert x.is_cuda, "attention shift only works on CUDA tensors"
         x = x.contiguous()
         taps = taps.contiguous().float()
-        nt, c, h, w = x.shape
-        assert nt % n_segment == 0, "batch (N*T) must be a multiple of n_segment"
-        out = torch.empty_like(x)
-        with _on_device(x.device), _lib.timed("attention_shift_forward", _lib.nbytes(x, out)):
-            _lib.check(_lib.lib().rb_attention_shift_forward(
-                _lib.ptr(x), _lib.ptr(taps), _lib.ptr(out), _lib.dtype_code(x), nt // n_segment, n_segment,
-                c, h * w, _lib.stream_handle(x.device)))
+        out = attention_mix_forward(x, taps, n_segment)
         ctx.save_for_backward(x, taps)
         ctx.n_segment = n_segment
         return out
@@ -40,19 +63,7 @@ class _AttentionMix(torch.autograd.Function):
         need_x, need_t = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if not (need_x or need_t):
             return None, None, None
-        grad_out = grad_out.contiguous()
-        nt, c, h, w = x.shape
-        n = nt // ctx.n_segment
-        gx = torch.empty_like(x) if need_x else None
-        gt = torch.empty_like(taps) if need_t else None
-        with _on_device(x.device):
-            L = _lib.lib()
-            nbytes = L.rb_attention_shift_backward_workspace_bytes(n, ctx.n_segment, c, h * w) if need_t else 0
-            ws = _lib.workspace(nbytes, x.device)
-            with _lib.timed("attention_shift_backward", _lib.nbytes(x, grad_out, gx)):
-                _lib.check(L.rb_attention_shift_backward(
-                    _lib.ptr(x), _lib.ptr(taps), _lib.ptr(grad_out), _lib.ptr(gx), _lib.ptr(gt), _lib.dtype_code(x),
-                    n, ctx.n_segment, c, h * w, _lib.ptr(ws), nbytes, _lib.stream_handle(x.device)))
+        gx, gt = attention_mix_backward(x, taps, grad_out.contiguous(), ctx.n_segment, need_x, need_t)
         return gx, gt, None
 
 

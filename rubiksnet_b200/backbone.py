@@ -97,6 +97,10 @@ class RubiksShiftBlock(nn.Module):
             return fused.eval_block(self, x)
         if FUSED_WHOLE_BLOCK and fused.rubiks_block_supported(self, x):
             return fused.rubiks_block(self, x)
+        if FUSED_WHOLE_BLOCK and fused.rubiks_down_block_supported(self, x):
+            return fused.rubiks_down_block(self, x)
+        if FUSED_WHOLE_BLOCK and fused.rubiks_aq_block_supported(self, x):
+            return fused.rubiks_aq_block(self, x)
         out = fused.bn_act(x, self.bn1, relu=True)
         if isinstance(self.shortcut, nn.Identity):
             shortcut = x

@@ -72,7 +72,7 @@ def evaluate(net, batches, num_crops=1, frames=8, process_group=None, device=Non
                 data = data.to(device, non_blocking=True)
                 if data.dtype == torch.uint8:
                     data = frames_to_clip(data.contiguous(), mean, std)
-                data = data.reshape(b * num_crops, frames, 3, data.shape[-2], data.shape[-1])
+                data = data.contiguous().view(b * num_crops, frames, 3, data.shape[-2], data.shape[-1])
                 if autocast_dtype is not None and device.type == "cuda":
                     with torch.autocast("cuda", dtype=autocast_dtype):
                         rst = net(data)

@@ -19,7 +19,8 @@ import torch.nn as nn
 from . import _lib, ops
 from .rubiksnet_cuda import _on_device
 
-__all__ = ["bn_act", "conv1x1", "se_gate", "stem_conv", "rubiks_block", "rubiks_block_supported"]
+__all__ = ["bn_act", "conv1x1", "se_gate", "stem_conv", "rubiks_block", "rubiks_block_supported", "rubiks_down_block",
+           "rubiks_down_block_supported", "rubiks_aq_block", "rubiks_aq_block_supported"]
 
 
 class _BNAct(torch.autograd.Function):
@@ -554,10 +555,11 @@ FUSE_SHIFT_CONV3 = False
 EPILOGUE_BN_STATS = False
 
 
-def _shift3d_forward(x, shift, frames):
+def _shift3d_forward(x, shift, frames, stride=1):
     from .shiftlib.rubiks3d.primitive import rubiks_shift_3d_forward
     nt, c, h, w = x.shape
-    return rubiks_shift_3d_forward(x.view(nt // frames, frames, c, h, w), shift, (1, 1, 1), 0).view(nt, c, h, w)
+    out = rubiks_shift_3d_forward(x.view(nt // frames, frames, c, h, w), shift, (1, stride, stride), 0)
+    return out.view(nt, c, out.shape[-2], out.shape[-1])
 
 
 class _RubiksBlockFn(torch.autograd.Function):
@@ -629,6 +631,207 @@ class _RubiksBlockFn(torch.autograd.Function):
         del gy2
         gx, dg1, db1 = ops.bn_backward(x, go, g, g1, mi1, sb1, tr1, relu=True, need_dx=need[0])
         return gx, dg1, db1, gw2, dg2, db2, gshift, gw3, None, None, None, None, None, None
+
+
+class _RubiksDownBlockFn(torch.autograd.Function):
+    """Down-sampling RubiksShiftBlock (first block of layer1..4: 3D shift with stride (1,2,2), 1x1 shortcut conv with stride 2,
+    rubiksnet/backbone.py:104-105,109-135) as one Function, bf16.  relu(bn1(x)) is never materialised: conv2 applies it in
+    its operand producer, and the shortcut conv -- which only sees every other row / column -- gets it from a BN-apply pass
+    over the sub-sampled quarter of x.  In the backward pass the shortcut's input gradient is added into the sub-sampled
+    positions of conv2's input gradient in place (one strided pass over a quarter of the elements) instead of autograd's
+    zero-fill + scatter + full-size add."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, x, g1, b1, w2, g2, b2, shift, w3, wsc, bn1, bn2, frames, normalize_grad, normalize_t_factor):
+        x = x.contiguous()
+        tr1, mom1, eps1, rm1, rv1 = _bn_cfg(bn1)
+        tr2, mom2, eps2, rm2, rv2 = _bn_cfg(bn2)
+        ni, hw = x.shape[0], x.shape[2] * x.shape[3]
+        w2_nk, w2_kn = _pack_weight(w2, ni, hw)
+        w3_nk, w3_kn = _pack_weight(w3, ni, hw // 4)
+        wsc_nk, wsc_kn = _pack_weight(wsc, ni, hw // 4)
+        _, mi1, sb1 = ops.bn_forward(x, g1, b1, rm1, rv1, tr1, mom1, eps1, relu=True, apply=False)
+        o_sub = ops.bn_apply(x[:, :, ::2, ::2].contiguous(), sb1, relu=True)  # relu(bn1(x)) where the shortcut looks
+        sc = ops.pw_conv(o_sub, wsc_nk, name="pw_conv", resident=True)
+        y2 = ops.pw_conv(x, w2_nk, in_scale_bias=sb1, name="pw_conv<bn+relu>", resident=True)
+        a2, mi2, sb2 = ops.bn_forward(y2, g2, b2, rm2, rv2, tr2, mom2, eps2, relu=True, apply=True)
+        s3 = _shift3d_forward(a2, shift, frames, stride=2)
+        out = ops.pw_conv(s3, w3_nk, residual=sc, name="pw_conv<+residual>", resident=True)
+        del sc
+        saved_w = [t for w in (w2_kn, w3_kn, wsc_kn) for t in (_wsave(w)[0],)]
+        ctx.wmeta = tuple(_wsave(w)[1] for w in (w2_kn, w3_kn, wsc_kn))
+        ctx.save_for_backward(x, o_sub, y2, a2, s3, mi1, sb1, mi2, sb2, g1, g2, w2, w3, wsc, shift, *saved_w)
+        ctx.cfg = (tr1, tr2, frames, normalize_grad, normalize_t_factor)
+        return out
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, g):
+        x, o_sub, y2, a2, s3, mi1, sb1, mi2, sb2, g1, g2, w2, w3, wsc, shift, w2_kn, w3_kn, wsc_kn = ctx.saved_tensors
+        tr1, tr2, frames, normalize_grad, normalize_t_factor = ctx.cfg
+        w2_kn, w3_kn, wsc_kn = (_wload(t, m) for t, m in zip((w2_kn, w3_kn, wsc_kn), ctx.wmeta))
+        g = g.contiguous()
+        need = ctx.needs_input_grad
+        gs = ops.pw_conv(g, w3_kn, name="pw_conv<dgrad>", resident=True)
+        gw3 = ops.pw_conv_wgrad(g, s3).view(w3.shape) if need[7] else None
+        del s3
+        ga2, gshift = ops.shift3d_backward(a2, shift, gs, frames, normalize_grad, normalize_t_factor, need_shift=need[6], stride=2)
+        del gs
+        gy2, dg2, db2 = ops.bn_backward(y2, ga2, None, g2, mi2, sb2, tr2, relu=True)
+        del ga2
+        go = ops.pw_conv(gy2, w2_kn, name="pw_conv<dgrad>", resident=True)
+        gw2 = ops.pw_conv_wgrad(gy2, x, in_scale_bias=sb1, name="pw_conv_wgrad<bn+relu>").view(w2.shape) if need[3] else None
+        del gy2
+        # shortcut path: `out = conv3(...) + sc` hands g to the shortcut conv unchanged
+        gwsc = ops.pw_conv_wgrad(g, o_sub).view(wsc.shape) if need[8] else None
+        go[:, :, ::2, ::2] += ops.pw_conv(g, wsc_kn, name="pw_conv<dgrad>", resident=True)
+        gx, dg1, db1 = ops.bn_backward(x, go, None, g1, mi1, sb1, tr1, relu=True, need_dx=need[0])
+        return gx, dg1, db1, gw2, dg2, db2, gshift, gw3, gwsc, None, None, None, None, None
+
+
+class _RubiksAQBlockFn(torch.autograd.Function):
+    """Identity-shortcut block of the attention-quantized variant (rubiksnet/models.py:100-104: AttentionShift in front of
+    conv2, the block keeps its 2D spatial shift) as one Function, bf16:
+        fwd  bn1 stats+apply | temporal mix | conv2 | bn2 stats+apply | 2D shift | conv3 + residual
+        bwd  conv3 dgrad / wgrad | 2D shift bwd | bn2 bwd | conv2 dgrad / wgrad | temporal mix bwd | bn1 bwd + shortcut gradient
+    `taps` is the [C, 3] softmax of the attention weights, computed by autograd outside (its gradient is returned)."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, x, g1, b1, taps, w2, g2, b2, shift, w3, bn1, bn2, frames, normalize_grad):
+        from .attention_shift import attention_mix_forward
+        from .shiftlib.rubiks2d.primitive import rubiks2d_forward
+        x = x.contiguous()
+        taps = taps.contiguous().float()
+        tr1, mom1, eps1, rm1, rv1 = _bn_cfg(bn1)
+        tr2, mom2, eps2, rm2, rv2 = _bn_cfg(bn2)
+        hw = x.shape[2] * x.shape[3]
+        w2_nk, w2_kn = _pack_weight(w2, x.shape[0], hw)
+        w3_nk, w3_kn = _pack_weight(w3, x.shape[0], hw)
+        o, mi1, sb1 = ops.bn_forward(x, g1, b1, rm1, rv1, tr1, mom1, eps1, relu=True, apply=True)
+        att = attention_mix_forward(o, taps, frames)
+        y2 = ops.pw_conv(att, w2_nk, name="pw_conv", resident=True)
+        a2, mi2, sb2 = ops.bn_forward(y2, g2, b2, rm2, rv2, tr2, mom2, eps2, relu=True, apply=True)
+        s3 = rubiks2d_forward(a2, shift, 1, 0)
+        out = ops.pw_conv(s3, w3_nk, residual=x, name="pw_conv<+residual>", resident=True)
+        w2_kn_t, m2 = _wsave(w2_kn)
+        w3_kn_t, m3 = _wsave(w3_kn)
+        ctx.save_for_backward(x, o, att, y2, a2, s3, mi1, sb1, mi2, sb2, g1, g2, w2, w3, shift, taps, w2_kn_t, w3_kn_t)
+        ctx.cfg = (tr1, tr2, frames, normalize_grad)
+        ctx.wmeta = (m2, m3)
+        return out
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, g):
+        from .attention_shift import attention_mix_backward
+        from .shiftlib.rubiks2d.primitive import rubiks2d_backward
+        x, o, att, y2, a2, s3, mi1, sb1, mi2, sb2, g1, g2, w2, w3, shift, taps, w2_kn, w3_kn = ctx.saved_tensors
+        tr1, tr2, frames, normalize_grad = ctx.cfg
+        w2_kn, w3_kn = _wload(w2_kn, ctx.wmeta[0]), _wload(w3_kn, ctx.wmeta[1])
+        g = g.contiguous()
+        need = ctx.needs_input_grad
+        gs = ops.pw_conv(g, w3_kn, name="pw_conv<dgrad>", resident=True)
+        gw3 = ops.pw_conv_wgrad(g, s3).view(w3.shape) if need[8] else None
+        del s3
+        ga2, gshift = rubiks2d_backward(gs, a2, shift, 1, 0, normalize_grad=normalize_grad, enable_shift_grad=bool(need[7]))
+        del gs
+        gy2, dg2, db2 = ops.bn_backward(y2, ga2, None, g2, mi2, sb2, tr2, relu=True)
+        del ga2
+        gatt = ops.pw_conv(gy2, w2_kn, name="pw_conv<dgrad>", resident=True)
+        gw2 = ops.pw_conv_wgrad(gy2, att).view(w2.shape) if need[4] else None
+        del gy2
+        go, gtaps = attention_mix_backward(o, taps, gatt, frames, need_x=True, need_t=bool(need[3]))
+        del gatt
+        # the shortcut gradient g is added inside the bn1 backward pass (no separate add over the tensor)
+        gx, dg1, db1 = ops.bn_backward(x, go, g, g1, mi1, sb1, tr1, relu=True, need_dx=need[0])
+        return gx, dg1, db1, gtaps, gw2, dg2, db2, (gshift if need[7] else None), gw3, None, None, None, None
+
+
+def rubiks_aq_block_supported(block, x):
+    """True when `block` is an identity-shortcut block of the attention-quantized variant that can run as _RubiksAQBlockFn."""
+    from .attention_shift import AttentionShift
+    from .shiftlib import RubiksShift2D
+    if not x.is_cuda or x.dtype != torch.bfloat16 or x.dim() != 4 or x.data_ptr() % 16 != 0:
+        return False
+    if not isinstance(block.shortcut, nn.Identity) or block.se is not None or not isinstance(block.conv2, nn.Sequential):
+        return False
+    if len(block.conv2) != 2 or type(block.conv2[0]) is not AttentionShift or not isinstance(block.conv2[1], nn.Conv2d):
+        return False
+    att, as3 = block.conv2[0], block.as3
+    if type(as3) is not RubiksShift2D or as3.stride != 1 or as3.padding != 0 or as3.quantize:
+        return False
+    if att.weight is None or x.shape[0] % att.n_segment != 0:
+        return False
+    params = (block.conv2[1].weight, block.conv3.weight, block.bn1.weight, block.bn2.weight, as3.shift, block.bn1.bias, block.bn2.bias)
+    if any(p is None or p.dtype != torch.float32 for p in params):
+        return False
+    for bn in (block.bn1, block.bn2):
+        if bn.track_running_stats and bn.running_mean is not None and (
+                bn.running_mean.dtype != torch.float32 or bn.running_var.dtype != torch.float32):
+            return False
+    return True
+
+
+def rubiks_aq_block(block, x):
+    for bn in (block.bn1, block.bn2):
+        if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+    att = block.conv2[0]
+    return _RubiksAQBlockFn.apply(
+        x, block.bn1.weight, block.bn1.bias, att.taps().float(), block.conv2[1].weight, block.bn2.weight, block.bn2.bias,
+        block.as3.shift, block.conv3.weight, block.bn1, block.bn2, att.n_segment, bool(block.as3.normalize_grad))
+
+
+def _block_common_ok(block, x):
+    """Conditions shared by the whole-block Functions: bf16 CUDA activations, no SE, plain conv2, a non-quantized 3D shift
+    without padding behind _Rubiks3DWrap, fp32 parameters and BatchNorm buffers."""
+    as3 = block.as3
+    r3 = getattr(as3, "rubiks3d", None)
+    if r3 is None or not x.is_cuda or x.dtype != torch.bfloat16 or x.dim() != 4:
+        return False
+    if block.se is not None or not isinstance(block.conv2, nn.Conv2d):
+        return False
+    if tuple(r3.padding) != (0, 0, 0) or r3.quantize:
+        return False
+    if not isinstance(r3.normalize_t_factor, (int, float)) or x.shape[0] % as3.n_segment != 0:
+        return False
+    params = [block.conv2.weight, block.conv3.weight, block.bn1.weight, block.bn2.weight, r3.shift, block.bn1.bias, block.bn2.bias]
+    if not isinstance(block.shortcut, nn.Identity):
+        params.append(block.shortcut.weight)
+    if any(p is None or p.dtype != torch.float32 for p in params):
+        return False
+    for bn in (block.bn1, block.bn2):  # the kernels update the running statistics in place as float *
+        if bn.track_running_stats and bn.running_mean is not None and (
+                bn.running_mean.dtype != torch.float32 or bn.running_var.dtype != torch.float32):
+            return False
+    if x.data_ptr() % 16 != 0:
+        return False
+    return getattr(r3, "shift_function", None) is _default_shift_function()
+
+
+def rubiks_down_block_supported(block, x):
+    """True when `block` is a down-sampling block that can run as _RubiksDownBlockFn: stride-2 1x1 shortcut conv, 3D shift
+    with stride (1,2,2), even map size."""
+    if not _block_common_ok(block, x) or not isinstance(block.shortcut, nn.Conv2d):
+        return False
+    sc = block.shortcut
+    if sc.kernel_size != (1, 1) or sc.stride != (2, 2) or sc.padding != (0, 0) or sc.bias is not None or sc.groups != 1:
+        return False
+    if tuple(block.as3.rubiks3d.stride) != (1, 2, 2) or x.shape[2] % 2 or x.shape[3] % 2:
+        return False
+    return True
+
+
+def rubiks_down_block(block, x):
+    for bn in (block.bn1, block.bn2):
+        if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+    r3 = block.as3.rubiks3d
+    return _RubiksDownBlockFn.apply(
+        x, block.bn1.weight, block.bn1.bias, block.conv2.weight, block.bn2.weight, block.bn2.bias, r3.shift, block.conv3.weight,
+        block.shortcut.weight, block.bn1, block.bn2, block.as3.n_segment, bool(r3.normalize_grad), float(r3.normalize_t_factor))
 
 
 def rubiks_block_supported(block, x):

@@ -280,14 +280,15 @@ def shift3d_pw_conv_wgrad(out_grad, x, shift, frames):
     return dw
 
 
-def shift3d_backward(x, shift, out_grad, frames, normalize_grad, normalize_t_factor, need_x=True, need_shift=True):
-    """x_grad / shift_grad of the stride-1 3D shift over x [N*T, C, H, W] (rb_shift3d_backward)."""
+def shift3d_backward(x, shift, out_grad, frames, normalize_grad, normalize_t_factor, need_x=True, need_shift=True, stride=1):
+    """x_grad / shift_grad of the 3D shift (temporal stride 1, spatial `stride`, no padding) over x [N*T, C, H, W]
+    (rb_shift3d_backward)."""
     nt, c, h, w = x.shape
     n = nt // frames
     x_grad = torch.empty_like(x) if need_x else None
     shift_grad = torch.empty_like(shift) if need_shift else None
     dt = _lib.dtype_code(x)
-    geo = (n, frames, c, h, w, 1, 1, 1, 0, 0, 0)
+    geo = (n, frames, c, h, w, 1, int(stride), int(stride), 0, 0, 0)
     with _on_device(x.device):
         L = _lib.lib()
         nbytes = L.rb_shift3d_backward_workspace_bytes(dt, *geo) if need_shift else 0

@@ -281,6 +281,104 @@ def test_whole_block_function_equals_module_graph(training, fuse_shift):
             assert _rel(gp1[name], gp0[name]) <= 2e-2, name
 
 
+@pytest.mark.parametrize("stage,hw", [("layer1", 56), ("layer3", 28), ("layer4", 14)])
+@pytest.mark.parametrize("training", [True, False])
+def test_down_sampling_block_function_equals_module_graph(stage, hw, training):
+    """Down-sampling blocks (stride-(1,2,2) shift, stride-2 shortcut conv) as ONE autograd Function -- bn1 folded into conv2's
+    producer, the shortcut fed from the sub-sampled quarter, its input gradient added in place -- vs the per-op path on
+    the same bf16 inputs: output, input gradient, every parameter gradient, running statistics."""
+    torch.manual_seed(7)
+    net = rb.RubiksNet(tier="tiny", num_classes=7, num_frames=8).cuda()
+    block = getattr(net.backbone, stage)[0]
+    assert not isinstance(block.shortcut, torch.nn.Identity)
+    block.train(training)
+    with torch.no_grad():
+        for bn in (block.bn1, block.bn2):
+            bn.weight.uniform_(0.5, 1.5)
+            bn.bias.uniform_(-0.3, 0.3)
+            bn.running_mean.uniform_(-0.2, 0.2)
+            bn.running_var.uniform_(0.5, 1.5)
+    x0 = torch.randn(16, block.conv2.in_channels, hw, hw, device="cuda").to(BF)
+    g = torch.randn(16, block.conv3.out_channels, hw // 2, hw // 2, device="cuda").to(BF)
+    results = []
+    for flag in (True, False):
+        backbone.FUSED_WHOLE_BLOCK = flag
+        try:
+            sd = {k: v.clone() for k, v in block.state_dict().items()}
+            block.zero_grad(set_to_none=True)
+            x = x0.clone().requires_grad_()
+            out = block(x)
+            fn_name = type(out.grad_fn).__name__
+            out.backward(g)
+            results.append((out.detach().float(), x.grad.float(), {n: p.grad.float().clone() for n, p in block.named_parameters()},
+                            (block.bn1.running_mean.clone(), block.bn2.running_var.clone()), fn_name))
+            block.load_state_dict(sd)
+        finally:
+            backbone.FUSED_WHOLE_BLOCK = True
+    (o1, gx1, gp1, rs1, n1), (o0, gx0, gp0, rs0, n0) = results
+    assert o1.shape == (16, block.conv3.out_channels, hw // 2, hw // 2)
+    assert "RubiksDownBlockFn" in n1 and "RubiksDownBlockFn" not in n0, (n1, n0)
+    assert _rel(o1, o0) <= 1e-2 and _rel(gx1, gx0) <= 2e-2
+    for a, b in zip(rs1, rs0):
+        assert _rel(a, b) <= 1e-3
+    for name in gp0:
+        if name.endswith("shift"):
+            d = (gp1[name] - gp0[name]).abs()
+            assert d.mean().item() <= 5e-3 and d.max().item() <= 0.25, (name, d.mean().item(), d.max().item())
+        else:
+            assert _rel(gp1[name], gp0[name]) <= 2e-2, name
+
+
+@pytest.mark.parametrize("stage,idx,hw", [("layer1", 1, 56), ("layer3", 2, 14), ("layer4", 1, 7)])
+@pytest.mark.parametrize("training", [True, False])
+def test_aq_block_function_equals_module_graph(stage, idx, hw, training):
+    """Identity-shortcut blocks of the attention-quantized variant (AttentionShift -> conv2, 2D shift) as ONE autograd
+    Function vs the per-op path on the same bf16 inputs: output, input gradient, every parameter gradient (incl. the
+    attention weights through the tap softmax), running statistics."""
+    torch.manual_seed(8)
+    net = rb.RubiksNet(tier="tiny", num_classes=7, num_frames=8, variant="rubiks3d-aq").cuda()
+    block = getattr(net.backbone, stage)[idx]
+    assert isinstance(block.shortcut, torch.nn.Identity)
+    block.train(training)
+    with torch.no_grad():
+        for bn in (block.bn1, block.bn2):
+            bn.weight.uniform_(0.5, 1.5)
+            bn.bias.uniform_(-0.3, 0.3)
+            bn.running_mean.uniform_(-0.2, 0.2)
+            bn.running_var.uniform_(0.5, 1.5)
+    cin = block.conv2[1].in_channels
+    x0 = torch.randn(16, cin, hw, hw, device="cuda").to(BF)
+    g = torch.randn(16, block.conv3.out_channels, hw, hw, device="cuda").to(BF)
+    results = []
+    for flag in (True, False):
+        backbone.FUSED_WHOLE_BLOCK = flag
+        try:
+            sd = {k: v.clone() for k, v in block.state_dict().items()}
+            block.zero_grad(set_to_none=True)
+            x = x0.clone().requires_grad_()
+            out = block(x)
+            fn_name = type(out.grad_fn).__name__
+            out.backward(g)
+            results.append((out.detach().float(), x.grad.float(), {n: p.grad.float().clone() for n, p in block.named_parameters()
+                                                                   if p.grad is not None},
+                            (block.bn1.running_mean.clone(), block.bn2.running_var.clone()), fn_name))
+            block.load_state_dict(sd)
+        finally:
+            backbone.FUSED_WHOLE_BLOCK = True
+    (o1, gx1, gp1, rs1, n1), (o0, gx0, gp0, rs0, n0) = results
+    assert "RubiksAQBlockFn" in n1 and "RubiksAQBlockFn" not in n0, (n1, n0)
+    assert set(gp1) == set(gp0) and any(k.endswith("conv2.0.weight") for k in gp1)
+    assert _rel(o1, o0) <= 1e-2 and _rel(gx1, gx0) <= 2e-2
+    for a, b in zip(rs1, rs0):
+        assert _rel(a, b) <= 1e-3
+    for name in gp0:
+        if name.endswith("shift"):
+            d = (gp1[name] - gp0[name]).abs()
+            assert d.mean().item() <= 5e-3 and d.max().item() <= 0.25, (name, d.mean().item(), d.max().item())
+        else:
+            assert _rel(gp1[name], gp0[name]) <= 2e-2, name
+
+
 @pytest.mark.parametrize("fuse_shift", [False, True])
 def test_training_step_uses_tensor_core_blocks(fuse_shift):
     """A bf16 autocast training step of RubiksNet-Tiny routes its identity-shortcut blocks through the tcgen05 kernels
@@ -298,10 +396,12 @@ def test_training_step_uses_tensor_core_blocks(fuse_shift):
         agg = _lib.timing.stop()
     finally:
         fused.FUSE_SHIFT_CONV3 = False
-    assert agg["pw_conv<bn+relu>"]["launches"] == 13             # 17 blocks - 4 down-sampling blocks
-    if fuse_shift:
+    # 13 identity-shortcut blocks + 4 down-sampling blocks, all as whole-block Functions with bn1 folded into conv2's producer
+    assert agg["pw_conv<bn+relu>"]["launches"] == 17
+    if fuse_shift:  # the single shift+conv3 launch exists for the stride-1 (identity) blocks
         assert agg["shift3d_pw_conv"]["launches"] == 13 and agg["shift3d_pw_conv_wgrad"]["launches"] == 13
+        assert agg["pw_conv<+residual>"]["launches"] == 4
     else:
-        assert agg["pw_conv<+residual>"]["launches"] == 13 and "shift3d_pw_conv" not in agg
+        assert agg["pw_conv<+residual>"]["launches"] == 17 and "shift3d_pw_conv" not in agg
     assert torch.isfinite(loss).item()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())

@@ -80,6 +80,26 @@ def misc_cases():
         ops.pw_conv_f32(x, w)
         ops.pw_conv_f32(x, w, residual=res, in_scale_bias=isb, out_scale_bias=osb, relu=True, resident=True)
         torch.cuda.synchronize()
+    # conv1 path (im2col in bf16 / fp32), GPU input pipeline, SE kernels, 2D shift on the tiled kernel (stride 2)
+    from rubiksnet_b200 import backbone, fused
+    from rubiksnet_b200.evaluate import frames_to_clip
+    conv = torch.nn.Conv2d(3, 24, 3, stride=2, padding=1, bias=False).cuda()
+    xi = torch.randn(2, 3, 32, 32, device="cuda")
+    with torch.autocast("cuda", dtype=BF):
+        y = fused.stem_conv(conv, xi)
+    y.float().sum().backward()
+    with torch.no_grad():
+        fused.stem_conv(conv, xi)
+    frames_to_clip(torch.randint(0, 256, (2, 9, 11, 6), dtype=torch.uint8, device="cuda"))
+    se = backbone.SELayer(24, reduction=12).cuda()
+    xs = torch.randn(4, 24, 7, 7, device="cuda").to(BF).requires_grad_()
+    fused.se_gate(xs, se).float().sum().backward()
+    for dtype in (torch.float32, BF):
+        x2 = torch.randn(8, 6, 28, 28, device="cuda").to(dtype).requires_grad_()
+        s2 = (torch.rand(2, 6, device="cuda") * 2 - 1).requires_grad_()
+        s2.data[:, 0] = 1.0
+        rubiks2d(x2, s2, stride=2).float().sum().backward()
+    torch.cuda.synchronize()
     print("misc ok", flush=True)
 
 
