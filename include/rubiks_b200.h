@@ -221,6 +221,11 @@ int rb_frames_to_clip(const void *frames_u8, void *out, int out_dtype, int N, in
 int rb_im2col3x3(const void *x, void *cols, int in_dtype, int out_dtype, int NI, int Cin, int H, int W, int stride, int Tpad,
                  void *stream);
 
+/* BatchNorm passes on small maps (a whole channel of a 16-bit tensor fits one CTA's shared memory: NI * HW * 2 bytes <= 216 KiB
+ * for the forward, twice that for the backward, and C >= 128) run as ONE channel-resident launch instead of the reduce /
+ * finalize / apply sequence.  1 (default) = on, 0 = always the streaming passes; process-global, for A/B measurements. */
+void rb_bn_set_resident(int enabled);
+
 /* Batch statistics -> (mean, invstd), (scale, bias) and the running-statistics update of nn.BatchNorm2d in training
  * mode, from partial sums [C][splits][2] over `count` elements per channel (what rb_bn_act_forward does after its own
  * reduction pass).  running_mean / running_var may be NULL. */

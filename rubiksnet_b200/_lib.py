@@ -36,6 +36,8 @@ def _declare(lib):
     lib.rb_set_impl.restype = None
     lib.rb_set_dependent_launch.argtypes = [i]
     lib.rb_set_dependent_launch.restype = None
+    lib.rb_bn_set_resident.argtypes = [i]
+    lib.rb_bn_set_resident.restype = None
     lib.rb_last_impl.restype = i
     lib.rb_out_len.argtypes = [i, i, i]
     lib.rb_out_len.restype = i
@@ -231,6 +233,11 @@ def set_impl(impl):
 def set_dependent_launch(enabled):
     """Programmatic dependent launch of every library kernel on (default) / off -- for A/B measurements."""
     lib().rb_set_dependent_launch(int(bool(enabled)))
+
+
+def set_bn_resident(enabled):
+    """Channel-resident one-launch BatchNorm passes on small maps on (default) / off -- for A/B measurements and tests."""
+    lib().rb_bn_set_resident(int(bool(enabled)))
 
 
 def last_impl():

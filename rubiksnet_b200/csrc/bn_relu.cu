@@ -293,6 +293,138 @@ k_bn_apply(const T *__restrict__ x, const T *__restrict__ dy, const T *__restric
     }
 }
 
+// ---- channel-resident forward pass (small maps) -------------------------------------------------------------------------
+// On the 14x14 / 7x7 maps (39 of the 51 blocks of RubiksNet-Large) a whole channel -- all NI planes of HW elements -- fits
+// one CTA's shared memory: 256 x 196 x 2 B = 100 KB.  One CTA per channel then does what the streaming path needs three
+// launches and a second read of the tensor for: it loads the channel ONCE (8 vectors in flight per thread), reduces the
+// statistics locally (no partial slices, no finalize kernel: the channel has one owner), and applies from shared memory;
+// with y == NULL it is the statistics pass alone in one launch.  Measured at 256 x 288 x 14x14 (tools/bench_bn.py):
+// stats+apply 0.030 -> 0.022-0.025 ms.  Same formulas as k_bn_stats_finalize; sums are fp32 per thread over <= 100
+// elements, then double.  (The backward twin -- x and dy resident, 200 KB, ONE CTA per SM -- was built and measured slower
+// than the streaming passes, 0.049 vs 0.046 ms: with one CTA per SM the load and the store phases of a wave do not
+// overlap; it was removed, gpurun_out/r02aj_bench_bn.log.)
+static constexpr int kRT = 512;  // two CTAs per SM (100 KB each): the load phase of one overlaps the store phase of the other
+static constexpr int kResSmem = 216 * 1024;
+static constexpr int kResMinC = 128;  // fewer channels than this leave most SMs without a CTA: streaming path instead
+static std::atomic<int> g_bn_resident{1};
+
+template <int MODE> static bool bn_resident_ok(int dtype, int NI, int C, int HW) {
+    if (!g_bn_resident.load(std::memory_order_relaxed)) return false;
+    if (dtype != RB_BF16 && dtype != RB_F16) return false;
+    if (C < kResMinC) return false;
+    return (size_t)NI * HW * 2 <= (size_t)kResSmem;
+}
+
+__device__ __forceinline__ void block_sum2(double &a, double &b, double (*red)[kRT / 32]) {
+    a = warp_sum(a);
+    b = warp_sum(b);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { red[0][warp] = a; red[1][warp] = b; }
+    __syncthreads();
+    a = 0; b = 0;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 0; w < kRT / 32; ++w) { a += red[0][w]; b += red[1][w]; }
+    }
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(kRT)
+k_bn_fwd_resident(const T *__restrict__ x, const float *__restrict__ gamma, const float *__restrict__ beta, float *running_mean,
+                  float *running_var, T *__restrict__ y, float *__restrict__ mean_invstd, float *__restrict__ scale_bias, int NI,
+                  int C, int HW, FastDiv vpp, float momentum, float eps, int relu) {
+    pdl_sync();
+    extern __shared__ __align__(16) unsigned char res_smem[];
+    T *xs = reinterpret_cast<T *>(res_smem);
+    __shared__ double red[2][kRT / 32];
+    __shared__ float coef[2];
+    const int c = blockIdx.x;
+    const uint32_t total = (uint32_t)NI * vpp.d;
+    const int64_t cs = (int64_t)C * HW;
+    const T *xc = x + (int64_t)c * HW;
+    constexpr int U = 8;  // loads in flight per thread
+    float s0 = 0.f, s1 = 0.f;
+    for (uint32_t i0 = threadIdx.x; i0 < total; i0 += kRT * U) {
+        Pack<T, V> v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t idx = i0 + u * kRT;
+            if (idx < total) {
+                const uint32_t n = fdiv(idx, vpp), j = idx - n * vpp.d;
+                v[u] = *reinterpret_cast<const Pack<T, V> *>(xc + n * cs + j * V);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t idx = i0 + u * kRT;
+            if (idx < total) {
+                if (y != nullptr) *reinterpret_cast<Pack<T, V> *>(xs + (size_t)idx * V) = v[u];  // statistics only: nothing to keep
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    const float f = tof(v[u].v[k]);
+                    s0 += f;
+                    s1 += f * f;
+                }
+            }
+        }
+    }
+    double d0 = (double)s0, d1 = (double)s1;
+    block_sum2(d0, d1, red);
+    if (threadIdx.x == 0) {
+        const double count = (double)NI * HW;
+        const double mean = d0 / count;
+        double var = d1 / count - mean * mean;
+        if (var < 0) var = 0;
+        const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+        mean_invstd[2 * c] = (float)mean;
+        mean_invstd[2 * c + 1] = invstd;
+        const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+        coef[0] = g * invstd;
+        coef[1] = b - (float)mean * g * invstd;
+        scale_bias[2 * c] = coef[0];
+        scale_bias[2 * c + 1] = coef[1];
+        if (running_mean) {
+            const double unbiased = count > 1 ? var * count / (count - 1) : var;
+            running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+            running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+        }
+    }
+    if (y == nullptr) return;
+    __syncthreads();
+    const float sc = coef[0], bi = coef[1];
+    T *yc = y + (int64_t)c * HW;
+    for (uint32_t idx = threadIdx.x; idx < total; idx += kRT) {
+        const uint32_t n = fdiv(idx, vpp), j = idx - n * vpp.d;
+        const Pack<T, V> xv = *reinterpret_cast<const Pack<T, V> *>(xs + (size_t)idx * V);
+        Pack<T, V> ov;
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            const float v = tof(xv.v[k]) * sc + bi;
+            ov.v[k] = cvt<T, float>(relu ? fmaxf(v, 0.f) : v);
+        }
+        *reinterpret_cast<Pack<T, V> *>(yc + n * cs + j * V) = ov;
+    }
+}
+
+template <typename T, int V, int MODE> static int bn_resident_attr() {
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (configured_dev != dev) {
+        cudaError_t e = cudaFuncSetAttribute(k_bn_fwd_resident<T, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, kResSmem);
+        if (e != cudaSuccess) return fail(RB_ERR_CUDA, "cudaFuncSetAttribute(bn resident): %s", cudaGetErrorString(e));
+        configured_dev = dev;
+    }
+    return RB_OK;
+}
+
+// widest vector (elements of a 2-byte type) dividing the plane size: plane starts are then aligned to it (base 16-byte aligned)
+static int bn_resident_vec(int HW) {
+    int V = 8;
+    while (V > 1 && HW % V != 0) V >>= 1;
+    return V;
+}
+
 static int bn_splits(int NI, int C) {
     int want = cdiv(4 * 148, C);
     if (want < 1) want = 1;
@@ -359,6 +491,30 @@ extern "C" int rb_bn_act_forward(const void *x, const float *gamma, const float 
     if (C > 65535) return fail(RB_ERR_UNSUPPORTED, "bn: C > 65535");
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
+    if (training && bn_resident_ok<0>(dtype, NI, C, HW)) {
+        // small maps: one CTA per channel keeps the channel in shared memory -- statistics + apply in ONE launch (statistics
+        // only, y == NULL: the same launch without the shared-memory copy, no partial slices and no finalize kernel)
+        const int V = bn_resident_vec(HW);
+        const FastDiv vpp = make_fastdiv((uint32_t)(HW / V));
+        const size_t smem = y ? (size_t)NI * HW * 2 : 0;
+#define RB_BN_RES_FWD(TT, VV)                                                                                                   \
+    do {                                                                                                                        \
+        if ((rc = bn_resident_attr<TT, VV, 0>())) return rc;                                                                    \
+        launch_kernel(k_bn_fwd_resident<TT, VV>, dim3(C), dim3(kRT), smem, s, (const TT *)x, gamma, beta, running_mean, running_var, \
+                      (TT *)y, mean_invstd, scale_bias, NI, C, HW, vpp, momentum, eps, relu);                                   \
+    } while (0)
+#define RB_BN_RES_FWD_T(TT)                                                                       \
+    switch (V) {                                                                                  \
+        case 8: RB_BN_RES_FWD(TT, 8); break;                                                      \
+        case 4: RB_BN_RES_FWD(TT, 4); break;                                                      \
+        case 2: RB_BN_RES_FWD(TT, 2); break;                                                      \
+        default: RB_BN_RES_FWD(TT, 1); break;                                                     \
+    }
+        if (dtype == RB_BF16) { RB_BN_RES_FWD_T(__nv_bfloat16) } else { RB_BN_RES_FWD_T(__half) }
+#undef RB_BN_RES_FWD_T
+#undef RB_BN_RES_FWD
+        return launched("k_bn_fwd_resident");
+    }
     if (training) {
         if (!workspace || workspace_bytes < bn_ws_bytes(NI, C))
             return fail(RB_ERR_WORKSPACE, "bn forward needs %zu workspace bytes", bn_ws_bytes(NI, C));
@@ -408,10 +564,10 @@ extern "C" int rb_bn_act_backward(const void *x, const void *dy, const void *res
         return fail(RB_ERR_INVALID_ARGUMENT, "bn: activation pointers must be 16-byte aligned");
     if (!workspace || workspace_bytes < bn_ws_bytes(NI, C))
         return fail(RB_ERR_WORKSPACE, "bn backward needs %zu workspace bytes", bn_ws_bytes(NI, C));
+    int rc;
     const int splits = bn_splits(NI, C);
     double *partial = (double *)workspace;
     float *coef = (float *)((char *)workspace + (size_t)C * splits * 2 * sizeof(double));
-    int rc;
     RB_DISPATCH_DTYPE(dtype, (launch_bn_reduce<T, 1>((const T *)x, (const T *)dy, mean_invstd, scale_bias, partial, NI, C,
                                                      HW, relu, splits, s)));
     if ((rc = launched("k_bn_reduce<bwd>"))) return rc;
@@ -431,3 +587,6 @@ extern "C" int rb_bn_act_backward(const void *x, const void *dy, const void *res
     });
     return launched("k_bn_apply<bwd>");
 }
+
+// 1 (default): small maps take the channel-resident one-launch passes; 0: always the streaming passes (A/B, tests)
+extern "C" void rb_bn_set_resident(int enabled) { g_bn_resident.store(enabled ? 1 : 0); }

@@ -262,3 +262,46 @@ def test_stem_conv_fp32_inference_and_fallbacks():
         y = fused.stem_conv(conv, xg)
     y.float().sum().backward()
     assert xg.grad is not None
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape", [(256, 288, 14, 14), (64, 576, 7, 7), (24, 144, 14, 14), (40, 130, 5, 6), (8, 128, 28, 28)])
+@pytest.mark.parametrize("residual", [False, True])
+def test_bn_channel_resident_passes_match_streaming(shape, dtype, residual):
+    """Small maps run the BatchNorm forward as ONE channel-resident launch (csrc/bn_relu.cu: k_bn_fwd_resident); same
+    statistics, outputs and -- through the saved statistics -- gradients as the streaming reduce / finalize / apply passes."""
+    from rubiksnet_b200 import _lib, ops
+    torch.manual_seed(13)
+    c = shape[1]
+    x = (torch.randn(shape, device="cuda") * 1.3 + 0.4).to(dtype)
+    dy = torch.randn(shape, device="cuda").to(dtype)
+    res = torch.randn(shape, device="cuda").to(dtype) if residual else None
+    g, b = torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda") * 0.3
+    out = {}
+    for mode in (True, False):
+        _lib.set_bn_resident(mode)
+        try:
+            rm, rv = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+            n0 = _lib.launch_count()
+            y, mi, sb = ops.bn_forward(x, g, b, rm, rv, True, 0.1, 1e-5, relu=True, apply=True)
+            nf = _lib.launch_count() - n0
+            dx, dg, db = ops.bn_backward(x, dy, res, g, mi, sb, True, relu=True)
+            nb = _lib.launch_count() - n0 - nf
+            out[mode] = (y.float(), mi, sb, rm, rv, dx.float(), dg, db, nf, nb)
+        finally:
+            _lib.set_bn_resident(True)
+    a, s = out[True], out[False]
+    assert a[8] == 1 and s[8] == 3 and a[9] == s[9] == 3, (a[8:], s[8:])  # forward: one launch instead of three
+    for i, tol in ((0, 1e-2), (1, 1e-5), (2, 1e-5), (3, 1e-6), (4, 1e-6), (5, 1e-2), (6, 2e-4), (7, 2e-4)):
+        assert _rel(a[i], s[i]) <= tol, (i, _rel(a[i], s[i]))
+    # and against torch in fp32
+    bn = nn.BatchNorm2d(c).cuda()
+    with torch.no_grad():
+        bn.weight.copy_(g)
+        bn.bias.copy_(b)
+    xr = x.float().requires_grad_()
+    yr = torch.relu(bn(xr))
+    yr.backward(dy.float())
+    assert _rel(a[0], yr) <= 1e-2
+    assert _rel(a[5], xr.grad + (res.float() if residual else 0)) <= 1e-2
+    assert _rel(a[3], bn.running_mean) <= 1e-4 and _rel(a[4], bn.running_var) <= 1e-4
