@@ -312,6 +312,12 @@ int rb_pw_weight_image_pack_multi(const rb_pw_pack_item_t *items_device, int cou
  * image_bwd = weight_kn [K,N] bf16. */
 int rb_pw_weight_pack_multi(const rb_pw_pack_item_t *items_device, int count, void *stream);
 
+/* rb_pw_conv_forward runs plain-producer convolutions (in_scale_bias == NULL, weight not transposed) on maps whose plane
+ * size is a multiple of 8 pixels (16-byte row pitch: 112x112, 56x56, 28x28) with 16-byte aligned tensors on the
+ * tensor-map TMA kernel (csrc/pw_conv3.cu: the TMA unit writes the UMMA operand layout and stores the output tile, no
+ * register round trip).  1 (default) = on, 0 = always the first kernel; process-global, for A/B measurements and tests. */
+void rb_pw_conv_tma_set_enabled(int enabled);
+
 /* Tiling override for rb_pw_conv_forward (process-global, like rb_set_impl): lower bound on the number of
  * output-channel splits (grid.y); more splits = a smaller resident weight block and a deeper activation ring per CTA
  * at the price of reading the activations once per split (from L2).  0 = automatic (default).  Changes the schedule

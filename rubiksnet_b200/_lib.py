@@ -38,6 +38,8 @@ def _declare(lib):
     lib.rb_set_dependent_launch.restype = None
     lib.rb_bn_set_resident.argtypes = [i]
     lib.rb_bn_set_resident.restype = None
+    lib.rb_pw_conv_tma_set_enabled.argtypes = [i]
+    lib.rb_pw_conv_tma_set_enabled.restype = None
     lib.rb_last_impl.restype = i
     lib.rb_out_len.argtypes = [i, i, i]
     lib.rb_out_len.restype = i
@@ -233,6 +235,11 @@ def set_impl(impl):
 def set_dependent_launch(enabled):
     """Programmatic dependent launch of every library kernel on (default) / off -- for A/B measurements."""
     lib().rb_set_dependent_launch(int(bool(enabled)))
+
+
+def set_pw_tma(enabled):
+    """Tensor-map TMA schedule of the plain 1x1 convolutions on large maps on (default) / off -- A/B measurements, tests."""
+    lib().rb_pw_conv_tma_set_enabled(int(bool(enabled)))
 
 
 def set_bn_resident(enabled):

@@ -1,0 +1,84 @@
+"""Tensor-map TMA schedule of the plain 1x1 convolutions on large maps (csrc/pw_conv3.cu) against the first tcgen05 kernel on
+the same bf16 tensors (same arithmetic: bf16 operands, fp32 accumulation, bf16 result, `+= shortcut` on the rounded value)
+and against fp32 math; the dispatcher must take it exactly where it applies."""
+import os
+import sys
+
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from helpers import REPO  # noqa: E402,F401
+
+from rubiksnet_b200 import _lib, ops  # noqa: E402
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(120)]
+BF = torch.bfloat16
+
+GEOMS = [  # (NI, K, N, H, W)
+    (8, 72, 72, 112, 112),   # layer0
+    (8, 72, 72, 56, 56),     # layer1.x: 24.5 tiles per image (half-empty last tile)
+    (8, 144, 144, 28, 28),   # layer2.x: two output-channel slices, 6.125 tiles per image
+    (8, 72, 144, 56, 56),    # layer2.0 conv2-like
+    (4, 32, 72, 112, 112),   # conv1 on the patch matrix
+    (3, 16, 8, 16, 8),       # one tile per image, smallest contraction
+    (2, 256, 128, 16, 16),   # longest contraction
+    (5, 40, 264, 24, 24),    # three slices of 88 channels
+]
+
+
+def _run(x, w, res, tma):
+    _lib.set_pw_tma(tma)
+    try:
+        n0 = _lib.launch_count()
+        out = ops.pw_conv(x, w, residual=res)
+        torch.cuda.synchronize()
+        return out, _lib.launch_count() - n0
+    finally:
+        _lib.set_pw_tma(True)
+
+
+@pytest.mark.parametrize("geom", GEOMS)
+@pytest.mark.parametrize("residual", [False, True])
+@pytest.mark.parametrize("packed", [True, False])
+def test_pw_conv_tma_matches_first_kernel(geom, residual, packed):
+    ni, k, n, h, w_ = geom
+    torch.manual_seed(sum(geom) + residual)
+    x = torch.randn(ni, k, h, w_, device="cuda").to(BF)
+    w = torch.randn(n, k, device="cuda") / k ** 0.5
+    res = torch.randn(ni, n, h, w_, device="cuda").to(BF) if residual else None
+    wk = ops.pw_weight_pack(w)[0] if packed else w
+    got, _ = _run(x, wk, res, True)
+    want, _ = _run(x, wk, res, False)
+    ref = torch.einsum("nk,ikhw->inhw", w.to(BF).float(), x.float())
+    if residual:
+        ref = ref.to(BF).float() + res.float()
+    scale = max(1.0, ref.abs().max().item())
+    assert (got.float() - ref).abs().max().item() <= 1e-2 * scale
+    assert (got.float() - want.float()).abs().max().item() <= 1e-2 * scale
+    # same operands, same accumulation order: the two kernels agree bit for bit almost everywhere
+    assert (got == want).float().mean().item() >= 0.999
+
+
+def test_pw_conv_tma_dispatch_rules():
+    torch.manual_seed(1)
+    w = torch.randn(72, 72, device="cuda") / 72 ** 0.5
+    sb = torch.stack([torch.rand(72, device="cuda") + 0.5, torch.randn(72, device="cuda")], dim=1).contiguous()
+
+    def kernel_of(fn):
+        _lib.timing.start()
+        fn()
+        torch.cuda.synchronize()
+        _lib.timing.stop()
+
+    x = torch.randn(4, 72, 28, 28, device="cuda").to(BF)
+    a = ops.pw_conv(x, w)                                  # 28x28: TMA schedule
+    x14 = torch.randn(4, 72, 14, 14, device="cuda").to(BF)
+    b = ops.pw_conv(x14, w)                                # 14x14 (392-byte rows): first kernel
+    c = ops.pw_conv(x, w, in_scale_bias=sb)                # bn+relu producer: first kernel
+    d = ops.pw_conv(x, w.t().contiguous(), transposed=True)  # transposed weight buffer: first kernel
+    torch.cuda.synchronize()
+    ref = torch.einsum("nk,ikhw->inhw", w.to(BF).float(), x.float())
+    assert (a.float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+    assert (d.float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+    assert b.shape == (4, 72, 14, 14) and c.shape == a.shape
