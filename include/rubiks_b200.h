@@ -323,6 +323,9 @@ void rb_pw_conv_tma_set_enabled(int enabled);
  * at the price of reading the activations once per split (from L2).  0 = automatic (default).  Changes the schedule
  * only, never the arithmetic. */
 void rb_pw_conv_set_tuning(int min_n_splits);
+/* tensor-map weight gradient (csrc/pw_wgrad3.cu), measurement knobs: pixel chunks issued together (1..4), 256-byte L2
+ * promotion in the tensor maps (0/1), ring depth cap (2..8; 0 = default) */
+void rb_pw_conv_wgrad_set_tuning(int burst, int l2_256, int max_stages);
 /* Same for the image kernel: depth of the operand ring (2..8), channels per K chunk (16 / 32) and the suspend-time hint
  * (ns) of its mbarrier waits; 0 = automatic / hardware default. */
 void rb_pw_conv_image_set_tuning(int operand_stages, int k_chunk, int wait_hint_ns);

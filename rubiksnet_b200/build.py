@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "librubiks_b200.so")
-SOURCES = ["abi.cu", "shift3d_generic.cu", "shift3d_tiled.cu", "shift3d_strip.cu", "shift2d_generic.cu", "attention_shift.cu", "bn_relu.cu", "se.cu", "pw_conv.cu", "pw_conv2.cu", "pw_conv_tf32.cu", "im2col.cu", "input_norm.cu", "pw_conv3.cu"]
+SOURCES = ["abi.cu", "shift3d_generic.cu", "shift3d_tiled.cu", "shift3d_strip.cu", "shift2d_generic.cu", "attention_shift.cu", "bn_relu.cu", "se.cu", "pw_conv.cu", "pw_conv2.cu", "pw_conv_tf32.cu", "im2col.cu", "input_norm.cu", "pw_conv3.cu", "pw_wgrad3.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

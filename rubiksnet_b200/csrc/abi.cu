@@ -89,6 +89,10 @@ void pw2_set_debug(int flags);
 bool pw3_supported(const void *x, const void *out, const void *res, int NI, int K, int N, int HW);
 int pw3_forward(const void *x, const void *w, int w_dt, const void *res, void *out, int NI, int K, int N, int HW, cudaStream_t s);
 void pw3_set_enabled(int on);
+size_t wg3_workspace(int NI, int M, int N, int HW);
+void wg3_set_tuning(int burst, int l2_256, int max_stages);
+bool wg3_supported(const void *g, const void *x, int NI, int M, int N, int HW);
+int wg3_run(const void *g, const void *x, float *dw, int NI, int M, int N, int HW, const float *x_sb, void *workspace, cudaStream_t s);
 int pw_tf32_forward(const float *x, const float *w, const float *res, float *out, int NI, int K, int N, int HW,
                     const float *in_sb, const float *out_sb, int relu, int resident, cudaStream_t s);
 int pw2_forward(const void *x, const void *wimg, const void *residual, void *out, int NI, int K, int N, int HW,
@@ -465,7 +469,8 @@ int rb_shift3d_pw_conv_forward(const void *x, const void *shift, const void *wei
 
 size_t rb_pw_conv_wgrad_workspace_bytes(int NI, int K, int N, int HW) {
     if (NI <= 0 || K <= 0 || N <= 0 || HW <= 0) return 0;
-    return (pw_conv_wgrad_workspace(NI, N, K, HW) + 255) & ~(size_t)255;
+    const size_t first = pw_conv_wgrad_workspace(NI, N, K, HW), tma = wg3_workspace(NI, N, K, HW);
+    return ((first > tma ? first : tma) + 255) & ~(size_t)255;
 }
 
 static int wgrad_common(const void *out_grad, const void *x, float *weight_grad, int dtype, int NI, int K, int N, int HW,
@@ -486,6 +491,8 @@ static int wgrad_common(const void *out_grad, const void *x, float *weight_grad,
     if (!workspace || workspace_bytes < need)
         return fail(RB_ERR_WORKSPACE, "pw_conv wgrad needs %zu workspace bytes, got %zu", need, workspace_bytes);
     // GEMM rows m = output channels (N of the conv), columns = input channels (K of the conv)
+    if (!shift && wg3_supported(out_grad, x, NI, N, K, HW))  // both operands through tensor-map TMA (csrc/pw_wgrad3.cu)
+        return wg3_run(out_grad, x, weight_grad, NI, N, K, HW, in_scale_bias, workspace, s);
     return pw_conv_wgrad(out_grad, x, weight_grad, NI, N, K, HW, in_scale_bias, shift, shift_dtype, T, H, W, workspace, s);
 }
 
@@ -507,6 +514,7 @@ int rb_shift3d_pw_conv_wgrad(const void *out_grad, const void *x, const void *sh
 }
 
 void rb_pw_conv_set_tuning(int min_n_splits) { pw_conv_set_tuning(min_n_splits); }
+void rb_pw_conv_wgrad_set_tuning(int burst, int l2_256, int max_stages) { wg3_set_tuning(burst, l2_256, max_stages); }
 void rb_pw_conv_image_set_tuning(int operand_stages, int k_chunk, int wait_hint_ns) {
     pw2_set_tuning(operand_stages, k_chunk, wait_hint_ns);
 }

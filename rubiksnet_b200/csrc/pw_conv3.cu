@@ -339,6 +339,7 @@ std::atomic<int> g_p3_enabled{1};
 }  // namespace
 
 void pw3_set_enabled(int on) { g_p3_enabled.store(on ? 1 : 0); }
+bool pw3_enabled() { return g_p3_enabled.load(std::memory_order_relaxed) != 0; }
 
 // 1 when the geometry (and the pointers' alignment) can run on k_pw3
 bool pw3_supported(const void *x, const void *out, const void *res, int NI, int K, int N, int HW) {

@@ -121,7 +121,10 @@ __device__ __forceinline__ float coef_sg(int d, bool integer) {
     return integer ? (d == -1 ? 1.f : 0.f) : (d == 0 ? 1.f : 0.f);
 }
 
-template <typename T, int MODE, int K>
+// S2 (backward, spatial stride 2): of the four (dy, dx) taps of an input position exactly one has even numerators, the
+// other three read the zero slot -- that path keeps ONE offset per position and multiplies by the selected weights, which
+// is the general expression with the zero terms dropped (bit-identical: x*w + 0*w' == x*w).
+template <typename T, int MODE, int K, bool S2 = false>
 __global__ void __launch_bounds__(kNW * 32) k_shift3d_tiled(const TiledArgs a) {
     pdl_sync();
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -249,7 +252,9 @@ __global__ void __launch_bounds__(kNW * 32) k_shift3d_tiled(const TiledArgs a) {
     const int P = th * Wd;  // destination positions per channel in this tile
     const int pstride = WPC * 32;
     const int p0 = wsub * 32 + lane;
-    int off[K][4];
+    int off[S2 ? 1 : K][4];
+    int osel[S2 ? K : 1];
+    float wWs[S2 ? K : 1], wHs[S2 ? K : 1], sgH[S2 ? K : 1], sgW[S2 ? K : 1];
     const float wH0 = 1.f - rH, wH1 = rH, wW0 = 1.f - rW, wW1 = rW, wT0 = 1.f - rT, wT1 = rT;
     const int chan_base = ZOFF + cl * HWs - rlo * Ws;
 #pragma unroll
@@ -257,6 +262,17 @@ __global__ void __launch_bounds__(kNW * 32) k_shift3d_tiled(const TiledArgs a) {
         const int p = p0 + k * pstride;
         const bool ok = c_ok && p < P && any_data;
         const int hl = p / Wd, wd = p - hl * Wd, hd = hd0 + hl;
+        if (S2) {
+            const int dy = (hd + fH) & 1, dx = (wd + fW) & 1;  // the tap whose numerators are even
+            const int hs = (hd + fH + dy) >> 1, ws = (wd + fW + dx) >> 1;
+            const bool v = ok && hs >= rlo && hs <= rhi && ws >= 0 && ws < Ws;
+            osel[k] = v ? chan_base + hs * Ws + ws : 0;
+            wHs[k] = dy ? wH1 : wH0;
+            wWs[k] = dx ? wW1 : wW0;
+            sgH[k] = dy ? -1.f : 1.f;
+            sgW[k] = dx ? -1.f : 1.f;
+            continue;
+        }
 #pragma unroll
         for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
@@ -273,7 +289,7 @@ __global__ void __launch_bounds__(kNW * 32) k_shift3d_tiled(const TiledArgs a) {
                     ws = nw >> (S - 1);
                 }
                 v = v && hs >= rlo && hs <= rhi && ws >= 0 && ws < Ws;
-                off[k][dy * 2 + dx] = v ? chan_base + hs * Ws + ws : 0;
+                off[S2 ? 0 : k][dy * 2 + dx] = v ? chan_base + hs * Ws + ws : 0;
             }
     }
     __syncthreads();  // head/tail/zero stores visible to every warp
@@ -316,9 +332,15 @@ __global__ void __launch_bounds__(kNW * 32) k_shift3d_tiled(const TiledArgs a) {
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 float cB = 0.f, cDH = 0.f, cDW = 0.f;
-                if (have) {
-                    const float q00 = lds<T>(sp + off[k][0]), q01 = lds<T>(sp + off[k][1]);
-                    const float q10 = lds<T>(sp + off[k][2]), q11 = lds<T>(sp + off[k][3]);
+                if (have && S2) {
+                    const float q = lds<T>(sp + osel[k]);
+                    const float rw = q * wWs[k];
+                    cB = wHs[k] * rw;
+                    cDH = sgH[k] * rw;
+                    cDW = wHs[k] * (sgW[k] * q);
+                } else if (have) {
+                    const float q00 = lds<T>(sp + off[S2 ? 0 : k][0]), q01 = lds<T>(sp + off[S2 ? 0 : k][1]);
+                    const float q10 = lds<T>(sp + off[S2 ? 0 : k][2]), q11 = lds<T>(sp + off[S2 ? 0 : k][3]);
                     const float r0 = q00 * wW0 + q01 * wW1, r1 = q10 * wW0 + q11 * wW1;
                     cB = wH0 * r0 + wH1 * r1;
                     if (MODE == MODE_BWD) {
@@ -528,19 +550,23 @@ bool shift3d_tiled_supported(int dt, const Geom3 &g, int quantize) {
     return true;
 }
 
-template <typename T, int MODE, int K> static int launch_k(const TiledArgs &a, cudaStream_t s) {
+template <typename T, int MODE, int K, bool S2> static int launch_ks(const TiledArgs &a, cudaStream_t s) {
     static thread_local int configured_dev = -1;
     int dev = 0;
     cudaGetDevice(&dev);
     if (configured_dev != dev) {
-        cudaError_t e = cudaFuncSetAttribute(k_shift3d_tiled<T, MODE, K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(k_shift3d_tiled<T, MODE, K, S2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              kSmemLimit);
         if (e != cudaSuccess) return fail(RB_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         configured_dev = dev;
     }
     const unsigned blocks = (unsigned)((int64_t)a.N * a.cfg.groups * a.cfg.row_tiles);
-    launch_kernel(k_shift3d_tiled<T, MODE, K>, dim3(blocks), dim3(kNW * 32), a.cfg.smem_bytes, s, a);
+    launch_kernel(k_shift3d_tiled<T, MODE, K, S2>, dim3(blocks), dim3(kNW * 32), a.cfg.smem_bytes, s, a);
     return launched(MODE == MODE_FWD ? "k_shift3d_tiled<fwd>" : "k_shift3d_tiled<bwd>");
+}
+template <typename T, int MODE, int K> static int launch_k(const TiledArgs &a, cudaStream_t s) {
+    if (MODE == MODE_BWD && a.S == 2) return launch_ks<T, MODE, K, (MODE == MODE_BWD)>(a, s);
+    return launch_ks<T, MODE, K, false>(a, s);
 }
 
 template <typename T, int MODE> static int launch_mode(const TiledArgs &a, cudaStream_t s) {

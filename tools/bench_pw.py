@@ -54,7 +54,13 @@ def main():
     ap.add_argument("--opstages", type=int, default=0, help="image kernel: operand ring depth (0 = auto)")
     ap.add_argument("--kc", type=int, default=0, help="image kernel: channels per K chunk, 16 or 32 (0 = auto)")
     ap.add_argument("--waitns", type=int, default=0, help="image kernel: mbarrier suspend-time hint in ns (0 = default)")
+    ap.add_argument("--wg", default="", help="tensor-map weight gradient knobs: burst,l2_256,max_stages")
+    ap.add_argument("--no-tma", action="store_true", help="tensor-map TMA schedules (k_pw3 / k_wg3) off: first kernels everywhere")
     a = ap.parse_args()
+    if a.no_tma:
+        _lib.set_pw_tma(False)
+    if a.wg:
+        _lib.lib().rb_pw_conv_wgrad_set_tuning(*[int(v) for v in a.wg.split(",")])
     _lib.lib().rb_pw_conv_set_tuning(a.splits)
     _lib.lib().rb_pw_conv_image_set_tuning(a.opstages, a.kc, a.waitns)
     modes = a.modes.split(",")
@@ -80,6 +86,7 @@ def main():
             "shift": (lambda: ops.shift3d_pw_conv(x, shift, w_nk, res, T), 3 * unit),
             "dgrad": (lambda: ops.pw_conv(g, w_kn), 2 * unit),
             "wgrad": (lambda: ops.pw_conv_wgrad(g, x), 2 * unit),
+            "wgrad_bn": (lambda: ops.pw_conv_wgrad(g, x, in_scale_bias=sb), 2 * unit),
             "wgrad_shift": (lambda: ops.shift3d_pw_conv_wgrad(g, x, shift, T), 2 * unit),
         }
         if ops.pw_image_supported(ni, c, c, h * h, True):
