@@ -127,6 +127,16 @@ int rb_attention_shift_backward(const void *x, const float *taps, const void *ou
                                 float *taps_grad, int dtype, int N, int T, int C, int HW,
                                 void *workspace, size_t workspace_bytes, void *stream);
 
+/* The same pair with the block's bn1 -> relu folded into the load (rubiksnet/backbone.py:123-125 in front of the
+ * AttentionShift of models.py:100-104): the mixed input is relu(x * scale[c] + bias[c]) rounded to `dtype`, with
+ * in_scale_bias fp32 [C,2] as written by rb_bn_act_forward -- the normalised tensor never exists in memory.
+ * x_grad is the gradient with respect to that normalised input (what rb_bn_act_backward takes as dy). */
+int rb_bn_attention_shift_forward(const void *x, const float *in_scale_bias, const float *taps, void *out, int dtype,
+                                  int N, int T, int C, int HW, void *stream);
+int rb_bn_attention_shift_backward(const void *x, const float *in_scale_bias, const float *taps, const void *out_grad,
+                                   void *x_grad, float *taps_grad, int dtype, int N, int T, int C, int HW,
+                                   void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---------------------------------------------------------------- BatchNorm (+ReLU) ------------ */
 
 /* The bn1->relu / bn2->relu / bn_last->relu stages of RubiksShiftBlock / RubiksNetBackbone

@@ -61,6 +61,10 @@ def _declare(lib):
     lib.rb_attention_shift_backward_workspace_bytes.restype = sz
     lib.rb_attention_shift_backward.argtypes = [vp] * 5 + [i, i, i, i, i, vp, sz, vp]
     lib.rb_attention_shift_backward.restype = i
+    lib.rb_bn_attention_shift_forward.argtypes = [vp, vp, vp, vp, i, i, i, i, i, vp]
+    lib.rb_bn_attention_shift_forward.restype = i
+    lib.rb_bn_attention_shift_backward.argtypes = [vp] * 6 + [i, i, i, i, i, vp, sz, vp]
+    lib.rb_bn_attention_shift_backward.restype = i
     fl = ctypes.c_float
     lib.rb_bn_workspace_bytes.argtypes = [i, i]
     lib.rb_bn_workspace_bytes.restype = sz

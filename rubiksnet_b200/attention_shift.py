@@ -15,21 +15,28 @@ from .rubiksnet_cuda import _on_device
 __all__ = ["AttentionShift", "attention_shift_mix"]
 
 
-def attention_mix_forward(x, taps, n_segment):
-    """Plain (no autograd) forward of the 3-tap temporal mix: x [N*T, C, H, W] contiguous, taps fp32 [C, 3]."""
+def attention_mix_forward(x, taps, n_segment, in_scale_bias=None):
+    """Plain (no autograd) forward of the 3-tap temporal mix: x [N*T, C, H, W] contiguous, taps fp32 [C, 3].
+    in_scale_bias fp32 [C, 2]: mix relu(x * scale + bias) instead of x (bn1 -> relu folded into the load)."""
     assert x.is_cuda, "attention shift only works on CUDA tensors"
     nt, c, h, w = x.shape
     assert nt % n_segment == 0, "batch (N*T) must be a multiple of n_segment"
     out = torch.empty_like(x)
     with _on_device(x.device), _lib.timed("attention_shift_forward", _lib.nbytes(x, out)):
-        _lib.check(_lib.lib().rb_attention_shift_forward(
-            _lib.ptr(x), _lib.ptr(taps), _lib.ptr(out), _lib.dtype_code(x), nt // n_segment, n_segment,
-            c, h * w, _lib.stream_handle(x.device)))
+        if in_scale_bias is None:
+            _lib.check(_lib.lib().rb_attention_shift_forward(
+                _lib.ptr(x), _lib.ptr(taps), _lib.ptr(out), _lib.dtype_code(x), nt // n_segment, n_segment,
+                c, h * w, _lib.stream_handle(x.device)))
+        else:
+            _lib.check(_lib.lib().rb_bn_attention_shift_forward(
+                _lib.ptr(x), _lib.ptr(in_scale_bias), _lib.ptr(taps), _lib.ptr(out), _lib.dtype_code(x), nt // n_segment,
+                n_segment, c, h * w, _lib.stream_handle(x.device)))
     return out
 
 
-def attention_mix_backward(x, taps, grad_out, n_segment, need_x=True, need_t=True):
-    """(x_grad, taps_grad) of attention_mix_forward; either may be skipped."""
+def attention_mix_backward(x, taps, grad_out, n_segment, need_x=True, need_t=True, in_scale_bias=None):
+    """(x_grad, taps_grad) of attention_mix_forward; either may be skipped.  With in_scale_bias, x is the tensor in front of
+    the folded bn -> relu and x_grad the gradient with respect to the normalised input."""
     nt, c, h, w = x.shape
     n = nt // n_segment
     gx = torch.empty_like(x) if need_x else None
@@ -39,9 +46,14 @@ def attention_mix_backward(x, taps, grad_out, n_segment, need_x=True, need_t=Tru
         nbytes = L.rb_attention_shift_backward_workspace_bytes(n, n_segment, c, h * w) if need_t else 0
         ws = _lib.workspace(nbytes, x.device)
         with _lib.timed("attention_shift_backward", _lib.nbytes(x, grad_out, gx)):
-            _lib.check(L.rb_attention_shift_backward(
-                _lib.ptr(x), _lib.ptr(taps), _lib.ptr(grad_out), _lib.ptr(gx), _lib.ptr(gt), _lib.dtype_code(x),
-                n, n_segment, c, h * w, _lib.ptr(ws), nbytes, _lib.stream_handle(x.device)))
+            if in_scale_bias is None:
+                _lib.check(L.rb_attention_shift_backward(
+                    _lib.ptr(x), _lib.ptr(taps), _lib.ptr(grad_out), _lib.ptr(gx), _lib.ptr(gt), _lib.dtype_code(x),
+                    n, n_segment, c, h * w, _lib.ptr(ws), nbytes, _lib.stream_handle(x.device)))
+            else:
+                _lib.check(L.rb_bn_attention_shift_backward(
+                    _lib.ptr(x), _lib.ptr(in_scale_bias), _lib.ptr(taps), _lib.ptr(grad_out), _lib.ptr(gx), _lib.ptr(gt),
+                    _lib.dtype_code(x), n, n_segment, c, h * w, _lib.ptr(ws), nbytes, _lib.stream_handle(x.device)))
     return gx, gt
 
 

@@ -2,11 +2,22 @@
 // [C*H*W,1,3] weight with repeat_interleave and runs a depth-wise F.conv1d with up to 903 168 groups
 // on a transposed view followed by .contiguous(): several passes over HBM.  Here every (n,c,p) column
 // of T frames is streamed once through registers: x is read once and out written once.
+//
+// AFF variants: the input is relu(x * scale[c] + bias[c]) rounded to the element type -- bn1 -> relu of the attention-quantized
+// block (rubiksnet/backbone.py:123-125 with models.py:100-104) folded into the load, so that the normalised tensor is never
+// written: the value is computed exactly as k_bn_apply would store it (one FMA, max, one rounding), hence bit-identical.
 #include "common.cuh"
 
 namespace rb {
 
 static constexpr int kAThreads = 128;
+
+template <typename T, bool AFF> __device__ __forceinline__ float a_in(const T *p, float sc, float bi) {
+    const float f = ld<float, T>(p);
+    if (!AFF) return f;
+    const T r = cvt<T, float>(fmaxf(f * sc + bi, 0.f));
+    return ld<float, T>(&r);
+}
 
 template <typename T, int V> struct alignas(sizeof(T) * V) APack { T v[V]; };
 
@@ -34,14 +45,16 @@ template <int V> __device__ __forceinline__ ASlot a_slot(int C, int HW, int vpc,
 }
 
 // x/out: [N, T, C, HW]; taps fp32 [C,3]
-template <typename T, int V>
+template <typename T, int V, bool AFF>
 __global__ void __launch_bounds__(kAThreads)
-k_attn_fwd(const T *__restrict__ x, const float *__restrict__ taps, T *__restrict__ out, int Tn, int C, int HW, int vpc, int CG) {
+k_attn_fwd(const T *__restrict__ x, const float *__restrict__ in_sb, const float *__restrict__ taps, T *__restrict__ out, int Tn, int C,
+           int HW, int vpc, int CG) {
     pdl_sync();
     const ASlot sl = a_slot<V>(C, HW, vpc, CG);
     if (!sl.active) return;
     const int c = sl.c, n = blockIdx.z;
     const float a0 = taps[c * 3 + 0], a1 = taps[c * 3 + 1], a2 = taps[c * 3 + 2];
+    const float sc = AFF ? in_sb[2 * c] : 1.f, bi = AFF ? in_sb[2 * c + 1] : 0.f;
     const int64_t fs = (int64_t)C * HW;
     const int64_t base = ((int64_t)n * Tn * C + c) * HW + sl.p;
     using P = APack<T, V>;
@@ -49,14 +62,14 @@ k_attn_fwd(const T *__restrict__ x, const float *__restrict__ taps, T *__restric
     {
         const P v0 = *reinterpret_cast<const P *>(x + base);
 #pragma unroll
-        for (int i = 0; i < V; ++i) { prev[i] = 0.f; cur[i] = ld<float, T>(&v0.v[i]); }
+        for (int i = 0; i < V; ++i) { prev[i] = 0.f; cur[i] = a_in<T, AFF>(&v0.v[i], sc, bi); }
     }
     for (int t = 0; t < Tn; ++t) {
         float nxt[V];
         if (t + 1 < Tn) {
             const P vn = *reinterpret_cast<const P *>(x + base + (t + 1) * fs);
 #pragma unroll
-            for (int i = 0; i < V; ++i) nxt[i] = ld<float, T>(&vn.v[i]);
+            for (int i = 0; i < V; ++i) nxt[i] = a_in<T, AFF>(&vn.v[i], sc, bi);
         } else {
 #pragma unroll
             for (int i = 0; i < V; ++i) nxt[i] = 0.f;
@@ -73,10 +86,10 @@ k_attn_fwd(const T *__restrict__ x, const float *__restrict__ taps, T *__restric
 }
 
 // gx[t] = a0 g[t+1] + a1 g[t] + a2 g[t-1];  gtaps[c,k] = sum g[t] x[t+k-1]
-template <typename T, int V>
+template <typename T, int V, bool AFF>
 __global__ void __launch_bounds__(kAThreads)
-k_attn_bwd(const T *__restrict__ x, const float *__restrict__ taps, const T *__restrict__ og, T *__restrict__ gx,
-           float *__restrict__ partial, int Tn, int C, int HW, int vpc, int CG, int want_gx, int want_gt) {
+k_attn_bwd(const T *__restrict__ x, const float *__restrict__ in_sb, const float *__restrict__ taps, const T *__restrict__ og,
+           T *__restrict__ gx, float *__restrict__ partial, int Tn, int C, int HW, int vpc, int CG, int want_gx, int want_gt) {
     pdl_sync();
     const ASlot sl = a_slot<V>(C, HW, vpc, CG);
     const int n = blockIdx.z;
@@ -85,6 +98,7 @@ k_attn_bwd(const T *__restrict__ x, const float *__restrict__ taps, const T *__r
     if (sl.active) {
         const int c = sl.c;
         const float a0 = taps[c * 3 + 0], a1 = taps[c * 3 + 1], a2 = taps[c * 3 + 2];
+        const float sc = AFF ? in_sb[2 * c] : 1.f, bi = AFF ? in_sb[2 * c + 1] : 0.f;
         const int64_t fs = (int64_t)C * HW;
         const int64_t base = ((int64_t)n * Tn * C + c) * HW + sl.p;
         float gprev[V], gcur[V], xprev[V], xcur[V];
@@ -95,7 +109,7 @@ k_attn_bwd(const T *__restrict__ x, const float *__restrict__ taps, const T *__r
             if (want_gt) {
                 const P x0 = *reinterpret_cast<const P *>(x + base);
 #pragma unroll
-                for (int i = 0; i < V; ++i) xcur[i] = ld<float, T>(&x0.v[i]);
+                for (int i = 0; i < V; ++i) xcur[i] = a_in<T, AFF>(&x0.v[i], sc, bi);
             }
         }
         for (int t = 0; t < Tn; ++t) {
@@ -110,7 +124,7 @@ k_attn_bwd(const T *__restrict__ x, const float *__restrict__ taps, const T *__r
                 if (want_gt) {
                     const P xn = *reinterpret_cast<const P *>(x + base + (t + 1) * fs);
 #pragma unroll
-                    for (int i = 0; i < V; ++i) xnxt[i] = ld<float, T>(&xn.v[i]);
+                    for (int i = 0; i < V; ++i) xnxt[i] = a_in<T, AFF>(&xn.v[i], sc, bi);
                 }
             }
             if (want_gx) {
@@ -212,8 +226,8 @@ APlan a_plan(int dtype, int N, int C, int HW, const void *p0, const void *p1, co
     }
 
 // NB: the frame count is called Tn below because RB_DISPATCH_DTYPE binds the element type to `T`.
-extern "C" int rb_attention_shift_forward(const void *x, const float *taps, void *out, int dtype,
-                                          int N, int Tn, int C, int HW, void *stream) {
+static int attn_forward(const void *x, const float *in_sb, const float *taps, void *out, int dtype, int N, int Tn, int C, int HW,
+                        void *stream) {
     if (N < 0 || Tn < 0 || C < 0 || HW < 0) return fail(RB_ERR_INVALID_ARGUMENT, "negative extent");
     if (dtype_size(dtype) == 0) return fail(RB_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
     if ((int64_t)N * Tn * C * HW == 0) return RB_OK;
@@ -221,9 +235,25 @@ extern "C" int rb_attention_shift_forward(const void *x, const float *taps, void
     if (C > 65535 || N > 65535) return fail(RB_ERR_UNSUPPORTED, "attention shift: C or N > 65535");
     const APlan p = a_plan(dtype, N, C, HW, x, out, nullptr);
     cudaStream_t s = (cudaStream_t)stream;
-    RB_DISPATCH_DTYPE(dtype, RB_ATTN_V(p.V, (launch_kernel(k_attn_fwd<T, (VV * sizeof(T) <= 16 ? VV : 1)>, p.grid, dim3(kAThreads), 0, s,
-                                                           (const T *)x, taps, (T *)out, Tn, C, HW, p.vpc, p.CG))));
+    if (in_sb) {
+        RB_DISPATCH_DTYPE(dtype, RB_ATTN_V(p.V, (launch_kernel(k_attn_fwd<T, (VV * sizeof(T) <= 16 ? VV : 1), true>, p.grid, dim3(kAThreads), 0,
+                                                               s, (const T *)x, in_sb, taps, (T *)out, Tn, C, HW, p.vpc, p.CG))));
+    } else {
+        RB_DISPATCH_DTYPE(dtype, RB_ATTN_V(p.V, (launch_kernel(k_attn_fwd<T, (VV * sizeof(T) <= 16 ? VV : 1), false>, p.grid, dim3(kAThreads), 0,
+                                                               s, (const T *)x, in_sb, taps, (T *)out, Tn, C, HW, p.vpc, p.CG))));
+    }
     return launched("k_attn_fwd");
+}
+
+extern "C" int rb_attention_shift_forward(const void *x, const float *taps, void *out, int dtype,
+                                          int N, int Tn, int C, int HW, void *stream) {
+    return attn_forward(x, nullptr, taps, out, dtype, N, Tn, C, HW, stream);
+}
+
+extern "C" int rb_bn_attention_shift_forward(const void *x, const float *in_scale_bias, const float *taps, void *out, int dtype,
+                                             int N, int Tn, int C, int HW, void *stream) {
+    if (!in_scale_bias) return fail(RB_ERR_INVALID_ARGUMENT, "null pointer");
+    return attn_forward(x, in_scale_bias, taps, out, dtype, N, Tn, C, HW, stream);
 }
 
 extern "C" size_t rb_attention_shift_backward_workspace_bytes(int N, int Tn, int C, int HW) {
@@ -232,10 +262,8 @@ extern "C" size_t rb_attention_shift_backward_workspace_bytes(int N, int Tn, int
     return (size_t)C * N * cdiv(HW, kAThreads) * 3 * sizeof(float);  // upper bound over every vector width
 }
 
-extern "C" int rb_attention_shift_backward(const void *x, const float *taps, const void *out_grad,
-                                           void *x_grad, float *taps_grad, int dtype, int N, int Tn,
-                                           int C, int HW, void *workspace, size_t workspace_bytes,
-                                           void *stream) {
+static int attn_backward(const void *x, const float *in_sb, const float *taps, const void *out_grad, void *x_grad, float *taps_grad,
+                         int dtype, int N, int Tn, int C, int HW, void *workspace, size_t workspace_bytes, void *stream) {
     if (N < 0 || Tn < 0 || C < 0 || HW < 0) return fail(RB_ERR_INVALID_ARGUMENT, "negative extent");
     if (dtype_size(dtype) == 0) return fail(RB_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
     cudaStream_t s = (cudaStream_t)stream;
@@ -251,13 +279,35 @@ extern "C" int rb_attention_shift_backward(const void *x, const float *taps, con
         return fail(RB_ERR_WORKSPACE, "attention shift backward needs %zu workspace bytes, got %zu",
                     need, workspace_bytes);
     const APlan p = a_plan(dtype, N, C, HW, x, out_grad, x_grad);
-    RB_DISPATCH_DTYPE(dtype, RB_ATTN_V(p.V, (launch_kernel(k_attn_bwd<T, (VV * sizeof(T) <= 16 ? VV : 1)>, p.grid, dim3(kAThreads), 0, s,
-                                                           (const T *)x, taps, (const T *)out_grad, (T *)x_grad, (float *)workspace, Tn,
-                                                           C, HW, p.vpc, p.CG, x_grad != nullptr, taps_grad != nullptr))));
+    if (in_sb) {
+        RB_DISPATCH_DTYPE(dtype, RB_ATTN_V(p.V, (launch_kernel(k_attn_bwd<T, (VV * sizeof(T) <= 16 ? VV : 1), true>, p.grid, dim3(kAThreads), 0,
+                                                               s, (const T *)x, in_sb, taps, (const T *)out_grad, (T *)x_grad,
+                                                               (float *)workspace, Tn, C, HW, p.vpc, p.CG, x_grad != nullptr,
+                                                               taps_grad != nullptr))));
+    } else {
+        RB_DISPATCH_DTYPE(dtype, RB_ATTN_V(p.V, (launch_kernel(k_attn_bwd<T, (VV * sizeof(T) <= 16 ? VV : 1), false>, p.grid, dim3(kAThreads), 0,
+                                                               s, (const T *)x, in_sb, taps, (const T *)out_grad, (T *)x_grad,
+                                                               (float *)workspace, Tn, C, HW, p.vpc, p.CG, x_grad != nullptr,
+                                                               taps_grad != nullptr))));
+    }
     int rc = launched("k_attn_bwd");
     if (rc || !taps_grad) return rc;
     const int warps = 4;
     launch_kernel(k_attn_finalize, dim3(cdiv(C, warps)), dim3(warps * 32), 0, s, (const float *)workspace,
                   (int)(p.grid.x * p.grid.z), taps_grad, C);
     return launched("k_attn_finalize");
+}
+
+extern "C" int rb_attention_shift_backward(const void *x, const float *taps, const void *out_grad,
+                                           void *x_grad, float *taps_grad, int dtype, int N, int Tn,
+                                           int C, int HW, void *workspace, size_t workspace_bytes,
+                                           void *stream) {
+    return attn_backward(x, nullptr, taps, out_grad, x_grad, taps_grad, dtype, N, Tn, C, HW, workspace, workspace_bytes, stream);
+}
+
+extern "C" int rb_bn_attention_shift_backward(const void *x, const float *in_scale_bias, const float *taps, const void *out_grad,
+                                              void *x_grad, float *taps_grad, int dtype, int N, int Tn, int C, int HW,
+                                              void *workspace, size_t workspace_bytes, void *stream) {
+    if (!in_scale_bias) return fail(RB_ERR_INVALID_ARGUMENT, "null pointer");
+    return attn_backward(x, in_scale_bias, taps, out_grad, x_grad, taps_grad, dtype, N, Tn, C, HW, workspace, workspace_bytes, stream);
 }

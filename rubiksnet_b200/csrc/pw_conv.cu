@@ -1309,29 +1309,6 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_pw_wgrad(const WgArgs a) {
     }
 }
 
-// partial: [splits][N][M] (M contiguous); out: [M][N].  Thread -> (n, m) with m fastest, so the slice reads are coalesced;
-// the transposed write of the small result is not, and does not matter.
-__global__ void k_wg_reduce(const float *__restrict__ partial, float *__restrict__ out, int splits, int M, int N) {
-    pdl_sync();
-    const int64_t count = (int64_t)M * N;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    // fixed summation order (deterministic); the loads of 8 slices are issued together
-    float s = 0.f;
-    const float *p = partial + i;
-    int k = 0;
-    for (; k + 8 <= splits; k += 8) {
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = __ldg(p + (int64_t)(k + j) * count);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) s += v[j];
-    }
-    for (; k < splits; ++k) s += __ldg(p + (int64_t)k * count);
-    const int n = (int)(i / M), m = (int)(i - (int64_t)n * M);
-    out[(int64_t)m * N + n] = s;
-}
-
 bool wg_plan(WgArgs &a, dim3 *grid, size_t *smem_bytes) {
     const int sb_bytes = round_up(2 * a.N * 4, 128);
     a.off_sb = kHdrBytes;
@@ -1500,6 +1477,8 @@ int pw_conv_forward(const void *x, const void *w, int w_dt, int w_trans, const v
 }
 
 // scratch bytes needed by pw_conv_wgrad: fp32 [splits, M, N]
+int wg_reduce(const float *partial, float *dw, int splits, int M, int N, cudaStream_t s);  // pw_wgrad3.cu
+
 size_t pw_conv_wgrad_workspace(int NI, int M, int N, int HW) {
     WgArgs a{};
     a.NI = NI; a.M = M; a.N = N; a.HW = HW;
@@ -1525,9 +1504,7 @@ int pw_conv_wgrad(const void *g, const void *x, float *dw, int NI, int M, int N,
     else if (prod == PROD_BNRELU) rc = wg_launch_vec<PROD_BNRELU>(a, grid, smem_bytes, s);
     else rc = wg_launch_vec<PROD_PLAIN>(a, grid, smem_bytes, s);
     if (rc) return rc;
-    const int64_t count = (int64_t)M * N;
-    launch_kernel(k_wg_reduce, dim3((unsigned)cdiv64(count, 256)), dim3(256), 0, s, a.partial, dw, (int)grid.x, M, N);
-    return launched("k_wg_reduce");
+    return wg_reduce(a.partial, dw, (int)grid.x, M, N, s);
 }
 
 }  // namespace rb

@@ -693,8 +693,9 @@ class _RubiksDownBlockFn(torch.autograd.Function):
 class _RubiksAQBlockFn(torch.autograd.Function):
     """Identity-shortcut block of the attention-quantized variant (rubiksnet/models.py:100-104: AttentionShift in front of
     conv2, the block keeps its 2D spatial shift) as one Function, bf16:
-        fwd  bn1 stats+apply | temporal mix | conv2 | bn2 stats+apply | 2D shift | conv3 + residual
+        fwd  bn1 stats | temporal mix of relu(bn1(x)) | conv2 | bn2 stats+apply | 2D shift | conv3 + residual
         bwd  conv3 dgrad / wgrad | 2D shift bwd | bn2 bwd | conv2 dgrad / wgrad | temporal mix bwd | bn1 bwd + shortcut gradient
+    relu(bn1(x)) is never written: both temporal-mix kernels apply it to x as they load (rb_bn_attention_shift_*).
     `taps` is the [C, 3] softmax of the attention weights, computed by autograd outside (its gradient is returned)."""
 
     @staticmethod
@@ -709,15 +710,15 @@ class _RubiksAQBlockFn(torch.autograd.Function):
         hw = x.shape[2] * x.shape[3]
         w2_nk, w2_kn = _pack_weight(w2, x.shape[0], hw)
         w3_nk, w3_kn = _pack_weight(w3, x.shape[0], hw)
-        o, mi1, sb1 = ops.bn_forward(x, g1, b1, rm1, rv1, tr1, mom1, eps1, relu=True, apply=True)
-        att = attention_mix_forward(o, taps, frames)
+        _, mi1, sb1 = ops.bn_forward(x, g1, b1, rm1, rv1, tr1, mom1, eps1, relu=True, apply=False)
+        att = attention_mix_forward(x, taps, frames, in_scale_bias=sb1)
         y2 = ops.pw_conv(att, w2_nk, name="pw_conv", resident=True)
         a2, mi2, sb2 = ops.bn_forward(y2, g2, b2, rm2, rv2, tr2, mom2, eps2, relu=True, apply=True)
         s3 = rubiks2d_forward(a2, shift, 1, 0)
         out = ops.pw_conv(s3, w3_nk, residual=x, name="pw_conv<+residual>", resident=True)
         w2_kn_t, m2 = _wsave(w2_kn)
         w3_kn_t, m3 = _wsave(w3_kn)
-        ctx.save_for_backward(x, o, att, y2, a2, s3, mi1, sb1, mi2, sb2, g1, g2, w2, w3, shift, taps, w2_kn_t, w3_kn_t)
+        ctx.save_for_backward(x, att, y2, a2, s3, mi1, sb1, mi2, sb2, g1, g2, w2, w3, shift, taps, w2_kn_t, w3_kn_t)
         ctx.cfg = (tr1, tr2, frames, normalize_grad)
         ctx.wmeta = (m2, m3)
         return out
@@ -727,7 +728,7 @@ class _RubiksAQBlockFn(torch.autograd.Function):
     def backward(ctx, g):
         from .attention_shift import attention_mix_backward
         from .shiftlib.rubiks2d.primitive import rubiks2d_backward
-        x, o, att, y2, a2, s3, mi1, sb1, mi2, sb2, g1, g2, w2, w3, shift, taps, w2_kn, w3_kn = ctx.saved_tensors
+        x, att, y2, a2, s3, mi1, sb1, mi2, sb2, g1, g2, w2, w3, shift, taps, w2_kn, w3_kn = ctx.saved_tensors
         tr1, tr2, frames, normalize_grad = ctx.cfg
         w2_kn, w3_kn = _wload(w2_kn, ctx.wmeta[0]), _wload(w3_kn, ctx.wmeta[1])
         g = g.contiguous()
@@ -742,7 +743,7 @@ class _RubiksAQBlockFn(torch.autograd.Function):
         gatt = ops.pw_conv(gy2, w2_kn, name="pw_conv<dgrad>", resident=True)
         gw2 = ops.pw_conv_wgrad(gy2, att).view(w2.shape) if need[4] else None
         del gy2
-        go, gtaps = attention_mix_backward(o, taps, gatt, frames, need_x=True, need_t=bool(need[3]))
+        go, gtaps = attention_mix_backward(x, taps, gatt, frames, need_x=True, need_t=bool(need[3]), in_scale_bias=sb1)
         del gatt
         # the shortcut gradient g is added inside the bn1 backward pass (no separate add over the tensor)
         gx, dg1, db1 = ops.bn_backward(x, go, g, g1, mi1, sb1, tr1, relu=True, need_dx=need[0])

@@ -57,3 +57,28 @@ def test_attention_mix_vs_oracle(shape, dtype, tol):
     gx[:, :-1] += a[None, None, :, 0, None, None] * gv[:, 1:]
     gx[:, 1:] += a[None, None, :, 2, None, None] * gv[:, :-1]
     assert_close(x.grad.double().cpu().numpy(), gx.reshape(xr.shape), tol, "x grad")
+
+
+@pytest.mark.parametrize("shape", [(16, 288, 14, 14), (16, 72, 28, 28), (8, 40, 7, 7), (24, 6, 5, 3)])
+def test_bn_folded_mix_is_bit_identical_to_the_two_pass_path(shape):
+    """rb_bn_attention_shift_{forward,backward}: relu(bn1(x)) applied as the kernels load == mixing the tensor that
+    rb_bn_act_forward would have written (same FMA, same rounding), for the output, the input gradient and the tap gradient."""
+    from rubiksnet_b200 import ops
+    from rubiksnet_b200.attention_shift import attention_mix_backward, attention_mix_forward
+    torch.manual_seed(sum(shape))
+    nt, c, h, w = shape
+    frames = 8
+    x = torch.randn(nt, c, h, w, device="cuda").to(torch.bfloat16)
+    gamma = torch.rand(c, device="cuda") + 0.5
+    beta = torch.randn(c, device="cuda") * 0.3
+    taps = torch.softmax(torch.randn(c, 3, device="cuda"), dim=1).contiguous()
+    o, _, sb = ops.bn_forward(x, gamma, beta, None, None, True, 0.1, 1e-5, relu=True, apply=True)
+    want = attention_mix_forward(o, taps, frames)
+    got = attention_mix_forward(x, taps, frames, in_scale_bias=sb)
+    assert torch.equal(got, want)
+    g = torch.randn_like(x)
+    gx_w, gt_w = attention_mix_backward(o, taps, g, frames)
+    gx_g, gt_g = attention_mix_backward(x, taps, g, frames, in_scale_bias=sb)
+    torch.cuda.synchronize()
+    assert torch.equal(gx_g, gx_w)
+    assert torch.equal(gt_g, gt_w)
