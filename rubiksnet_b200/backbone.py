@@ -152,18 +152,23 @@ class RubiksNetBackbone(nn.Module):
     def forward(self, x):
         x = fused.stem_conv(self.conv1, x) if FUSED_BLOCK else self.conv1(x)
         packing = _use_fused(x) and x.dtype == torch.bfloat16
+        counting = _use_fused(x) and self.training
         if packing:
             fused.begin_step_pack(self)  # every conv-weight image of the network in one launch
+        if counting:
+            fused.begin_step_counters(self)  # every BatchNorm batch counter in one launch
         try:
             for i in range(5):
                 x = getattr(self, "layer%d" % i)(x)
+            if _use_fused(x):
+                x = self.avgpool(fused.bn_act(x, self.bn_last, relu=True))
+            else:
+                x = self.avgpool(self.relu(self.bn_last(x)))
         finally:
             if packing:
                 fused.end_step_pack(self)
-        if _use_fused(x):
-            x = self.avgpool(fused.bn_act(x, self.bn_last, relu=True))
-        else:
-            x = self.avgpool(self.relu(self.bn_last(x)))
+            if counting:
+                fused.end_step_counters()
         return self.fc(x.view(x.size(0), -1))
 
     def get_optim_policy(self, shift_lr_mult=0.01):

@@ -87,7 +87,8 @@ void pw2_set_tuning(int op_stages, int kc, int wait_ns);
 void pw2_set_debug(int flags);
 #endif
 bool pw3_supported(const void *x, const void *out, const void *res, int NI, int K, int N, int HW);
-int pw3_forward(const void *x, const void *w, int w_dt, const void *res, void *out, int NI, int K, int N, int HW, cudaStream_t s);
+int pw3_forward(const void *x, const void *w, int w_dt, const void *res, void *out, int NI, int K, int N, int HW, const float *a_sb,
+                cudaStream_t s);
 void pw3_set_enabled(int on);
 size_t wg3_workspace(int NI, int M, int N, int HW);
 void wg3_set_tuning(int burst, int l2_256, int max_stages);
@@ -362,9 +363,9 @@ int rb_pw_conv_forward(const void *x, const void *weight, int weight_dtype, int 
             return fail(RB_ERR_INVALID_ARGUMENT, "a packed weight image carries its orientation (rb_pw_weight_image_pack)");
         return pw2_forward(x, weight, residual, out, NI, K, N, HW, in_scale_bias, (cudaStream_t)stream);
     }
-    // large maps (16-byte row pitch), plain producer: the tensor-map TMA schedule (csrc/pw_conv3.cu)
-    if (!in_scale_bias && !weight_transposed && pw3_supported(x, out, residual, NI, K, N, HW))
-        return pw3_forward(x, weight, weight_dtype, residual, out, NI, K, N, HW, (cudaStream_t)stream);
+    // large maps (16-byte row pitch): the tensor-map TMA schedule (csrc/pw_conv3.cu)
+    if (!weight_transposed && pw3_supported(x, out, residual, NI, K, N, HW))
+        return pw3_forward(x, weight, weight_dtype, residual, out, NI, K, N, HW, in_scale_bias, (cudaStream_t)stream);
     return pw_conv_forward(x, weight, weight_dtype, weight_transposed != 0, residual, out, NI, K, N, HW, in_scale_bias,
                            nullptr, 0, 0, 0, 0, (cudaStream_t)stream);
 }

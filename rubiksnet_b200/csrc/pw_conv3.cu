@@ -4,10 +4,11 @@
 // round trip on either side, which is what bounds k_pw_conv on these maps (csrc/pw_conv.cu: LDG -> registers -> STS
 // producers, TMEM -> registers -> staging -> STG epilogue; 0.28 ms against cuBLAS's 0.17 ms at 72 ch x 112x112).
 //
-//     out[i, n, p] = sum_k W[n, k] * x[i, k, p]  (+ residual[i, n, p])          plain producer only
+//     out[i, n, p] = sum_k W[n, k] * A(i, k, p)  (+ residual[i, n, p])     A = x  or  relu(x * scale[k] + bias[k])
 //
-// (conv3 + shortcut, the shortcut conv, conv1 on the patch matrix, and every input gradient; conv2 with the bn1+relu
-// producer needs the operand in registers and stays on k_pw_conv.)
+// (conv3 + shortcut, the shortcut conv, conv1 on the patch matrix, every input gradient, and conv2 behind bn1 -> relu: eight
+// extra warps apply the affine + ReLU in place on a landed stage -- 16-byte shared-memory vectors, a channel is a row -- and
+// hand it to the MMA warp through `ready`.)
 //
 //   tile       = 128 consecutive pixels of ONE image x all K channels: two boxes of (64 pixels x K rows) = the two 64-pixel
 //                column blocks of the operand (LBO apart); pixels beyond the plane are zero-filled by the TMA unit on the
@@ -16,6 +17,7 @@
 //   warp 1     one elected thread issues tcgen05.mma (128 x 128 x 16), accumulators double-buffered in tensor memory
 //   warps 2-9  epilogue: tcgen05.ld -> bf16 (+ residual from the staging buffer) -> staging buffer (same swizzled box
 //              layout) -> one thread issues the two TMA stores of the tile
+//   warps 10-17 (BN+ReLU producer only) relu(x*s+b) on the stage between `full` and `ready`
 //   weights    resident [128 x Kpad] K-major block (<= 128 output channels per CTA, more go to grid.y), staged before the
 //              dependency wait when RB_W_RESIDENT
 // Arithmetic is the same as k_pw_conv: bf16 operands, fp32 accumulation in TMEM, result rounded to bf16, `+= shortcut` on
@@ -33,14 +35,18 @@ namespace {
 constexpr int kP3Warps = 10;
 constexpr int kP3Threads = kP3Warps * 32;
 constexpr int kP3EpiWarp0 = 2, kP3NumEpi = 8;
+constexpr int kP3BnWarp0 = 10, kP3NumBn = 8;  // launched only with the BN+ReLU producer
+constexpr int kP3ThreadsBn = (kP3BnWarp0 + kP3NumBn) * 32;
 constexpr int kP3MaxStages = 6;
 constexpr int kP3Smem = 227 * 1024;
-constexpr int kP3Hdr = 1024;
+constexpr int kP3Hdr = 4096;  // barriers [0, 512) + (scale, bias) of up to 256 input channels [512, 2560)
+constexpr int kP3SbOff = 512;
 constexpr int kP3Rows = 128;  // output channels per CTA = MMA M
 constexpr int kP3Npx = 128;
 
 struct P3Args {
     const void *w;  // bf16 [N, K] (rb_pw_weight_pack) or fp32 [N, K]
+    const float *a_sb;  // BN+ReLU producer: (scale, bias) pairs [K, 2]; NULL = plain
     int w_f32, w_resident, has_res;
     int NI, K, N, HW;
     int Kpad, Ncta, stages, tiles_per_image, total_tiles;
@@ -48,10 +54,13 @@ struct P3Args {
 };
 
 struct P3Hdr {
-    uint64_t full[kP3MaxStages], empty[kP3MaxStages], tmem_full[2], tmem_empty[2], res_full[2], stg_free[2];
+    uint64_t full[kP3MaxStages], empty[kP3MaxStages], ready[kP3MaxStages], tmem_full[2], tmem_empty[2], res_full[2], stg_free[2];
     uint32_t tmem_base;
 };
-static_assert(sizeof(P3Hdr) <= kP3Hdr, "header");
+static_assert(sizeof(P3Hdr) <= kP3SbOff, "header");
+__device__ __forceinline__ uint32_t p3_bn_relu2(uint32_t w, float sc, float bi) {
+    return pack_bf16x2(fmaxf(fmaf(bf16_lo(w), sc, bi), 0.f), fmaxf(fmaf(bf16_hi(w), sc, bi), 0.f));
+}
 
 __device__ __forceinline__ void p3_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -85,10 +94,10 @@ __device__ __forceinline__ uint32_t p3_add_bf16x2(uint32_t a, uint32_t b) {
 
 // weight block W[n0 + n, k] -> (k/8)*w_lbo + (n/8)*128 + (n%8)*16 + (k%8)*2; rows >= nrows and columns >= K are zero
 __device__ __forceinline__ void p3_stage_weights(const P3Args &a, unsigned char *smem_w, int n0, int nrows, int tid) {
-    const int kg = a.Kpad >> 3, total = kP3Rows * kg;
+    const int kg = a.Kpad >> 3, total = kP3Rows * kg, nthreads = (int)blockDim.x;
     const __nv_bfloat16 *wb = reinterpret_cast<const __nv_bfloat16 *>(a.w);
     const float *wf = reinterpret_cast<const float *>(a.w);
-    for (int u = tid; u < total; u += kP3Threads) {
+    for (int u = tid; u < total; u += nthreads) {
         const int n = u / kg, g = u - n * kg;
         uint4 o = make_uint4(0u, 0u, 0u, 0u);
         if (n < nrows && g * 8 < a.K) {
@@ -104,7 +113,7 @@ __device__ __forceinline__ void p3_stage_weights(const P3Args &a, unsigned char 
     }
 }
 
-__global__ void __launch_bounds__(kP3Threads, 1)
+__global__ void __launch_bounds__(kP3ThreadsBn, 1)
 k_pw3(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
       const P3Args a) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -119,6 +128,7 @@ k_pw3(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtenso
         for (int i = 0; i < kP3MaxStages; ++i) {
             mbar_init(&hdr->full[i], 1);
             mbar_init(&hdr->empty[i], 1);
+            mbar_init(&hdr->ready[i], kP3NumBn);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&hdr->tmem_full[i], 1);
@@ -137,7 +147,7 @@ k_pw3(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtenso
     if (a.Kpad > a.K) {
         const int pad_rows = a.Kpad - a.K;  // a whole 8-row group (K % 8 == 0, Kpad % 16 == 0): 1 KiB per column block
         const int per_stage = 2 * pad_rows * 8;  // 16-byte chunks
-        for (int u = tid; u < a.stages * per_stage; u += kP3Threads) {
+        for (int u = tid; u < a.stages * per_stage; u += (int)blockDim.x) {
             const int st = u / per_stage, r = u - st * per_stage;
             const int blk = r / (pad_rows * 8), c = r - blk * (pad_rows * 8);
             *reinterpret_cast<uint4 *>(smem + a.off_a + (size_t)st * a.stage_bytes + (size_t)blk * (a.Kpad * 128) + (size_t)a.K * 128 + c * 16) =
@@ -147,6 +157,9 @@ k_pw3(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtenso
     if (a.w_resident) p3_stage_weights(a, smem_w, n0, nrows, tid);
     pdl_sync();
     if (!a.w_resident) p3_stage_weights(a, smem_w, n0, nrows, tid);
+    float *smem_sb = reinterpret_cast<float *>(smem + kP3SbOff);
+    if (a.a_sb != nullptr)
+        for (int k = tid; k < 2 * a.K; k += (int)blockDim.x) smem_sb[k] = a.a_sb[k];  // (scale, bias) interleaved as given
     fence_proxy_async_smem();  // weights + zero rows (generic proxy) -> visible to the tensor core
     tc_fence_before();
     __syncthreads();
@@ -198,7 +211,7 @@ k_pw3(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtenso
                 const int as = it & 1;
                 const uint32_t aph = (uint32_t)(it >> 1) & 1u;
                 mbar_wait(&hdr->tmem_empty[as], aph ^ 1u);
-                mbar_wait(&hdr->full[slot], phase);
+                mbar_wait(a.a_sb != nullptr ? &hdr->ready[slot] : &hdr->full[slot], phase);
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)as * kP3Npx;
                 uint32_t a_lo = a_lo0, b_lo = b_lo0 + (uint32_t)slot * (a.stage_bytes >> 4);
@@ -213,6 +226,33 @@ k_pw3(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtenso
             }
         }
         __syncwarp();
+    } else if (warp >= kP3BnWarp0) {
+        // ================================ BN + ReLU on the landed stage ==============================================
+        const int bt = tid - kP3BnWarp0 * 32;
+        const int units = a.K * 8;  // 16-byte chunks per 64-pixel column block; chunk u lies in channel row u / 8
+        int slot = 0;
+        uint32_t phase = 0;
+        for (int tile = tile0; tile < a.total_tiles; tile += tstride) {
+            mbar_wait(&hdr->full[slot], phase);
+            const uint32_t base = s_a + (uint32_t)slot * a.stage_bytes;
+#pragma unroll 1
+            for (int blk = 0; blk < 2; ++blk) {
+                const uint32_t bb = base + (uint32_t)blk * ((uint32_t)a.Kpad * 128u);
+                for (int u = bt; u < units; u += kP3NumBn * 32) {
+                    const float2 sb = reinterpret_cast<const float2 *>(smem_sb)[u >> 3];
+                    uint4 v = p3_lds128(bb + (uint32_t)u * 16u);
+                    v.x = p3_bn_relu2(v.x, sb.x, sb.y);
+                    v.y = p3_bn_relu2(v.y, sb.x, sb.y);
+                    v.z = p3_bn_relu2(v.z, sb.x, sb.y);
+                    v.w = p3_bn_relu2(v.w, sb.x, sb.y);
+                    p3_sts128(bb + (uint32_t)u * 16u, v);
+                }
+            }
+            fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&hdr->ready[slot]);
+            if (++slot == a.stages) { slot = 0; phase ^= 1u; }
+        }
     } else {
         // ================================ epilogue =================================================================
         // warp -> TMEM lane quarter (hardware: warp id % 4) and one of the two 64-pixel column blocks
@@ -352,8 +392,10 @@ bool pw3_supported(const void *x, const void *out, const void *res, int NI, int 
     return p3_plan(a, &grid, &smem) && p3_encoder() != nullptr;
 }
 
-int pw3_forward(const void *x, const void *w, int w_dt, const void *res, void *out, int NI, int K, int N, int HW, cudaStream_t s) {
+int pw3_forward(const void *x, const void *w, int w_dt, const void *res, void *out, int NI, int K, int N, int HW, const float *a_sb,
+                cudaStream_t s) {
     P3Args a{};
+    a.a_sb = a_sb;
     a.w = w; a.w_f32 = (w_dt & ~RB_W_RESIDENT) == RB_F32; a.w_resident = (w_dt & RB_W_RESIDENT) != 0; a.has_res = res != nullptr;
     a.NI = NI; a.K = K; a.N = N; a.HW = HW;
     dim3 grid;
@@ -372,7 +414,7 @@ int pw3_forward(const void *x, const void *w, int w_dt, const void *res, void *o
         if (e != cudaSuccess) return fail(RB_ERR_CUDA, "cudaFuncSetAttribute(k_pw3): %s", cudaGetErrorString(e));
         configured_dev = dev;
     }
-    launch_kernel(k_pw3, grid, dim3(kP3Threads), smem_bytes, s, mx, mo, mr, a);
+    launch_kernel(k_pw3, grid, dim3(a_sb ? kP3ThreadsBn : kP3Threads), smem_bytes, s, mx, mo, mr, a);
     return launched("k_pw3");
 }
 

@@ -13,6 +13,8 @@
 
 All are autograd Functions over [N*T, C, H, W] activations; parameters stay fp32 (activations may be bf16).
 """
+import threading
+
 import torch
 import torch.nn as nn
 
@@ -107,12 +109,40 @@ def _aligned(t):
     return t if t.data_ptr() % 16 == 0 else t.clone(memory_format=torch.contiguous_format)
 
 
+class _StepCounters(threading.local):
+    """nn.BatchNorm2d counts its training batches in `num_batches_tracked`; one `add_` per layer is 103 one-thread launches
+    in a RubiksNet-Large step.  A network-level forward (RubiksNetBackbone) bumps every counter with ONE multi-tensor add
+    and the per-layer code then skips the modules it covered."""
+    done = None
+
+
+_STEP_COUNTERS = _StepCounters()
+
+
+def begin_step_counters(owner):
+    bns = [m for m in owner.modules() if isinstance(m, nn.BatchNorm2d) and m.training and m.track_running_stats
+           and m.num_batches_tracked is not None and m.num_batches_tracked.is_cuda]
+    if bns:
+        torch._foreach_add_([m.num_batches_tracked for m in bns], 1)
+    _STEP_COUNTERS.done = {id(m) for m in bns}
+
+
+def end_step_counters():
+    _STEP_COUNTERS.done = None
+
+
+def _count_batch(bn):
+    if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        done = _STEP_COUNTERS.done
+        if done is None or id(bn) not in done:
+            bn.num_batches_tracked.add_(1)
+
+
 def bn_act(x, bn, relu=True):
     """relu(bn(x)) with torch.nn.BatchNorm2d semantics (batch statistics + running-stat update in training
     mode, running statistics in eval mode) for a CUDA NCHW tensor."""
     training = bn.training or bn.running_mean is None
-    if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked.add_(1)
+    _count_batch(bn)
     rs = _RunningStats(bn)
     out = _BNAct.apply(_aligned(x), _f32(bn.weight), _f32(bn.bias), rs.mean, rs.var, training, _bn_momentum(bn), bn.eps, relu)
     rs.commit()
@@ -777,8 +807,7 @@ def rubiks_aq_block_supported(block, x):
 
 def rubiks_aq_block(block, x):
     for bn in (block.bn1, block.bn2):
-        if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
-            bn.num_batches_tracked.add_(1)
+        _count_batch(bn)
     att = block.conv2[0]
     return _RubiksAQBlockFn.apply(
         x, block.bn1.weight, block.bn1.bias, att.taps().float(), block.conv2[1].weight, block.bn2.weight, block.bn2.bias,
@@ -827,8 +856,7 @@ def rubiks_down_block_supported(block, x):
 
 def rubiks_down_block(block, x):
     for bn in (block.bn1, block.bn2):
-        if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
-            bn.num_batches_tracked.add_(1)
+        _count_batch(bn)
     r3 = block.as3.rubiks3d
     return _RubiksDownBlockFn.apply(
         x, block.bn1.weight, block.bn1.bias, block.conv2.weight, block.bn2.weight, block.bn2.bias, r3.shift, block.conv3.weight,
@@ -869,8 +897,7 @@ def _default_shift_function():
 
 def rubiks_block(block, x):
     for bn in (block.bn1, block.bn2):
-        if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
-            bn.num_batches_tracked.add_(1)
+        _count_batch(bn)
     r3 = block.as3.rubiks3d
     # statistics of x reduced by the conv3 epilogue of the block that produced it (attached to the tensor below)
     x_stats = getattr(x, "_rb_bn_stats", None) if EPILOGUE_BN_STATS else None

@@ -305,3 +305,26 @@ def test_bn_channel_resident_passes_match_streaming(shape, dtype, residual):
     assert _rel(a[0], yr) <= 1e-2
     assert _rel(a[5], xr.grad + (res.float() if residual else 0)) <= 1e-2
     assert _rel(a[3], bn.running_mean) <= 1e-4 and _rel(a[4], bn.running_var) <= 1e-4
+
+
+@pytest.mark.parametrize("variant", ["rubiks3d", "rubiks3d-aq"])
+def test_every_batchnorm_counter_advances_once_per_training_forward(variant):
+    """The backbone bumps all num_batches_tracked counters with one multi-tensor add; the per-layer code must then skip them
+    (and still count on its own when a block is called outside a backbone forward, or in eval mode not at all)."""
+    torch.manual_seed(0)
+    net = rb.RubiksNet(tier="tiny", num_classes=5, num_frames=8, variant=variant).cuda().train()
+    x = torch.randn(8, 3, 224, 224, device="cuda")
+    bns = [m for m in net.modules() if isinstance(m, nn.BatchNorm2d)]
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        net(x)
+        net(x)
+    assert all(int(m.num_batches_tracked) == 2 for m in bns), sorted({int(m.num_batches_tracked) for m in bns})
+    net.eval()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        net(x)
+    assert all(int(m.num_batches_tracked) == 2 for m in bns)
+    blk = net.backbone.layer0[0]
+    blk.train()
+    xb = torch.randn(8, blk.bn1.num_features, 16, 16, device="cuda").to(torch.bfloat16)
+    blk(xb)
+    assert int(blk.bn1.num_batches_tracked) == 3 and int(blk.bn2.num_batches_tracked) == 3

@@ -27,11 +27,11 @@ GEOMS = [  # (NI, K, N, H, W)
 ]
 
 
-def _run(x, w, res, tma):
+def _run(x, w, res, tma, sb=None):
     _lib.set_pw_tma(tma)
     try:
         n0 = _lib.launch_count()
-        out = ops.pw_conv(x, w, residual=res)
+        out = ops.pw_conv(x, w, residual=res, in_scale_bias=sb)
         torch.cuda.synchronize()
         return out, _lib.launch_count() - n0
     finally:
@@ -60,6 +60,29 @@ def test_pw_conv_tma_matches_first_kernel(geom, residual, packed):
     assert (got == want).float().mean().item() >= 0.999
 
 
+@pytest.mark.parametrize("geom", GEOMS)
+@pytest.mark.parametrize("residual", [False, True])
+def test_pw_conv_tma_bn_relu_producer(geom, residual):
+    """conv2 behind bn1 -> relu: the affine + ReLU applied in place on the TMA-staged operand == the register producer of the
+    first kernel (same FMA, same rounding) == fp32 math on the rounded operand."""
+    ni, k, n, h, w_ = geom
+    torch.manual_seed(sum(geom) + 7 + residual)
+    x = torch.randn(ni, k, h, w_, device="cuda").to(BF)
+    w = torch.randn(n, k, device="cuda") / k ** 0.5
+    sb = torch.stack([torch.rand(k, device="cuda") + 0.5, torch.randn(k, device="cuda") * 0.5], dim=1).contiguous()
+    res = torch.randn(ni, n, h, w_, device="cuda").to(BF) if residual else None
+    wk = ops.pw_weight_pack(w)[0]
+    got, _ = _run(x, wk, res, True, sb)
+    want, _ = _run(x, wk, res, False, sb)
+    a = torch.relu(x.float() * sb[:, 0].view(1, -1, 1, 1) + sb[:, 1].view(1, -1, 1, 1)).to(BF).float()
+    ref = torch.einsum("nk,ikhw->inhw", w.to(BF).float(), a)
+    if residual:
+        ref = ref.to(BF).float() + res.float()
+    scale = max(1.0, ref.abs().max().item())
+    assert (got.float() - ref).abs().max().item() <= 1e-2 * scale
+    assert (got == want).float().mean().item() >= 0.999
+
+
 def test_pw_conv_tma_dispatch_rules():
     torch.manual_seed(1)
     w = torch.randn(72, 72, device="cuda") / 72 ** 0.5
@@ -75,7 +98,7 @@ def test_pw_conv_tma_dispatch_rules():
     a = ops.pw_conv(x, w)                                  # 28x28: TMA schedule
     x14 = torch.randn(4, 72, 14, 14, device="cuda").to(BF)
     b = ops.pw_conv(x14, w)                                # 14x14 (392-byte rows): first kernel
-    c = ops.pw_conv(x, w, in_scale_bias=sb)                # bn+relu producer: first kernel
+    c = ops.pw_conv(x, w, in_scale_bias=sb)                # bn+relu producer: TMA schedule + in-place transform warps
     d = ops.pw_conv(x, w.t().contiguous(), transposed=True)  # transposed weight buffer: first kernel
     torch.cuda.synchronize()
     ref = torch.einsum("nk,ikhw->inhw", w.to(BF).float(), x.float())
