@@ -59,6 +59,8 @@ def parse():
                     help="replay the whole step from a CUDA graph (rubiksnet_b200.graph.GraphedStep); off = eager launches")
     ap.add_argument("--pdl", default="on", choices=["on", "off"],
                     help="programmatic dependent launch of the library's kernels (rb_set_dependent_launch); off = A/B arm")
+    ap.add_argument("--tma", default="on", choices=["on", "off"],
+                    help="tensor-map TMA schedules of the 1x1 convs / weight gradients on 16-byte-pitch maps (k_pw3, k_wg3); off = A/B arm")
     return ap.parse_args()
 
 
@@ -507,6 +509,9 @@ def main():
         from rubiksnet_b200 import _lib as _rb_lib
         _rb_lib.set_dependent_launch(args.pdl == "on")
         config["dependent_launch"] = args.pdl
+        if args.tma == "off":
+            _rb_lib.set_pw_tma(False)
+            config["tensor_map_schedules"] = "off"
     tr = Trainer("ours" if args.impl == "ours" else "reference", args, world)
     clips, labels = synthetic_batch(args.batch, 100 + rank)
     dclips, dlabels = clips.cuda(), labels.cuda()

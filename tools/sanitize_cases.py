@@ -69,6 +69,9 @@ def misc_cases():
         xd = x.detach()
         y, mi, sb = ops.bn_forward(xd, bn_g, bn_b, rm, rv, True, 0.1, 1e-5, relu=True, apply=True)
         ops.bn_backward(xd, torch.randn_like(xd), xd, bn_g, mi, sb, True, relu=True)
+        from rubiksnet_b200.attention_shift import attention_mix_backward, attention_mix_forward
+        attention_mix_forward(xd, taps.detach(), 8, in_scale_bias=sb)  # bn1 -> relu folded into the temporal mix
+        attention_mix_backward(xd, taps.detach(), torch.randn_like(xd), 8, in_scale_bias=sb)
         torch.cuda.synchronize()
     # tcgen05 kind::tf32 kernel: vector and scalar paths, producer / epilogue folds, split contraction; SE kernels; pack fence
     for ni, k, n, h in ((4, 54, 54, 14), (2, 216, 432, 7), (2, 432, 72, 7), (3, 20, 12, 5)):
