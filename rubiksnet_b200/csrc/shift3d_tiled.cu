@@ -95,7 +95,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             : "memory");
     } while (!ok);
 }
-template <typename T, int K> struct alignas(sizeof(T) * K > 16 ? 16 : sizeof(T) * K) TPack { T v[K]; };
 template <typename T> __device__ __forceinline__ float lds(const T *p) { return ld<float, T>(p); }
 template <typename T> __device__ __forceinline__ float ldg_stream(const T *p) { return ld<float, T>(p); }
 template <> __device__ __forceinline__ float ldg_stream<float>(const float *p) { return __ldcs(p); }
@@ -251,11 +250,11 @@ __global__ void __launch_bounds__(kNW * 32) k_shift3d_tiled(const TiledArgs a) {
 
     // ---- per-item tap offsets (element index relative to the frame's stage pointer; 0 = zero) ----
     const int P = th * Wd;  // destination positions per channel in this tile
-    // position k of a thread: lanes interleaved (adjacent lanes -> adjacent elements), or -- S2 -- K CONSECUTIVE positions per
-    // thread, so that x is read and x_grad written with one K-element vector access per frame instead of K 2-byte ones
-    // (the stride-2 backward was bound by the latency of those narrow accesses, not by bytes: fp32 and bf16 took the same time)
-    const int pstride = S2 ? 1 : WPC * 32;
-    const int p0 = S2 ? (wsub * 32 + lane) * K : wsub * 32 + lane;
+    // position k of a thread: lanes interleaved (adjacent lanes -> adjacent elements).  (K CONSECUTIVE positions per thread,
+    // one K-element vector access to x / x_grad per frame, was measured on the stride-2 backward and is slower in bf16:
+    // 0.822 -> 0.911 ms at 72 ch x 112x112, profiles/r02z_bench_shift.log vs gpurun_out/wg3_shift.log.)
+    const int pstride = WPC * 32;
+    const int p0 = wsub * 32 + lane;
     int off[S2 ? 1 : K][4];
     int osel[S2 ? K : 1];
     float wWs[S2 ? K : 1], wHs[S2 ? K : 1], sgH[S2 ? K : 1], sgW[S2 ? K : 1];
@@ -310,10 +309,6 @@ __global__ void __launch_bounds__(kNW * 32) k_shift3d_tiled(const TiledArgs a) {
     };
 
     float accT = 0.f, accH = 0.f, accW = 0.f;
-    // this thread's K positions are one aligned, fully valid vector of x / x_grad in every frame
-    const bool vec_io = S2 && c_ok && p0 + K <= P && ((dst_chan | dst_fs) % K) == 0 &&
-                        ((reinterpret_cast<uintptr_t>(a.dst) | reinterpret_cast<uintptr_t>(a.xin)) % (K * ES)) == 0;
-
     if (!slow) {
         // ================= streaming path =================
         float pB[K], pDH[K], pDW[K];
@@ -325,23 +320,12 @@ __global__ void __launch_bounds__(kNW * 32) k_shift3d_tiled(const TiledArgs a) {
             const bool have = any_data && ts >= 0 && ts < Tn;
             float xv[K];
             if (MODE == MODE_BWD) {
-                if (S2 && vec_io) {
 #pragma unroll
-                    for (int k = 0; k < K; ++k) xv[k] = 0.f;
-                    if (want_grad && td >= 0) {
-                        const TPack<T, K> pk = *reinterpret_cast<const TPack<T, K> *>(xin + dst_chan + td * dst_fs + p0);
-#pragma unroll
-                        for (int k = 0; k < K; ++k) xv[k] = ld<float, T>(&pk.v[k]);
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        const int p = p0 + k * pstride;
-                        xv[k] = (want_grad && td >= 0 && c_ok && p < P) ? ldg_stream<T>(xin + dst_chan + td * dst_fs + p) : 0.f;
-                    }
+                for (int k = 0; k < K; ++k) {
+                    const int p = p0 + k * pstride;
+                    xv[k] = (want_grad && td >= 0 && c_ok && p < P) ? ldg_stream<T>(xin + dst_chan + td * dst_fs + p) : 0.f;
                 }
             }
-            TPack<T, K> ov;
             const T *sp = nullptr;
             if (have) {
                 mbar_wait(&bars[ts], 0);
@@ -369,8 +353,7 @@ __global__ void __launch_bounds__(kNW * 32) k_shift3d_tiled(const TiledArgs a) {
                 if (td >= 0) {
                     const int p = p0 + k * pstride;
                     const float v = a.mode2d ? pB[k] : wT0 * pB[k] + wT1 * cB;
-                    if (S2 && vec_io) ov.v[k] = cvt<T, float>(v);
-                    else if (want_dst && c_ok && p < P) dst[dst_chan + td * dst_fs + p] = cvt<T, float>(v);
+                    if (want_dst && c_ok && p < P) dst[dst_chan + td * dst_fs + p] = cvt<T, float>(v);
                     if (MODE == MODE_BWD) {
                         accT += xv[k] * (pB[k] - cB);
                         accH += xv[k] * (a.mode2d ? pDH[k] : wT0 * pDH[k] + wT1 * cDH);
@@ -380,7 +363,6 @@ __global__ void __launch_bounds__(kNW * 32) k_shift3d_tiled(const TiledArgs a) {
                 pB[k] = cB;
                 if (MODE == MODE_BWD) { pDH[k] = cDH; pDW[k] = cDW; }
             }
-            if (S2 && vec_io && want_dst && td >= 0) *reinterpret_cast<TPack<T, K> *>(dst + dst_chan + td * dst_fs + p0) = ov;
         }
     } else {
         // ================= integer-shift slow path (BWD only, warp-uniform) =================
