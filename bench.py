@@ -376,7 +376,10 @@ def summarize_roofline(agg):
             f[key] += d[key]
     top_family = max(fam, key=lambda k: fam[k]["ms"])
     if top_family in ("pw_conv", "pw_conv_wgrad", "pw_conv_tf32"):
-        label = {"pw_conv": "k_pw_conv (all roles: ", "pw_conv_wgrad": "k_pw_wgrad (all roles: ",
+        # the bf16 families run on two schedules each: register-staged (k_pw_conv / k_pw_wgrad; k_pw2 on 7x7 maps) and, on
+        # maps with a 16-byte row pitch, tensor-map TMA (k_pw3 / k_wg3)
+        label = {"pw_conv": "1x1-conv forward / input-gradient GEMMs k_pw_conv + k_pw3 + k_pw2 (all roles: ",
+                 "pw_conv_wgrad": "1x1-conv weight-gradient GEMMs k_pw_wgrad + k_wg3 (all roles: ",
                  "pw_conv_tf32": "k_pw_tf32 (all roles: "}[top_family]
         label += ", ".join(sorted(n for n in agg if family(n) == top_family)) + ")"
         agg = dict(agg)

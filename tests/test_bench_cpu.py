@@ -25,7 +25,7 @@ def test_roofline_summary_merges_kernel_roles():
            "bn_backward": {"bytes": 23 * 10 ** 9, "flops": 0, "ms": 6.3, "launches": 94},
            "pw_conv_wgrad": {"bytes": 6 * 10 ** 9, "flops": 10 ** 11, "ms": 4.4, "launches": 59}}
     r = bench.summarize_roofline(agg)
-    assert r["kernel"].startswith("k_pw_conv") and r["bound"] == "hbm" and r["unit"] == "GB/s"
+    assert "k_pw_conv" in r["kernel"] and "k_pw3" in r["kernel"] and r["bound"] == "hbm" and r["unit"] == "GB/s"
     assert abs(r["achieved"] - 1400.0) < 1e-6 and r["launches_per_step"] == 145
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-3
     assert {k["kernel"] for k in r["all_kernels"]} == set(agg)
