@@ -54,6 +54,7 @@ def main():
     ap.add_argument("--opstages", type=int, default=0, help="image kernel: operand ring depth (0 = auto)")
     ap.add_argument("--kc", type=int, default=0, help="image kernel: channels per K chunk, 16 or 32 (0 = auto)")
     ap.add_argument("--waitns", type=int, default=0, help="image kernel: mbarrier suspend-time hint in ns (0 = default)")
+    ap.add_argument("--geom", default="", help="extra geometry name,C,H,W (e.g. pad14,288,25,8 = a 14x14 map at a 200-element pitch)")
     ap.add_argument("--wg", default="", help="tensor-map weight gradient knobs: burst,l2_256,max_stages")
     ap.add_argument("--no-tma", action="store_true", help="tensor-map TMA schedules (k_pw3 / k_wg3) off: first kernels everywhere")
     a = ap.parse_args()
@@ -66,14 +67,18 @@ def main():
     modes = a.modes.split(",")
     T = 8
     print("device:", torch.cuda.get_device_name(0))
-    for name, c, h in LAYERS:
+    layers = [(n, c, h, h) for n, c, h in LAYERS]
+    if a.geom:
+        gn, gc, gh, gw = a.geom.split(",")
+        layers.append((gn, int(gc), int(gh), int(gw)))
+    for name, c, h, wd in layers:
         if a.only and a.only != name:
             continue
         ni = a.batch * T
-        x = torch.randn(ni, c, h, h, device="cuda").to(BF)
+        x = torch.randn(ni, c, h, wd, device="cuda").to(BF)
         w = torch.randn(c, c, device="cuda") / c ** 0.5
-        res = torch.randn(ni, c, h, h, device="cuda").to(BF)
-        g = torch.randn(ni, c, h, h, device="cuda").to(BF)
+        res = torch.randn(ni, c, h, wd, device="cuda").to(BF)
+        g = torch.randn(ni, c, h, wd, device="cuda").to(BF)
         shift = torch.rand(3, c, device="cuda") * 2 - 1
         sb = torch.stack([torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda")], dim=1).contiguous()
         unit = x.numel() * 2
@@ -89,7 +94,7 @@ def main():
             "wgrad_bn": (lambda: ops.pw_conv_wgrad(g, x, in_scale_bias=sb), 2 * unit),
             "wgrad_shift": (lambda: ops.shift3d_pw_conv_wgrad(g, x, shift, T), 2 * unit),
         }
-        if ops.pw_image_supported(ni, c, c, h * h, True):
+        if ops.pw_image_supported(ni, c, c, h * wd, True):
             img_f, img_b = ops.pw_weight_images(w)
             cases.update({
                 "fwd2": (lambda: ops.pw_conv(x, img_f), 2 * unit),
