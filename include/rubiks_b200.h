@@ -203,6 +203,9 @@ int rb_pw_conv_forward_stats(const void *x, const void *weight, int weight_dtype
                              const void *residual, void *out, int dtype, int NI, int K, int N, int HW,
                              const float *in_scale_bias, double *stats_partial, size_t stats_bytes, int *stats_splits,
                              void *stream);
+/* 1 when the statistics epilogue costs (almost) nothing for this geometry -- the tensor-map schedule, where an epilogue thread
+ * owns a whole channel row -- i.e. when a caller should prefer rb_pw_conv_forward_stats over a separate statistics pass. */
+int rb_pw_conv_stats_preferred(int NI, int K, int N, int HW);
 
 /* 1x1 convolution on fp32 activations as a tcgen05 kind::tf32 GEMM (csrc/pw_conv_tf32.cu): the fp32 inference path of
  * RubiksShiftBlock (rubiksnet/backbone.py:123-135; the reference runs cuDNN TF32 convolutions between separate BatchNorm /

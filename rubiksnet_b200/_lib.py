@@ -112,6 +112,8 @@ def _declare(lib):
     lib.rb_pw_conv_image_supported.restype = i
     lib.rb_pw_conv_image_set_tuning.argtypes = [i, i, i]
     lib.rb_pw_conv_image_set_tuning.restype = None
+    lib.rb_pw_conv_stats_preferred.argtypes = [i, i, i, i]
+    lib.rb_pw_conv_stats_preferred.restype = i
     lib.rb_pw_conv_set_tuning.argtypes = [i]
     lib.rb_pw_conv_set_tuning.restype = None
     lib.rb_pw_conv_wgrad_set_tuning.argtypes = [i, i, i]

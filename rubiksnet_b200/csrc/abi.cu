@@ -88,7 +88,8 @@ void pw2_set_debug(int flags);
 #endif
 bool pw3_supported(const void *x, const void *out, const void *res, int NI, int K, int N, int HW);
 int pw3_forward(const void *x, const void *w, int w_dt, const void *res, void *out, int NI, int K, int N, int HW, const float *a_sb,
-                cudaStream_t s);
+                cudaStream_t s, double *stats = nullptr, size_t stats_bytes = 0, int *stats_splits = nullptr);
+bool pw3_stats_preferred(int NI, int K, int N, int HW);
 void pw3_set_enabled(int on);
 size_t wg3_workspace(int NI, int M, int N, int HW);
 void wg3_set_tuning(int burst, int l2_256, int max_stages);
@@ -423,8 +424,16 @@ int rb_pw_conv_forward_stats(const void *x, const void *weight, int weight_dtype
     if ((int64_t)NI * K * HW > 0x7fffffffLL || (int64_t)NI * N * HW > 0x7fffffffLL)
         return fail(RB_ERR_UNSUPPORTED, "tensors with more than 2^31-1 elements are not supported");
     if (!x || !weight || !out || !stats_partial || !stats_splits) return fail(RB_ERR_INVALID_ARGUMENT, "null pointer");
+    if (!weight_transposed && pw3_supported(x, out, residual, NI, K, N, HW))  // thread-local sums in the TMA schedule's epilogue
+        return pw3_forward(x, weight, weight_dtype, residual, out, NI, K, N, HW, in_scale_bias, (cudaStream_t)stream, stats_partial,
+                           stats_bytes, stats_splits);
     return pw_conv_forward(x, weight, weight_dtype, weight_transposed != 0, residual, out, NI, K, N, HW, in_scale_bias,
                            nullptr, 0, 0, 0, 0, (cudaStream_t)stream, stats_partial, stats_bytes, stats_splits);
+}
+
+int rb_pw_conv_stats_preferred(int NI, int K, int N, int HW) {
+    if (NI <= 0 || K <= 0 || N <= 0 || HW <= 0) return 0;
+    return pw3_stats_preferred(NI, K, N, HW) ? 1 : 0;
 }
 
 int rb_bn_stats_finalize(const double *partial, int splits, int C, double count, const float *gamma, const float *beta,

@@ -47,6 +47,8 @@ constexpr int kP3Npx = 128;
 struct P3Args {
     const void *w;  // bf16 [N, K] (rb_pw_weight_pack) or fp32 [N, K]
     const float *a_sb;  // BN+ReLU producer: (scale, bias) pairs [K, 2]; NULL = plain
+    double *stats;      // BatchNorm statistics of the output: [N][stats_splits][2] (sum, sum of squares); NULL = none
+    int stats_splits;   // 2 * gridDim.x: one slot per CTA and 64-pixel column block
     int w_f32, w_resident, has_res;
     int NI, K, N, HW;
     int Kpad, Ncta, stages, tiles_per_image, total_tiles;
@@ -113,6 +115,9 @@ __device__ __forceinline__ void p3_stage_weights(const P3Args &a, unsigned char 
     }
 }
 
+// STATS: the epilogue also reduces the BatchNorm statistics of the output (a separate instantiation: the extra registers and
+// arithmetic slow the plain epilogue down, 0.176 -> 0.217 ms at 72 ch x 112x112, even when they are skipped at run time)
+template <bool STATS>
 __global__ void __launch_bounds__(kP3ThreadsBn, 1)
 k_pw3(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
       const P3Args a) {
@@ -259,6 +264,9 @@ k_pw3(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtenso
         const int q = warp & 3, blk = (warp - kP3EpiWarp0) >> 2;
         const int row = q * 32 + lane;  // CTA-local output channel of this thread's TMEM lane
         const bool row_ok = row < nrows;
+        // BatchNorm statistics of the output (a.stats): this thread owns output channel `row` of every tile's column block
+        // `blk` for the whole kernel, so the two sums never leave its registers until the end
+        float st1 = 0.f, st2 = 0.f;
         int it = 0;
         for (int tile = tile0; tile < a.total_tiles; tile += tstride, ++it) {
             const int as = it & 1, b = it & 1;
@@ -294,6 +302,17 @@ k_pw3(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtenso
                             o = make_uint4(p3_add_bf16x2(o.x, r.x), p3_add_bf16x2(o.y, r.y), p3_add_bf16x2(o.z, r.z), p3_add_bf16x2(o.w, r.w));
                         }
                         p3_sts128(addr, o);
+                        // of the stored (bf16-rounded) values, as a statistics pass over the tensor would read them; chunks
+                        // beyond the plane (the half-empty last tile of an image) are not part of it
+                        if (STATS && px0 + blk * 64 + (h * 4 + c) * 8 < a.HW) {
+                            const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float lo = bf16_lo(ow[e]), hi = bf16_hi(ow[e]);
+                                st1 += lo + hi;
+                                st2 = fmaf(lo, lo, fmaf(hi, hi, st2));
+                            }
+                        }
                     }
                 }
             }
@@ -309,6 +328,11 @@ k_pw3(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtenso
             }
         }
         if (warp == kP3EpiWarp0 && lane == 0) p3_wait_all();  // global writes complete before the grid retires
+        if (STATS && row_ok) {
+            double *o = a.stats + ((int64_t)(n0 + row) * a.stats_splits + (blockIdx.x * 2 + blk)) * 2;
+            o[0] = (double)st1;
+            o[1] = (double)st2;
+        }
     }
 
     tc_fence_before();
@@ -392,8 +416,18 @@ bool pw3_supported(const void *x, const void *out, const void *res, int NI, int 
     return p3_plan(a, &grid, &smem) && p3_encoder() != nullptr;
 }
 
+// BatchNorm statistics in the epilogue are worth it on this schedule (an epilogue thread owns a channel row: thread-local sums)
+bool pw3_stats_preferred(int NI, int K, int N, int HW) {
+    if (!g_p3_enabled.load(std::memory_order_relaxed) || p3_encoder() == nullptr) return false;
+    P3Args a{};
+    a.NI = NI; a.K = K; a.N = N; a.HW = HW;
+    dim3 grid;
+    size_t smem;
+    return p3_plan(a, &grid, &smem);
+}
+
 int pw3_forward(const void *x, const void *w, int w_dt, const void *res, void *out, int NI, int K, int N, int HW, const float *a_sb,
-                cudaStream_t s) {
+                cudaStream_t s, double *stats, size_t stats_bytes, int *stats_splits) {
     P3Args a{};
     a.a_sb = a_sb;
     a.w = w; a.w_f32 = (w_dt & ~RB_W_RESIDENT) == RB_F32; a.w_resident = (w_dt & RB_W_RESIDENT) != 0; a.has_res = res != nullptr;
@@ -402,6 +436,13 @@ int pw3_forward(const void *x, const void *w, int w_dt, const void *res, void *o
     size_t smem_bytes = 0;
     if (!p3_plan(a, &grid, &smem_bytes)) return fail(RB_ERR_UNSUPPORTED, "pw3: geometry not supported");
     if (reinterpret_cast<uintptr_t>(w) & 15) return fail(RB_ERR_INVALID_ARGUMENT, "pw3: weight must be 16-byte aligned");
+    if (stats != nullptr) {
+        a.stats = stats;
+        a.stats_splits = 2 * (int)grid.x;
+        if (stats_bytes < (size_t)N * a.stats_splits * 2 * sizeof(double))
+            return fail(RB_ERR_WORKSPACE, "pw3: statistics need %zu bytes", (size_t)N * a.stats_splits * 2 * sizeof(double));
+        if (stats_splits) *stats_splits = a.stats_splits;
+    }
     CUtensorMap mx, mo, mr;
     if (!p3_make_map(&mx, x, NI, K, HW, K) || !p3_make_map(&mo, out, NI, N, HW, a.Ncta) ||
         !p3_make_map(&mr, res ? res : out, NI, N, HW, a.Ncta))
@@ -410,11 +451,13 @@ int pw3_forward(const void *x, const void *w, int w_dt, const void *res, void *o
     int dev = 0;
     cudaGetDevice(&dev);
     if (configured_dev != dev) {
-        cudaError_t e = cudaFuncSetAttribute(k_pw3, cudaFuncAttributeMaxDynamicSharedMemorySize, kP3Smem);
+        cudaError_t e = cudaFuncSetAttribute(k_pw3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kP3Smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pw3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kP3Smem);
         if (e != cudaSuccess) return fail(RB_ERR_CUDA, "cudaFuncSetAttribute(k_pw3): %s", cudaGetErrorString(e));
         configured_dev = dev;
     }
-    launch_kernel(k_pw3, grid, dim3(a_sb ? kP3ThreadsBn : kP3Threads), smem_bytes, s, mx, mo, mr, a);
+    if (stats != nullptr) launch_kernel(k_pw3<true>, grid, dim3(a_sb ? kP3ThreadsBn : kP3Threads), smem_bytes, s, mx, mo, mr, a);
+    else launch_kernel(k_pw3<false>, grid, dim3(a_sb ? kP3ThreadsBn : kP3Threads), smem_bytes, s, mx, mo, mr, a);
     return launched("k_pw3");
 }
 

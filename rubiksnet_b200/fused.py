@@ -612,7 +612,10 @@ class _RubiksBlockFn(torch.autograd.Function):
             mi1, sb1 = ops.bn_finalize(x_stats, count, g1, b1, rm1, rv1, mom1, eps1)
         else:
             _, mi1, sb1 = ops.bn_forward(x, g1, b1, rm1, rv1, tr1, mom1, eps1, relu=True, apply=False)
-        if tr2 and EPILOGUE_BN_STATS and not isinstance(w2_nk, ops.WeightImage):
+        # ... always where the epilogue statistics are free (tensor-map schedule on 16-byte-pitch maps: an epilogue thread owns
+        # a channel row), everywhere with EPILOGUE_BN_STATS (slower than the separate pass on the other kernels)
+        mid, cout = w2.shape[0], w3.shape[0]
+        if tr2 and not isinstance(w2_nk, ops.WeightImage) and (EPILOGUE_BN_STATS or ops.pw_stats_preferred(x.shape[0], x.shape[1], mid, hw)):
             y2, st2 = ops.pw_conv(x, w2_nk, in_scale_bias=sb1, name="pw_conv<bn+relu>", stats=True, resident=True)
             mi2, sb2 = ops.bn_finalize(st2, count, g2, b2, rm2, rv2, mom2, eps2)
             a2 = ops.bn_apply(y2, sb2, relu=True)
@@ -625,7 +628,7 @@ class _RubiksBlockFn(torch.autograd.Function):
             out = ops.shift3d_pw_conv(a2, shift, w3_nk, x, frames)
         else:
             s3 = _shift3d_forward(a2, shift, frames)
-            if EPILOGUE_BN_STATS and not isinstance(w3_nk, ops.WeightImage):
+            if not isinstance(w3_nk, ops.WeightImage) and (EPILOGUE_BN_STATS or ops.pw_stats_preferred(x.shape[0], mid, cout, hw)):
                 out, out_stats = ops.pw_conv(s3, w3_nk, residual=x, name="pw_conv<+residual>", stats=True, resident=True)
             else:
                 out = ops.pw_conv(s3, w3_nk, residual=x, name="pw_conv<+residual>", resident=True)
@@ -900,7 +903,7 @@ def rubiks_block(block, x):
         _count_batch(bn)
     r3 = block.as3.rubiks3d
     # statistics of x reduced by the conv3 epilogue of the block that produced it (attached to the tensor below)
-    x_stats = getattr(x, "_rb_bn_stats", None) if EPILOGUE_BN_STATS else None
+    x_stats = getattr(x, "_rb_bn_stats", None)
     out, partial, splits = _RubiksBlockFn.apply(
         x, block.bn1.weight, block.bn1.bias, block.conv2.weight, block.bn2.weight, block.bn2.bias, r3.shift,
         block.conv3.weight, block.bn1, block.bn2, block.as3.n_segment, bool(r3.normalize_grad),

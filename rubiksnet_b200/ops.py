@@ -182,6 +182,12 @@ def pw_conv(x, weight, residual=None, in_scale_bias=None, transposed=False, name
     return out
 
 
+def pw_stats_preferred(ni, k, n, hw):
+    """True when pw_conv(..., stats=True) reduces the BatchNorm statistics of its output at (almost) no cost for this geometry
+    (the tensor-map schedule: 16-byte row pitch) -- prefer it to a separate statistics pass over the tensor."""
+    return bool(_lib.lib().rb_pw_conv_stats_preferred(int(ni), int(k), int(n), int(hw)))
+
+
 def pw_conv_f32(x, weight, residual=None, in_scale_bias=None, out_scale_bias=None, relu=False, resident=False,
                 name="pw_conv_tf32"):
     """fp32 1x1 convolution on the tcgen05 kind::tf32 kernel (inference path):

@@ -105,3 +105,30 @@ def test_pw_conv_tma_dispatch_rules():
     assert (a.float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
     assert (d.float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
     assert b.shape == (4, 72, 14, 14) and c.shape == a.shape
+
+
+@pytest.mark.parametrize("geom", [(8, 72, 72, 56, 56), (8, 144, 144, 28, 28), (5, 40, 264, 24, 24), (3, 16, 8, 16, 8)])
+@pytest.mark.parametrize("mode", ["plain", "residual", "bn"])
+def test_pw_conv_tma_epilogue_statistics(geom, mode):
+    """BatchNorm statistics reduced in the TMA schedule's epilogue (thread-local sums per channel row) == sums over the stored
+    bf16 tensor, incl. the half-empty last tile of an image and the relu(bias) columns beyond the plane of the BN producer."""
+    ni, k, n, h, w_ = geom
+    torch.manual_seed(sum(geom) + len(mode))
+    x = torch.randn(ni, k, h, w_, device="cuda").to(BF)
+    w = torch.randn(n, k, device="cuda") / k ** 0.5
+    res = torch.randn(ni, n, h, w_, device="cuda").to(BF) if mode == "residual" else None
+    sb = torch.stack([torch.rand(k, device="cuda") + 0.5, torch.randn(k, device="cuda") * 0.5 + 0.3], dim=1).contiguous() if mode == "bn" else None
+    assert ops.pw_stats_preferred(ni, k, n, h * w_)
+    wk = ops.pw_weight_pack(w)[0]
+    out, (partial, splits) = ops.pw_conv(x, wk, residual=res, in_scale_bias=sb, stats=True)
+    plain = ops.pw_conv(x, wk, residual=res, in_scale_bias=sb)
+    torch.cuda.synchronize()
+    assert torch.equal(out, plain)
+    st = partial[: n * splits * 2].view(n, splits, 2).sum(1)
+    o64 = out.double()
+    want1, want2 = o64.sum((0, 2, 3)), (o64 * o64).sum((0, 2, 3))
+    count = ni * h * w_
+    assert (st[:, 0] - want1).abs().max().item() <= 1e-4 * count ** 0.5 * max(1.0, o64.abs().max().item())
+    assert ((st[:, 1] - want2).abs() / want2.clamp_min(1.0)).max().item() <= 1e-4
+    # 14x14 maps are not on this schedule: no preference, the separate statistics pass stays
+    assert not ops.pw_stats_preferred(8, 288, 288, 196)

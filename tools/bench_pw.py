@@ -88,6 +88,8 @@ def main():
             "fwd": (lambda: ops.pw_conv(x, w_nk), 2 * unit),
             "res": (lambda: ops.pw_conv(x, w_nk, residual=res), 3 * unit),
             "bn": (lambda: ops.pw_conv(x, w_nk, in_scale_bias=sb), 2 * unit),
+            "res_st": (lambda: ops.pw_conv(x, w_nk, residual=res, stats=True), 3 * unit),  # + BatchNorm statistics of the output
+            "bn_st": (lambda: ops.pw_conv(x, w_nk, in_scale_bias=sb, stats=True), 2 * unit),
             "shift": (lambda: ops.shift3d_pw_conv(x, shift, w_nk, res, T), 3 * unit),
             "dgrad": (lambda: ops.pw_conv(g, w_kn), 2 * unit),
             "wgrad": (lambda: ops.pw_conv_wgrad(g, x), 2 * unit),
