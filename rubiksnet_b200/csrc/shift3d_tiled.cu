@@ -309,7 +309,63 @@ __global__ void __launch_bounds__(kNW * 32) k_shift3d_tiled(const TiledArgs a) {
     };
 
     float accT = 0.f, accH = 0.f, accW = 0.f;
-    if (!slow) {
+    if (!slow && S2) {
+        // ================= streaming path, stride-2 backward =================
+        // ncu on the generic loop below (72 ch x 112x112, profiles/r02z_ncu_s2_bwd.txt): 84 warp instructions per position and
+        // frame at 67 % issue utilisation, and 27 % of the stall samples on the first use of the x value loaded at the top of
+        // the same step.  Here the per-position predicates and the x / x_grad pointers are hoisted out of the frame loop
+        // (one pointer bump per frame), and x of frame t is fetched one step ahead of its use.
+        bool okk[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) okk[k] = c_ok && p0 + k * pstride < P;
+        const T *xnext = want_grad ? xin + dst_chan + p0 : nullptr;  // x of the frame fetched next
+        T *dcur = want_dst ? dst + dst_chan + p0 : nullptr;          // x_grad of the frame completed next
+        T xpre[K];
+        float pB[K], pDH[K], pDW[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) { pB[k] = 0.f; pDH[k] = 0.f; pDW[k] = 0.f; xpre[k] = cvt<T, float>(0.f); }
+        for (int step = 0; step <= Tn; ++step) {
+            const int ts = step + fT;
+            const bool have = any_data && ts >= 0 && ts < Tn;
+            const bool emit = step >= 1;  // destination frame step - 1 is completed by this step
+            float xv[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) xv[k] = ld<float, T>(&xpre[k]);  // fetched during the previous step
+            if (want_grad && step < Tn) {
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+                    if (okk[k]) xpre[k] = xnext[k * pstride];
+                xnext += dst_fs;
+            }
+            const T *sp = nullptr;
+            if (have) {
+                mbar_wait(&bars[ts], 0);
+                sp = stage_ptr(ts);
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                float cB = 0.f, cDH = 0.f, cDW = 0.f;
+                if (have) {
+                    const float q = lds<T>(sp + osel[k]);
+                    const float rw = q * wWs[k];
+                    cB = wHs[k] * rw;
+                    cDH = sgH[k] * rw;
+                    cDW = wHs[k] * (sgW[k] * q);
+                }
+                if (emit) {
+                    const float v = a.mode2d ? pB[k] : wT0 * pB[k] + wT1 * cB;
+                    if (want_dst && okk[k]) dcur[k * pstride] = cvt<T, float>(v);
+                    accT += xv[k] * (pB[k] - cB);
+                    accH += xv[k] * (a.mode2d ? pDH[k] : wT0 * pDH[k] + wT1 * cDH);
+                    accW += xv[k] * (a.mode2d ? pDW[k] : wT0 * pDW[k] + wT1 * cDW);
+                }
+                pB[k] = cB;
+                pDH[k] = cDH;
+                pDW[k] = cDW;
+            }
+            if (emit && want_dst) dcur += dst_fs;
+        }
+    } else if (!slow) {
         // ================= streaming path =================
         float pB[K], pDH[K], pDW[K];
 #pragma unroll
@@ -334,13 +390,7 @@ __global__ void __launch_bounds__(kNW * 32) k_shift3d_tiled(const TiledArgs a) {
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 float cB = 0.f, cDH = 0.f, cDW = 0.f;
-                if (have && S2) {
-                    const float q = lds<T>(sp + osel[k]);
-                    const float rw = q * wWs[k];
-                    cB = wHs[k] * rw;
-                    cDH = sgH[k] * rw;
-                    cDW = wHs[k] * (sgW[k] * q);
-                } else if (have) {
+                if (have) {
                     const float q00 = lds<T>(sp + off[S2 ? 0 : k][0]), q01 = lds<T>(sp + off[S2 ? 0 : k][1]);
                     const float q10 = lds<T>(sp + off[S2 ? 0 : k][2]), q11 = lds<T>(sp + off[S2 ? 0 : k][3]);
                     const float r0 = q00 * wW0 + q01 * wW1, r1 = q10 * wW0 + q11 * wW1;
