@@ -269,7 +269,83 @@ __global__ void __launch_bounds__(kSNT) k_shift3d_strip(const StripArgs a) {
     if (any_data && (CG > 1 || slow))
         for (int t = 0; t < Tn; ++t) s_wait(&bars[t]);
 
-    if (!slow) {
+    if (!slow && CW == 2) {
+        // 16-bit types: a thread's two columns go through every formula together as PACKED fp32 pairs (FFMA2 / FMUL2 on
+        // sm_100).  ncu on the scalar loop below (profiles/r02z_ncu_shift_kernels.txt): 53-56 warp instructions per element in
+        // the backward pass at IPC 1.9-2.2 -- the three-register FFMA / FMUL issue every other cycle per scheduler, so
+        // the fma pipe, not memory, bounds the kernel; the packed forms do two lanes per issue slot.  Same formulas, same
+        // association (mul then fma); the shift-gradient sums are kept per column and added at the end.
+        const float2 wa0 = make_float2(wa[0][0], wa[CW - 1][0]), wa1 = make_float2(wa[0][1], wa[CW - 1][1]);
+        const float2 vf0 = make_float2(vf[0], vf[1]), nvf1 = make_float2(-vf[1], -vf[CW]);
+        const float2 wH0v = make_float2(wH0, wH0), wH1v = make_float2(wH1, wH1);
+        const float2 wT0v = make_float2(wT0, wT0), wT1v = make_float2(wT1, wT1);
+        const float2 neg1 = make_float2(-1.f, -1.f), zero2 = make_float2(0.f, 0.f);
+        float2 pB[R], xp[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) { pB[k] = zero2; xp[k] = zero2; }
+        float2 aT = zero2, aH = zero2, aW = zero2;
+        for (int step = 0; step <= Tn; ++step) {
+            const int ts = step + fT;
+            const bool have = any_data && ts >= 0 && ts < Tn;
+            float2 xn[R];
+            if (MODE == SMODE_BWD) {
+#pragma unroll
+                for (int k = 0; k < R; ++k) {
+                    xn[k] = zero2;
+                    if (want_grad && step < Tn && active && k < nrows) {
+                        float t2[CW];
+                        s_load<T, VEC>(xin + dbase + step * dst_fs + k * W, t2, ncols);
+                        xn[k] = make_float2(t2[0], t2[CW - 1]);
+                    }
+                }
+            }
+            auto consume = [&](int k, const float2 Bk, const float2 DHk, const float2 DWk) {
+                if (step >= 1 && want_dst && active && k < nrows) {
+                    const float2 v2 = a.mode2d ? pB[k] : __ffma2_rn(wT1v, Bk, __fmul2_rn(wT0v, pB[k]));  // 2D: frames are independent images
+                    float v[CW];
+                    v[0] = v2.x;
+                    v[CW - 1] = v2.y;
+                    s_store<T, VEC>(dst + dbase + (step - 1) * dst_fs + k * W, v, ncols);
+                }
+                if (MODE == SMODE_BWD) {
+                    const float2 xm = a.mode2d ? xn[k] : __ffma2_rn(wT1v, xp[k], __fmul2_rn(wT0v, xn[k]));
+                    const float2 xd = __ffma2_rn(xp[k], neg1, xn[k]);
+                    aT = __ffma2_rn(Bk, xd, aT);
+                    aH = __ffma2_rn(DHk, xm, aH);
+                    aW = __ffma2_rn(DWk, xm, aW);
+                    xp[k] = xn[k];
+                }
+                pB[k] = Bk;
+            };
+            if (have) {
+                if (CG == 1) s_wait(&bars[ts]);
+                const unsigned char *fp = stages + (size_t)ts * cf.stage_bytes + mis_tab[ts];
+                float2 Lp = zero2, Ep = zero2;
+#pragma unroll
+                for (int j = 0; j <= R; ++j) {
+                    const T *rp = reinterpret_cast<const T *>(fp + rowoff[j]);
+                    const float q0 = s_tof(rp[0]), q1 = s_tof(rp[1]), q2 = s_tof(rp[CW]);
+                    const float2 qa = make_float2(q0, q1), qb = make_float2(q1, q2);
+                    const float2 L = __ffma2_rn(qb, wa1, __fmul2_rn(qa, wa0));
+                    const float2 E = (MODE == SMODE_BWD) ? __ffma2_rn(qb, nvf1, __fmul2_rn(qa, vf0)) : zero2;
+                    if (j >= 1) {
+                        const float2 Bk = __ffma2_rn(wH1v, L, __fmul2_rn(wH0v, Lp));
+                        const float2 DHk = __ffma2_rn(L, neg1, Lp);
+                        const float2 DWk = __ffma2_rn(wH1v, E, __fmul2_rn(wH0v, Ep));
+                        consume(j - 1, Bk, DHk, DWk);
+                    }
+                    Lp = L;
+                    Ep = E;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < R; ++k) consume(k, zero2, zero2, zero2);
+            }
+        }
+        accT = aT.x + aT.y;
+        accH = aH.x + aH.y;
+        accW = aW.x + aW.y;
+    } else if (!slow) {
         float pB[R][CW], xp[R][CW];
 #pragma unroll
         for (int k = 0; k < R; ++k)
