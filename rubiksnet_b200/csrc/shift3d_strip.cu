@@ -114,6 +114,24 @@ template <typename T, bool VEC> __device__ __forceinline__ void s_load(const T *
     }
 }
 
+// the same CW = 2 elements as one raw 32-bit word (element 0 in the low half), converted where they are used: the packed
+// backward loop keeps x of three frames in flight (previous / current / prefetched) at one register per row each
+template <typename T, bool VEC> __device__ __forceinline__ uint32_t s_load_raw(const T *p, int ncols) {
+    if (sizeof(T) != 2) return 0u;  // fp32 takes the scalar loop (CW == 1)
+    if (VEC) return __ldg(reinterpret_cast<const uint32_t *>(p));
+    const uint32_t lo = *reinterpret_cast<const unsigned short *>(p);
+    const uint32_t hi = ncols > 1 ? *reinterpret_cast<const unsigned short *>(p + 1) : 0u;
+    return lo | (hi << 16);
+}
+template <typename T> __device__ __forceinline__ float2 s_raw_to_f2(uint32_t w);
+template <> __device__ __forceinline__ float2 s_raw_to_f2<__nv_bfloat16>(uint32_t w) {
+    return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+template <> __device__ __forceinline__ float2 s_raw_to_f2<__half>(uint32_t w) {
+    return __half22float2(*reinterpret_cast<const __half2 *>(&w));
+}
+template <> __device__ __forceinline__ float2 s_raw_to_f2<float>(uint32_t) { return make_float2(0.f, 0.f); }  // never used (CW == 1)
+
 __device__ __forceinline__ float sc_a(int d, float r) { return d == 0 ? 1.f - r : (d == 1 ? r : 0.f); }
 __device__ __forceinline__ float sc_b(int d, float r, bool integer) { return integer ? (d == 1 ? 1.f : 0.f) : sc_a(d, r); }
 __device__ __forceinline__ float sc_sg(int d, bool integer) {
@@ -125,7 +143,7 @@ template <typename T, int MODE, int R, bool VEC>
 // (forcing 5 CTAs/SM on the backward -- 96 registers, 28 bytes of spills instead of 125 registers -- was measured SLOWER on every
 // geometry, 0.631 -> 0.761 ms at 112x112 and 0.052 -> 0.058 ms at 14x14, gpurun_out/r02ae: the kernel is issue-bound, not
 // residency-bound)
-__global__ void __launch_bounds__(kSNT) k_shift3d_strip(const StripArgs a) {
+__global__ void __launch_bounds__(kSNT, MODE == SMODE_BWD ? 4 : 7) k_shift3d_strip(const StripArgs a) {
     pdl_sync();
     constexpr int ES = (int)sizeof(T);
     constexpr int CW = StripTraits<T>::CW;
@@ -280,24 +298,27 @@ __global__ void __launch_bounds__(kSNT) k_shift3d_strip(const StripArgs a) {
         const float2 wH0v = make_float2(wH0, wH0), wH1v = make_float2(wH1, wH1);
         const float2 wT0v = make_float2(wT0, wT0), wT1v = make_float2(wT1, wT1);
         const float2 neg1 = make_float2(-1.f, -1.f), zero2 = make_float2(0.f, 0.f);
-        float2 pB[R], xp[R];
+        float2 pB[R];
+        // x of frame step - 1 / step / step + 1 as raw words: the frame needed at step s + 1 is fetched during step s, so its
+        // latency hides behind a whole step (ncu: 15-30 % of the stall samples sat on the first use of a same-step load)
+        uint32_t xwp[R], xwc[R], xwn[R];
+        const bool fetch = (MODE == SMODE_BWD) && want_grad && active;
+        const T *xrow = fetch ? xin + dbase : nullptr;
 #pragma unroll
-        for (int k = 0; k < R; ++k) { pB[k] = zero2; xp[k] = zero2; }
+        for (int k = 0; k < R; ++k) {
+            pB[k] = zero2;
+            xwp[k] = 0u;
+            xwc[k] = (fetch && k < nrows && Tn > 0) ? s_load_raw<T, VEC>(xrow + k * W, ncols) : 0u;
+            xwn[k] = 0u;
+        }
         float2 aT = zero2, aH = zero2, aW = zero2;
         for (int step = 0; step <= Tn; ++step) {
             const int ts = step + fT;
             const bool have = any_data && ts >= 0 && ts < Tn;
-            float2 xn[R];
             if (MODE == SMODE_BWD) {
+                xrow += dst_fs;  // frame step + 1
 #pragma unroll
-                for (int k = 0; k < R; ++k) {
-                    xn[k] = zero2;
-                    if (want_grad && step < Tn && active && k < nrows) {
-                        float t2[CW];
-                        s_load<T, VEC>(xin + dbase + step * dst_fs + k * W, t2, ncols);
-                        xn[k] = make_float2(t2[0], t2[CW - 1]);
-                    }
-                }
+                for (int k = 0; k < R; ++k) xwn[k] = (fetch && step + 1 < Tn && k < nrows) ? s_load_raw<T, VEC>(xrow + k * W, ncols) : 0u;
             }
             auto consume = [&](int k, const float2 Bk, const float2 DHk, const float2 DWk) {
                 if (step >= 1 && want_dst && active && k < nrows) {
@@ -308,12 +329,12 @@ __global__ void __launch_bounds__(kSNT) k_shift3d_strip(const StripArgs a) {
                     s_store<T, VEC>(dst + dbase + (step - 1) * dst_fs + k * W, v, ncols);
                 }
                 if (MODE == SMODE_BWD) {
-                    const float2 xm = a.mode2d ? xn[k] : __ffma2_rn(wT1v, xp[k], __fmul2_rn(wT0v, xn[k]));
-                    const float2 xd = __ffma2_rn(xp[k], neg1, xn[k]);
+                    const float2 xn = s_raw_to_f2<T>(xwc[k]), xq = s_raw_to_f2<T>(xwp[k]);
+                    const float2 xm = a.mode2d ? xn : __ffma2_rn(wT1v, xq, __fmul2_rn(wT0v, xn));
+                    const float2 xd = __ffma2_rn(xq, neg1, xn);
                     aT = __ffma2_rn(Bk, xd, aT);
                     aH = __ffma2_rn(DHk, xm, aH);
                     aW = __ffma2_rn(DWk, xm, aW);
-                    xp[k] = xn[k];
                 }
                 pB[k] = Bk;
             };
@@ -340,6 +361,10 @@ __global__ void __launch_bounds__(kSNT) k_shift3d_strip(const StripArgs a) {
             } else {
 #pragma unroll
                 for (int k = 0; k < R; ++k) consume(k, zero2, zero2, zero2);
+            }
+            if (MODE == SMODE_BWD) {
+#pragma unroll
+                for (int k = 0; k < R; ++k) { xwp[k] = xwc[k]; xwc[k] = xwn[k]; }
             }
         }
         accT = aT.x + aT.y;

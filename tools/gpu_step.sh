@@ -12,6 +12,6 @@ print("  top:", r['kernel'][:60], r['kernel_ms_per_step'], r['frac'])
 for k in r['all_kernels'][:12]: print("  %-28s %7.3f ms %5d %7.1f GB/s %.3f" % (k['kernel'][:28],k['kernel_ms_per_step'],k['launches_per_step'],k['achieved'],k['frac']))
 PY
 }
-for l in layer0 layer1.x layer2.x; do timeout -k 10 100 python tools/bench_pw.py --iters 10 --modes fwd,bn,bn_st,res,res_st,cublas --only $l 2>&1 | grep layer; done | tee $O/${TAG}_pw.log
+for l in layer0 layer1.x layer2.x; do timeout -k 10 100 python tools/bench_pw.py --iters 10 --modes fwd,bn,res,dgrad,wgrad,wgrad_bn,cublas --only $l 2>&1 | grep layer; done | tee $O/${TAG}_pw.log
 timeout -k 10 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $O/${TAG}_bench_c3.json 2> $O/${TAG}_bench_c3.err; summ $O/${TAG}_bench_c3.json; tail -2 $O/${TAG}_bench_c3.err | cut -c1-300
 timeout -k 10 300 python bench.py --variant rubiks3d-aq --steps 10 --warmup 3 --no-cpu-baseline > $O/${TAG}_bench_c4.json 2> $O/${TAG}_bench_c4.err; summ $O/${TAG}_bench_c4.json
