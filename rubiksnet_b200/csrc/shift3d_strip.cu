@@ -312,6 +312,9 @@ __global__ void __launch_bounds__(kSNT, MODE == SMODE_BWD ? 4 : 7) k_shift3d_str
             xwn[k] = 0u;
         }
         float2 aT = zero2, aH = zero2, aW = zero2;
+        const bool mode2d = a.mode2d != 0;
+        const uint32_t rmask = active ? ((1u << nrows) - 1u) : 0u;  // row slots of this thread that exist
+        T *dprev = want_dst ? dst + dbase : nullptr;                 // destination frame step - 1, row 0 of this thread
         for (int step = 0; step <= Tn; ++step) {
             const int ts = step + fT;
             const bool have = any_data && ts >= 0 && ts < Tn;
@@ -320,17 +323,20 @@ __global__ void __launch_bounds__(kSNT, MODE == SMODE_BWD ? 4 : 7) k_shift3d_str
 #pragma unroll
                 for (int k = 0; k < R; ++k) xwn[k] = (fetch && step + 1 < Tn && k < nrows) ? s_load_raw<T, VEC>(xrow + k * W, ncols) : 0u;
             }
+            const bool emit = step >= 1 && want_dst;
             auto consume = [&](int k, const float2 Bk, const float2 DHk, const float2 DWk) {
-                if (step >= 1 && want_dst && active && k < nrows) {
-                    const float2 v2 = a.mode2d ? pB[k] : __ffma2_rn(wT1v, Bk, __fmul2_rn(wT0v, pB[k]));  // 2D: frames are independent images
+                // the value is computed for every row slot, only the store is predicated (a branch around the whole body cost a
+                // BSSY / BRA / BSYNC triple and a three-term 64-bit address per row)
+                const float2 v2 = mode2d ? pB[k] : __ffma2_rn(wT1v, Bk, __fmul2_rn(wT0v, pB[k]));  // 2D: frames are independent images
+                if (emit && ((rmask >> k) & 1u)) {
                     float v[CW];
                     v[0] = v2.x;
                     v[CW - 1] = v2.y;
-                    s_store<T, VEC>(dst + dbase + (step - 1) * dst_fs + k * W, v, ncols);
+                    s_store<T, VEC>(dprev + k * W, v, ncols);
                 }
                 if (MODE == SMODE_BWD) {
                     const float2 xn = s_raw_to_f2<T>(xwc[k]), xq = s_raw_to_f2<T>(xwp[k]);
-                    const float2 xm = a.mode2d ? xn : __ffma2_rn(wT1v, xq, __fmul2_rn(wT0v, xn));
+                    const float2 xm = mode2d ? xn : __ffma2_rn(wT1v, xq, __fmul2_rn(wT0v, xn));
                     const float2 xd = __ffma2_rn(xq, neg1, xn);
                     aT = __ffma2_rn(Bk, xd, aT);
                     aH = __ffma2_rn(DHk, xm, aH);
@@ -366,6 +372,7 @@ __global__ void __launch_bounds__(kSNT, MODE == SMODE_BWD ? 4 : 7) k_shift3d_str
 #pragma unroll
                 for (int k = 0; k < R; ++k) { xwp[k] = xwc[k]; xwc[k] = xwn[k]; }
             }
+            if (emit) dprev += dst_fs;
         }
         accT = aT.x + aT.y;
         accH = aH.x + aH.y;
