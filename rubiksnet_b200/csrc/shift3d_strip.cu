@@ -383,6 +383,9 @@ __global__ void __launch_bounds__(kSNT, MODE == SMODE_BWD ? 4 : 7) k_shift3d_str
         for (int k = 0; k < R; ++k)
 #pragma unroll
             for (int i = 0; i < CW; ++i) { pB[k][i] = 0.f; xp[k][i] = 0.f; }
+        const bool mode2d = a.mode2d != 0;
+        const uint32_t rmask = active ? ((1u << nrows) - 1u) : 0u;  // row slots of this thread that exist
+        T *dprev = want_dst ? dst + dbase : nullptr;                 // destination frame step - 1, row 0 of this thread
         for (int step = 0; step <= Tn; ++step) {
             const int ts = step + fT;
             const bool have = any_data && ts >= 0 && ts < Tn;
@@ -396,18 +399,18 @@ __global__ void __launch_bounds__(kSNT, MODE == SMODE_BWD ? 4 : 7) k_shift3d_str
                         s_load<T, VEC>(xin + dbase + step * dst_fs + k * W, xn[k], ncols);
                 }
             }
-            // consume(k, B, DH, DW): finish output row k of destination frame step-1 and accumulate the shift gradient
+            const bool emit = step >= 1 && want_dst;
+            // consume(k, B, DH, DW): finish output row k of destination frame step-1 and accumulate the shift gradient (the value
+            // is computed for every row slot, only the store is predicated -- as in the packed loop above)
             auto consume = [&](int k, const float *Bk, const float *DHk, const float *DWk) {
-                if (step >= 1 && want_dst && active && k < nrows) {
-                    float v[CW];
+                float v[CW];
 #pragma unroll
-                    for (int i = 0; i < CW; ++i) v[i] = a.mode2d ? pB[k][i] : wT0 * pB[k][i] + wT1 * Bk[i];  // 2D: frames are independent images
-                    s_store<T, VEC>(dst + dbase + (step - 1) * dst_fs + k * W, v, ncols);
-                }
+                for (int i = 0; i < CW; ++i) v[i] = mode2d ? pB[k][i] : wT0 * pB[k][i] + wT1 * Bk[i];  // 2D: frames are independent images
+                if (emit && ((rmask >> k) & 1u)) s_store<T, VEC>(dprev + k * W, v, ncols);
 #pragma unroll
                 for (int i = 0; i < CW; ++i) {
                     if (MODE == SMODE_BWD) {
-                        const float xm = a.mode2d ? xn[k][i] : wT0 * xn[k][i] + wT1 * xp[k][i];
+                        const float xm = mode2d ? xn[k][i] : wT0 * xn[k][i] + wT1 * xp[k][i];
                         const float xd = xn[k][i] - xp[k][i];
                         accT += Bk[i] * xd;
                         accH += DHk[i] * xm;
@@ -453,6 +456,7 @@ __global__ void __launch_bounds__(kSNT, MODE == SMODE_BWD ? 4 : 7) k_shift3d_str
 #pragma unroll
                 for (int k = 0; k < R; ++k) consume(k, zero, zero, zero);
             }
+            if (emit) dprev += dst_fs;
         }
     } else if (active) {
         // ---- exact-integer shift component: tap-by-tap evaluation of the reference's rule ----------------
