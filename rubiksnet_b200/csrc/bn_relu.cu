@@ -293,6 +293,102 @@ k_bn_apply(const T *__restrict__ x, const T *__restrict__ dy, const T *__restric
     }
 }
 
+// The same passes for 16-bit types on planes whose size is a multiple of 4 (every map of RubiksNet: 112x112 ... 14x14; not 7x7):
+// the two 4-element halves of a 128-bit vector each lie inside ONE plane, so the per-element "did the plane end here" test
+// of k_bn_apply disappears (two coefficient sets per vector instead), and the arithmetic runs on packed fp32 pairs (FFMA2).
+// ncu on k_bn_apply<bf16, 0> at 14x14: 77 % issue utilisation -- the streaming passes are instruction-bound on L2-resident maps.
+template <typename T, int MODE>
+__global__ void __launch_bounds__(kBT)
+k_bn_apply_h(const T *__restrict__ x, const T *__restrict__ dy, const T *__restrict__ residual,
+             const float *__restrict__ scale_bias, const float *__restrict__ coef, T *__restrict__ out,
+             int64_t total, int C, FastDiv hw, int relu) {
+    pdl_sync();
+    constexpr int V = 8;
+    static_assert(sizeof(T) == 2, "16-bit element types");
+    const int64_t nvec = total / V;  // HW % 4 == 0 and the tensor holds whole planes: total % 4 == 0; a 4-element tail is possible
+    const Pack<T, V> *xp = reinterpret_cast<const Pack<T, V> *>(x);
+    const Pack<T, V> *gp = reinterpret_cast<const Pack<T, V> *>(dy);
+    const Pack<T, V> *rp = reinterpret_cast<const Pack<T, V> *>(residual);
+    Pack<T, V> *op = reinterpret_cast<Pack<T, V> *>(out);
+    const int HW = (int)hw.d;
+    const float2 zero2 = make_float2(0.f, 0.f);
+    for (int64_t v = (int64_t)blockIdx.x * kBT + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * kBT) {
+        const uint32_t e0 = (uint32_t)(v * V);
+        const uint32_t plane = fdiv(e0, hw);
+        const int within = (int)(e0 - plane * (uint32_t)HW);
+        const int c0 = (int)(plane % (uint32_t)C);
+        const int c1 = within + 4 < HW ? c0 : (c0 + 1 == C ? 0 : c0 + 1);  // channel of the second half
+        const Pack<T, V> xv = xp[v];
+        Pack<T, V> gv, rv, ov;
+        if (MODE == 1) {
+            gv = gp[v];
+            if (residual) rv = rp[v];
+        }
+        const float2 sb0 = __ldg(reinterpret_cast<const float2 *>(scale_bias) + c0), sb1 = __ldg(reinterpret_cast<const float2 *>(scale_bias) + c1);
+        float4 k0 = make_float4(0.f, 0.f, 0.f, 0.f), k1 = k0;
+        if (MODE == 1) {
+            k0 = __ldg(reinterpret_cast<const float4 *>(coef) + c0);
+            k1 = __ldg(reinterpret_cast<const float4 *>(coef) + c1);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float2 sc = h ? make_float2(sb1.x, sb1.x) : make_float2(sb0.x, sb0.x);
+            const float2 bi = h ? make_float2(sb1.y, sb1.y) : make_float2(sb0.y, sb0.y);
+            const float4 kk = h ? k1 : k0;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int k = h * 4 + j * 2;
+                const float2 f = make_float2(tof(xv.v[k]), tof(xv.v[k + 1]));
+                const float2 y = __ffma2_rn(f, sc, bi);
+                if (MODE == 0) {
+                    ov.v[k] = cvt<T, float>(relu ? fmaxf(y.x, 0.f) : y.x);
+                    ov.v[k + 1] = cvt<T, float>(relu ? fmaxf(y.y, 0.f) : y.y);
+                } else {
+                    float2 g = make_float2(tof(gv.v[k]), tof(gv.v[k + 1]));
+                    if (relu && !(y.x > 0.f)) g.x = 0.f;
+                    if (relu && !(y.y > 0.f)) g.y = 0.f;
+                    // c1 * g + c2 * f + c3
+                    float2 d = __ffma2_rn(make_float2(kk.x, kk.x), g, __ffma2_rn(make_float2(kk.y, kk.y), f, make_float2(kk.z, kk.z)));
+                    if (residual) d = __fadd2_rn(d, make_float2(tof(rv.v[k]), tof(rv.v[k + 1])));
+                    ov.v[k] = cvt<T, float>(d.x);
+                    ov.v[k + 1] = cvt<T, float>(d.y);
+                }
+            }
+        }
+        op[v] = ov;
+    }
+    (void)zero2;
+    // tail: total % 8 is 0 or 4 elements (one half vector), handled by the first threads of block 0
+    if (blockIdx.x == 0 && threadIdx.x < (int)(total - nvec * V)) {
+        const int64_t e = nvec * V + threadIdx.x;
+        const int c = (int)((e / HW) % C);
+        const float f = tof(x[e]);
+        const float y = f * scale_bias[2 * c] + scale_bias[2 * c + 1];
+        if (MODE == 0) {
+            out[e] = cvt<T, float>(relu ? fmaxf(y, 0.f) : y);
+        } else {
+            float g = tof(dy[e]);
+            if (relu && !(y > 0.f)) g = 0.f;
+            float d = coef[4 * c] * g + (coef[4 * c + 1] * f + coef[4 * c + 2]);
+            if (residual) d += tof(residual[e]);
+            out[e] = cvt<T, float>(d);
+        }
+    }
+}
+
+// 16-bit element types on planes of a multiple of 4 elements take the halves kernel
+template <typename T, int MODE>
+static void launch_bn_apply(int blocks, cudaStream_t s, const T *x, const T *dy, const T *residual, const float *scale_bias,
+                            const float *coef, T *out, int64_t total, int C, FastDiv hw, int relu) {
+    if constexpr (sizeof(T) == 2) {
+        if (hw.d % 4 == 0) {
+            launch_kernel(k_bn_apply_h<T, MODE>, dim3(blocks), dim3(kBT), 0, s, x, dy, residual, scale_bias, coef, out, total, C, hw, relu);
+            return;
+        }
+    }
+    launch_kernel(k_bn_apply<T, MODE>, dim3(blocks), dim3(kBT), 0, s, x, dy, residual, scale_bias, coef, out, total, C, hw, relu);
+}
+
 // ---- channel-resident forward pass (small maps) -------------------------------------------------------------------------
 // On the 14x14 / 7x7 maps (39 of the 51 blocks of RubiksNet-Large) a whole channel -- all NI planes of HW elements -- fits
 // one CTA's shared memory: 256 x 196 x 2 B = 100 KB.  One CTA per channel then does what the streaming path needs three
@@ -465,7 +561,7 @@ int rb::bn_apply_forward(const void *x, const float *scale_bias, void *y, int dt
         const int cap = sm_count() * 16;
         if (blocks > cap) blocks = cap;
         if (blocks < 1) blocks = 1;
-        launch_kernel(k_bn_apply<T, 0>, dim3(blocks), dim3(kBT), 0, s, (const T *)x, nullptr, nullptr, scale_bias, nullptr, (T *)y, total, C, hw, relu);
+        launch_bn_apply<T, 0>(blocks, s, (const T *)x, nullptr, nullptr, scale_bias, nullptr, (T *)y, total, C, hw, relu);
     });
     return launched("k_bn_apply<fwd>");
 }
@@ -538,8 +634,7 @@ extern "C" int rb_bn_act_forward(const void *x, const float *gamma, const float 
         const int cap = sm_count() * 16;
         if (blocks > cap) blocks = cap;
         if (blocks < 1) blocks = 1;
-        launch_kernel(k_bn_apply<T, 0>, dim3(blocks), dim3(kBT), 0, s, (const T *)x, nullptr, nullptr, scale_bias, nullptr, (T *)y, total, C, hw,
-                                               relu);
+        launch_bn_apply<T, 0>(blocks, s, (const T *)x, nullptr, nullptr, scale_bias, nullptr, (T *)y, total, C, hw, relu);
     });
     return launched("k_bn_apply<fwd>");
 }
@@ -582,8 +677,7 @@ extern "C" int rb_bn_act_backward(const void *x, const void *dy, const void *res
         const int cap = sm_count() * 16;
         if (blocks > cap) blocks = cap;
         if (blocks < 1) blocks = 1;
-        launch_kernel(k_bn_apply<T, 1>, dim3(blocks), dim3(kBT), 0, s, (const T *)x, (const T *)dy, (const T *)residual, scale_bias, coef,
-                                               (T *)dx, total, C, hw, relu);
+        launch_bn_apply<T, 1>(blocks, s, (const T *)x, (const T *)dy, (const T *)residual, scale_bias, coef, (T *)dx, total, C, hw, relu);
     });
     return launched("k_bn_apply<bwd>");
 }
