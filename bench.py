@@ -55,6 +55,9 @@ def parse():
     ap.add_argument("--graph-multi", default="whole", choices=["whole", "fwdbwd"],
                     help="N > 1: capture the whole step including the NCCL all-reduce and the SGD update (whole), or only "
                          "forward + backward with the exchange and the update eager (fwdbwd, round-1 behaviour)")
+    ap.add_argument("--sgd", default="fused", choices=["fused", "foreach"],
+                    help="torch.optim.SGD implementation of both arms: one fused multi-tensor kernel per chunk (default) or the "
+                         "foreach kernel sequence (the setting of the runs before r02zd)")
     ap.add_argument("--graph", default="on", choices=["on", "off"],
                     help="replay the whole step from a CUDA graph (rubiksnet_b200.graph.GraphedStep); off = eager launches")
     ap.add_argument("--pdl", default="on", choices=["on", "off"],
@@ -209,7 +212,7 @@ class Trainer:
         other = [p for n, p in self.net.named_parameters() if not n.endswith("shift")]
         # shift parameters get lr * 0.01 as in scripts/example_finetune.py:49-64
         self.opt = torch.optim.SGD([{"params": shift_params, "lr": 1e-4}, {"params": other}], lr=1e-2,
-                                   momentum=0.9, weight_decay=1e-4, foreach=True)
+                                   momentum=0.9, weight_decay=1e-4, **({"fused": True} if args.sgd == "fused" else {"foreach": True}))
         self.loss_fn = torch.nn.CrossEntropyLoss()
         self.graphed = None
 
@@ -487,6 +490,8 @@ def main():
                          "whole step replayed from one CUDA graph" if args.gpus == 1 or args.graph_multi == "whole" else
                          "forward + backward replayed from one CUDA graph, NCCL all-reduce + SGD eager"),
               "l2": "working set per step (>10 GB of activations) far exceeds the 126 MB L2; no flush needed"}
+    if not args.infer:
+        config["optimizer"] = "torch.optim.SGD(momentum=0.9, weight_decay=1e-4, %s=True), both arms" % args.sgd
 
     if args.impl == "reference":
         ref_ok = os.path.isdir(os.path.join(REPO, "baseline", "_ref", "rubiksnet"))

@@ -381,7 +381,7 @@ template <typename T, int MODE>
 static void launch_bn_apply(int blocks, cudaStream_t s, const T *x, const T *dy, const T *residual, const float *scale_bias,
                             const float *coef, T *out, int64_t total, int C, FastDiv hw, int relu) {
     if constexpr (sizeof(T) == 2) {
-        if (hw.d % 4 == 0) {
+        if (hw.d % 4 == 0 && total < (int64_t(1) << 32)) {  // the halves kernel indexes elements in 32 bits
             launch_kernel(k_bn_apply_h<T, MODE>, dim3(blocks), dim3(kBT), 0, s, x, dy, residual, scale_bias, coef, out, total, C, hw, relu);
             return;
         }

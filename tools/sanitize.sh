@@ -6,7 +6,7 @@ OUT=gpurun_out
 mkdir -p "$OUT"
 CS=/usr/local/cuda/bin/compute-sanitizer
 for tool in memcheck racecheck; do
-  for grp in pw shift misc; do
+  for grp in ${GROUPS_:-pw shift misc bn}; do
     log="$OUT/${TAG}_sanitizer_${tool}_${grp}.log"
     timeout 200 "$CS" --tool "$tool" --print-limit 20 --error-exitcode 3 python tools/sanitize_cases.py "$grp" > "$log" 2>&1
     echo "$tool $grp exit=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' "$log" | tail -1)"

@@ -106,8 +106,31 @@ def misc_cases():
     print("misc ok", flush=True)
 
 
+def bn_cases():
+    """BatchNorm passes on every dispatch path: the halves kernel of the 16-bit types (planes of a multiple of 4 elements,
+    vectors that straddle two planes, a 4-element tail), the per-element kernel (odd planes, fp32), the channel-resident
+    forward, with / without the shortcut gradient."""
+    for dtype in (BF, torch.float16, torch.float32):
+        for ni, c, h in ((16, 24, 14), (3, 5, 6), (2, 7, 7), (4, 8, 28), (40, 6, 14)):
+            x = torch.randn(ni, c, h, h, device="cuda").to(dtype)
+            g, b = torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda")
+            rm, rv = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+            for relu in (True, False):
+                y, mi, sb = ops.bn_forward(x, g, b, rm, rv, True, 0.1, 1e-5, relu=relu, apply=True)
+                ops.bn_forward(x, g, b, rm, rv, True, 0.1, 1e-5, relu=relu, apply=False)
+                ops.bn_apply(x, sb, relu=relu)
+                dy = torch.randn_like(x)
+                ops.bn_backward(x, dy, None, g, mi, sb, True, relu=relu)
+                ops.bn_backward(x, dy, torch.randn_like(x), g, mi, sb, True, relu=relu)
+            ops.bn_forward(x, g, b, rm, rv, False, 0.1, 1e-5, relu=True, apply=True)  # eval coefficients
+            torch.cuda.synchronize()
+    print("bn ok", flush=True)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["pw", "shift", "misc"]
+    which = sys.argv[1:] or ["pw", "shift", "misc", "bn"]
+    if "bn" in which:
+        bn_cases()
     if "pw" in which:
         pw_cases()
     if "shift" in which:
