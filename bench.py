@@ -52,9 +52,12 @@ def parse():
     ap.add_argument("--ref-autocast", action="store_true",
                     help="--impl reference only: run the reference model under bf16 autocast with .float() casts around its "
                          "(fp32-only) shift ops -- the like-for-like precision arm of SURVEY 8d(1)")
-    ap.add_argument("--graph-multi", default="whole", choices=["whole", "fwdbwd"],
+    ap.add_argument("--graph-multi", default="auto", choices=["auto", "whole", "fwdbwd"],
                     help="N > 1: capture the whole step including the NCCL all-reduce and the SGD update (whole), or only "
-                         "forward + backward with the exchange and the update eager (fwdbwd, round-1 behaviour)")
+                         "forward + backward with the exchange and the update eager (fwdbwd, round-1 behaviour).  auto = whole "
+                         "on 2 GPUs, fwdbwd beyond: the whole-step capture was only ever run on 2 GPUs (2 023 vs 2 013 clips/s "
+                         "there, profiles/r02zd_bench_c5_2gpu_ours.json / r02ze_bench_c5_2gpu_fwdbwd.json), the fwdbwd path on "
+                         "2 and 8 (SCALE_r01.json)")
     ap.add_argument("--sgd", default="fused", choices=["fused", "foreach"],
                     help="torch.optim.SGD implementation of both arms: one fused multi-tensor kernel per chunk (default) or the "
                          "foreach kernel sequence (the setting of the runs before r02zd)")
@@ -64,7 +67,10 @@ def parse():
                     help="programmatic dependent launch of the library's kernels (rb_set_dependent_launch); off = A/B arm")
     ap.add_argument("--tma", default="on", choices=["on", "off"],
                     help="tensor-map TMA schedules of the 1x1 convs / weight gradients on 16-byte-pitch maps (k_pw3, k_wg3); off = A/B arm")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.graph_multi == "auto":
+        args.graph_multi = "whole" if args.gpus <= 2 else "fwdbwd"
+    return args
 
 
 # --------------------------------------------------------------------------------------------- helpers

@@ -34,3 +34,24 @@ def test_roofline_summary_merges_kernel_roles():
     assert bench.summarize_roofline({}) is None
     r = bench.summarize_roofline({"bn_backward": agg["bn_backward"], "pw_conv": {"bytes": 1, "flops": 0, "ms": 0.1, "launches": 1}})
     assert r["kernel"] == "bn_backward" and r["traffic"] is None
+
+
+def test_cli_defaults_and_multi_gpu_launch_mode():
+    """No flags = N=1, a K/W that finish in minutes, fused SGD in both arms; --graph-multi auto resolves to the launch
+    mode that was verified on that many GPUs (whole-step capture on <= 2, forward+backward capture beyond)."""
+    bench = _bench()
+
+    def parse(*argv):
+        old, sys.argv = sys.argv, ["bench.py", *argv]
+        try:
+            return bench.parse()
+        finally:
+            sys.argv = old
+    a = parse()
+    assert (a.gpus, a.impl, a.batch, a.tier, a.variant, a.dtype, a.sgd) == (1, "ours", 32, "large", "rubiks3d", "bf16", "fused")
+    assert a.warmup >= 3 and 1 <= a.steps <= 20
+    assert a.graph_multi == "whole"
+    assert parse("--gpus", "2").graph_multi == "whole"
+    assert parse("--gpus", "4").graph_multi == "fwdbwd"
+    assert parse("--gpus", "8").graph_multi == "fwdbwd"
+    assert parse("--gpus", "8", "--graph-multi", "whole").graph_multi == "whole"
